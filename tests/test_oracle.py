@@ -1,0 +1,137 @@
+"""Pin the CPU oracle against the golden vectors produced by the reference itself
+(tests/golden/make_golden.py).  CPU only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_unet as npo
+from oracle import torch_unet as tpo
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden import det_state_dict, TRAIN_LR, TRAIN_WD  # noqa: E402
+
+
+def _rand(shape, seed):
+    return torch.rand(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def test_state_dict_is_the_published_model(best_sd):
+    # README.md:10-11 -- 486,409 parameters, 1.86 MB
+    assert len(best_sd) == 64
+    assert sum(v.numel() for v in best_sd.values()) == 486409
+    assert best_sd["enc1.0.weight"].shape == (8, 1, 3, 3)
+    assert best_sd["upconv4.weight"].shape == (128, 64, 2, 2)
+    assert best_sd["output_conv.weight"].shape == (1, 8, 1, 1)
+
+
+def test_torch_oracle_matches_reference_png(best_sd, golden):
+    g = golden("lw_png.npz")
+    for i in (1, 2):
+        x = torch.from_numpy(g[f"x{i}_u8"].astype(np.float32) / 255.0)[None, None]
+        with torch.no_grad():
+            y = tpo.lightweight_forward(x, best_sd)[0, 0].numpy()
+        assert np.abs(y - g[f"y{i}"]).max() <= 1e-5
+
+
+def test_torch_oracle_matches_reference_random_and_taps(best_sd, golden):
+    g = golden("lw_rand.npz")
+    taps = {}
+    with torch.no_grad():
+        y = tpo.lightweight_forward(_rand((2, 1, 64, 64), 0), best_sd, taps=taps)
+    assert np.abs(y.numpy() - g["y_2x64x64_seed0"]).max() <= 1e-5
+    names = [k for k in g.files if k.startswith("tap/")]
+    assert len(names) == 23  # 18 conv3x3 + 4 convT + head
+    for k in names:
+        key = k[4:]
+        if key == "output_conv":
+            continue
+        ref = g[k]
+        assert np.abs(taps[key].numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), key
+    with torch.no_grad():
+        assert np.abs(tpo.lightweight_forward(_rand((1, 1, 96, 80), 1), best_sd).numpy()
+                      - g["y_1x96x80_seed1"]).max() <= 1e-5
+        assert np.abs(tpo.lightweight_forward(_rand((3, 1, 16, 16), 2), best_sd).numpy()
+                      - g["y_3x16x16_seed2"]).max() <= 1e-5
+
+
+def test_numpy_oracle_matches_reference(best_sd, golden):
+    g = golden("lw_rand.npz")
+    sd = {k: v.numpy() for k, v in best_sd.items()}
+    x = _rand((2, 1, 64, 64), 0).numpy()
+    y32 = npo.lightweight_unet_forward(x, sd)
+    assert np.abs(y32 - g["y_2x64x64_seed0"]).max() <= 2e-5
+    y64 = npo.lightweight_unet_forward(x.astype(np.float64), sd)
+    assert np.abs(y64 - g["y_2x64x64_seed0"]).max() <= 2e-5
+    x = _rand((3, 1, 16, 16), 2).numpy()
+    assert np.abs(npo.lightweight_unet_forward(x, sd) - g["y_3x16x16_seed2"]).max() <= 2e-5
+
+
+def test_numpy_oracle_full_size_row(best_sd, golden):
+    g = golden("lw_rand.npz")
+    sd = {k: v.numpy() for k, v in best_sd.items()}
+    x = _rand((2, 1, 512, 512), 0)[:1].numpy()
+    y = npo.lightweight_unet_forward(x, sd)
+    assert np.abs(y[0, 0, 255] - g["y_2x512x512_seed0_row255"][0]).max() <= 2e-5
+
+
+def test_oracles_match_reference_variants(golden):
+    g = golden("lw_variants.npz")
+    for fs, hw in ((16, 64), (64, 32)):
+        tmpl = {k: tuple(int(s) for s in sh.split(",")) for k, sh in zip(g[f"keys_fs{fs}"], g[f"shapes_fs{fs}"])}
+        sd = det_state_dict(tmpl, seed=100 + fs)
+        x = _rand((2, 1, hw, hw), 5)
+        with torch.no_grad():
+            y = tpo.lightweight_forward(x, {k: torch.from_numpy(v) for k, v in sd.items()}).numpy()
+        ref = g[f"y_fs{fs}_2x{hw}x{hw}_seed5"]
+        assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    tmpl = {k: tuple(int(s) for s in sh.split(",")) for k, sh in zip(g["keys_fs12"], g["shapes_fs12"])}
+    sd = det_state_dict(tmpl, seed=112)
+    x = _rand((2, 3, 32, 48), 6)
+    ref = g["y_fs12_in3_out2_2x32x48_seed6"]
+    with torch.no_grad():
+        y = tpo.lightweight_forward(x, {k: torch.from_numpy(v) for k, v in sd.items()}).numpy()
+    assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    y = npo.lightweight_unet_forward(x.numpy(), sd)
+    assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    # divisor search gives 6 groups for 12 channels, 8 for 24/48/96/192
+    assert [npo._groups_lightweight(c, 8) for c in (12, 24, 48, 96, 192)] == [6, 8, 8, 8, 8]
+    assert list(g["gn_groups_fs12"][:4]) == [6, 6, 8, 8]
+
+
+def test_oracles_match_reference_optimized(golden):
+    g = golden("opt_rand.npz")
+    tmpl = {k: tuple(int(s) for s in sh.split(",")) for k, sh in zip(g["keys"], g["shapes"])}
+    assert len(tmpl) == 76 and int(g["n_params"]) == 2163969
+    sd = det_state_dict(tmpl, seed=1234)
+    assert abs(sum(float(np.abs(v).astype(np.float64).sum()) for v in sd.values()) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for shape, seed, key in (((2, 1, 64, 64), 3, "y_2x64x64_seed3"), ((1, 1, 48, 80), 4, "y_1x48x80_seed4")):
+        x = _rand(shape, seed)
+        ref = g[key]
+        with torch.no_grad():
+            y = tpo.optimized_forward(x, tsd).numpy()
+        assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+        y = npo.optimized_unet_forward(x.numpy(), sd)
+        assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_train_step_oracle_matches_reference(best_sd, golden):
+    g = golden("lw_train.npz")
+    x, t = _rand((2, 1, 64, 64), 0), _rand((2, 1, 64, 64), 1)
+    r = tpo.train_step(best_sd, x, t, lr=TRAIN_LR, weight_decay=TRAIN_WD, max_norm=1.0)
+    assert abs(r["loss"] - float(g["loss"])) <= 1e-6
+    assert abs(r["total_norm"] - float(g["total_norm"])) <= 1e-4
+    for k in best_sd:
+        gr = g["grad/" + k]
+        assert np.abs(r["grads"][k].numpy() - gr).max() <= 1e-5 + 1e-4 * np.abs(gr).max(), k
+        assert np.abs(r["new_params"][k].numpy() - g["new/" + k]).max() <= 2e-6, k
+
+
+def test_l1_grad_restatement():
+    o = np.array([[0.2, 0.5], [0.7, 0.1]])
+    t = np.array([[0.5, 0.5], [0.1, 0.4]])
+    assert npo.l1_loss(o, t) == pytest.approx(0.3)
+    assert np.array_equal(npo.l1_loss_grad(o, t), np.array([[-0.25, 0.0], [0.25, -0.25]]))
