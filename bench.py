@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Headline benchmark: LightweightUNet de-glaring inference, images/sec (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one forward pass of the 486,409-parameter best_model UNet over one batch of 64 synthetic
+1x512x512 grayscale images per GPU (BASELINE.json configs[1]); batches shard over GPUs with no
+collective (weak scaling).  `value` is device-resident throughput (CUDA events, max over ranks);
+`e2e` goes through the ORT-shaped `InferenceSession.run_pinned` -> `dg_lw_infer_host` C-ABI call with
+pinned HOST buffers, H2D + D2H inside the timed region.  `roofline` is for the dominant kernel,
+timed live with CUDA events by `dg_lw_profile`.  `cpu_baseline` / `--impl reference` time the CPU
+oracle port of the reference's PyTorch-CPU path (oracle/torch_unet.py -- the reference itself cannot
+travel to the GPU box) on all host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "unet_deglare_512x512_images_per_sec"
+UNIT = "images/s"
+LAYERS = ["enc1.0", "enc1.3", "enc2.0", "enc2.3", "enc3.0", "enc3.3", "enc4.0", "enc4.3", "bottleneck.0",
+          "bottleneck.3", "up4+dec4.0", "dec4.3", "up3+dec3.0", "dec3.3", "up2+dec2.0", "dec2.3", "up1+dec1.0",
+          "dec1.3", "head"]
+
+
+def algorithmic_bytes_per_image(H, W, fs=8, esize=2):
+    """SURVEY.md section 8(d) minimal-traffic model, per kernel: every raw conv output written once and read once
+    per consumer, input fp32 read once, output fp32 written once; pooled/up-sampled/concat tensors never stored."""
+    f = [fs << i for i in range(5)]
+    px = [(H >> i) * (W >> i) for i in range(5)]
+    out = []
+    out.append(px[0] * 4 + px[0] * f[0] * esize)                                   # enc1.0: image in, raw out
+    out.append(2 * px[0] * f[0] * esize)                                            # enc1.3
+    for l in range(1, 5):
+        out.append(px[l - 1] * f[l - 1] * esize + px[l] * f[l] * esize)             # encL.0 reads full-res producer
+        out.append(2 * px[l] * f[l] * esize)                                        # encL.3
+    for l in (3, 2, 1, 0):
+        out.append(px[l + 1] * f[l + 1] * esize + 2 * px[l] * f[l] * esize)         # up + dec.0: low, skip, out
+        out.append(2 * px[l] * f[l] * esize)                                        # dec.3
+    out.append(px[0] * f[0] * esize + px[0] * 4)                                    # head
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for t, l in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        for l in rows:
+            parts = [p.strip() for p in l.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(batch, reps, H, W):
+    """Oracle port of the reference's PyTorch-CPU path on all host cores; returns (images/s, cores)."""
+    import torch
+    from oracle import torch_unet as tpo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = torch.load(os.path.join(ROOT, "weights", "best_model.pth"))
+    x = torch.rand(batch, 1, H, W, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        tpo.lightweight_forward(x[:1], sd)
+        times = []
+        for _ in range(reps):
+            t = time.perf_counter()
+            tpo.lightweight_forward(x, sd)
+            times.append(time.perf_counter() - t)
+    return batch / statistics.median(times), cores, times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    t0 = time.perf_counter()
+    import torch
+    from oracle import torch_unet as tpo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = torch.load(os.path.join(ROOT, "weights", "best_model.pth"))
+    x = torch.rand(batch, 1, args.hw, args.hw, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            tpo.lightweight_forward(x, sd)
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            tpo.lightweight_forward(x, sd)
+        dt = time.perf_counter() - t
+    rate = batch * args.steps / dt
+    sample = f"{args.steps} steps x {batch} images of 1x{args.hw}x{args.hw}, fp32, torch CPU {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"best_model.pth LightweightUNet inference, bounded sample of batch {batch} x 1x{args.hw}x{args.hw} "
+                               "(configs[1] shape), reference PyTorch-CPU path via oracle port", "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--storage", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--hw", type=int, default=512)
+    ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--path", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    import image_enhancement_deglaring_b200 as dg
+    from image_enhancement_deglaring_b200 import _lib
+    from image_enhancement_deglaring_b200.session import InferenceSession
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    H = W = args.hw
+    B = args.batch
+    sd = torch.load(os.path.join(ROOT, "weights", "best_model.pth"))
+    net = dg.LightweightUNet(storage=args.storage, path=args.path)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    x = torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(rank)).to(dev)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            y = net(x)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            y = net(x)
+        e1.record()
+        barrier()
+        t1 = time.perf_counter()
+        launches = _lib.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the reference-facing session API, host buffers in and out ------------
+    sess = InferenceSession(net, chunk=8)
+    hx, hy = sess.pinned_buffers(B, H, W)
+    hx.copy_(x.cpu())
+    for _ in range(2):
+        sess.run_pinned(hx, hy)
+    barrier()
+    te = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        sess.run_pinned(hx, hy)
+    barrier()
+    e2e_s = time.perf_counter() - te
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(t.item())
+    e2e_err = float((hy.to(dev) - y).abs().max())
+
+    # ---- per-kernel device times (CUDA events on the launching stream) -> roofline of the dominant kernel
+    roofline = None
+    if rank == 0:
+        ws = torch.empty(net.workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+        yy = torch.empty_like(y)
+        acc = [0.0] * 19
+        reps = max(3, min(args.steps, 10))
+        buf = (C.c_float * 19)()
+        for it in range(reps + 1):
+            _lib.check(_lib.load().dg_lw_profile(C.byref(net.c_params()), x.data_ptr(), yy.data_ptr(), B, H, W,
+                                                 ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream, buf))
+            if it:
+                acc = [a + b for a, b in zip(acc, buf)]
+        per_kernel_ms = [a / reps for a in acc]
+        esize = 4 if args.storage == "fp32" else 2
+        abytes = [b * B for b in algorithmic_bytes_per_image(H, W, 8, esize)]
+        top = max(range(19), key=lambda i: per_kernel_ms[i])
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = abytes[top] / (per_kernel_ms[top] * 1e-3) / 1e9
+        net_bytes = sum(abytes)
+        roofline = {
+            "bound": "hbm", "kernel": LAYERS[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+            "kernel_ms": per_kernel_ms[top], "kernel_share_of_step": per_kernel_ms[top] / sum(per_kernel_ms),
+            "whole_net": {"algorithmic_bytes_per_step": net_bytes, "achieved": net_bytes / (ms_max / args.steps * 1e-3) / 1e9,
+                          "frac": net_bytes / (ms_max / args.steps * 1e-3) / 1e9 / peak},
+            "per_kernel": {n: {"ms": round(m, 4), "GBps": round(b / (m * 1e-3) / 1e9, 1)}
+                           for n, m, b in zip(LAYERS, per_kernel_ms, abytes)},
+        }
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        reps = 3
+        rate, cores, times = cpu_reference_rate(args.ref_batch, reps, H, W)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"median of {reps} forwards of {args.ref_batch} x 1x{H}x{W} fp32 images, torch CPU, "
+                                  f"{cores} threads ({sum(times):.1f} s of CPU work)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.storage, "data": "synthetic",
+            "config": {"workload": f"best_model.pth LightweightUNet (486,409 params) batched inference, batch {B} x 1x{H}x{W} "
+                                   f"per GPU, {args.storage} storage / fp32 accumulate (BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "global_batch": B * world, "sharding": "images over ranks, no collective",
+                       "l2": f"inputs+intermediates per step ({sum(algorithmic_bytes_per_image(H, W)) * B / 2**20:.0f} MiB) exceed the 126 MB L2; no flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 4, "d2h_bytes_per_step": B * H * W * 4,
+                    "steps": e2e_steps, "api": "InferenceSession.run_pinned -> dg_lw_infer_host (pinned host buffers)",
+                    "max_abs_vs_device_path": e2e_err},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,339 @@
+// C-ABI entry points + the native LightweightUNet orchestrator (see include/deglare.h).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return 10;
+    }
+    return 0;
+}
+
+static int validate_src(const dg_src& s, const char* who) {
+    if (s.raw == nullptr) { set_error("%s: null source pointer", who); return 2; }
+    if (s.channels < 1) { set_error("%s: bad channel count %d", who, s.channels); return 2; }
+    if (s.stats != nullptr) {
+        if (s.gamma == nullptr || s.beta == nullptr) { set_error("%s: GroupNorm affine missing", who); return 2; }
+        if (s.groups < 1 || s.channels % s.groups != 0) {
+            set_error("%s: %d channels not divisible into %d groups", who, s.channels, s.groups);
+            return 2;
+        }
+    }
+    if (s.xform == DG_X_CONVT2 && (s.ct_w == nullptr || s.ct_b == nullptr || s.ct_cout < 1)) {
+        set_error("%s: ConvTranspose parameters missing", who);
+        return 2;
+    }
+    if (s.xform < DG_X_SAME || s.xform > DG_X_IMAGE) { set_error("%s: bad xform %d", who, s.xform); return 2; }
+    return 0;
+}
+
+// ---- LightweightUNet plan -----------------------------------------------------------------
+struct LwPlan {
+    int f[5];
+    int conv_c[18], conv_h[18], conv_w[18];
+    size_t raw_off[18], stats_off[18];
+    size_t stats_bytes, total_bytes;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline size_t dtype_size(int dt) { return dt == DG_F32 ? 4 : 2; }
+static inline int block_level(int b) { return b < 5 ? b : 8 - b; }
+
+static int make_plan(const dg_lw_params* p, int N, int H, int W, LwPlan* pl) {
+    if (p == nullptr) { set_error("null params"); return 2; }
+    if (N < 1 || H < 16 || W < 16 || (H % 16) || (W % 16)) {
+        // 500x500 raises at the first torch.cat in the reference (src/model.py:116); here it is an error too
+        set_error("input %dx%dx%d: H and W must be positive multiples of 16", N, H, W);
+        return 3;
+    }
+    if (p->dtype < DG_F32 || p->dtype > DG_BF16) { set_error("bad dtype %d", p->dtype); return 2; }
+    if (p->features_start < 1 || p->in_channels < 1 || p->out_channels < 1) { set_error("bad channel configuration"); return 2; }
+    for (int l = 0; l < 5; ++l) pl->f[l] = p->features_start << l;
+    size_t off = 0;
+    for (int i = 0; i < 18; ++i) {
+        const int lvl = block_level(i / 2);
+        pl->conv_c[i] = pl->f[lvl];
+        pl->conv_h[i] = H >> lvl;
+        pl->conv_w[i] = W >> lvl;
+        pl->stats_off[i] = off;
+        off += (size_t)N * pl->conv_c[i] * 2 * sizeof(double);
+    }
+    pl->stats_bytes = off;
+    off = align_up(off, 256);
+    for (int i = 0; i < 18; ++i) {
+        pl->raw_off[i] = off;
+        off += align_up((size_t)N * pl->conv_h[i] * pl->conv_w[i] * pl->conv_c[i] * dtype_size(p->dtype), 256);
+    }
+    pl->total_bytes = off;
+    return 0;
+}
+
+static dg_src gn_src(const dg_lw_params* p, const LwPlan& pl, char* ws, int conv_idx, int xform) {
+    dg_src s;
+    memset(&s, 0, sizeof(s));
+    const int b = conv_idx / 2, j = conv_idx % 2;
+    s.raw = ws + pl.raw_off[conv_idx];
+    s.stats = reinterpret_cast<const double*>(ws + pl.stats_off[conv_idx]);
+    s.gamma = p->gn_w[b][j];
+    s.beta = p->gn_b[b][j];
+    s.channels = pl.conv_c[conv_idx];
+    s.groups = p->groups[b];
+    s.xform = xform;
+    s.silu = 1;
+    return s;
+}
+
+static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, int H, int W, void* workspace,
+                      size_t ws_bytes, const float* target, double* l1_sum, cudaStream_t stream,
+                      cudaEvent_t* evs = nullptr) {
+    LwPlan pl;
+    int rc = make_plan(p, N, H, W, &pl);
+    if (rc) return rc;
+    if (workspace == nullptr || ws_bytes < pl.total_bytes) {
+        set_error("workspace too small: %zu < %zu", ws_bytes, pl.total_bytes);
+        return 4;
+    }
+    if (x == nullptr || y == nullptr) { set_error("null input/output"); return 2; }
+    char* ws = static_cast<char*>(workspace);
+    cudaError_t e = cudaMemsetAsync(ws, 0, pl.stats_bytes, stream);
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 10; }
+
+    if (evs) cudaEventRecord(evs[0], stream);
+    for (int i = 0; i < 18; ++i) {
+        const int b = i / 2;
+        dg_conv3x3_args a;
+        memset(&a, 0, sizeof(a));
+        a.dtype = p->dtype;
+        a.N = N; a.H = pl.conv_h[i]; a.W = pl.conv_w[i];
+        a.cout = pl.conv_c[i];
+        a.weight = p->conv_w[b][i % 2];
+        a.out = ws + pl.raw_off[i];
+        a.out_stats = reinterpret_cast<double*>(ws + pl.stats_off[i]);
+        a.eps = 1e-5f;
+        a.path = p->path;
+        a.nsrc = 1;
+        if (i == 0) {
+            memset(&a.src[0], 0, sizeof(dg_src));
+            a.src[0].raw = x;
+            a.src[0].channels = p->in_channels;
+            a.src[0].groups = 1;
+            a.src[0].xform = DG_X_IMAGE;
+        } else if (i % 2 == 1) {
+            a.src[0] = gn_src(p, pl, ws, i - 1, DG_X_SAME);
+        } else if (b < 5) {
+            a.src[0] = gn_src(p, pl, ws, i - 1, DG_X_POOL2);        // pool1..4, src/model.py:107-112
+        } else {
+            const int lvl = block_level(b), u = b - 5;
+            a.src[0] = gn_src(p, pl, ws, i - 1, DG_X_CONVT2);      // upconv4..1, src/model.py:115-127
+            a.src[0].ct_w = p->up_w[u];
+            a.src[0].ct_b = p->up_b[u];
+            a.src[0].ct_cout = pl.f[lvl];
+            a.src[1] = gn_src(p, pl, ws, 2 * lvl + 1, DG_X_SAME);  // skip: torch.cat((up, skip), 1)
+            a.nsrc = 2;
+        }
+        rc = dg_conv3x3_fused(&a, reinterpret_cast<dg_stream_t>(stream));
+        if (rc) return rc;
+        if (evs) cudaEventRecord(evs[i + 1], stream);
+    }
+    dg_head_args h;
+    memset(&h, 0, sizeof(h));
+    h.src = gn_src(p, pl, ws, 17, DG_X_SAME);
+    h.dtype = p->dtype;
+    h.N = N; h.H = H; h.W = W;
+    h.cout = p->out_channels;
+    h.weight = p->head_w;
+    h.bias = p->head_b;
+    h.out = y;
+    h.target = target;
+    h.l1_sum = l1_sum;
+    h.eps = 1e-5f;
+    rc = dg_head1x1(&h, reinterpret_cast<dg_stream_t>(stream));
+    if (evs) cudaEventRecord(evs[19], stream);
+    return rc;
+}
+
+// ---- host-buffer pipeline state --------------------------------------------------------------
+struct HostPipe {
+    bool ready = false;
+    cudaStream_t s_in, s_cmp, s_out;
+    cudaEvent_t in_done[2], cmp_done[2], out_done[2];
+};
+static HostPipe g_pipe;
+
+static int pipe_init() {
+    if (g_pipe.ready) return 0;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&g_pipe.s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&g_pipe.s_cmp, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&g_pipe.s_out, cudaStreamNonBlocking)) != cudaSuccess) {
+        set_error("stream create: %s", cudaGetErrorString(e));
+        return 10;
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&g_pipe.in_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g_pipe.cmp_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g_pipe.out_done[i], cudaEventDisableTiming);
+    }
+    g_pipe.ready = true;
+    return 0;
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" {
+
+const char* dg_last_error_string(void) { return g_err; }
+int dg_version(void) { return 100; }
+uint64_t dg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dg_conv3x3_fused(const dg_conv3x3_args* a, dg_stream_t stream) {
+    if (a == nullptr) { set_error("conv3x3: null args"); return 2; }
+    if (a->nsrc < 1 || a->nsrc > 2) { set_error("conv3x3: nsrc %d", a->nsrc); return 2; }
+    if (a->N < 1 || a->H < 1 || a->W < 1 || a->cout < 1) { set_error("conv3x3: bad shape"); return 3; }
+    if (a->weight == nullptr || a->out == nullptr) { set_error("conv3x3: null weight/out"); return 2; }
+    for (int s = 0; s < a->nsrc; ++s) {
+        int rc = validate_src(a->src[s], "conv3x3");
+        if (rc) return rc;
+        const int xf = a->src[s].xform;
+        if ((xf == DG_X_UP2 || xf == DG_X_CONVT2) && ((a->H | a->W) & 1)) {
+            set_error("conv3x3: up-sampled source needs even H, W (got %dx%d)", a->H, a->W);
+            return 3;
+        }
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->path != 1) {
+        bool handled = false;
+        int rc = conv3x3_tc_launch(*a, st, &handled);
+        if (rc) return rc;
+        if (handled) return 0;
+        if (a->path == 2) { set_error("conv3x3: tensor-core path does not cover this configuration"); return 3; }
+    }
+    return conv3x3_generic_launch(*a, st);
+}
+
+int dg_head1x1(const dg_head_args* a, dg_stream_t stream) {
+    if (a == nullptr) { set_error("head: null args"); return 2; }
+    int rc = validate_src(a->src, "head");
+    if (rc) return rc;
+    if (a->src.xform != DG_X_SAME) { set_error("head: source must be same-resolution"); return 3; }
+    if (a->weight == nullptr || a->bias == nullptr || a->out == nullptr) { set_error("head: null pointer"); return 2; }
+    return head_launch(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_lw_workspace_bytes(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, size_t* bytes) {
+    LwPlan pl;
+    int rc = make_plan(p, N, H, W, &pl);
+    if (rc) return rc;
+    if (bytes) *bytes = pl.total_bytes;
+    return 0;
+}
+
+int dg_lw_layout(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, int32_t idx, size_t* raw_offset,
+                 size_t* stats_offset, int32_t* channels, int32_t* h, int32_t* w) {
+    LwPlan pl;
+    int rc = make_plan(p, N, H, W, &pl);
+    if (rc) return rc;
+    if (idx < 0 || idx >= 18) { set_error("layout: conv index %d", idx); return 2; }
+    if (raw_offset) *raw_offset = pl.raw_off[idx];
+    if (stats_offset) *stats_offset = pl.stats_off[idx];
+    if (channels) *channels = pl.conv_c[idx];
+    if (h) *h = pl.conv_h[idx];
+    if (w) *w = pl.conv_w[idx];
+    return 0;
+}
+
+int dg_lw_forward(const dg_lw_params* p, const float* x, float* y, int32_t N, int32_t H, int32_t W, void* workspace,
+                  size_t workspace_bytes, const float* target, double* l1_sum, dg_stream_t stream) {
+    return lw_forward(p, x, y, N, H, W, workspace, workspace_bytes, target, l1_sum,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_lw_profile(const dg_lw_params* p, const float* x, float* y, int32_t N, int32_t H, int32_t W, void* workspace,
+                  size_t workspace_bytes, dg_stream_t stream, float* ms19) {
+    if (ms19 == nullptr) { set_error("profile: null output"); return 2; }
+    cudaEvent_t evs[20];
+    for (int i = 0; i < 20; ++i) cudaEventCreate(&evs[i]);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = lw_forward(p, x, y, N, H, W, workspace, workspace_bytes, nullptr, nullptr, st, evs);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == 0 && e != cudaSuccess) { set_error("profile: %s", cudaGetErrorString(e)); rc = 10; }
+    if (rc == 0)
+        for (int i = 0; i < 19; ++i) cudaEventElapsedTime(&ms19[i], evs[i], evs[i + 1]);
+    for (int i = 0; i < 20; ++i) cudaEventDestroy(evs[i]);
+    return rc;
+}
+
+int dg_lw_host_scratch_bytes(const dg_lw_params* p, int32_t chunk, int32_t H, int32_t W, size_t* bytes) {
+    LwPlan pl;
+    int rc = make_plan(p, chunk, H, W, &pl);
+    if (rc) return rc;
+    const size_t in_b = align_up((size_t)chunk * p->in_channels * H * W * sizeof(float), 256);
+    const size_t out_b = align_up((size_t)chunk * p->out_channels * H * W * sizeof(float), 256);
+    if (bytes) *bytes = 2 * in_b + 2 * out_b + pl.total_bytes;
+    return 0;
+}
+
+int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, int32_t N, int32_t H, int32_t W,
+                     int32_t chunk, void* dev_ws, size_t dev_ws_bytes) {
+    if (chunk < 1) { set_error("infer_host: chunk %d", chunk); return 2; }
+    if (chunk > N) chunk = N;
+    LwPlan pl;
+    int rc = make_plan(p, chunk, H, W, &pl);
+    if (rc) return rc;
+    size_t need = 0;
+    dg_lw_host_scratch_bytes(p, chunk, H, W, &need);
+    if (dev_ws == nullptr || dev_ws_bytes < need) { set_error("infer_host: scratch %zu < %zu", dev_ws_bytes, need); return 4; }
+    if (host_x == nullptr || host_y == nullptr) { set_error("infer_host: null host buffer"); return 2; }
+    if ((rc = pipe_init())) return rc;
+    const size_t in_img = (size_t)p->in_channels * H * W, out_img = (size_t)p->out_channels * H * W;
+    const size_t in_b = align_up(chunk * in_img * sizeof(float), 256);
+    const size_t out_b = align_up(chunk * out_img * sizeof(float), 256);
+    char* base = static_cast<char*>(dev_ws);
+    float* dx[2] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + in_b)};
+    float* dy[2] = {reinterpret_cast<float*>(base + 2 * in_b), reinterpret_cast<float*>(base + 2 * in_b + out_b)};
+    void* ws = base + 2 * in_b + 2 * out_b;
+    HostPipe& P = g_pipe;
+    const int nchunks = (N + chunk - 1) / chunk;
+    for (int i = 0; i < nchunks; ++i) {
+        const int b = i & 1;
+        const int n0 = i * chunk;
+        const int nn = (N - n0 < chunk) ? (N - n0) : chunk;
+        if (i >= 2) cudaStreamWaitEvent(P.s_in, P.cmp_done[b], 0);  // dx[b] consumed by chunk i-2
+        cudaMemcpyAsync(dx[b], host_x + (size_t)n0 * in_img, nn * in_img * sizeof(float), cudaMemcpyHostToDevice, P.s_in);
+        cudaEventRecord(P.in_done[b], P.s_in);
+        cudaStreamWaitEvent(P.s_cmp, P.in_done[b], 0);
+        if (i >= 2) cudaStreamWaitEvent(P.s_cmp, P.out_done[b], 0);  // dy[b] drained by chunk i-2
+        rc = lw_forward(p, dx[b], dy[b], nn, H, W, ws, pl.total_bytes, nullptr, nullptr, P.s_cmp);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        cudaEventRecord(P.cmp_done[b], P.s_cmp);
+        cudaStreamWaitEvent(P.s_out, P.cmp_done[b], 0);
+        cudaMemcpyAsync(host_y + (size_t)n0 * out_img, dy[b], nn * out_img * sizeof(float), cudaMemcpyDeviceToHost, P.s_out);
+        cudaEventRecord(P.out_done[b], P.s_out);
+    }
+    cudaError_t e = cudaStreamSynchronize(P.s_out);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(P.s_cmp);
+    if (e != cudaSuccess) { set_error("infer_host: %s", cudaGetErrorString(e)); return 10; }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// Shared device helpers for the de-glaring UNet kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "deglare.h"
+
+namespace dg {
+
+// ---- storage traits: activations live in HBM as T, arithmetic is fp32 -----------------
+template <typename T> struct Store;
+template <> struct Store<float> {
+    static __device__ __forceinline__ float to_f(float v) { return v; }
+    static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct Store<__half> {
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct Store<__nv_bfloat16> {
+    static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// load `cn` (<= 8) consecutive channels starting at p into v[0..8); 128-bit path when `vec`
+template <typename T>
+__device__ __forceinline__ void load8(const T* __restrict__ p, int cn, bool vec, float (&v)[8]) {
+    if (vec) {
+        if constexpr (sizeof(T) == 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+            const T* h = reinterpret_cast<const T*>(&a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = Store<T>::to_f(h[k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (k < cn) ? Store<T>::to_f(p[k]) : 0.f;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store8(T* __restrict__ p, int cn, bool vec, const float (&v)[8]) {
+    if (vec) {
+        if constexpr (sizeof(T) == 4) {
+            reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+            uint4 a;
+            T* h = reinterpret_cast<T*>(&a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) h[k] = Store<T>::from_f(v[k]);
+            *reinterpret_cast<uint4*>(p) = a;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < cn) p[k] = Store<T>::from_f(v[k]);
+    }
+}
+
+// x * sigmoid(x); __expf is ex2.approx based (rel. err ~2^-21), the divide is IEEE.
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// GroupNorm coefficients of channel c of sample n from per-channel (sum, sumsq):
+//   y = raw * a + b  with  a = rstd*gamma, b = beta - mean*a   (biased variance, eps inside sqrt)
+__device__ __forceinline__ void gn_coef(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, int n, int C, int groups, int c,
+                                        double plane, float eps, float& a, float& b) {
+    const int cpg = C / groups;
+    const int g0 = (c / cpg) * cpg;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+        s1 += stats[(size_t)(n * C + g0 + k) * 2];
+        s2 += stats[(size_t)(n * C + g0 + k) * 2 + 1];
+    }
+    const double cnt = plane * cpg;
+    const double mean = s1 / cnt;
+    double var = s2 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = rsqrt(var + (double)eps);
+    a = (float)(rstd * (double)gamma[c]);
+    b = (float)((double)beta[c] - mean * rstd * (double)gamma[c]);
+}
+
+}  // namespace dg
+
+// ---- host side ---------------------------------------------------------------------------
+namespace dg {
+void set_error(const char* fmt, ...);
+void count_launch();
+int check_launch(const char* what);
+int conv3x3_generic_launch(const dg_conv3x3_args& a, cudaStream_t stream);
+int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
+int head_launch(const dg_head_args& a, cudaStream_t stream);
+}  // namespace dg

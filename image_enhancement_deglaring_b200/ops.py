@@ -1,0 +1,101 @@
+"""Thin per-op wrappers over the C-ABI (used by tests and by the training autograd path).
+
+Tensors are torch CUDA tensors; this module only marshals pointers -- the arithmetic is in csrc/.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (DG_BF16, DG_F16, DG_F32, DG_X_CONVT2, DG_X_IMAGE, DG_X_POOL2, DG_X_SAME, DG_X_UP2,  # noqa: F401
+                   DgConv3x3Args, DgHeadArgs, DgSrc)
+
+TORCH_DTYPE = {DG_F32: torch.float32, DG_F16: torch.float16, DG_BF16: torch.bfloat16}
+DTYPE_OF_TORCH = {v: k for k, v in TORCH_DTYPE.items()}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("image_enhancement_deglaring_b200 runs on CUDA tensors only (no CPU fallback)")
+
+
+def pack_conv3x3(w):
+    """nn.Conv2d weight [Co,Ci,3,3] -> [3,3,Ci,Co] fp32 contiguous."""
+    return w.detach().float().permute(2, 3, 1, 0).contiguous()
+
+
+def pack_convt2x2(w):
+    """nn.ConvTranspose2d weight [Ci,Co,2,2] -> [2,2,Ci,Co] fp32 contiguous."""
+    return w.detach().float().permute(2, 3, 0, 1).contiguous()
+
+
+def make_src(raw, channels, xform=DG_X_SAME, stats=None, gamma=None, beta=None, groups=1, silu=True,
+             scale=None, ct_w=None, ct_b=None, ct_cout=0):
+    _require_cuda(raw, stats, gamma, beta, scale, ct_w, ct_b)
+    s = DgSrc()
+    s.raw = _ptr(raw)
+    s.stats = _ptr(stats)
+    s.gamma = _ptr(gamma)
+    s.beta = _ptr(beta)
+    s.scale = _ptr(scale)
+    s.ct_w = _ptr(ct_w)
+    s.ct_b = _ptr(ct_b)
+    s.channels = channels
+    s.groups = groups
+    s.xform = xform
+    s.silu = 1 if silu else 0
+    s.ct_cout = ct_cout
+    return s
+
+
+def _stream(stream):
+    return (torch.cuda.current_stream() if stream is None else stream).cuda_stream
+
+
+def conv3x3_fused(srcs, weight, cout, N, H, W, dtype, out=None, out_stats=None, act_sum=None, path=0, stream=None,
+                  eps=1e-5):
+    """Fused 3x3 conv over the concat of `srcs` (list of DgSrc).  Returns (raw NHWC out, stats [N,cout,2] f64)."""
+    lib = _lib.load()
+    dev = weight.device
+    if out is None:
+        out = torch.empty((N, H, W, cout), dtype=TORCH_DTYPE[dtype], device=dev)
+    if out_stats is None:
+        out_stats = torch.zeros((N, cout, 2), dtype=torch.float64, device=dev)
+    a = DgConv3x3Args()
+    for i, s in enumerate(srcs):
+        a.src[i] = s
+    a.nsrc = len(srcs)
+    a.dtype = dtype
+    a.N, a.H, a.W, a.cout = N, H, W, cout
+    a.weight = _ptr(weight)
+    a.out = _ptr(out)
+    a.out_stats = _ptr(out_stats)
+    a.act_sum = _ptr(act_sum)
+    a.eps = eps
+    a.path = path
+    _lib.check(lib.dg_conv3x3_fused(C.byref(a), _stream(stream)))
+    return out, out_stats
+
+
+def head1x1(src, weight, bias, N, H, W, dtype, out=None, target=None, l1_sum=None, stream=None, eps=1e-5):
+    lib = _lib.load()
+    cout = weight.shape[0]
+    if out is None:
+        out = torch.empty((N, cout, H, W), dtype=torch.float32, device=weight.device)
+    a = DgHeadArgs()
+    a.src = src
+    a.dtype = dtype
+    a.N, a.H, a.W, a.cout = N, H, W, cout
+    a.weight = _ptr(weight)
+    a.bias = _ptr(bias)
+    a.out = _ptr(out)
+    a.target = _ptr(target)
+    a.l1_sum = _ptr(l1_sum)
+    a.eps = eps
+    _lib.check(lib.dg_head1x1(C.byref(a), _stream(stream)))
+    return out

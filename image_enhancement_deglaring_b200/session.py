@@ -1,0 +1,97 @@
+"""`onnxruntime.InferenceSession`-shaped front end over the B200 kernels.
+
+api/app.py:84 builds `ort.InferenceSession(best_model.onnx)` and api/app.py:171 calls
+`ort_session.run([output_name], {input_name: float32 ndarray [1,1,512,512]})`; evaluate.py:95-125
+wraps the same call.  This class exposes exactly that protocol (`run`, `get_inputs`, `get_outputs`)
+but routes the batch through `dg_lw_infer_host` (include/deglare.h): HOST buffers in, HOST buffers
+out, with the H2D copy, the forward and the D2H copy pipelined over image chunks inside the library.
+
+    sess = InferenceSession("weights/best_model.pth")        # or an nn.Module
+    out = sess.run([sess.get_outputs()[0].name], {sess.get_inputs()[0].name: x})[0]
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import LightweightUNet
+
+NodeArg = namedtuple("NodeArg", "name shape type")
+
+
+class InferenceSession:
+    def __init__(self, model, providers=None, *, storage="fp32", chunk=8, device="cuda:0"):
+        if isinstance(model, (str, bytes)):
+            ckpt = torch.load(model, map_location="cpu")
+            if "model_state_dict" in ckpt:  # optimized_train.py:63-73 checkpoint layout
+                ckpt = ckpt["model_state_dict"]
+            net = LightweightUNet(storage=storage)
+            net.load_state_dict(ckpt, strict=True)
+            model = net.to(device).eval()
+        self.model = model
+        self.chunk = chunk
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("InferenceSession needs the model on a CUDA device (no CPU fallback)")
+        self._in = NodeArg("input", ["batch_size", model.in_channels, "height", "width"], "tensor(float)")
+        self._out = NodeArg("output", ["batch_size", model.out_channels, "height", "width"], "tensor(float)")
+        self._scratch = None
+        self._scratch_key = None
+        self._pin_in = None
+        self._pin_out = None
+
+    def get_inputs(self):
+        return [self._in]
+
+    def get_outputs(self):
+        return [self._out]
+
+    def get_providers(self):
+        return ["B200DeglareExecutionProvider"]
+
+    # ---- pinned staging -----------------------------------------------------------------------------
+    def pinned_buffers(self, N, H, W):
+        """Pinned host (input, output) tensors of the right shape; numpy views of them passed to run() /
+        run_pinned() are used in place (zero extra host copies)."""
+        m = self.model
+        if self._pin_in is None or tuple(self._pin_in.shape) != (N, m.in_channels, H, W):
+            self._pin_in = torch.empty((N, m.in_channels, H, W), dtype=torch.float32).pin_memory()
+            self._pin_out = torch.empty((N, m.out_channels, H, W), dtype=torch.float32).pin_memory()
+        return self._pin_in, self._pin_out
+
+    def _scratch_for(self, chunk, H, W):
+        key = (chunk, H, W)
+        if self._scratch_key != key:
+            n = C.c_size_t(0)
+            _lib.check(_lib.load().dg_lw_host_scratch_bytes(C.byref(self.model.c_params()), chunk, H, W, C.byref(n)))
+            self._scratch = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+            self._scratch_key = key
+        return self._scratch
+
+    def run_pinned(self, x_host, y_host):
+        """x_host/y_host: contiguous float32 CPU tensors (pinned for full PCIe rate).  Blocks until y_host is filled."""
+        N, _, H, W = x_host.shape
+        chunk = min(self.chunk, N)
+        scratch = self._scratch_for(chunk, H, W)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dg_lw_infer_host(C.byref(self.model.c_params()), x_host.data_ptr(), y_host.data_ptr(),
+                                                    N, H, W, chunk, scratch.data_ptr(), scratch.numel()))
+        return y_host
+
+    def run(self, output_names, input_feed, run_options=None):
+        x = input_feed[self._in.name]
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 4 or x.shape[1] != self.model.in_channels:
+            raise RuntimeError(f"expected input [N,{self.model.in_channels},H,W], got {x.shape}")
+        N, _, H, W = x.shape
+        xt = torch.from_numpy(x)
+        if xt.is_pinned():
+            y = torch.empty((N, self.model.out_channels, H, W), dtype=torch.float32).pin_memory()
+            self.run_pinned(xt, y)
+            return [y.numpy()]
+        pin_in, pin_out = self.pinned_buffers(N, H, W)
+        pin_in.copy_(xt)
+        self.run_pinned(pin_in, pin_out)
+        return [pin_out.numpy().copy()]

@@ -1,0 +1,172 @@
+/*
+ * deglare.h -- C-ABI of the B200-native UNet de-glaring kernels (libdeglare.so).
+ *
+ * The reference (JTZ18/image-enhancement-deglaring) is 100% Python and has no FFI of
+ * its own: its hot path is the nn.Module protocol of src/model.py:LightweightUNet and
+ * src/optimized_model.py:OptimizedUNet, executed by torch ATen operators.  This header
+ * is the drop-in boundary SURVEY.md section 8(b) specifies: plain pointers and sizes,
+ * no torch types, every entry point citing the reference code it replaces.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name says `host`.  The caller (PyTorch's
+ *    caching allocator in the shipped binding) owns every buffer; the library keeps no
+ *    state between calls except the last error string.
+ *  - The caller passes the CUDA stream; nothing in here synchronises the device except
+ *    the *_host entry points, which own their private streams and return when the result
+ *    is in host memory.
+ *  - Return 0 on success, non-zero on error (dg_last_error_string() explains).  Errors are
+ *    never thrown across the boundary and there is NO CPU fallback: an unsupported shape
+ *    is an error.
+ *  - Activations between kernels are "raw" conv outputs (pre-GroupNorm) in NHWC with
+ *    storage type `dtype`; GroupNorm statistics travel beside them as per-(n, channel)
+ *    double (sum, sum of squares) pairs and are applied, with SiLU, on the CONSUMER's
+ *    load.  Pooled / up-sampled / concatenated / normalised tensors never exist in HBM.
+ */
+#ifndef DEGLARE_H_
+#define DEGLARE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* dg_stream_t; /* cudaStream_t */
+
+/* storage type of intermediate activations (accumulation is always fp32) */
+enum { DG_F32 = 0, DG_F16 = 1, DG_BF16 = 2 };
+
+/* how a source tensor is mapped onto the consumer conv's input grid */
+enum {
+    DG_X_SAME = 0,   /* same resolution                                                  */
+    DG_X_POOL2 = 1,  /* nn.AvgPool2d(2,2) of the activated source   src/model.py:35-41   */
+    DG_X_UP2 = 2,    /* nn.Upsample(x2, nearest)          src/optimized_model.py:112     */
+    DG_X_CONVT2 = 3, /* nn.ConvTranspose2d(k=2,s=2)+bias  src/model.py:47-53             */
+    DG_X_IMAGE = 4   /* network input: fp32 NCHW, no norm, no activation                 */
+};
+
+/* One input of a fused 3x3 conv.  The consumer applies, while staging its halo tile:
+ *   y = raw * a_c + b_c          a_c = rstd*gamma_c, b_c = beta_c - mean*a_c   (GroupNorm, src/model.py:94,97)
+ *   y = y * sigmoid(y)           if silu                                      (SiLU, src/model.py:95,98)
+ *   y = y * scale[n][c]          if scale != NULL   (ChannelAttention, src/optimized_model.py:199-202)
+ * then the spatial transform `xform`.  For DG_X_CONVT2 the tensor described by
+ * raw/stats/gamma/beta has `channels` = Cin of the transposed conv at half resolution and
+ * contributes `ct_cout` channels to the concat. */
+typedef struct {
+    const void* raw;      /* NHWC [N,Hs,Ws,channels] in `dtype` (fp32 NCHW for DG_X_IMAGE) */
+    const double* stats;  /* [N,channels,2] (sum, sumsq) of `raw`; NULL = no GroupNorm     */
+    const float* gamma;   /* [channels] GroupNorm weight                                   */
+    const float* beta;    /* [channels] GroupNorm bias                                     */
+    const float* scale;   /* [N,channels] post-activation multiplier or NULL               */
+    const float* ct_w;    /* DG_X_CONVT2: weights packed [2][2][channels][ct_cout] fp32    */
+    const float* ct_b;    /* DG_X_CONVT2: bias [ct_cout]                                   */
+    int32_t channels;
+    int32_t groups;       /* GroupNorm groups over `channels`                              */
+    int32_t xform;        /* DG_X_*                                                        */
+    int32_t silu;         /* apply SiLU after the affine                                   */
+    int32_t ct_cout;      /* DG_X_CONVT2 only                                              */
+    int32_t reserved;
+} dg_src;
+
+/* Fused 3x3 conv, stride 1, zero pad 1, no bias, over the channel concat (src[0], src[1]).
+ * Replaces, per call, one nn.Conv2d(3x3) of LightweightUNet._block (src/model.py:93,96) /
+ * OptimizedUNet._block/_upblock (src/optimized_model.py:91-98,111-116) TOGETHER WITH the
+ * GroupNorm+SiLU (+AvgPool2d / ConvTranspose2d / Upsample / torch.cat / ChannelAttention scale)
+ * that precede it, and accumulates the GroupNorm statistics of its own output. */
+typedef struct {
+    dg_src src[2];
+    int32_t nsrc;
+    int32_t dtype;        /* DG_F32 / DG_F16 / DG_BF16: storage of src raws and of `out`   */
+    int32_t N, H, W;      /* output (= conv input grid) size                               */
+    int32_t cout;
+    const float* weight;  /* packed [3][3][Cin_total][cout] fp32                           */
+    void* out;            /* NHWC [N,H,W,cout] raw conv output                             */
+    double* out_stats;    /* [N,cout,2], must be zero on entry; accumulated atomically     */
+    double* act_sum;      /* optional [N,src[0].channels]: sum over pixels of the ACTIVATED
+                             src[0] (for ChannelAttention's global average); zero on entry  */
+    float eps;            /* GroupNorm eps of the sources (1e-5)                           */
+    int32_t path;         /* 0 = auto, 1 = force generic CUDA-core path, 2 = force tensor-core path */
+} dg_conv3x3_args;
+
+int dg_conv3x3_fused(const dg_conv3x3_args* args, dg_stream_t stream);
+
+/* Output head: GroupNorm+SiLU of the last block, then nn.Conv2d(C, out_channels, 1) + bias
+ * (src/model.py:57,131; src/optimized_model.py:74,158).  fp32 NCHW output.  If `target` is
+ * given, also accumulates sum|out-target| into *l1_sum (nn.L1Loss forward, optimized_train.py:439). */
+typedef struct {
+    dg_src src;
+    int32_t dtype;
+    int32_t N, H, W;
+    int32_t cout;
+    const float* weight;  /* [cout][channels] */
+    const float* bias;    /* [cout]           */
+    float* out;           /* [N,cout,H,W] fp32 */
+    const float* target;  /* optional [N,cout,H,W] */
+    double* l1_sum;       /* optional, zero on entry */
+    float eps;
+    int32_t reserved;
+} dg_head_args;
+
+int dg_head1x1(const dg_head_args* args, dg_stream_t stream);
+
+/* ---- whole-network entry points (native orchestrator) ------------------------------- */
+
+#define DG_MAX_BLOCKS 10  /* enc1-4, bottleneck, dec4-1 */
+
+/* Parameters of a LightweightUNet (src/model.py:14-57).  Device pointers to fp32 tensors:
+ * conv weights packed [3][3][Cin][Cout]; ConvTranspose weights packed [2][2][Cin][Cout]. */
+typedef struct {
+    int32_t in_channels, out_channels, features_start, dtype;
+    int32_t groups[DG_MAX_BLOCKS];          /* GroupNorm groups of block b (both norms)    */
+    const float* conv_w[DG_MAX_BLOCKS][2];  /* block b: `.0.weight`, `.3.weight`           */
+    const float* gn_w[DG_MAX_BLOCKS][2];    /* `.1.weight`, `.4.weight`                    */
+    const float* gn_b[DG_MAX_BLOCKS][2];    /* `.1.bias`, `.4.bias`                        */
+    const float* up_w[4];                   /* upconv4..upconv1                            */
+    const float* up_b[4];
+    const float* head_w;                    /* output_conv.weight [out][f0]                */
+    const float* head_b;
+    int32_t path;                           /* 0 auto, 1 generic, 2 tensor-core            */
+    int32_t reserved;
+} dg_lw_params;
+
+/* Bytes of workspace dg_lw_forward needs for an [N,in,H,W] batch (raw activations of all 18
+ * convs + statistics; everything backward needs stays live in it). */
+int dg_lw_workspace_bytes(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, size_t* bytes);
+
+/* LightweightUNet.forward (src/model.py:101-133): x fp32 [N,in,H,W] -> y fp32 [N,out,H,W].
+ * H, W multiples of 16.  Optional target/l1_sum as in dg_head1x1. */
+int dg_lw_forward(const dg_lw_params* p, const float* x, float* y, int32_t N, int32_t H, int32_t W,
+                  void* workspace, size_t workspace_bytes, const float* target, double* l1_sum,
+                  dg_stream_t stream);
+
+/* Byte offset of the raw output of conv `idx` (0..17, forward order) inside the workspace, and of
+ * its statistics; for tests and for backward. */
+int dg_lw_layout(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, int32_t idx,
+                 size_t* raw_offset, size_t* stats_offset, int32_t* channels, int32_t* h, int32_t* w);
+
+/* One forward with a CUDA-event pair around each of its 19 kernels (18 fused convs + head), recorded on
+ * `stream`; synchronises the stream and writes the per-kernel milliseconds to ms19[19].  For bench.py's
+ * roofline line -- the events add launch gaps, so use dg_lw_forward for throughput. */
+int dg_lw_profile(const dg_lw_params* p, const float* x, float* y, int32_t N, int32_t H, int32_t W,
+                  void* workspace, size_t workspace_bytes, dg_stream_t stream, float* ms19);
+
+/* End-to-end inference from HOST buffers (what api/app.py:171 `ort_session.run` and
+ * evaluate.py:245 do from the caller's point of view): pipelines H2D copy, forward and D2H
+ * copy over `chunk`-image slices on private streams; returns when host_y is complete.
+ * host_x/host_y should be pinned for full PCIe rate.  `dev_ws` is caller-owned device scratch of
+ * dg_lw_host_scratch_bytes() bytes. */
+int dg_lw_host_scratch_bytes(const dg_lw_params* p, int32_t chunk, int32_t H, int32_t W, size_t* bytes);
+int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, int32_t N, int32_t H,
+                     int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes);
+
+/* ---- misc --------------------------------------------------------------------------- */
+const char* dg_last_error_string(void);
+int dg_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t dg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEGLARE_H_ */

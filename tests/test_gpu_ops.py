@@ -1,0 +1,189 @@
+"""GPU parity of each fused op (through the C-ABI) against the oracle's decomposition."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import torch_unet as tpo
+
+pytestmark = pytest.mark.gpu
+
+ops = pytest.importorskip("image_enhancement_deglaring_b200.ops")
+
+TOL = {ops.DG_F32: 2e-5, ops.DG_F16: 2e-3, ops.DG_BF16: 1.6e-2}   # relative to max|ref|
+DTYPES = [ops.DG_F32, ops.DG_F16, ops.DG_BF16]
+
+
+def _rs(seed):
+    return np.random.RandomState(seed)
+
+
+def _nhwc(t, dtype):
+    """NCHW fp32 CPU -> NHWC storage-dtype CUDA, and the value the kernel will actually see (NCHW fp32 CPU)."""
+    q = t.permute(0, 2, 3, 1).contiguous().to(ops.TORCH_DTYPE[dtype]).cuda()
+    seen = q.float().cpu().permute(0, 3, 1, 2).contiguous()
+    return q, seen
+
+
+def _stats(seen):
+    s = torch.stack((seen.double().sum(dim=(2, 3)), (seen.double() ** 2).sum(dim=(2, 3))), dim=2)
+    return s.cuda().contiguous()
+
+
+def _gn_params(rs, c):
+    return (torch.from_numpy((1 + 0.3 * rs.standard_normal(c)).astype(np.float32)),
+            torch.from_numpy((0.3 * rs.standard_normal(c)).astype(np.float32)))
+
+
+def _check(out_nhwc, stats, ref, dtype, what):
+    got = out_nhwc.float().cpu().permute(0, 3, 1, 2)
+    scale = max(1.0, float(ref.abs().max()))
+    err = float((got - ref).abs().max())
+    assert err <= TOL[dtype] * scale, f"{what}: max err {err:.3e} (scale {scale:.2f})"
+    # statistics are those of the STORED (rounded) values
+    want = torch.stack((got.double().sum(dim=(2, 3)), (got.double() ** 2).sum(dim=(2, 3))), dim=2)
+    serr = float((stats.cpu() - want).abs().max() / max(1.0, float(want.abs().max())))
+    assert serr <= 1e-5, f"{what}: stats rel err {serr:.3e}"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cin,cout,H,W", [(1, 8, 32, 64), (3, 12, 16, 48), (1, 16, 48, 40)])
+def test_conv_image_source(dtype, cin, cout, H, W):
+    rs = _rs(1)
+    N = 2
+    x = torch.from_numpy(rs.rand(N, cin, H, W).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * 0.4).astype(np.float32))
+    src = ops.make_src(x.cuda(), cin, xform=ops.DG_X_IMAGE, silu=False)
+    out, st = ops.conv3x3_fused([src], ops.pack_conv3x3(w.cuda()), cout, N, H, W, dtype, path=1)
+    torch.cuda.synchronize()
+    _check(out, st, F.conv2d(x, w, None, 1, 1), dtype, "image conv")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cin,cout,groups,H,W", [(8, 8, 8, 64, 64), (16, 16, 8, 32, 96), (32, 32, 8, 16, 16),
+                                                   (64, 64, 8, 8, 32), (128, 128, 8, 4, 4), (12, 12, 6, 16, 32),
+                                                   (16, 16, 1, 16, 16), (8, 8, 8, 40, 33)])
+def test_conv_same_gn_silu(dtype, cin, cout, groups, H, W):
+    rs = _rs(2)
+    N = 2
+    raw = torch.from_numpy((rs.standard_normal((N, cin, H, W)) * 3 + 1).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, cin)
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
+    src = ops.make_src(q, cin, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=groups)
+    out, st = ops.conv3x3_fused([src], ops.pack_conv3x3(w.cuda()), cout, N, H, W, dtype, path=1)
+    torch.cuda.synchronize()
+    ref = F.conv2d(tpo.gn_silu(seen, groups, g, b), w, None, 1, 1)
+    _check(out, st, ref, dtype, "same conv")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 16, 32, 32), (64, 128, 4, 8), (12, 24, 8, 24)])
+def test_conv_pool_source(dtype, cin, cout, H, W):
+    rs = _rs(3)
+    N = 2
+    groups = 4
+    raw = torch.from_numpy((rs.standard_normal((N, cin, 2 * H, 2 * W)) * 2 - 0.5).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, cin)
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
+    src = ops.make_src(q, cin, xform=ops.DG_X_POOL2, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=groups)
+    act_sum = torch.zeros((N, cin), dtype=torch.float64, device="cuda")
+    out, st = ops.conv3x3_fused([src], ops.pack_conv3x3(w.cuda()), cout, N, H, W, dtype, act_sum=act_sum, path=1)
+    torch.cuda.synchronize()
+    act = tpo.gn_silu(seen, groups, g, b)
+    _check(out, st, F.conv2d(F.avg_pool2d(act, 2, 2), w, None, 1, 1), dtype, "pool conv")
+    want = act.double().sum(dim=(2, 3))
+    assert float((act_sum.cpu() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("c,H,W", [(8, 64, 64), (16, 32, 32), (64, 8, 8), (12, 16, 32), (160, 4, 4)])
+def test_conv_convt_cat(dtype, c, H, W):
+    """dec block first conv: ConvTranspose2d(2c->c) of the activated low-res tensor, cat (up, skip), conv 2c->c."""
+    rs = _rs(4)
+    N = 2
+    gl = 4
+    low = torch.from_numpy((rs.standard_normal((N, 2 * c, H // 2, W // 2)) * 2).astype(np.float32))
+    skip = torch.from_numpy((rs.standard_normal((N, c, H, W)) * 2 + 0.3).astype(np.float32))
+    ql, seen_l = _nhwc(low, dtype)
+    qs, seen_s = _nhwc(skip, dtype)
+    g1, b1 = _gn_params(rs, 2 * c)
+    g2, b2 = _gn_params(rs, c)
+    ctw = torch.from_numpy((rs.standard_normal((2 * c, c, 2, 2)) * (1.0 / np.sqrt(2 * c))).astype(np.float32))
+    ctb = torch.from_numpy((rs.standard_normal(c) * 0.2).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((c, 2 * c, 3, 3)) * (1.0 / np.sqrt(18 * c))).astype(np.float32))
+    s0 = ops.make_src(ql, 2 * c, xform=ops.DG_X_CONVT2, stats=_stats(seen_l), gamma=g1.cuda(), beta=b1.cuda(),
+                      groups=gl, ct_w=ops.pack_convt2x2(ctw.cuda()), ct_b=ctb.cuda(), ct_cout=c)
+    s1 = ops.make_src(qs, c, stats=_stats(seen_s), gamma=g2.cuda(), beta=b2.cuda(), groups=gl)
+    out, st = ops.conv3x3_fused([s0, s1], ops.pack_conv3x3(w.cuda()), c, N, H, W, dtype, path=1)
+    torch.cuda.synchronize()
+    up = F.conv_transpose2d(tpo.gn_silu(seen_l, gl, g1, b1), ctw, ctb, stride=2)
+    ref = F.conv2d(torch.cat((up, tpo.gn_silu(seen_s, gl, g2, b2)), 1), w, None, 1, 1)
+    _check(out, st, ref, dtype, "convT+cat conv")
+
+
+@pytest.mark.parametrize("dtype", [ops.DG_F32, ops.DG_F16])
+def test_conv_up2_and_scaled_skip(dtype):
+    """OptimizedUNet pieces: nearest x2 source (src/optimized_model.py:112) and SE-scaled skip (:199-202)."""
+    rs = _rs(5)
+    N, c, H, W = 2, 16, 16, 32
+    low = torch.from_numpy((rs.standard_normal((N, 2 * c, H // 2, W // 2)) * 2).astype(np.float32))
+    ql, seen_l = _nhwc(low, dtype)
+    g1, b1 = _gn_params(rs, 2 * c)
+    w = torch.from_numpy((rs.standard_normal((c, 2 * c, 3, 3)) * 0.06).astype(np.float32))
+    s0 = ops.make_src(ql, 2 * c, xform=ops.DG_X_UP2, stats=_stats(seen_l), gamma=g1.cuda(), beta=b1.cuda(), groups=8)
+    out, st = ops.conv3x3_fused([s0], ops.pack_conv3x3(w.cuda()), c, N, H, W, dtype, path=1)
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.interpolate(tpo.gn_silu(seen_l, 8, g1, b1), scale_factor=2, mode="nearest"), w, None, 1, 1)
+    _check(out, st, ref, dtype, "up2 conv")
+
+    a = torch.from_numpy((rs.standard_normal((N, c, H, W))).astype(np.float32))
+    s = torch.from_numpy((rs.standard_normal((N, c, H, W)) * 2).astype(np.float32))
+    qa, seen_a = _nhwc(a, dtype)
+    qs, seen_s = _nhwc(s, dtype)
+    ga, ba = _gn_params(rs, c)
+    gs, bs = _gn_params(rs, c)
+    scale = torch.from_numpy(rs.rand(N, c).astype(np.float32))
+    w2 = torch.from_numpy((rs.standard_normal((c, 2 * c, 3, 3)) * 0.06).astype(np.float32))
+    sa = ops.make_src(qa, c, stats=_stats(seen_a), gamma=ga.cuda(), beta=ba.cuda(), groups=4)
+    ss = ops.make_src(qs, c, stats=_stats(seen_s), gamma=gs.cuda(), beta=bs.cuda(), groups=4, scale=scale.cuda())
+    out, st = ops.conv3x3_fused([sa, ss], ops.pack_conv3x3(w2.cuda()), c, N, H, W, dtype, path=1)
+    torch.cuda.synchronize()
+    cat = torch.cat((tpo.gn_silu(seen_a, 4, ga, ba), tpo.gn_silu(seen_s, 4, gs, bs) * scale[:, :, None, None]), 1)
+    _check(out, st, F.conv2d(cat, w2, None, 1, 1), dtype, "cat(scaled skip) conv")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("c,oc", [(8, 1), (16, 1), (12, 2)])
+def test_head_and_l1(dtype, c, oc):
+    rs = _rs(6)
+    N, H, W = 2, 48, 32
+    groups = 4
+    raw = torch.from_numpy((rs.standard_normal((N, c, H, W)) * 2).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, c)
+    w = torch.from_numpy((rs.standard_normal((oc, c, 1, 1)) * 0.3).astype(np.float32))
+    bias = torch.from_numpy(rs.standard_normal(oc).astype(np.float32))
+    tgt = torch.from_numpy(rs.rand(N, oc, H, W).astype(np.float32))
+    src = ops.make_src(q, c, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=groups)
+    l1 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    out = ops.head1x1(src, w.reshape(oc, c).contiguous().cuda(), bias.cuda(), N, H, W, dtype, target=tgt.cuda(), l1_sum=l1)
+    torch.cuda.synchronize()
+    ref = F.conv2d(tpo.gn_silu(seen, groups, g, b), w, bias)
+    err = float((out.cpu() - ref).abs().max())
+    assert err <= 2e-5 * max(1.0, float(ref.abs().max())), f"head err {err:.3e}"
+    want = float((ref - tgt).abs().double().sum())
+    assert abs(float(l1.item()) - want) <= 1e-4 * want
+
+
+def test_errors_are_loud():
+    with pytest.raises(RuntimeError):
+        ops.make_src(torch.zeros(4), 1)  # CPU tensor
+    x = torch.zeros(1, 1, 15, 16, device="cuda")
+    w = torch.zeros(3, 3, 2, 8, device="cuda")
+    low = torch.zeros(1, 7, 8, 2, device="cuda")
+    src = ops.make_src(low, 2, xform=ops.DG_X_UP2, silu=False)
+    with pytest.raises(RuntimeError, match="even"):
+        ops.conv3x3_fused([src], w, 8, 1, 15, 16, ops.DG_F32)
+    del x
