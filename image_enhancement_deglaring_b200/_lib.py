@@ -20,7 +20,7 @@ DTYPE_CODES = {"fp32": DG_F32, "fp16": DG_F16, "bf16": DG_BF16}
 class DgSrc(C.Structure):
     _fields_ = [
         ("raw", C.c_void_p), ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
-        ("scale", C.c_void_p), ("ct_w", C.c_void_p), ("ct_b", C.c_void_p),
+        ("scale", C.c_void_p), ("ct_w", C.c_void_p), ("ct_b", C.c_void_p), ("ct_w_tc", C.c_void_p),
         ("channels", C.c_int32), ("groups", C.c_int32), ("xform", C.c_int32), ("silu", C.c_int32),
         ("ct_cout", C.c_int32), ("reserved", C.c_int32),
     ]
@@ -30,8 +30,8 @@ class DgConv3x3Args(C.Structure):
     _fields_ = [
         ("src", DgSrc * 2), ("nsrc", C.c_int32), ("dtype", C.c_int32),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("cout", C.c_int32),
-        ("weight", C.c_void_p), ("out", C.c_void_p), ("out_stats", C.c_void_p), ("act_sum", C.c_void_p),
-        ("eps", C.c_float), ("path", C.c_int32),
+        ("weight", C.c_void_p), ("weight_tc", C.c_void_p), ("out", C.c_void_p), ("out_stats", C.c_void_p),
+        ("act_sum", C.c_void_p), ("eps", C.c_float), ("path", C.c_int32),
     ]
 
 
@@ -49,6 +49,7 @@ class DgLwParams(C.Structure):
         ("dtype", C.c_int32), ("groups", C.c_int32 * DG_MAX_BLOCKS),
         ("conv_w", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("gn_w", (C.c_void_p * 2) * DG_MAX_BLOCKS),
         ("gn_b", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w", C.c_void_p * 4), ("up_b", C.c_void_p * 4),
+        ("conv_w_tc", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w_tc", C.c_void_p * 4),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("path", C.c_int32), ("reserved", C.c_int32),
     ]
 
@@ -70,6 +71,10 @@ SYMBOLS = {
                                            C.POINTER(C.c_size_t)]),
     "dg_lw_infer_host": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_size_t]),
+    "dg_tc_conv3x3_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "dg_pack_conv3x3_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "dg_tc_convt2x2_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "dg_pack_convt2x2_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_last_error_string": (C.c_char_p, []),
     "dg_version": (C.c_int, []),
     "dg_launch_count": (C.c_uint64, []),

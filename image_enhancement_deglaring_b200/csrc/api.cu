@@ -125,6 +125,7 @@ static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, in
         a.N = N; a.H = pl.conv_h[i]; a.W = pl.conv_w[i];
         a.cout = pl.conv_c[i];
         a.weight = p->conv_w[b][i % 2];
+        a.weight_tc = p->conv_w_tc[b][i % 2];
         a.out = ws + pl.raw_off[i];
         a.out_stats = reinterpret_cast<double*>(ws + pl.stats_off[i]);
         a.eps = 1e-5f;
@@ -145,6 +146,7 @@ static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, in
             a.src[0] = gn_src(p, pl, ws, i - 1, DG_X_CONVT2);      // upconv4..1, src/model.py:115-127
             a.src[0].ct_w = p->up_w[u];
             a.src[0].ct_b = p->up_b[u];
+            a.src[0].ct_w_tc = p->up_w_tc[u];
             a.src[0].ct_cout = pl.f[lvl];
             a.src[1] = gn_src(p, pl, ws, 2 * lvl + 1, DG_X_SAME);  // skip: torch.cat((up, skip), 1)
             a.nsrc = 2;
@@ -238,6 +240,23 @@ int dg_head1x1(const dg_head_args* a, dg_stream_t stream) {
     if (a->src.xform != DG_X_SAME) { set_error("head: source must be same-resolution"); return 3; }
     if (a->weight == nullptr || a->bias == nullptr || a->out == nullptr) { set_error("head: null pointer"); return 2; }
     return head_launch(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_tc_conv3x3_bytes(int32_t cin, int32_t cout, size_t* bytes) {
+    if (bytes == nullptr) { set_error("null bytes"); return 2; }
+    return tc_conv3x3_bytes(cin, cout, bytes);
+}
+int dg_pack_conv3x3_tc(const float* w, void* out, int32_t cin, int32_t cout, int32_t dtype, dg_stream_t stream) {
+    if (w == nullptr || out == nullptr) { set_error("pack: null pointer"); return 2; }
+    return pack_conv3x3_tc(w, out, cin, cout, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+int dg_tc_convt2x2_bytes(int32_t cin, int32_t cout, size_t* bytes) {
+    if (bytes == nullptr) { set_error("null bytes"); return 2; }
+    return tc_convt_bytes(cin, cout, bytes);
+}
+int dg_pack_convt2x2_tc(const float* w, void* out, int32_t cin, int32_t cout, int32_t dtype, dg_stream_t stream) {
+    if (w == nullptr || out == nullptr) { set_error("pack: null pointer"); return 2; }
+    return pack_convt_tc(w, out, cin, cout, dtype, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dg_lw_workspace_bytes(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, size_t* bytes) {

@@ -1,11 +1,608 @@
-// Tensor-core (HMMA) implicit-GEMM path of dg_conv3x3_fused for 16-bit storage.
-// Stage B -- not yet implemented: every configuration falls through to the generic CUDA-core kernel.
+// Tensor-core implicit-GEMM path of dg_conv3x3_fused for 16-bit storage (fp16 / bf16, fp32 accumulate).
+//
+// One CTA (8 warps) computes a TH x TW output tile of one image for all COUT channels:
+//   1. weights (pre-packed B tiles) stream into shared memory with cp.async (resident, or one tap per
+//      stage, double buffered, for the deep layers);
+//   2. the haloed input tile is staged ONCE into shared memory as 16-bit "channel planes"
+//      [CIN/8][(TH+2)*(TW+2)][8] after the consumer-side prologue -- GroupNorm apply + SiLU, and either
+//      identity, 2x2 average pool, or (MODE_UPCAT) ConvTranspose2d(2,2)+bias of the activated low-res tile
+//      computed on the tensor cores and scattered next to the activated skip tile (torch.cat never exists);
+//   3. the 3x3 conv is 9 shifted GEMMs over that tile: A fragments come straight from the planes with
+//      ldmatrix (a tap shift is a +16 B/pixel address offset, so no im2col copy), B fragments from the
+//      packed weights, mma.sync.m16n8k16 accumulates in fp32 registers;
+//   4. the epilogue rounds to the storage type, stores NHWC, and reduces the GroupNorm statistics of the
+//      stored values (warp shuffles -> shared atomics -> one double atomic per channel per CTA).
+//
+// Why mma.sync and not tcgen05 here: for COUT = 8..32 the UMMA A operand (128 pixels x 16 k) must be re-read
+// from shared memory for every 8..32 output channels, which is shared-memory-bandwidth bound at ~1/8..1/2 of
+// the tensor rate; HMMA keeps A in registers across n-tiles and the measured rate (tools/mma_bench.cu:
+// 557 TFLOP/s dense, 990 MAC/clk/SM) is enough to sit under the HBM time of the level-1/2 layers.
+//
+// Reference semantics: src/model.py:92-99, :35-41, :47-53, :116-128 (see conv3x3_generic.cu).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dg {
-int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled) {
-    (void)a; (void)stream;
+
+enum { M_SAME = 0, M_POOL = 1, M_UPCAT = 2 };
+constexpr int TC_THREADS = 256;
+
+struct TcArgs {
+    const void* src0; const double* st0; const float* g0; const float* b0; int groups0;
+    const void* src1; const double* st1; const float* g1; const float* b1; int groups1;
+    const void* wgt; const void* ctw; const float* ctb;
+    void* out; double* out_stats;
+    int N, H, W; float eps;
+};
+
+// ---- small PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    if constexpr (std::is_same<T, __half>::value) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    } else {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) {
+    return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+}
+
+// x * sigmoid(x) with ex2.approx + rcp.approx (the IEEE divide of silu_f costs 4x the issue slots)
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+
+// GroupNorm apply + SiLU on 8 packed 16-bit channels; cf = (a, b) pairs of those channels
+template <typename T>
+__device__ __forceinline__ void act8(const uint4& raw, const float2* __restrict__ cf, float (&y)[8]) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 v = unpack2<T>(w[k]);
+        const float2 c0 = cf[2 * k], c1 = cf[2 * k + 1];
+        y[2 * k] = silu_fast(fmaf(v.x, c0.x, c0.y));
+        y[2 * k + 1] = silu_fast(fmaf(v.y, c1.x, c1.y));
+    }
+}
+
+// ---- compile-time geometry -------------------------------------------------------------------------
+constexpr int pad_plane(int pix, int nc8) {
+    // plane stride (in 16-byte pixels) chosen so that the nc8 planes written by one quarter-warp of a
+    // pixel-major staging pass land in distinct banks: stride == 8/nc8 (mod 8), or 1 (mod 8) for nc8 >= 8
+    const int want = nc8 >= 8 ? 1 : (nc8 <= 1 ? 0 : 8 / nc8);
+    if (nc8 <= 1) return pix;
+    int p = pix;
+    while (p % 8 != want) ++p;
+    return p;
+}
+
+template <int CIN_, int COUT_, int MODE_, int TH_, int TW_, int WM_, int WN_, bool STREAM_>
+struct Geo {
+    static constexpr int CIN = CIN_, COUT = COUT_, MODE = MODE_, TH = TH_, TW = TW_, WM = WM_, WN = WN_;
+    static constexpr bool STREAM = STREAM_;
+    static constexpr int PH = TH + 2, PW = TW + 2, NC8 = CIN / 8;
+    static constexpr int PLANE = pad_plane(PH * PW, NC8);
+    static constexpr int KC = CIN >= 16 ? CIN / 16 : 1;
+    static constexpr int NCHUNK = CIN == 8 ? 5 : 9 * KC;
+    static constexpr int SEGS = TW / 16, MTILES = TH * SEGS, MPW = MTILES / WM, NT = COUT / 8 / WN;
+    static constexpr int MG = (MPW * NT * 4 <= 64) ? MPW : (64 / (NT * 4));
+    static constexpr int STAGE_CHUNKS = STREAM ? KC : NCHUNK;
+    static constexpr int NSTAGE = STREAM ? 9 : 1;
+    // MODE_UPCAT: ConvTranspose2d(CIN -> COUT) of the half-res tile, skip has COUT channels
+    static constexpr int CU = COUT, CL = CIN, NCL8 = CL / 8;
+    static constexpr int LPH = TH / 2 + 2, LPW = TW / 2 + 2, LM = LPH * LPW;
+    static constexpr int LPLANE = pad_plane(LM, NCL8);
+    static constexpr int LMT = (LM + 15) / 16;
+    static constexpr int CT_CHUNKS = CL / 16, CT_N = 4 * CU, CT_NT = CT_N / 8, CT_NTG = CT_NT < 8 ? CT_NT : 8;
+    static constexpr int NCOEF = MODE == M_UPCAT ? (CL + CU) : CIN;
+    // shared memory carve-up (bytes)
+    static constexpr int ACT_BYTES = NC8 * PLANE * 16;
+    static constexpr int WGT_BYTES = (STREAM ? 2 : 1) * STAGE_CHUNKS * COUT * 32;
+    static constexpr int COEF_BYTES = NCOEF * 8;
+    static constexpr int STAT_BYTES = COUT * 2 * 4;
+    static constexpr int LOW_BYTES = MODE == M_UPCAT ? NCL8 * LPLANE * 16 : 0;
+    static constexpr int CTW_BYTES = MODE == M_UPCAT ? CT_CHUNKS * 2 * CT_N * 16 : 0;
+    static constexpr int CTB_BYTES = MODE == M_UPCAT ? CU * 4 : 0;
+    static constexpr int OFF_ACT = 0;
+    static constexpr int OFF_WGT = OFF_ACT + ACT_BYTES;
+    static constexpr int OFF_LOW = OFF_WGT + WGT_BYTES;
+    static constexpr int OFF_CTW = OFF_LOW + LOW_BYTES;
+    static constexpr int OFF_COEF = OFF_CTW + CTW_BYTES;
+    static constexpr int OFF_STAT = OFF_COEF + COEF_BYTES;
+    static constexpr int OFF_CTB = OFF_STAT + STAT_BYTES;
+    static constexpr int SMEM_BYTES = OFF_CTB + CTB_BYTES;
+    static_assert(WM * WN == 8, "8 warps");
+    static_assert(MTILES % WM == 0 && (COUT / 8) % WN == 0, "tile split");
+    static_assert(MPW % MG == 0, "m-tile groups");
+    static_assert(!STREAM || (MG == MPW && CIN >= 16), "streamed weights need all accumulators live");
+    static_assert(NT == 1 || NT % 2 == 0, "n-tiles come in ldmatrix.x4 pairs");
+    static_assert(MODE != M_UPCAT || CIN == 2 * COUT, "UPCAT: ConvTranspose 2C->C + skip C");
+    static_assert(CIN % 8 == 0 && COUT % 8 == 0 && TW % 16 == 0 && TH % 2 == 0, "shape");
+};
+
+// stage a same-resolution (or 2x2-average-pooled) activated source into planes [plane0, plane0 + C/8)
+template <typename T, typename G, int C, bool POOL>
+__device__ __forceinline__ void stage_planes(unsigned char* act, const T* __restrict__ raw, const float2* __restrict__ cf,
+                                             int plane0, int n, int y0, int x0, int H, int W) {
+    constexpr int NC = C / 8;
+    for (int idx = threadIdx.x; idx < G::PH * G::PW * NC; idx += TC_THREADS) {
+        const int c8 = idx % NC;
+        const int pix = idx / NC;
+        const int r = pix / G::PW, c = pix % G::PW;
+        const int gy = y0 + r - 1, gx = x0 + c - 1;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            float y[8];
+            if constexpr (POOL) {
+                const int Ws = 2 * W;
+                const T* base = raw + ((size_t)(n * 2 * H + 2 * gy) * Ws + 2 * gx) * C + c8 * 8;
+                const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(base));
+                const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(base + C));
+                const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * C));
+                const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * C + C));
+                float t[8];
+                act8<T>(q00, cf + c8 * 8, y);
+                act8<T>(q01, cf + c8 * 8, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) y[k] += t[k];
+                act8<T>(q10, cf + c8 * 8, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) y[k] += t[k];
+                act8<T>(q11, cf + c8 * 8, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) y[k] = (y[k] + t[k]) * 0.25f;
+            } else {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * H + gy) * W + gx) * C + c8 * 8));
+                act8<T>(q, cf + c8 * 8, y);
+            }
+            o.x = pack2<T>(y[0], y[1]);
+            o.y = pack2<T>(y[2], y[3]);
+            o.z = pack2<T>(y[4], y[5]);
+            o.w = pack2<T>(y[6], y[7]);
+        }
+        *reinterpret_cast<uint4*>(act + ((size_t)(plane0 + c8) * G::PLANE + pix) * 16) = o;
+    }
+}
+
+template <typename T, typename G>
+__global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* act = smem + G::OFF_ACT;
+    unsigned char* wgt = smem + G::OFF_WGT;
+    float2* coef = reinterpret_cast<float2*>(smem + G::OFF_COEF);
+    float* statf = reinterpret_cast<float*>(smem + G::OFF_STAT);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % G::WM, wn = warp / G::WM;
+    const int n = blockIdx.z;
+    const int y0 = blockIdx.y * G::TH, x0 = blockIdx.x * G::TW;
+    const int H = p.H, W = p.W;
+
+    // ---- (0) start the weight traffic ----------------------------------------------------------------
+    auto load_stage = [&](int stage, int buf) {
+        constexpr int BYTES = G::STAGE_CHUNKS * G::COUT * 32;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wgt) + (size_t)stage * BYTES;
+        const uint32_t dst = smem_u32(wgt) + buf * BYTES;
+        for (int i = tid * 16; i < BYTES; i += TC_THREADS * 16) cp_async16(dst + i, src + i);
+    };
+    load_stage(0, 0);
+    if constexpr (G::MODE == M_UPCAT) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.ctw);
+        const uint32_t dst = smem_u32(smem + G::OFF_CTW);
+        for (int i = tid * 16; i < G::CTW_BYTES; i += TC_THREADS * 16) cp_async16(dst + i, src + i);
+    }
+    cp_async_commit();
+
+    // ---- (1) GroupNorm coefficients (a, b) per source channel ---------------------------------------
+    if constexpr (G::MODE == M_UPCAT) {
+        for (int c = tid; c < G::CL + G::CU; c += TC_THREADS) {
+            float a, b;
+            if (c < G::CL)
+                gn_coef(p.st0, p.g0, p.b0, n, G::CL, p.groups0, c, (double)(H / 2) * (W / 2), p.eps, a, b);
+            else
+                gn_coef(p.st1, p.g1, p.b1, n, G::CU, p.groups1, c - G::CL, (double)H * W, p.eps, a, b);
+            coef[c] = make_float2(a, b);
+        }
+        float* ctb = reinterpret_cast<float*>(smem + G::OFF_CTB);
+        for (int c = tid; c < G::CU; c += TC_THREADS) ctb[c] = p.ctb[c];
+    } else {
+        const double plane = G::MODE == M_POOL ? (double)(2 * H) * (2 * W) : (double)H * W;
+        for (int c = tid; c < G::CIN; c += TC_THREADS) {
+            float a, b;
+            gn_coef(p.st0, p.g0, p.b0, n, G::CIN, p.groups0, c, plane, p.eps, a, b);
+            coef[c] = make_float2(a, b);
+        }
+    }
+    for (int c = tid; c < 2 * G::COUT; c += TC_THREADS) statf[c] = 0.f;
+    __syncthreads();
+
+    // ---- (2) stage the activated halo tile ------------------------------------------------------------
+    if constexpr (G::MODE == M_SAME) {
+        stage_planes<T, G, G::CIN, false>(act, reinterpret_cast<const T*>(p.src0), coef, 0, n, y0, x0, H, W);
+    } else if constexpr (G::MODE == M_POOL) {
+        stage_planes<T, G, G::CIN, true>(act, reinterpret_cast<const T*>(p.src0), coef, 0, n, y0, x0, H, W);
+    } else {
+        // skip -> planes [CU/8, 2CU/8)
+        stage_planes<T, G, G::CU, false>(act, reinterpret_cast<const T*>(p.src1), coef + G::CL, G::CU / 8, n, y0, x0, H, W);
+        // activated low-res tile -> low planes
+        unsigned char* low = smem + G::OFF_LOW;
+        const T* raw = reinterpret_cast<const T*>(p.src0);
+        const int Hl = H / 2, Wl = W / 2;
+        const int li0 = (y0 >> 1) - 1, lj0 = (x0 >> 1) - 1;
+        for (int idx = tid; idx < G::LM * G::NCL8; idx += TC_THREADS) {
+            const int c8 = idx % G::NCL8;
+            const int lp = idx / G::NCL8;
+            const int gi = li0 + lp / G::LPW, gj = lj0 + lp % G::LPW;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (gi >= 0 && gi < Hl && gj >= 0 && gj < Wl) {
+                float y[8];
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * Hl + gi) * Wl + gj) * G::CL + c8 * 8));
+                act8<T>(q, coef + c8 * 8, y);
+                o.x = pack2<T>(y[0], y[1]);
+                o.y = pack2<T>(y[2], y[3]);
+                o.z = pack2<T>(y[4], y[5]);
+                o.w = pack2<T>(y[6], y[7]);
+            }
+            *reinterpret_cast<uint4*>(low + ((size_t)c8 * G::LPLANE + lp) * 16) = o;
+        }
+        cp_async_wait<0>();  // ConvTranspose weights (and conv stage 0) have landed
+        __syncthreads();
+        // ---- (2b) ConvTranspose2d(2,2) on the tensor cores: [low pixels x CL] x [CL x 4*CU] -------------
+        const uint32_t low_u = smem_u32(low);
+        const uint32_t ctw_u = smem_u32(smem + G::OFF_CTW);
+        const float* ctb = reinterpret_cast<const float*>(smem + G::OFF_CTB);
+        for (int mt = warp; mt < G::LMT; mt += 8) {
+            int lp_lane = mt * 16 + (lane & 15);
+            if (lp_lane > G::LM - 1) lp_lane = G::LM - 1;
+#pragma unroll 1
+            for (int ng = 0; ng < G::CT_NT; ng += G::CT_NTG) {
+                float acc[G::CT_NTG][4];
+#pragma unroll
+                for (int i = 0; i < G::CT_NTG; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < G::CT_CHUNKS; ++ch) {
+                    uint32_t a0, a1, a2, a3;
+                    ldsm_x4(low_u + (uint32_t)(((2 * ch + (lane >> 4)) * G::LPLANE + lp_lane) * 16), a0, a1, a2, a3);
+#pragma unroll
+                    for (int np = 0; np < G::CT_NTG / 2; ++np) {
+                        uint32_t b0, b1, b2, b3;
+                        const int nrow = (ng + 2 * np + (lane >> 4)) * 8 + (lane & 7);
+                        ldsm_x4(ctw_u + (uint32_t)(((ch * 2 + ((lane >> 3) & 1)) * G::CT_N + nrow) * 16), b0, b1, b2, b3);
+                        mma16816<T>(acc[2 * np], a0, a1, a2, a3, b0, b1);
+                        mma16816<T>(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+                    }
+                }
+                // scatter (+bias) into the up planes [0, CU/8); outside the image the concat is zero-padded
+#pragma unroll
+                for (int i = 0; i < G::CT_NTG; ++i) {
+                    const int nn = (ng + i) * 8 + 2 * (lane & 3);
+                    const int pos = nn / G::CU, co = nn % G::CU;
+                    const float bias0 = ctb[co], bias1 = ctb[co + 1];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int lp = mt * 16 + (lane >> 2) + 8 * hf;
+                        if (lp < G::LM) {
+                            const int r = 2 * (lp / G::LPW) + (pos >> 1) - 1;
+                            const int c = 2 * (lp % G::LPW) + (pos & 1) - 1;
+                            if (r >= 0 && r < G::PH && c >= 0 && c < G::PW) {
+                                const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+                                uint32_t v = 0u;
+                                if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+                                    v = pack2<T>(acc[i][2 * hf] + bias0, acc[i][2 * hf + 1] + bias1);
+                                *reinterpret_cast<uint32_t*>(act + ((size_t)(co >> 3) * G::PLANE + r * G::PW + c) * 16 +
+                                                             (co & 7) * 2) = v;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- (3) main loop: 9 shifted GEMMs ------------------------------------------------------------------
+    const uint32_t act_u = smem_u32(act);
+    const uint32_t wgt_u = smem_u32(wgt);
+    const int nt0 = wn * G::NT;
+    // per-lane B row offset inside a chunk (bytes): matrix = lane>>3 -> (k-half, n-tile of the pair)
+    const uint32_t b_lane = G::NT == 1 ? (uint32_t)(((((lane >> 3) & 1) * G::COUT) + nt0 * 8 + (lane & 7)) * 16)
+                                       : (uint32_t)(((((lane >> 3) & 1) * G::COUT) + (nt0 + (lane >> 4)) * 8 + (lane & 7)) * 16);
+    float s1[G::NT][2], s2[G::NT][2];
+#pragma unroll
+    for (int i = 0; i < G::NT; ++i) s1[i][0] = s1[i][1] = s2[i][0] = s2[i][1] = 0.f;
+    T* outp = reinterpret_cast<T*>(p.out);
+
+#pragma unroll 1
+    for (int g = 0; g < G::MPW; g += G::MG) {
+        float acc[G::MG][G::NT][4];
+        uint32_t a_pix[G::MG];  // byte offset of this lane's A row (pixel) for each m-tile, tap (0,0), plane 0
+#pragma unroll
+        for (int m = 0; m < G::MG; ++m) {
+            const int mt = wm + G::WM * (g + m);
+            const int row = mt / G::SEGS, seg = mt % G::SEGS;
+            a_pix[m] = (uint32_t)((row * G::PW + seg * 16 + (lane & 15)) * 16);
+#pragma unroll
+            for (int i = 0; i < G::NT; ++i) acc[m][i][0] = acc[m][i][1] = acc[m][i][2] = acc[m][i][3] = 0.f;
+        }
+#pragma unroll 1
+        for (int stage = 0; stage < G::NSTAGE; ++stage) {
+            if constexpr (G::STREAM) {
+                if (stage + 1 < G::NSTAGE) {
+                    load_stage(stage + 1, (stage + 1) & 1);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
+            } else {
+                if (g == 0) {
+                    cp_async_wait<0>();
+                    __syncthreads();  // weights + staged tile visible to every warp
+                }
+            }
+            const uint32_t wbuf = wgt_u + (G::STREAM ? (uint32_t)((stage & 1) * G::STAGE_CHUNKS * G::COUT * 32) : 0u);
+#pragma unroll
+            for (int j = 0; j < G::STAGE_CHUNKS; ++j) {
+                // A offsets of this chunk: lanes 0-15 feed k 0..7, lanes 16-31 feed k 8..15
+                uint32_t a_off;
+                if constexpr (G::CIN == 8) {
+                    const int t_lo = 2 * j, t_hi = (2 * j + 1 < 9) ? 2 * j + 1 : 8;
+                    const int o_lo = ((t_lo / 3) * G::PW + (t_lo % 3)) * 16, o_hi = ((t_hi / 3) * G::PW + (t_hi % 3)) * 16;
+                    a_off = (uint32_t)(o_lo + (lane >> 4) * (o_hi - o_lo));
+                } else {
+                    const int tap = G::STREAM ? stage : j / G::KC;
+                    const int cp = G::STREAM ? j : j % G::KC;
+                    a_off = (uint32_t)((((2 * cp + (lane >> 4)) * G::PLANE) + (tap / 3) * G::PW + (tap % 3)) * 16);
+                }
+                uint32_t bf[G::NT][2];
+                if constexpr (G::NT == 1) {
+                    ldsm_x2(wbuf + (uint32_t)(j * 2 * G::COUT * 16) + b_lane, bf[0][0], bf[0][1]);
+                } else {
+#pragma unroll
+                    for (int np = 0; np < G::NT / 2; ++np)
+                        ldsm_x4(wbuf + (uint32_t)((j * 2 * G::COUT + np * 16) * 16) + b_lane, bf[2 * np][0], bf[2 * np][1],
+                                bf[2 * np + 1][0], bf[2 * np + 1][1]);
+                }
+#pragma unroll
+                for (int m = 0; m < G::MG; ++m) {
+                    uint32_t a0, a1, a2, a3;
+                    ldsm_x4(act_u + a_pix[m] + a_off, a0, a1, a2, a3);
+#pragma unroll
+                    for (int i = 0; i < G::NT; ++i) mma16816<T>(acc[m][i], a0, a1, a2, a3, bf[i][0], bf[i][1]);
+                }
+            }
+            if constexpr (G::STREAM) __syncthreads();  // everyone is done with this buffer before it is refilled
+        }
+        // ---- (4) epilogue for this group of m-tiles ------------------------------------------------------
+#pragma unroll
+        for (int m = 0; m < G::MG; ++m) {
+            const int mt = wm + G::WM * (g + m);
+            const int row = mt / G::SEGS, seg = mt % G::SEGS;
+            const int gy = y0 + row;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int gx = x0 + seg * 16 + (lane >> 2) + 8 * hf;
+                if (gy < H && gx < W) {
+                    T* o = outp + ((size_t)(n * H + gy) * W + gx) * G::COUT + nt0 * 8 + 2 * (lane & 3);
+#pragma unroll
+                    for (int i = 0; i < G::NT; ++i) {
+                        const uint32_t v = pack2<T>(acc[m][i][2 * hf], acc[m][i][2 * hf + 1]);
+                        *reinterpret_cast<uint32_t*>(o + i * 8) = v;
+                        const float2 f = unpack2<T>(v);  // statistics of the STORED values
+                        s1[i][0] += f.x; s2[i][0] = fmaf(f.x, f.x, s2[i][0]);
+                        s1[i][1] += f.y; s2[i][1] = fmaf(f.y, f.y, s2[i][1]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- (5) GroupNorm statistics: lanes with equal lane&3 hold the same channels -------------------------
+#pragma unroll
+    for (int i = 0; i < G::NT; ++i)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            float a = s1[i][k], b = s2[i][k];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane < 4) {
+                const int ch = (nt0 + i) * 8 + 2 * lane + k;
+                atomicAdd(&statf[2 * ch], a);
+                atomicAdd(&statf[2 * ch + 1], b);
+            }
+        }
+    __syncthreads();
+    if (p.out_stats != nullptr)
+        for (int c = tid; c < 2 * G::COUT; c += TC_THREADS)
+            atomicAdd(p.out_stats + (size_t)n * G::COUT * 2 + c, (double)statf[c]);
+}
+
+// ---- weight packing kernels ------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, T* __restrict__ out, int cin, int cout, int nchunk) {
+    // out[chunk][kh][co][8]
+    const int total = nchunk * 2 * cout * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i & 7;
+        const int co = (i >> 3) % cout;
+        const int kh = (i / (8 * cout)) & 1;
+        const int chunk = i / (16 * cout);
+        int tap, ci;
+        if (cin == 8) {
+            tap = 2 * chunk + kh;
+            ci = e;
+        } else {
+            const int kc = cin / 16;
+            tap = chunk / kc;
+            ci = (chunk % kc) * 16 + kh * 8 + e;
+        }
+        const float v = tap < 9 ? w[((size_t)tap * cin + ci) * cout + co] : 0.f;
+        out[i] = Store<T>::from_f(v);
+    }
+}
+
+template <typename T>
+__global__ void pack_convt_tc_kernel(const float* __restrict__ w, T* __restrict__ out, int cl, int cu) {
+    // w [2][2][cl][cu] -> out[chunk = ci/16][kh][n = pos*cu + co][8]
+    const int ctn = 4 * cu;
+    const int total = (cl / 16) * 2 * ctn * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i & 7;
+        const int nn = (i >> 3) % ctn;
+        const int kh = (i / (8 * ctn)) & 1;
+        const int chunk = i / (16 * ctn);
+        const int ci = chunk * 16 + kh * 8 + e;
+        const int pos = nn / cu, co = nn % cu;
+        out[i] = Store<T>::from_f(w[((size_t)pos * cl + ci) * cu + co]);
+    }
+}
+
+static int tc_nchunk(int cin) { return cin == 8 ? 5 : 9 * (cin / 16); }
+
+int tc_conv3x3_bytes(int cin, int cout, size_t* bytes) {
+    if (cin < 8 || (cin != 8 && cin % 16) || cout % 8) { set_error("tc packing: unsupported %d -> %d", cin, cout); return 3; }
+    *bytes = (size_t)tc_nchunk(cin) * cout * 32;
+    return 0;
+}
+int tc_convt_bytes(int cl, int cu, size_t* bytes) {
+    if (cl % 16 || cu % 8) { set_error("tc convT packing: unsupported %d -> %d", cl, cu); return 3; }
+    *bytes = (size_t)cl * 4 * cu * 2;
+    return 0;
+}
+int pack_conv3x3_tc(const float* w, void* out, int cin, int cout, int dtype, cudaStream_t st) {
+    size_t bytes;
+    int rc = tc_conv3x3_bytes(cin, cout, &bytes);
+    if (rc) return rc;
+    const int total = (int)(bytes / 2);
+    const int blocks = (total + 255) / 256;
+    if (dtype == DG_F16) pack_conv3x3_tc_kernel<__half><<<blocks, 256, 0, st>>>(w, (__half*)out, cin, cout, tc_nchunk(cin));
+    else if (dtype == DG_BF16) pack_conv3x3_tc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)out, cin, cout, tc_nchunk(cin));
+    else { set_error("tc packing needs a 16-bit dtype"); return 2; }
+    count_launch();
+    return check_launch("pack_conv3x3_tc");
+}
+int pack_convt_tc(const float* w, void* out, int cl, int cu, int dtype, cudaStream_t st) {
+    size_t bytes;
+    int rc = tc_convt_bytes(cl, cu, &bytes);
+    if (rc) return rc;
+    const int total = (int)(bytes / 2);
+    const int blocks = (total + 255) / 256;
+    if (dtype == DG_F16) pack_convt_tc_kernel<__half><<<blocks, 256, 0, st>>>(w, (__half*)out, cl, cu);
+    else if (dtype == DG_BF16) pack_convt_tc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)out, cl, cu);
+    else { set_error("tc packing needs a 16-bit dtype"); return 2; }
+    count_launch();
+    return check_launch("pack_convt_tc");
+}
+
+// ---- dispatch -----------------------------------------------------------------------------------------------
+template <typename T, typename G>
+static int launch_geo(const TcArgs& t, cudaStream_t st) {
+    auto kern = conv3x3_tc_kernel<T, G>;
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%d B): %s", G::SMEM_BYTES, cudaGetErrorString(e)); return 4; }
+        attr_done = true;
+    }
+    dim3 grid((t.W + G::TW - 1) / G::TW, (t.H + G::TH - 1) / G::TH, t.N);
+    kern<<<grid, TC_THREADS, G::SMEM_BYTES, st>>>(t);
+    count_launch();
+    return check_launch("conv3x3_tc");
+}
+
+template <typename T>
+static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin, cudaStream_t st, bool* handled) {
+    *handled = true;
+    const int cout = a.cout;
+#define DG_TC(CI, CO, MD, TH, TW, WM, WN, ST) \
+    if (cin == CI && cout == CO && mode == MD) return launch_geo<T, Geo<CI, CO, MD, TH, TW, WM, WN, ST>>(t, st);
+    DG_TC(8, 8, M_SAME, 16, 64, 8, 1, false)      // enc1.3, dec1.3
+    DG_TC(8, 16, M_POOL, 16, 64, 8, 1, false)     // enc2.0
+    DG_TC(16, 16, M_SAME, 16, 64, 8, 1, false)    // enc2.3, dec2.3
+    DG_TC(16, 32, M_POOL, 16, 32, 8, 1, false)    // enc3.0
+    DG_TC(32, 32, M_SAME, 16, 32, 8, 1, false)    // enc3.3, dec3.3
+    DG_TC(32, 64, M_POOL, 8, 32, 4, 2, false)     // enc4.0
+    DG_TC(64, 64, M_SAME, 8, 32, 4, 2, true)      // enc4.3, dec4.3
+    DG_TC(64, 128, M_POOL, 4, 32, 2, 4, true)     // bottleneck.0
+    DG_TC(128, 128, M_SAME, 4, 32, 2, 4, true)    // bottleneck.3
+    DG_TC(128, 64, M_UPCAT, 8, 16, 4, 2, true)    // upconv4 + dec4.0
+    DG_TC(64, 32, M_UPCAT, 8, 32, 4, 2, true)     // upconv3 + dec3.0
+    DG_TC(32, 16, M_UPCAT, 8, 64, 8, 1, false)    // upconv2 + dec2.0
+    DG_TC(16, 8, M_UPCAT, 16, 64, 8, 1, false)    // upconv1 + dec1.0
+#undef DG_TC
     *handled = false;
     return 0;
 }
+
+int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (a.dtype != DG_F16 && a.dtype != DG_BF16) return 0;
+    if (a.weight_tc == nullptr || a.act_sum != nullptr) return 0;
+    const dg_src& s0 = a.src[0];
+    TcArgs t;
+    memset(&t, 0, sizeof(t));
+    int mode, cin;
+    if (a.nsrc == 1 && (s0.xform == DG_X_SAME || s0.xform == DG_X_POOL2)) {
+        if (s0.stats == nullptr || !s0.silu || s0.scale != nullptr) return 0;
+        mode = s0.xform == DG_X_SAME ? M_SAME : M_POOL;
+        cin = s0.channels;
+    } else if (a.nsrc == 2 && s0.xform == DG_X_CONVT2 && a.src[1].xform == DG_X_SAME) {
+        const dg_src& s1 = a.src[1];
+        if (s0.stats == nullptr || s1.stats == nullptr || !s0.silu || !s1.silu || s0.scale || s1.scale) return 0;
+        if (s0.ct_w_tc == nullptr || s0.ct_cout != a.cout || s1.channels != a.cout || s0.channels != 2 * a.cout) return 0;
+        if ((a.H | a.W) & 1) return 0;
+        mode = M_UPCAT;
+        cin = s0.channels;
+        t.src1 = s1.raw; t.st1 = s1.stats; t.g1 = s1.gamma; t.b1 = s1.beta; t.groups1 = s1.groups;
+        t.ctw = s0.ct_w_tc; t.ctb = s0.ct_b;
+    } else {
+        return 0;
+    }
+    // 128-bit loads need 16-byte aligned bases
+    if ((reinterpret_cast<uintptr_t>(s0.raw) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.weight_tc) |
+         reinterpret_cast<uintptr_t>(t.src1) | reinterpret_cast<uintptr_t>(t.ctw)) & 15)
+        return 0;
+    if (a.N > 65535) return 0;
+    t.src0 = s0.raw; t.st0 = s0.stats; t.g0 = s0.gamma; t.b0 = s0.beta; t.groups0 = s0.groups;
+    t.wgt = a.weight_tc;
+    t.out = a.out; t.out_stats = a.out_stats;
+    t.N = a.N; t.H = a.H; t.W = a.W; t.eps = a.eps;
+    if (a.dtype == DG_F16) return dispatch<__half>(a, t, mode, cin, stream, handled);
+    return dispatch<__nv_bfloat16>(a, t, mode, cin, stream, handled);
+}
+
 }  // namespace dg

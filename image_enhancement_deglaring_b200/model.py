@@ -109,7 +109,9 @@ class LightweightUNet(nn.Module):
                 w = ops.pack_conv3x3(blk[ci].weight)
                 g = blk[gi].weight.detach().float().contiguous()
                 bt = blk[gi].bias.detach().float().contiguous()
-                keep += [w, g, bt]
+                wtc = ops.pack_conv3x3_tc(w, pc.dtype) if self.path != 1 else None
+                keep += [w, g, bt, wtc]
+                pc.conv_w_tc[b][j] = None if wtc is None else wtc.data_ptr()
                 pc.conv_w[b][j] = w.data_ptr()
                 pc.gn_w[b][j] = g.data_ptr()
                 pc.gn_b[b][j] = bt.data_ptr()
@@ -117,7 +119,9 @@ class LightweightUNet(nn.Module):
             m = getattr(self, name)
             w = ops.pack_convt2x2(m.weight)
             bt = m.bias.detach().float().contiguous()
-            keep += [w, bt]
+            wtc = ops.pack_convt2x2_tc(w, pc.dtype) if self.path != 1 else None
+            keep += [w, bt, wtc]
+            pc.up_w_tc[u] = None if wtc is None else wtc.data_ptr()
             pc.up_w[u] = w.data_ptr()
             pc.up_b[u] = bt.data_ptr()
         hw = self.output_conv.weight.detach().float().reshape(self.out_channels, -1).contiguous()

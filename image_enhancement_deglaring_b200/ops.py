@@ -34,10 +34,39 @@ def pack_convt2x2(w):
     return w.detach().float().permute(2, 3, 0, 1).contiguous()
 
 
+def pack_conv3x3_tc(w_packed, dtype, stream=None):
+    """fp32 [3,3,Ci,Co] -> the HMMA kernels' B-tile packing in `dtype` (dg_pack_conv3x3_tc); None if unsupported."""
+    lib = _lib.load()
+    ci, co = int(w_packed.shape[2]), int(w_packed.shape[3])
+    n = C.c_size_t(0)
+    if dtype == DG_F32 or lib.dg_tc_conv3x3_bytes(ci, co, C.byref(n)) != 0:
+        return None
+    out = torch.empty(n.value // 2, dtype=TORCH_DTYPE[dtype], device=w_packed.device)
+    _lib.check(lib.dg_pack_conv3x3_tc(w_packed.data_ptr(), out.data_ptr(), ci, co, dtype, _stream(stream)))
+    return out
+
+
+def pack_convt2x2_tc(w_packed, dtype, stream=None):
+    """fp32 [2,2,Ci,Co] -> tensor-core packing (dg_pack_convt2x2_tc); None if unsupported."""
+    lib = _lib.load()
+    ci, co = int(w_packed.shape[2]), int(w_packed.shape[3])
+    n = C.c_size_t(0)
+    if dtype == DG_F32 or lib.dg_tc_convt2x2_bytes(ci, co, C.byref(n)) != 0:
+        return None
+    out = torch.empty(n.value // 2, dtype=TORCH_DTYPE[dtype], device=w_packed.device)
+    _lib.check(lib.dg_pack_convt2x2_tc(w_packed.data_ptr(), out.data_ptr(), ci, co, dtype, _stream(stream)))
+    return out
+
+
 def make_src(raw, channels, xform=DG_X_SAME, stats=None, gamma=None, beta=None, groups=1, silu=True,
-             scale=None, ct_w=None, ct_b=None, ct_cout=0):
-    _require_cuda(raw, stats, gamma, beta, scale, ct_w, ct_b)
+             scale=None, ct_w=None, ct_b=None, ct_cout=0, ct_w_tc=None):
+    _require_cuda(raw, stats, gamma, beta, scale, ct_w, ct_b, ct_w_tc)
     s = DgSrc()
+    s.ct_w_tc = _ptr(ct_w_tc)
+    s._keep_tc = ct_w_tc
+    # the struct only carries raw pointers: pin the tensors to it so temporaries passed inline by the caller
+    # stay alive until the launch (after which the caching allocator's stream ordering protects them)
+    s._keep = (raw, stats, gamma, beta, scale, ct_w, ct_b)
     s.raw = _ptr(raw)
     s.stats = _ptr(stats)
     s.gamma = _ptr(gamma)
@@ -58,7 +87,7 @@ def _stream(stream):
 
 
 def conv3x3_fused(srcs, weight, cout, N, H, W, dtype, out=None, out_stats=None, act_sum=None, path=0, stream=None,
-                  eps=1e-5):
+                  eps=1e-5, weight_tc=None):
     """Fused 3x3 conv over the concat of `srcs` (list of DgSrc).  Returns (raw NHWC out, stats [N,cout,2] f64)."""
     lib = _lib.load()
     dev = weight.device
@@ -68,11 +97,12 @@ def conv3x3_fused(srcs, weight, cout, N, H, W, dtype, out=None, out_stats=None, 
         out_stats = torch.zeros((N, cout, 2), dtype=torch.float64, device=dev)
     a = DgConv3x3Args()
     for i, s in enumerate(srcs):
-        a.src[i] = s
+        a.src[i] = s  # copies the struct; `srcs` (and the tensors pinned to it) outlive the call below
     a.nsrc = len(srcs)
     a.dtype = dtype
     a.N, a.H, a.W, a.cout = N, H, W, cout
     a.weight = _ptr(weight)
+    a.weight_tc = _ptr(weight_tc)
     a.out = _ptr(out)
     a.out_stats = _ptr(out_stats)
     a.act_sum = _ptr(act_sum)

@@ -61,6 +61,7 @@ typedef struct {
     const float* scale;   /* [N,channels] post-activation multiplier or NULL               */
     const float* ct_w;    /* DG_X_CONVT2: weights packed [2][2][channels][ct_cout] fp32    */
     const float* ct_b;    /* DG_X_CONVT2: bias [ct_cout]                                   */
+    const void* ct_w_tc;  /* DG_X_CONVT2: optional tensor-core packing (dg_pack_convt2x2_tc) */
     int32_t channels;
     int32_t groups;       /* GroupNorm groups over `channels`                              */
     int32_t xform;        /* DG_X_*                                                        */
@@ -81,6 +82,8 @@ typedef struct {
     int32_t N, H, W;      /* output (= conv input grid) size                               */
     int32_t cout;
     const float* weight;  /* packed [3][3][Cin_total][cout] fp32                           */
+    const void* weight_tc;/* optional tensor-core packing of the same weights (dg_pack_conv3x3_tc),
+                             in `dtype`; NULL = generic CUDA-core path only                 */
     void* out;            /* NHWC [N,H,W,cout] raw conv output                             */
     double* out_stats;    /* [N,cout,2], must be zero on entry; accumulated atomically     */
     double* act_sum;      /* optional [N,src[0].channels]: sum over pixels of the ACTIVATED
@@ -124,6 +127,8 @@ typedef struct {
     const float* gn_b[DG_MAX_BLOCKS][2];    /* `.1.bias`, `.4.bias`                        */
     const float* up_w[4];                   /* upconv4..upconv1                            */
     const float* up_b[4];
+    const void* conv_w_tc[DG_MAX_BLOCKS][2];/* optional tensor-core packings (16-bit dtypes) */
+    const void* up_w_tc[4];
     const float* head_w;                    /* output_conv.weight [out][f0]                */
     const float* head_b;
     int32_t path;                           /* 0 auto, 1 generic, 2 tensor-core            */
@@ -159,6 +164,16 @@ int dg_lw_profile(const dg_lw_params* p, const float* x, float* y, int32_t N, in
 int dg_lw_host_scratch_bytes(const dg_lw_params* p, int32_t chunk, int32_t H, int32_t W, size_t* bytes);
 int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, int32_t N, int32_t H,
                      int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes);
+
+/* ---- tensor-core weight packing (16-bit storage types) ---------------------------------
+ * The HMMA implicit-GEMM kernels read B operands as ldmatrix-ready tiles
+ *   [chunk][k-half(2)][cout][8]  of `dtype`,  one chunk = 16 values of K = (tap, cin):
+ *   cin >= 16: chunk = tap*(cin/16) + cin/16-block;   cin == 8: chunk j = taps (2j, 2j+1), tap 9 = zeros.
+ * `w` is the fp32 [3][3][cin][cout] (resp. [2][2][cin][cout]) packing; returns bytes via *bytes. */
+int dg_tc_conv3x3_bytes(int32_t cin, int32_t cout, size_t* bytes);
+int dg_pack_conv3x3_tc(const float* w, void* out, int32_t cin, int32_t cout, int32_t dtype, dg_stream_t stream);
+int dg_tc_convt2x2_bytes(int32_t cin, int32_t cout, size_t* bytes);
+int dg_pack_convt2x2_tc(const float* w, void* out, int32_t cin, int32_t cout, int32_t dtype, dg_stream_t stream);
 
 /* ---- misc --------------------------------------------------------------------------- */
 const char* dg_last_error_string(void);

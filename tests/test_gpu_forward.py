@@ -134,12 +134,13 @@ def test_against_oracle_random_batches(best_sd):
 
 def test_shape_and_device_errors(best_sd):
     net = _net(best_sd)
-    with pytest.raises(RuntimeError, match="multiples of 16"):
-        net(torch.zeros(1, 1, 500, 500, device="cuda"))
-    with pytest.raises(RuntimeError, match="CUDA"):
-        net(torch.zeros(1, 1, 16, 16))
-    with pytest.raises(RuntimeError):
-        net(torch.zeros(1, 2, 16, 16, device="cuda"))
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="multiples of 16"):
+            net(torch.zeros(1, 1, 500, 500, device="cuda"))
+        with pytest.raises(RuntimeError, match="CUDA"):
+            net(torch.zeros(1, 1, 16, 16))
+        with pytest.raises(RuntimeError):
+            net(torch.zeros(1, 2, 16, 16, device="cuda"))
 
 
 def test_state_dict_roundtrip_and_param_update(best_sd):

@@ -187,3 +187,102 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError, match="even"):
         ops.conv3x3_fused([src], w, 8, 1, 15, 16, ops.DG_F32)
     del x
+
+
+# ---- tensor-core (HMMA) path: every LightweightUNet(features_start=8) layer configuration -------------------
+TC_DTYPES = [ops.DG_F16, ops.DG_BF16]
+
+
+def _tc_check(out_tc, st_tc, out_ref, st_ref, dtype, what):
+    """TC path vs generic path on identical stored inputs: same math up to fp32 summation order and one
+    16-bit rounding of the activated tile -> agree within a few storage ulps of the largest value."""
+    a, b = out_tc.float(), out_ref.float()
+    scale = max(1.0, float(b.abs().max()))
+    err = float((a - b).abs().max())
+    tol = (6e-3 if dtype == ops.DG_F16 else 4e-2) * scale
+    assert err <= tol, f"{what}: TC vs generic max err {err:.3e} (scale {scale:.2f})"
+    serr = float((st_tc - st_ref).abs().max() / max(1.0, float(st_ref.abs().max())))
+    assert serr <= 2e-2, f"{what}: stats rel err {serr:.3e}"
+    got = a.double()
+    want = torch.stack((got.sum(dim=(1, 2)), (got ** 2).sum(dim=(1, 2))), dim=2)
+    s2 = float((st_tc - want).abs().max() / max(1.0, float(want.abs().max())))
+    assert s2 <= 1e-5, f"{what}: stats do not match stored values ({s2:.3e})"
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 8, 64, 128), (16, 16, 32, 64), (32, 32, 32, 32), (64, 64, 16, 32),
+                                            (128, 128, 8, 32), (8, 8, 48, 80), (16, 16, 24, 40), (128, 128, 2, 2),
+                                            (64, 64, 6, 10)])
+def test_tc_same(dtype, cin, cout, H, W):
+    rs = _rs(11)
+    N = 2
+    raw = torch.from_numpy((rs.standard_normal((N, cin, H, W)) * 3 + 1).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, cin)
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
+    wp = ops.pack_conv3x3(w.cuda())
+    wtc = ops.pack_conv3x3_tc(wp, dtype)
+    st = _stats(seen)
+    src = ops.make_src(q, cin, stats=st, gamma=g.cuda(), beta=b.cuda(), groups=8)
+    o_ref, s_ref = ops.conv3x3_fused([src], wp, cout, N, H, W, dtype, path=1)
+    o_tc, s_tc = ops.conv3x3_fused([src], wp, cout, N, H, W, dtype, path=2, weight_tc=wtc)
+    torch.cuda.synchronize()
+    _tc_check(o_tc, s_tc, o_ref, s_ref, dtype, f"tc same {cin}->{cout}")
+    ref = F.conv2d(tpo.gn_silu(seen, 8, g, b), w, None, 1, 1)
+    err = float((o_tc.float().cpu().permute(0, 3, 1, 2) - ref).abs().max())
+    assert err <= (6e-3 if dtype == ops.DG_F16 else 4e-2) * max(1.0, float(ref.abs().max())), f"vs oracle {err:.3e}"
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 16, 32, 64), (16, 32, 16, 32), (32, 64, 16, 32), (64, 128, 8, 32),
+                                            (8, 16, 24, 40), (64, 128, 1, 1)])
+def test_tc_pool(dtype, cin, cout, H, W):
+    rs = _rs(12)
+    N = 2
+    raw = torch.from_numpy((rs.standard_normal((N, cin, 2 * H, 2 * W)) * 2 - 0.5).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, cin)
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
+    wp = ops.pack_conv3x3(w.cuda())
+    wtc = ops.pack_conv3x3_tc(wp, dtype)
+    src = ops.make_src(q, cin, xform=ops.DG_X_POOL2, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=8)
+    o_ref, s_ref = ops.conv3x3_fused([src], wp, cout, N, H, W, dtype, path=1)
+    o_tc, s_tc = ops.conv3x3_fused([src], wp, cout, N, H, W, dtype, path=2, weight_tc=wtc)
+    torch.cuda.synchronize()
+    _tc_check(o_tc, s_tc, o_ref, s_ref, dtype, f"tc pool {cin}->{cout}")
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("c,H,W", [(8, 64, 128), (16, 32, 64), (32, 16, 32), (64, 16, 32), (8, 48, 80), (16, 24, 40),
+                                     (64, 2, 2), (32, 6, 10)])
+def test_tc_convt_cat(dtype, c, H, W):
+    rs = _rs(13)
+    N = 2
+    low = torch.from_numpy((rs.standard_normal((N, 2 * c, H // 2, W // 2)) * 2).astype(np.float32))
+    skip = torch.from_numpy((rs.standard_normal((N, c, H, W)) * 2 + 0.3).astype(np.float32))
+    ql, seen_l = _nhwc(low, dtype)
+    qs, seen_s = _nhwc(skip, dtype)
+    g1, b1 = _gn_params(rs, 2 * c)
+    g2, b2 = _gn_params(rs, c)
+    ctw = torch.from_numpy((rs.standard_normal((2 * c, c, 2, 2)) * (1.0 / np.sqrt(2 * c))).astype(np.float32))
+    ctb = torch.from_numpy((rs.standard_normal(c) * 0.2).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((c, 2 * c, 3, 3)) * (1.0 / np.sqrt(18 * c))).astype(np.float32))
+    wp = ops.pack_conv3x3(w.cuda())
+    ctp = ops.pack_convt2x2(ctw.cuda())
+    s0 = ops.make_src(ql, 2 * c, xform=ops.DG_X_CONVT2, stats=_stats(seen_l), gamma=g1.cuda(), beta=b1.cuda(),
+                      groups=8, ct_w=ctp, ct_b=ctb.cuda(), ct_cout=c, ct_w_tc=ops.pack_convt2x2_tc(ctp, dtype))
+    s1 = ops.make_src(qs, c, stats=_stats(seen_s), gamma=g2.cuda(), beta=b2.cuda(), groups=8)
+    o_ref, s_ref = ops.conv3x3_fused([s0, s1], wp, c, N, H, W, dtype, path=1)
+    o_tc, s_tc = ops.conv3x3_fused([s0, s1], wp, c, N, H, W, dtype, path=2, weight_tc=ops.pack_conv3x3_tc(wp, dtype))
+    torch.cuda.synchronize()
+    _tc_check(o_tc, s_tc, o_ref, s_ref, dtype, f"tc convT+cat {2 * c}->{c}")
+
+
+def test_tc_path_refuses_unsupported():
+    w = torch.zeros(3, 3, 24, 24, device="cuda")
+    raw = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.float16)
+    st = torch.ones(1, 24, 2, dtype=torch.float64, device="cuda")
+    g = torch.ones(24, device="cuda")
+    src = ops.make_src(raw, 24, stats=st, gamma=g, beta=g, groups=8)
+    with pytest.raises(RuntimeError, match="tensor-core"):
+        ops.conv3x3_fused([src], w, 24, 1, 8, 8, ops.DG_F16, path=2)
