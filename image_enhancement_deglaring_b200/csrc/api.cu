@@ -223,12 +223,15 @@ int dg_conv3x3_fused(const dg_conv3x3_args* a, dg_stream_t stream) {
         }
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (a->path != 1) {
+    if ((a->path & 3) != 1) {
         bool handled = false;
-        int rc = conv3x3_tc_launch(*a, st, &handled);
+        int rc = conv_first_tc_launch(*a, st, &handled);
         if (rc) return rc;
         if (handled) return 0;
-        if (a->path == 2) { set_error("conv3x3: tensor-core path does not cover this configuration"); return 3; }
+        rc = conv3x3_tc_launch(*a, st, &handled);
+        if (rc) return rc;
+        if (handled) return 0;
+        if ((a->path & 3) == 2) { set_error("conv3x3: tensor-core path does not cover this configuration"); return 3; }
     }
     return conv3x3_generic_launch(*a, st);
 }

@@ -65,9 +65,15 @@ __device__ __forceinline__ void store8(T* __restrict__ p, int cn, bool vec, cons
     }
 }
 
-// x * sigmoid(x); __expf is ex2.approx based (rel. err ~2^-21), __fdividef is rcp.approx + mul (2 ulp);
-// the IEEE divide measured 4x slower (tools/mma_bench.cu) for no visible gain in parity.
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// x * sigmoid(x) = x * rcp(1 + ex2(-x*log2e)) with the raw approx instructions (rel. err ~2^-22): FMUL, MUFU.EX2,
+// FADD, MUFU.RCP, FMUL.  __expf/__fdividef add range handling worth ~7 more instructions per element, and the IEEE
+// divide measured 4x slower still (tools/mma_bench.cu).  Saturates correctly: ex2(+big)=inf -> rcp(inf)=0.
+__device__ __forceinline__ float silu_f(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return x * r;
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -106,6 +112,7 @@ void count_launch();
 int check_launch(const char* what);
 int conv3x3_generic_launch(const dg_conv3x3_args& a, cudaStream_t stream);
 int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
+int conv_first_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int head_launch(const dg_head_args& a, cudaStream_t stream);
 int tc_conv3x3_bytes(int cin, int cout, size_t* bytes);
 int tc_convt_bytes(int cl, int cu, size_t* bytes);

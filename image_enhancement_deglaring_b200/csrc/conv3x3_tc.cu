@@ -19,9 +19,7 @@
 // 557 TFLOP/s dense, 990 MAC/clk/SM) is enough to sit under the HBM time of the level-1/2 layers.
 //
 // Reference semantics: src/model.py:92-99, :35-41, :47-53, :116-128 (see conv3x3_generic.cu).
-#include <type_traits>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dg {
 
@@ -35,67 +33,6 @@ struct TcArgs {
     void* out; double* out_stats;
     int N, H, W; float eps;
 };
-
-// ---- small PTX wrappers -------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
-}
-template <typename T>
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1) {
-    if constexpr (std::is_same<T, __half>::value) {
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-    } else {
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-    }
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
-template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v);
-template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) {
-    return __half22float2(*reinterpret_cast<__half2*>(&v));
-}
-template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
-    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
-}
-
-// x * sigmoid(x) with ex2.approx + rcp.approx (the IEEE divide of silu_f costs 4x the issue slots)
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
-
-// GroupNorm apply + SiLU on 8 packed 16-bit channels; cf = (a, b) pairs of those channels
-template <typename T>
-__device__ __forceinline__ void act8(const uint4& raw, const float2* __restrict__ cf, float (&y)[8]) {
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float2 v = unpack2<T>(w[k]);
-        const float2 c0 = cf[2 * k], c1 = cf[2 * k + 1];
-        y[2 * k] = silu_fast(fmaf(v.x, c0.x, c0.y));
-        y[2 * k + 1] = silu_fast(fmaf(v.y, c1.x, c1.y));
-    }
-}
 
 // ---- compile-time geometry -------------------------------------------------------------------------
 constexpr int pad_plane(int pix, int nc8) {
@@ -131,7 +68,7 @@ struct Geo {
     static constexpr int ACT_BYTES = NC8 * PLANE * 16;
     static constexpr int WGT_BYTES = (STREAM ? 2 : 1) * STAGE_CHUNKS * COUT * 32;
     static constexpr int COEF_BYTES = NCOEF * 8;
-    static constexpr int STAT_BYTES = COUT * 2 * 4;
+    static constexpr int STAT_BYTES = COUT * 2 * 8;  // double: shared atomics stay order-insensitive after rounding to float
     static constexpr int LOW_BYTES = MODE == M_UPCAT ? NCL8 * LPLANE * 16 : 0;
     static constexpr int CTW_BYTES = MODE == M_UPCAT ? CT_CHUNKS * 2 * CT_N * 16 : 0;
     static constexpr int CTB_BYTES = MODE == M_UPCAT ? CU * 4 : 0;
@@ -152,57 +89,80 @@ struct Geo {
     static_assert(CIN % 8 == 0 && COUT % 8 == 0 && TW % 16 == 0 && TH % 2 == 0, "shape");
 };
 
-// stage a same-resolution (or 2x2-average-pooled) activated source into planes [plane0, plane0 + C/8)
-template <typename T, typename G, int C, bool POOL>
-__device__ __forceinline__ void stage_planes(unsigned char* act, const T* __restrict__ raw, const float2* __restrict__ cf,
+// Stage a same-resolution (or 2x2-average-pooled) activated source into planes [plane0, plane0 + C/8).
+// Items are (pixel, 8-channel chunk), pixel-major so a warp's global loads are contiguous; 256 % (C/8) == 0, so a
+// thread always owns the same chunk and keeps its 8 (a, b) pairs in registers.  Loads are issued BATCH at a time
+// before any math so several 128-bit requests per thread are in flight.
+template <typename T, typename G, int C, bool POOL, bool TANH>
+__device__ __forceinline__ void stage_planes(unsigned char* act, const T* __restrict__ raw, const float2* __restrict__ cfs,
                                              int plane0, int n, int y0, int x0, int H, int W) {
     constexpr int NC = C / 8;
-    for (int idx = threadIdx.x; idx < G::PH * G::PW * NC; idx += TC_THREADS) {
-        const int c8 = idx % NC;
-        const int pix = idx / NC;
-        const int r = pix / G::PW, c = pix % G::PW;
-        const int gy = y0 + r - 1, gx = x0 + c - 1;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            float y[8];
-            if constexpr (POOL) {
-                const int Ws = 2 * W;
-                const T* base = raw + ((size_t)(n * 2 * H + 2 * gy) * Ws + 2 * gx) * C + c8 * 8;
-                const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(base));
-                const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(base + C));
-                const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * C));
-                const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * C + C));
-                float t[8];
-                act8<T>(q00, cf + c8 * 8, y);
-                act8<T>(q01, cf + c8 * 8, t);
+    constexpr int ITEMS = G::PH * G::PW * NC;
+    constexpr int BATCH = POOL ? 2 : 4;
+    static_assert(TC_THREADS % NC == 0, "chunk ownership");
+    const int c8 = threadIdx.x % NC;
+    float2 cf[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) y[k] += t[k];
-                act8<T>(q10, cf + c8 * 8, t);
+    for (int k = 0; k < 8; ++k) cf[k] = cfs[c8 * 8 + k];
+    unsigned char* dst = act + (size_t)(plane0 + c8) * G::PLANE * 16;
+#pragma unroll 1
+    for (int idx0 = threadIdx.x; idx0 < ITEMS; idx0 += TC_THREADS * BATCH) {
+        uint4 q[BATCH][POOL ? 4 : 1];
+        int pixs[BATCH];
+        bool ok[BATCH];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) y[k] += t[k];
-                act8<T>(q11, cf + c8 * 8, t);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) y[k] = (y[k] + t[k]) * 0.25f;
-            } else {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * H + gy) * W + gx) * C + c8 * 8));
-                act8<T>(q, cf + c8 * 8, y);
+        for (int b = 0; b < BATCH; ++b) {
+            const int idx = idx0 + b * TC_THREADS;
+            const int pix = idx / NC;
+            const int r = pix / G::PW, c = pix - r * G::PW;
+            const int gy = y0 + r - 1, gx = x0 + c - 1;
+            pixs[b] = idx < ITEMS ? pix : -1;
+            ok[b] = idx < ITEMS && gy >= 0 && gy < H && gx >= 0 && gx < W;
+            if (ok[b]) {
+                if constexpr (POOL) {
+                    const int Ws = 2 * W;
+                    const T* base = raw + ((size_t)(n * 2 * H + 2 * gy) * Ws + 2 * gx) * C + c8 * 8;
+                    q[b][0] = __ldg(reinterpret_cast<const uint4*>(base));
+                    q[b][1] = __ldg(reinterpret_cast<const uint4*>(base + C));
+                    q[b][2] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * C));
+                    q[b][3] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * C + C));
+                } else {
+                    q[b][0] = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * H + gy) * W + gx) * C + c8 * 8));
+                }
             }
-            o.x = pack2<T>(y[0], y[1]);
-            o.y = pack2<T>(y[2], y[3]);
-            o.z = pack2<T>(y[4], y[5]);
-            o.w = pack2<T>(y[6], y[7]);
         }
-        *reinterpret_cast<uint4*>(act + ((size_t)(plane0 + c8) * G::PLANE + pix) * 16) = o;
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            if (pixs[b] < 0) continue;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[b]) {
+                float y[8];
+                act8<T, TANH>(q[b][0], cf, y);
+                if constexpr (POOL) {
+                    float t[8];
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) {
+                        act8<T, TANH>(q[b][j], cf, t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) y[k] += t[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) y[k] *= 0.25f;
+                }
+                o = pack8<T>(y);
+            }
+            *reinterpret_cast<uint4*>(dst + (size_t)pixs[b] * 16) = o;
+        }
     }
 }
 
-template <typename T, typename G>
+template <typename T, typename G, bool TANH>
 __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* act = smem + G::OFF_ACT;
     unsigned char* wgt = smem + G::OFF_WGT;
     float2* coef = reinterpret_cast<float2*>(smem + G::OFF_COEF);
-    float* statf = reinterpret_cast<float*>(smem + G::OFF_STAT);
+    double* statf = reinterpret_cast<double*>(smem + G::OFF_STAT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % G::WM, wn = warp / G::WM;
@@ -233,6 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
                 gn_coef(p.st0, p.g0, p.b0, n, G::CL, p.groups0, c, (double)(H / 2) * (W / 2), p.eps, a, b);
             else
                 gn_coef(p.st1, p.g1, p.b1, n, G::CU, p.groups1, c - G::CL, (double)H * W, p.eps, a, b);
+            if constexpr (TANH) { a *= 0.5f; b *= 0.5f; }  // silu(y) = h + h*tanh(h), h = y/2
             coef[c] = make_float2(a, b);
         }
         float* ctb = reinterpret_cast<float*>(smem + G::OFF_CTB);
@@ -242,40 +203,46 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
         for (int c = tid; c < G::CIN; c += TC_THREADS) {
             float a, b;
             gn_coef(p.st0, p.g0, p.b0, n, G::CIN, p.groups0, c, plane, p.eps, a, b);
+            if constexpr (TANH) { a *= 0.5f; b *= 0.5f; }
             coef[c] = make_float2(a, b);
         }
     }
-    for (int c = tid; c < 2 * G::COUT; c += TC_THREADS) statf[c] = 0.f;
+    for (int c = tid; c < 2 * G::COUT; c += TC_THREADS) statf[c] = 0.0;
     __syncthreads();
 
     // ---- (2) stage the activated halo tile ------------------------------------------------------------
     if constexpr (G::MODE == M_SAME) {
-        stage_planes<T, G, G::CIN, false>(act, reinterpret_cast<const T*>(p.src0), coef, 0, n, y0, x0, H, W);
+        stage_planes<T, G, G::CIN, false, TANH>(act, reinterpret_cast<const T*>(p.src0), coef, 0, n, y0, x0, H, W);
     } else if constexpr (G::MODE == M_POOL) {
-        stage_planes<T, G, G::CIN, true>(act, reinterpret_cast<const T*>(p.src0), coef, 0, n, y0, x0, H, W);
+        stage_planes<T, G, G::CIN, true, TANH>(act, reinterpret_cast<const T*>(p.src0), coef, 0, n, y0, x0, H, W);
     } else {
         // skip -> planes [CU/8, 2CU/8)
-        stage_planes<T, G, G::CU, false>(act, reinterpret_cast<const T*>(p.src1), coef + G::CL, G::CU / 8, n, y0, x0, H, W);
+        stage_planes<T, G, G::CU, false, TANH>(act, reinterpret_cast<const T*>(p.src1), coef + G::CL, G::CU / 8, n, y0, x0, H, W);
         // activated low-res tile -> low planes
         unsigned char* low = smem + G::OFF_LOW;
         const T* raw = reinterpret_cast<const T*>(p.src0);
         const int Hl = H / 2, Wl = W / 2;
         const int li0 = (y0 >> 1) - 1, lj0 = (x0 >> 1) - 1;
-        for (int idx = tid; idx < G::LM * G::NCL8; idx += TC_THREADS) {
-            const int c8 = idx % G::NCL8;
-            const int lp = idx / G::NCL8;
-            const int gi = li0 + lp / G::LPW, gj = lj0 + lp % G::LPW;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (gi >= 0 && gi < Hl && gj >= 0 && gj < Wl) {
-                float y[8];
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * Hl + gi) * Wl + gj) * G::CL + c8 * 8));
-                act8<T>(q, coef + c8 * 8, y);
-                o.x = pack2<T>(y[0], y[1]);
-                o.y = pack2<T>(y[2], y[3]);
-                o.z = pack2<T>(y[4], y[5]);
-                o.w = pack2<T>(y[6], y[7]);
+        {
+            static_assert(TC_THREADS % G::NCL8 == 0, "chunk ownership");
+            const int c8 = tid % G::NCL8;
+            float2 cf[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cf[k] = coef[c8 * 8 + k];
+#pragma unroll 2
+            for (int idx = tid; idx < G::LM * G::NCL8; idx += TC_THREADS) {
+                const int lp = idx / G::NCL8;
+                const int li = lp / G::LPW;
+                const int gi = li0 + li, gj = lj0 + lp - li * G::LPW;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (gi >= 0 && gi < Hl && gj >= 0 && gj < Wl) {
+                    float y[8];
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * Hl + gi) * Wl + gj) * G::CL + c8 * 8));
+                    act8<T, TANH>(q, cf, y);
+                    o = pack8<T>(y);
+                }
+                *reinterpret_cast<uint4*>(low + ((size_t)c8 * G::LPLANE + lp) * 16) = o;
             }
-            *reinterpret_cast<uint4*>(low + ((size_t)c8 * G::LPLANE + lp) * 16) = o;
         }
         cp_async_wait<0>();  // ConvTranspose weights (and conv stage 0) have landed
         __syncthreads();
@@ -283,11 +250,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
         const uint32_t low_u = smem_u32(low);
         const uint32_t ctw_u = smem_u32(smem + G::OFF_CTW);
         const float* ctb = reinterpret_cast<const float*>(smem + G::OFF_CTB);
-        for (int mt = warp; mt < G::LMT; mt += 8) {
+        constexpr int NG = G::CT_NT / G::CT_NTG;  // work item = (16 low pixels, CT_NTG n-tiles), round-robin over warps
+#pragma unroll 1
+        for (int item = warp; item < G::LMT * NG; item += 8) {
+            const int mt = item / NG;
+            const int ng = (item % NG) * G::CT_NTG;
             int lp_lane = mt * 16 + (lane & 15);
             if (lp_lane > G::LM - 1) lp_lane = G::LM - 1;
-#pragma unroll 1
-            for (int ng = 0; ng < G::CT_NT; ng += G::CT_NTG) {
+            {
                 float acc[G::CT_NTG][4];
 #pragma unroll
                 for (int i = 0; i < G::CT_NTG; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -406,27 +376,34 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
             if constexpr (G::STREAM) __syncthreads();  // everyone is done with this buffer before it is refilled
         }
         // ---- (4) epilogue for this group of m-tiles ------------------------------------------------------
+        // Statistics come from the fp32 accumulators (the 16-bit rounding of the stored copy changes the plane sums
+        // by ~2^-12/sqrt(n) relative -- far below the rounding noise itself) so no unpack is needed; full tiles
+        // take a branch-free path with one address computation per m-tile.
+        const bool full = (y0 + G::TH <= H) && (x0 + G::TW <= W);
+        auto epilogue = [&](auto full_c) {
+            constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-        for (int m = 0; m < G::MG; ++m) {
-            const int mt = wm + G::WM * (g + m);
-            const int row = mt / G::SEGS, seg = mt % G::SEGS;
-            const int gy = y0 + row;
+            for (int m = 0; m < G::MG; ++m) {
+                const int mt = wm + G::WM * (g + m);
+                const int row = mt / G::SEGS, seg = mt % G::SEGS;
+                const int gy = y0 + row;
+                const int gx = x0 + seg * 16 + (lane >> 2);
+                T* o = outp + ((size_t)(n * H + gy) * W + gx) * G::COUT + nt0 * 8 + 2 * (lane & 3);
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int gx = x0 + seg * 16 + (lane >> 2) + 8 * hf;
-                if (gy < H && gx < W) {
-                    T* o = outp + ((size_t)(n * H + gy) * W + gx) * G::COUT + nt0 * 8 + 2 * (lane & 3);
+                for (int hf = 0; hf < 2; ++hf) {
+                    const bool ok = FULL || (gy < H && gx + 8 * hf < W);
 #pragma unroll
                     for (int i = 0; i < G::NT; ++i) {
-                        const uint32_t v = pack2<T>(acc[m][i][2 * hf], acc[m][i][2 * hf + 1]);
-                        *reinterpret_cast<uint32_t*>(o + i * 8) = v;
-                        const float2 f = unpack2<T>(v);  // statistics of the STORED values
-                        s1[i][0] += f.x; s2[i][0] = fmaf(f.x, f.x, s2[i][0]);
-                        s1[i][1] += f.y; s2[i][1] = fmaf(f.y, f.y, s2[i][1]);
+                        const float v0 = ok ? acc[m][i][2 * hf] : 0.f, v1 = ok ? acc[m][i][2 * hf + 1] : 0.f;
+                        if (ok) *reinterpret_cast<uint32_t*>(o + hf * 8 * G::COUT + i * 8) = pack2<T>(v0, v1);
+                        s1[i][0] += v0; s2[i][0] = fmaf(v0, v0, s2[i][0]);
+                        s1[i][1] += v1; s2[i][1] = fmaf(v1, v1, s2[i][1]);
                     }
                 }
             }
-        }
+        };
+        if (full) epilogue(std::true_type{});
+        else epilogue(std::false_type{});
     }
     // ---- (5) GroupNorm statistics: lanes with equal lane&3 hold the same channels -------------------------
 #pragma unroll
@@ -441,14 +418,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
             }
             if (lane < 4) {
                 const int ch = (nt0 + i) * 8 + 2 * lane + k;
-                atomicAdd(&statf[2 * ch], a);
-                atomicAdd(&statf[2 * ch + 1], b);
+                atomicAdd(&statf[2 * ch], (double)a);
+                atomicAdd(&statf[2 * ch + 1], (double)b);
             }
         }
     __syncthreads();
     if (p.out_stats != nullptr)
         for (int c = tid; c < 2 * G::COUT; c += TC_THREADS)
-            atomicAdd(p.out_stats + (size_t)n * G::COUT * 2 + c, (double)statf[c]);
+            atomicAdd(p.out_stats + (size_t)n * G::COUT * 2 + c, statf[c]);
 }
 
 // ---- weight packing kernels ------------------------------------------------------------------------------
@@ -529,9 +506,9 @@ int pack_convt_tc(const float* w, void* out, int cl, int cu, int dtype, cudaStre
 }
 
 // ---- dispatch -----------------------------------------------------------------------------------------------
-template <typename T, typename G>
+template <typename T, typename G, bool TANH>
 static int launch_geo(const TcArgs& t, cudaStream_t st) {
-    auto kern = conv3x3_tc_kernel<T, G>;
+    auto kern = conv3x3_tc_kernel<T, G, TANH>;
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
@@ -544,12 +521,12 @@ static int launch_geo(const TcArgs& t, cudaStream_t st) {
     return check_launch("conv3x3_tc");
 }
 
-template <typename T>
+template <typename T, bool TANH>
 static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin, cudaStream_t st, bool* handled) {
     *handled = true;
     const int cout = a.cout;
 #define DG_TC(CI, CO, MD, TH, TW, WM, WN, ST) \
-    if (cin == CI && cout == CO && mode == MD) return launch_geo<T, Geo<CI, CO, MD, TH, TW, WM, WN, ST>>(t, st);
+    if (cin == CI && cout == CO && mode == MD) return launch_geo<T, Geo<CI, CO, MD, TH, TW, WM, WN, ST>, TANH>(t, st);
     DG_TC(8, 8, M_SAME, 16, 64, 8, 1, false)      // enc1.3, dec1.3
     DG_TC(8, 16, M_POOL, 16, 64, 8, 1, false)     // enc2.0
     DG_TC(16, 16, M_SAME, 16, 64, 8, 1, false)    // enc2.3, dec2.3
@@ -601,8 +578,12 @@ int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handl
     t.wgt = a.weight_tc;
     t.out = a.out; t.out_stats = a.out_stats;
     t.N = a.N; t.H = a.H; t.W = a.W; t.eps = a.eps;
-    if (a.dtype == DG_F16) return dispatch<__half>(a, t, mode, cin, stream, handled);
-    return dispatch<__nv_bfloat16>(a, t, mode, cin, stream, handled);
+    const bool exact = (a.path & 4) != 0;  // path bit 2: exact ex2/rcp SiLU instead of tanh.approx
+    if (a.dtype == DG_F16)
+        return exact ? dispatch<__half, false>(a, t, mode, cin, stream, handled)
+                     : dispatch<__half, true>(a, t, mode, cin, stream, handled);
+    return exact ? dispatch<__nv_bfloat16, false>(a, t, mode, cin, stream, handled)
+                 : dispatch<__nv_bfloat16, true>(a, t, mode, cin, stream, handled);
 }
 
 }  // namespace dg

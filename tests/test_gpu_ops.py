@@ -205,8 +205,9 @@ def _tc_check(out_tc, st_tc, out_ref, st_ref, dtype, what):
     assert serr <= 2e-2, f"{what}: stats rel err {serr:.3e}"
     got = a.double()
     want = torch.stack((got.sum(dim=(1, 2)), (got ** 2).sum(dim=(1, 2))), dim=2)
+    # TC statistics are taken from the fp32 accumulators, the stored copy is rounded once more
     s2 = float((st_tc - want).abs().max() / max(1.0, float(want.abs().max())))
-    assert s2 <= 1e-5, f"{what}: stats do not match stored values ({s2:.3e})"
+    assert s2 <= (3e-4 if dtype == ops.DG_F16 else 3e-3), f"{what}: stats do not match stored values ({s2:.3e})"
 
 
 @pytest.mark.parametrize("dtype", TC_DTYPES)
@@ -276,6 +277,46 @@ def test_tc_convt_cat(dtype, c, H, W):
     o_tc, s_tc = ops.conv3x3_fused([s0, s1], wp, c, N, H, W, dtype, path=2, weight_tc=ops.pack_conv3x3_tc(wp, dtype))
     torch.cuda.synchronize()
     _tc_check(o_tc, s_tc, o_ref, s_ref, dtype, f"tc convT+cat {2 * c}->{c}")
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("cout,H,W", [(8, 64, 128), (16, 32, 64), (8, 48, 80), (8, 16, 16), (16, 2, 6)])
+def test_tc_first_layer(dtype, cout, H, W):
+    rs = _rs(14)
+    N = 3
+    x = torch.from_numpy(rs.rand(N, 1, H, W).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((cout, 1, 3, 3)) * 0.4).astype(np.float32))
+    src = ops.make_src(x.cuda(), 1, xform=ops.DG_X_IMAGE, silu=False)
+    out, st = ops.conv3x3_fused([src], ops.pack_conv3x3(w.cuda()), cout, N, H, W, dtype, path=2)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, None, 1, 1)
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    err = float((got - ref).abs().max())
+    assert err <= (4e-3 if dtype == ops.DG_F16 else 3e-2) * max(1.0, float(ref.abs().max())), f"first layer err {err:.3e}"
+    want = torch.stack((got.double().sum(dim=(2, 3)), (got.double() ** 2).sum(dim=(2, 3))), dim=2)
+    serr = float((st.cpu() - want).abs().max() / max(1.0, float(want.abs().max())))
+    assert serr <= (3e-4 if dtype == ops.DG_F16 else 3e-3), f"first layer stats {serr:.3e}"
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+def test_tc_exact_and_tanh_silu_agree(dtype):
+    """path bit 2 selects the ex2/rcp SiLU in the staging prologue instead of tanh.approx."""
+    rs = _rs(15)
+    N, cin, cout, H, W = 2, 16, 16, 32, 64
+    raw = torch.from_numpy((rs.standard_normal((N, cin, H, W)) * 3 + 1).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, cin)
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
+    wp = ops.pack_conv3x3(w.cuda())
+    wtc = ops.pack_conv3x3_tc(wp, dtype)
+    src = ops.make_src(q, cin, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=8)
+    o_t, _ = ops.conv3x3_fused([src], wp, cout, N, H, W, dtype, path=2, weight_tc=wtc)
+    o_e, _ = ops.conv3x3_fused([src], wp, cout, N, H, W, dtype, path=6, weight_tc=wtc)
+    torch.cuda.synchronize()
+    ref = F.conv2d(tpo.gn_silu(seen, 8, g, b), w, None, 1, 1)
+    tol = (4e-3 if dtype == ops.DG_F16 else 3e-2) * max(1.0, float(ref.abs().max()))
+    for o in (o_t, o_e):
+        assert float((o.float().cpu().permute(0, 3, 1, 2) - ref).abs().max()) <= tol
 
 
 def test_tc_path_refuses_unsupported():
