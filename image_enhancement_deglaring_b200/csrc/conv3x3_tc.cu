@@ -54,7 +54,10 @@ struct Geo {
     static constexpr int KC = CIN >= 16 ? CIN / 16 : 1;
     static constexpr int NCHUNK = CIN == 8 ? 5 : 9 * KC;
     static constexpr int SEGS = TW / 16, MTILES = TH * SEGS, MPW = MTILES / WM, NT = COUT / 8 / WN;
-    static constexpr int MG = (MPW * NT * 4 <= 64) ? MPW : (64 / (NT * 4));
+    // accumulator budget per thread: 32 registers for the narrow memory-bound layers (more CTAs per SM), 64 for the
+    // compute-heavy ones (B-fragment reuse; with streamed weights all m-tiles of a warp stay live across tap stages)
+    static constexpr int ACC_REGS = (STREAM || COUT > 16) ? 64 : 32;
+    static constexpr int MG = (MPW * NT * 4 <= ACC_REGS) ? MPW : (ACC_REGS / (NT * 4));
     static constexpr int STAGE_CHUNKS = STREAM ? KC : NCHUNK;
     static constexpr int NSTAGE = STREAM ? 9 : 1;
     // MODE_UPCAT: ConvTranspose2d(CIN -> COUT) of the half-res tile, skip has COUT channels
@@ -91,49 +94,55 @@ struct Geo {
 
 // Stage a same-resolution (or 2x2-average-pooled) activated source into planes [plane0, plane0 + C/8).
 // Items are (pixel, 8-channel chunk), pixel-major so a warp's global loads are contiguous; 256 % (C/8) == 0, so a
-// thread always owns the same chunk and keeps its 8 (a, b) pairs in registers.  Loads are issued BATCH at a time
-// before any math so several 128-bit requests per thread are in flight.
+// thread always owns the same chunk and keeps its 8 (a, b) pairs in registers.  The item slots of a thread are split
+// into ITERS batches of BATCH; all loads of a batch are issued before any math (several 128-bit requests in flight
+// per thread), and the slot count is matched to the tile so few slots are wasted on index arithmetic (profile r1b:
+// 44% of the staging instructions were addressing).  `src` points at image n; offsets are 32-bit.
 template <typename T, typename G, int C, bool POOL, bool TANH>
-__device__ __forceinline__ void stage_planes(unsigned char* act, const T* __restrict__ raw, const float2* __restrict__ cfs,
-                                             int plane0, int n, int y0, int x0, int H, int W) {
+__device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned char* __restrict__ src,
+                                             const float2* __restrict__ cfs, int plane0, int y0, int x0, int H, int W) {
     constexpr int NC = C / 8;
-    constexpr int ITEMS = G::PH * G::PW * NC;
-    constexpr int BATCH = POOL ? 2 : 4;
+    constexpr int NPIX = G::PH * G::PW;
+    constexpr int PSTRIDE = TC_THREADS / NC;                       // pixels between two slots of a thread
+    constexpr int NSLOT = (NPIX + PSTRIDE - 1) / PSTRIDE;
+    constexpr int MAXB = POOL ? 2 : 5;
+    constexpr int ITERS = (NSLOT + MAXB - 1) / MAXB;
+    constexpr int BATCH = (NSLOT + ITERS - 1) / ITERS;
     static_assert(TC_THREADS % NC == 0, "chunk ownership");
     const int c8 = threadIdx.x % NC;
+    const int p0 = threadIdx.x / NC;
     float2 cf[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) cf[k] = cfs[c8 * 8 + k];
     unsigned char* dst = act + (size_t)(plane0 + c8) * G::PLANE * 16;
+    const uint32_t rowb = (uint32_t)(POOL ? 2 * W : W) * C * 2;    // source row pitch in bytes
 #pragma unroll 1
-    for (int idx0 = threadIdx.x; idx0 < ITEMS; idx0 += TC_THREADS * BATCH) {
+    for (int it = 0; it < ITERS; ++it) {
         uint4 q[BATCH][POOL ? 4 : 1];
         int pixs[BATCH];
         bool ok[BATCH];
 #pragma unroll
         for (int b = 0; b < BATCH; ++b) {
-            const int idx = idx0 + b * TC_THREADS;
-            const int pix = idx / NC;
+            const int pix = p0 + (it * BATCH + b) * PSTRIDE;
             const int r = pix / G::PW, c = pix - r * G::PW;
             const int gy = y0 + r - 1, gx = x0 + c - 1;
-            pixs[b] = idx < ITEMS ? pix : -1;
-            ok[b] = idx < ITEMS && gy >= 0 && gy < H && gx >= 0 && gx < W;
+            pixs[b] = pix;
+            ok[b] = pix < NPIX && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
             if (ok[b]) {
                 if constexpr (POOL) {
-                    const int Ws = 2 * W;
-                    const T* base = raw + ((size_t)(n * 2 * H + 2 * gy) * Ws + 2 * gx) * C + c8 * 8;
+                    const unsigned char* base = src + ((uint32_t)(2 * gy) * rowb + (uint32_t)(2 * gx * C + c8 * 8) * 2);
                     q[b][0] = __ldg(reinterpret_cast<const uint4*>(base));
-                    q[b][1] = __ldg(reinterpret_cast<const uint4*>(base + C));
-                    q[b][2] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * C));
-                    q[b][3] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)Ws * C + C));
+                    q[b][1] = __ldg(reinterpret_cast<const uint4*>(base + C * 2));
+                    q[b][2] = __ldg(reinterpret_cast<const uint4*>(base + rowb));
+                    q[b][3] = __ldg(reinterpret_cast<const uint4*>(base + rowb + C * 2));
                 } else {
-                    q[b][0] = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * H + gy) * W + gx) * C + c8 * 8));
+                    q[b][0] = __ldg(reinterpret_cast<const uint4*>(src + ((uint32_t)gy * rowb + (uint32_t)(gx * C + c8 * 8) * 2)));
                 }
             }
         }
 #pragma unroll
         for (int b = 0; b < BATCH; ++b) {
-            if (pixs[b] < 0) continue;
+            if (pixs[b] >= NPIX) continue;
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (ok[b]) {
                 float y[8];
@@ -151,7 +160,7 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const T* __rest
                 }
                 o = pack8<T>(y);
             }
-            *reinterpret_cast<uint4*>(dst + (size_t)pixs[b] * 16) = o;
+            *reinterpret_cast<uint4*>(dst + (uint32_t)pixs[b] * 16) = o;
         }
     }
 }
@@ -212,12 +221,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
 
     // ---- (2) stage the activated halo tile ------------------------------------------------------------
     if constexpr (G::MODE == M_SAME) {
-        stage_planes<T, G, G::CIN, false, TANH>(act, reinterpret_cast<const T*>(p.src0), coef, 0, n, y0, x0, H, W);
+        stage_planes<T, G, G::CIN, false, TANH>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 2,
+                                                coef, 0, y0, x0, H, W);
     } else if constexpr (G::MODE == M_POOL) {
-        stage_planes<T, G, G::CIN, true, TANH>(act, reinterpret_cast<const T*>(p.src0), coef, 0, n, y0, x0, H, W);
+        stage_planes<T, G, G::CIN, true, TANH>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 8,
+                                               coef, 0, y0, x0, H, W);
     } else {
         // skip -> planes [CU/8, 2CU/8)
-        stage_planes<T, G, G::CU, false, TANH>(act, reinterpret_cast<const T*>(p.src1), coef + G::CL, G::CU / 8, n, y0, x0, H, W);
+        stage_planes<T, G, G::CU, false, TANH>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::CU * 2,
+                                               coef + G::CL, G::CU / 8, y0, x0, H, W);
         // activated low-res tile -> low planes
         unsigned char* low = smem + G::OFF_LOW;
         const T* raw = reinterpret_cast<const T*>(p.src0);
@@ -274,26 +286,39 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
                         mma16816<T>(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
                     }
                 }
-                // scatter (+bias) into the up planes [0, CU/8); outside the image the concat is zero-padded
+                // scatter (+bias) into the up planes [0, CU/8); outside the image the concat is zero-padded.
+                // Geometry of the two accumulator rows is n-tile independent: low pixel (li, lj) feeds the 2x2 block at
+                // tile (2li-1+a, 2lj-1+b); bit (2a+b) of `okm` = inside the staged tile, bit 4+(2a+b) = inside the image.
+                uint32_t boff[2], okm[2];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int lp = mt * 16 + (lane >> 2) + 8 * hf;
+                    const int li = lp / G::LPW, lj = lp - li * G::LPW;
+                    const int r0 = 2 * li - 1, c0 = 2 * lj - 1;
+                    boff[hf] = (uint32_t)((r0 * G::PW + c0) * 16);
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int ab = 0; ab < 4; ++ab) {
+                        const int r = r0 + (ab >> 1), c = c0 + (ab & 1);
+                        const bool in_tile = lp < G::LM && (unsigned)r < (unsigned)G::PH && (unsigned)c < (unsigned)G::PW;
+                        const bool in_img = (unsigned)(y0 - 1 + r) < (unsigned)H && (unsigned)(x0 - 1 + c) < (unsigned)W;
+                        m |= (in_tile ? 1u : 0u) << ab;
+                        m |= ((in_tile && in_img) ? 1u : 0u) << (4 + ab);
+                    }
+                    okm[hf] = m;
+                }
 #pragma unroll
                 for (int i = 0; i < G::CT_NTG; ++i) {
                     const int nn = (ng + i) * 8 + 2 * (lane & 3);
                     const int pos = nn / G::CU, co = nn % G::CU;
                     const float bias0 = ctb[co], bias1 = ctb[co + 1];
+                    const uint32_t poff = (uint32_t)((((pos >> 1) * G::PW + (pos & 1)) + (co >> 3) * G::PLANE) * 16 + (co & 7) * 2);
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
-                        const int lp = mt * 16 + (lane >> 2) + 8 * hf;
-                        if (lp < G::LM) {
-                            const int r = 2 * (lp / G::LPW) + (pos >> 1) - 1;
-                            const int c = 2 * (lp % G::LPW) + (pos & 1) - 1;
-                            if (r >= 0 && r < G::PH && c >= 0 && c < G::PW) {
-                                const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-                                uint32_t v = 0u;
-                                if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-                                    v = pack2<T>(acc[i][2 * hf] + bias0, acc[i][2 * hf + 1] + bias1);
-                                *reinterpret_cast<uint32_t*>(act + ((size_t)(co >> 3) * G::PLANE + r * G::PW + c) * 16 +
-                                                             (co & 7) * 2) = v;
-                            }
+                        if ((okm[hf] >> pos) & 1u) {
+                            const uint32_t v = ((okm[hf] >> (4 + pos)) & 1u)
+                                                   ? pack2<T>(acc[i][2 * hf] + bias0, acc[i][2 * hf + 1] + bias1) : 0u;
+                            *reinterpret_cast<uint32_t*>(act + boff[hf] + poff) = v;
                         }
                     }
                 }

@@ -38,15 +38,44 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
     const int H = p.H, W = p.W;
 
     // ---- stage the haloed input tile (fp32 -> T), zero outside the image ------------------------------
+    // Per tile row: 16 aligned float4 groups (the 64 interior pixels; tile column = 1 + 4j..4 + 4j) and the two halo
+    // columns.  In tileB (shifted copy) a group is one aligned 8-byte store; in tileA it straddles 4-byte words.
     const float* img = p.x + (size_t)n * H * W;
-    for (int idx = tid; idx < F_PH * F_PW; idx += F_THREADS) {
-        const int r = idx / F_PW, c = idx - r * F_PW;
-        const int gy = y0 + r - 1, gx = x0 + c - 1;
-        float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(img + (size_t)gy * W + gx);
-        const T h = Store<T>::from_f(v);
-        tileA[r * F_PA + c] = h;
-        if (c >= 1) tileB[r * F_PA + c - 1] = h;
+    const bool vec_ok = (x0 + F_TW <= W) && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    for (int idx = tid; idx < F_PH * 18; idx += F_THREADS) {
+        const int r = idx / 18, j = idx - r * 18;
+        const int gy = y0 + r - 1;
+        const bool rowok = (unsigned)gy < (unsigned)H;
+        T* ra = tileA + r * F_PA;
+        T* rb = tileB + r * F_PA;
+        if (j < 16) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int gx = x0 + 4 * j;
+            if (rowok) {
+                if (vec_ok) {
+                    v = __ldg(reinterpret_cast<const float4*>(img + (size_t)gy * W + gx));
+                } else {
+                    if (gx < W) v.x = __ldg(img + (size_t)gy * W + gx);
+                    if (gx + 1 < W) v.y = __ldg(img + (size_t)gy * W + gx + 1);
+                    if (gx + 2 < W) v.z = __ldg(img + (size_t)gy * W + gx + 2);
+                    if (gx + 3 < W) v.w = __ldg(img + (size_t)gy * W + gx + 3);
+                }
+            }
+            const uint32_t lo = pack2<T>(v.x, v.y), hi = pack2<T>(v.z, v.w);
+            const int c = 1 + 4 * j;                                   // tile column of v.x
+            *reinterpret_cast<uint2*>(rb + c - 1) = make_uint2(lo, hi);  // tileB[r][c-1 .. c+2]
+            reinterpret_cast<unsigned short*>(ra)[c] = (unsigned short)(lo & 0xffffu);
+            *reinterpret_cast<uint32_t*>(ra + c + 1) = (lo >> 16) | (hi << 16);
+            reinterpret_cast<unsigned short*>(ra)[c + 3] = (unsigned short)(hi >> 16);
+        } else {
+            const int c = j == 16 ? 0 : F_PW - 1;
+            const int gx = x0 + c - 1;
+            float v = 0.f;
+            if (rowok && (unsigned)gx < (unsigned)W) v = __ldg(img + (size_t)gy * W + gx);
+            const T h = Store<T>::from_f(v);
+            ra[c] = h;
+            if (c >= 1) rb[c - 1] = h;
+        }
     }
     if (tid < 2 * COUT) statd[tid] = 0.0;
 

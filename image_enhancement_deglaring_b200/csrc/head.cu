@@ -77,8 +77,11 @@ int head_launch(const dg_head_args& a, cudaStream_t stream) {
         set_error("head: out_channels %d not in 1..%d", a.cout, HEAD_MAX_OC);
         return 3;
     }
+    // >= 8 pixels per thread when the image allows it: the per-block prologue (GroupNorm coefficients in double,
+    // weights to shared memory) was most of the kernel at one pixel per thread (profile r1b: 11.6 warp-inst/pixel)
     const int HW = a.H * a.W;
-    int bx = (HW + HEAD_THREADS - 1) / HEAD_THREADS;
+    int bx = (HW + HEAD_THREADS * 8 - 1) / (HEAD_THREADS * 8);
+    if (bx < 1) bx = 1;
     if (bx > 1024) bx = 1024;
     dim3 grid(bx, a.N);
     const size_t smem = (size_t)(2 + a.cout) * a.src.channels * sizeof(float);

@@ -207,7 +207,7 @@ def _tc_check(out_tc, st_tc, out_ref, st_ref, dtype, what):
     want = torch.stack((got.sum(dim=(1, 2)), (got ** 2).sum(dim=(1, 2))), dim=2)
     # TC statistics are taken from the fp32 accumulators, the stored copy is rounded once more
     s2 = float((st_tc - want).abs().max() / max(1.0, float(want.abs().max())))
-    assert s2 <= (3e-4 if dtype == ops.DG_F16 else 3e-3), f"{what}: stats do not match stored values ({s2:.3e})"
+    assert s2 <= (6e-4 if dtype == ops.DG_F16 else 5e-3), f"{what}: stats do not match stored values ({s2:.3e})"
 
 
 @pytest.mark.parametrize("dtype", TC_DTYPES)
@@ -295,7 +295,7 @@ def test_tc_first_layer(dtype, cout, H, W):
     assert err <= (4e-3 if dtype == ops.DG_F16 else 3e-2) * max(1.0, float(ref.abs().max())), f"first layer err {err:.3e}"
     want = torch.stack((got.double().sum(dim=(2, 3)), (got.double() ** 2).sum(dim=(2, 3))), dim=2)
     serr = float((st.cpu() - want).abs().max() / max(1.0, float(want.abs().max())))
-    assert serr <= (3e-4 if dtype == ops.DG_F16 else 3e-3), f"first layer stats {serr:.3e}"
+    assert serr <= (6e-4 if dtype == ops.DG_F16 else 5e-3), f"first layer stats {serr:.3e}"
 
 
 @pytest.mark.parametrize("dtype", TC_DTYPES)
