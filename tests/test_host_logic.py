@@ -1,0 +1,124 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the nn.Module surface matches the
+reference's state_dict contract, errors are loud without a GPU, and the multi-rank host logic works over gloo."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from image_enhancement_deglaring_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "deglare.h")).read()
+    declared = set(re.findall(r"\b(dg_[a-z0-9_]+)\s*\(", hdr))
+    assert {"dg_conv3x3_fused", "dg_head1x1", "dg_lw_forward", "dg_lw_infer_host"} <= declared
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/deglare.h but not exported"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    assert lib.dg_version() >= 100
+    assert lib.dg_launch_count() == 0  # nothing may launch without a GPU
+
+
+def test_struct_layouts_match_header_sizes():
+    import ctypes as C
+    from image_enhancement_deglaring_b200 import _lib
+    # 8 pointers + 6 int32; 2 srcs + 6 int32 + 5 pointers + float + int32; ...
+    assert C.sizeof(_lib.DgSrc) == 8 * 8 + 6 * 4
+    assert C.sizeof(_lib.DgConv3x3Args) == 2 * C.sizeof(_lib.DgSrc) + 6 * 4 + 5 * 8 + 8
+    assert C.sizeof(_lib.DgHeadArgs) == C.sizeof(_lib.DgSrc) + 5 * 4 + 4 + 5 * 8 + 8
+
+
+def test_module_surface_matches_reference_contract(best_sd, golden):
+    import image_enhancement_deglaring_b200 as dg
+    net = dg.LightweightUNet()
+    assert dg.count_parameters(net) == 486409                     # README.md:10
+    assert abs(dg.get_model_size_mb(net) - 1.8555) < 1e-3         # README.md:11
+    assert list(net.state_dict().keys()) == [k for k in net.state_dict()]
+    assert set(net.state_dict().keys()) == set(best_sd.keys())
+    res = net.load_state_dict(best_sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in net.state_dict().items():
+        assert v.dtype == torch.float32 and tuple(v.shape) == tuple(best_sd[k].shape)
+    # constructor arguments of src/model.py:14, including the group-divisor search for odd widths
+    g = golden("lw_variants.npz")
+    odd = dg.LightweightUNet(in_channels=3, out_channels=2, num_groups=8, features_start=12)
+    assert list(odd.state_dict().keys()) == list(g["keys_fs12"])
+    assert [",".join(map(str, v.shape)) for v in odd.state_dict().values()] == list(g["shapes_fs12"])
+    assert [m.num_groups for m in odd.modules() if isinstance(m, torch.nn.GroupNorm)] == list(g["gn_groups_fs12"])
+    assert "GroupNorm(8, 8" in str(net) and "ConvTranspose2d(128, 64" in str(net)
+
+
+def test_no_cpu_fallback():
+    import image_enhancement_deglaring_b200 as dg
+    net = dg.LightweightUNet()
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            net(torch.zeros(1, 1, 16, 16))
+    from image_enhancement_deglaring_b200.session import InferenceSession
+    with pytest.raises(RuntimeError, match="CUDA"):
+        InferenceSession(net)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "image_enhancement_deglaring_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_shard_range_partitions_exactly():
+    from image_enhancement_deglaring_b200.parallel import shard_range
+    for n in (0, 1, 7, 64, 65):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _ddp_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from image_enhancement_deglaring_b200.parallel import FlatGradBucket, shard_range
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 1))
+    bucket = FlatGradBucket(lin.parameters())
+    x = torch.arange(40, dtype=torch.float32).reshape(8, 5) / 40.0
+    lo, hi = shard_range(8, rank, world)
+    bucket.zero_()
+    lin(x[lo:hi]).abs().mean().backward()
+    # every .grad must still alias the flat bucket after backward
+    off = 0
+    for p in bucket.params:
+        assert p.grad.data_ptr() == bucket.flat[off:off + p.numel()].data_ptr()
+        off += p.numel()
+    flat = bucket.allreduce_mean().clone()
+    if rank == 0:
+        torch.save(flat, out)
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_world2(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    out = str(tmp_path / "flat.pt")
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 1))
+    x = torch.arange(40, dtype=torch.float32).reshape(8, 5) / 40.0
+    # mean over equal shards of per-shard mean losses == global mean loss
+    lin(x).abs().mean().backward()
+    want = torch.cat([p.grad.flatten() for p in lin.parameters()])
+    assert torch.allclose(got, want, atol=1e-6)
