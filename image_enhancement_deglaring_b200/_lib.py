@@ -50,6 +50,7 @@ class DgLwParams(C.Structure):
         ("conv_w", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("gn_w", (C.c_void_p * 2) * DG_MAX_BLOCKS),
         ("gn_b", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w", C.c_void_p * 4), ("up_b", C.c_void_p * 4),
         ("conv_w_tc", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w_tc", C.c_void_p * 4),
+        ("conv_w_flip", (C.c_void_p * 2) * DG_MAX_BLOCKS),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("path", C.c_int32), ("reserved", C.c_int32),
     ]
 
@@ -65,6 +66,13 @@ SYMBOLS = {
     "dg_lw_layout": (C.c_int, [C.POINTER(DgLwParams), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_int32),
                                C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dg_lw_num_params": (C.c_int, [C.POINTER(DgLwParams), C.POINTER(C.c_size_t)]),
+    "dg_lw_backward_workspace_bytes": (C.c_int, [C.POINTER(DgLwParams), C.c_int32, C.c_int32, C.c_int32,
+                                                 C.POINTER(C.c_size_t)]),
+    "dg_lw_backward": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "dg_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p]),
     "dg_lw_profile": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]),
     "dg_lw_host_scratch_bytes": (C.c_int, [C.POINTER(DgLwParams), C.c_int32, C.c_int32, C.c_int32,
@@ -103,6 +111,20 @@ def load():
 def check(rc):
     if rc != 0:
         raise RuntimeError(f"libdeglare error {rc}: {load().dg_last_error_string().decode()}")
+
+
+_generation = 0
+
+
+def bump_generation():
+    """Called by code that rewrites parameter memory without torch ops (FusedAdamW): modules key their packed-weight
+    caches on this counter in addition to the tensors' own version counters."""
+    global _generation
+    _generation += 1
+
+
+def generation():
+    return _generation
 
 
 def launch_count():

@@ -172,6 +172,188 @@ static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, in
     return rc;
 }
 
+// ---- LightweightUNet backward ------------------------------------------------------------------
+// Flat gradient layout = the module's parameters() order and the parameters' own memory layouts:
+//   per block: conv0.weight [Co][Ci][3][3], gn0.weight, gn0.bias, conv1.weight, gn1.weight, gn1.bias
+//   order: enc1..enc4, bottleneck, (upconvK.weight [Ci][Co][2][2], upconvK.bias, decK block) for K=4..1, head w, head b
+struct GradLayout {
+    size_t conv_w[9][2], gn_w[9][2], gn_b[9][2], up_w[4], up_b[4], head_w, head_b, total;
+};
+
+static void make_grad_layout(const dg_lw_params* p, const LwPlan& pl, GradLayout* g) {
+    size_t off = 0;
+    auto block = [&](int b) {
+        const int lvl = block_level(b);
+        const int c = pl.f[lvl];
+        const int cin0 = b == 0 ? p->in_channels : (b < 5 ? pl.f[lvl - 1] : 2 * c);
+        g->conv_w[b][0] = off; off += (size_t)c * cin0 * 9;
+        g->gn_w[b][0] = off; off += c;
+        g->gn_b[b][0] = off; off += c;
+        g->conv_w[b][1] = off; off += (size_t)c * c * 9;
+        g->gn_w[b][1] = off; off += c;
+        g->gn_b[b][1] = off; off += c;
+    };
+    for (int b = 0; b < 5; ++b) block(b);
+    for (int b = 5; b < 9; ++b) {
+        const int lvl = block_level(b), u = b - 5;
+        g->up_w[u] = off; off += (size_t)pl.f[lvl + 1] * pl.f[lvl] * 4;
+        g->up_b[u] = off; off += pl.f[lvl];
+        block(b);
+    }
+    g->head_w = off; off += (size_t)p->out_channels * pl.f[0];
+    g->head_b = off; off += p->out_channels;
+    g->total = off;
+}
+
+struct BwdPlan {
+    size_t p_off[18], g_off[18], t_off[18], low_off[4], coef_off, p_bytes, total;
+    int cin_tot[18];
+};
+
+static void make_bwd_plan(const dg_lw_params* p, const LwPlan& pl, int N, BwdPlan* bp) {
+    size_t off = 0;
+    for (int i = 0; i < 18; ++i) { bp->p_off[i] = off; off += (size_t)N * pl.conv_c[i] * 2 * sizeof(double); }
+    bp->p_bytes = off;
+    off = align_up(off, 256);
+    int maxc = 0;
+    for (int i = 0; i < 18; ++i) {
+        const int b = i / 2, lvl = block_level(b);
+        bp->cin_tot[i] = i == 0 ? p->in_channels : (i % 2 ? pl.conv_c[i] : (b < 5 ? pl.f[lvl - 1] : 2 * pl.f[lvl]));
+        bp->g_off[i] = off;
+        off += align_up((size_t)N * pl.conv_h[i] * pl.conv_w[i] * pl.conv_c[i] * sizeof(float), 256);
+        bp->t_off[i] = off;
+        if (i > 0) off += align_up((size_t)N * pl.conv_h[i] * pl.conv_w[i] * bp->cin_tot[i] * sizeof(float), 256);
+        if (pl.conv_c[i] > maxc) maxc = pl.conv_c[i];
+    }
+    for (int u = 0; u < 4; ++u) {
+        const int lvl = 3 - u;  // upconv4 produces level 3 from level 4
+        bp->low_off[u] = off;
+        off += align_up((size_t)N * (pl.conv_h[2 * lvl + 2]) * (pl.conv_w[2 * lvl + 2]) * pl.f[lvl + 1] * sizeof(float), 256);
+    }
+    bp->coef_off = off;
+    off += align_up((size_t)N * maxc * 2 * sizeof(float), 256);
+    bp->total = off;
+}
+
+static void fwd_conv_args(const dg_lw_params* p, const LwPlan& pl, char* ws, const float* x, int N, int i, dg_conv3x3_args* a) {
+    const int b = i / 2;
+    memset(a, 0, sizeof(*a));
+    a->dtype = p->dtype;
+    a->N = N; a->H = pl.conv_h[i]; a->W = pl.conv_w[i];
+    a->cout = pl.conv_c[i];
+    a->weight = p->conv_w[b][i % 2];
+    a->weight_tc = p->conv_w_tc[b][i % 2];
+    a->out = ws + pl.raw_off[i];
+    a->out_stats = reinterpret_cast<double*>(ws + pl.stats_off[i]);
+    a->eps = 1e-5f;
+    a->path = p->path;
+    a->nsrc = 1;
+    if (i == 0) {
+        a->src[0].raw = x;
+        a->src[0].channels = p->in_channels;
+        a->src[0].groups = 1;
+        a->src[0].xform = DG_X_IMAGE;
+    } else if (i % 2 == 1) {
+        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_SAME);
+    } else if (b < 5) {
+        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_POOL2);       // pool1..4, src/model.py:107-112
+    } else {
+        const int lvl = block_level(b), u = b - 5;
+        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_CONVT2);     // upconv4..1, src/model.py:115-127
+        a->src[0].ct_w = p->up_w[u];
+        a->src[0].ct_b = p->up_b[u];
+        a->src[0].ct_w_tc = p->up_w_tc[u];
+        a->src[0].ct_cout = pl.f[lvl];
+        a->src[1] = gn_src(p, pl, ws, 2 * lvl + 1, DG_X_SAME); // skip: torch.cat((up, skip), 1)
+        a->nsrc = 2;
+    }
+}
+
+static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_y, int N, int H, int W, void* fwd_ws,
+                       size_t fwd_bytes, void* bwd_ws, size_t bwd_bytes, float* grads, cudaStream_t st) {
+    LwPlan pl;
+    int rc = make_plan(p, N, H, W, &pl);
+    if (rc) return rc;
+    BwdPlan bp;
+    make_bwd_plan(p, pl, N, &bp);
+    GradLayout gl;
+    make_grad_layout(p, pl, &gl);
+    if (fwd_ws == nullptr || fwd_bytes < pl.total_bytes || bwd_ws == nullptr || bwd_bytes < bp.total) {
+        set_error("backward: workspace too small (fwd %zu/%zu, bwd %zu/%zu)", fwd_bytes, pl.total_bytes, bwd_bytes, bp.total);
+        return 4;
+    }
+    if (x == nullptr || grad_y == nullptr || grads == nullptr) { set_error("backward: null pointer"); return 2; }
+    for (int b = 0; b < 9; ++b)
+        for (int j = 0; j < 2; ++j)
+            if ((2 * b + j) > 0 && p->conv_w_flip[b][j] == nullptr) { set_error("backward: flipped weights missing"); return 2; }
+    char* fw = static_cast<char*>(fwd_ws);
+    char* bw = static_cast<char*>(bwd_ws);
+    cudaError_t e = cudaMemsetAsync(bw, 0, bp.p_bytes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(grads, 0, gl.total * sizeof(float), st);
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 10; }
+    auto G = [&](int i) { return reinterpret_cast<float*>(bw + bp.g_off[i]); };
+    auto T = [&](int i) { return reinterpret_cast<float*>(bw + bp.t_off[i]); };
+    auto P = [&](int i) { return reinterpret_cast<double*>(bw + bp.p_off[i]); };
+    auto raw = [&](int i) { return static_cast<const void*>(fw + pl.raw_off[i]); };
+    auto stats = [&](int i) { return reinterpret_cast<const double*>(fw + pl.stats_off[i]); };
+    auto act_bwd = [&](int j, const float* da, int sa, int oa, const float* db, int sb, int ob) {
+        return act_bwd_launch(p->dtype, raw(j), stats(j), p->gn_w[j / 2][j % 2], p->gn_b[j / 2][j % 2], da, sa, oa, db, sb, ob, G(j),
+                              P(j), N, pl.conv_h[j], pl.conv_w[j], pl.conv_c[j], p->groups[j / 2], 1e-5f, st);
+    };
+    // head: src/model.py:131 backward
+    rc = head_bwd_launch(p->dtype, raw(17), stats(17), p->gn_w[8][1], p->gn_b[8][1], grad_y, p->head_w, G(17), P(17),
+                         grads + gl.head_w, grads + gl.head_b, N, H, W, pl.conv_c[17], p->out_channels, p->groups[8], 1e-5f, st);
+    if (rc) return rc;
+    for (int i = 17; i >= 0; --i) {
+        const int b = i / 2, j = i % 2, C = pl.conv_c[i], Hi = pl.conv_h[i], Wi = pl.conv_w[i];
+        // G_i -> dR_i in place, dgamma / dbeta
+        rc = gn_bwd_apply_launch(p->dtype, raw(i), stats(i), p->gn_w[b][j], P(i), G(i), grads + gl.gn_w[b][j], grads + gl.gn_b[b][j],
+                                 N, Hi, Wi, C, p->groups[b], 1e-5f, st);
+        if (rc) return rc;
+        // dW_i: same sources as the forward conv, correlated with dR_i; written in the parameter's [Co][Ci][3][3] layout
+        dg_conv3x3_args a;
+        fwd_conv_args(p, pl, fw, x, N, i, &a);
+        rc = conv3x3_wgrad_launch(a, G(i), grads + gl.conv_w[b][j], /*tap*/ 1, /*ci*/ 9, /*co*/ 9 * bp.cin_tot[i], st);
+        if (rc) return rc;
+        if (i == 0) break;
+        // dA_in = conv3x3(dR_i, flipped weights): the forward kernel on an identity fp32 source
+        dg_conv3x3_args d;
+        memset(&d, 0, sizeof(d));
+        d.dtype = DG_F32;
+        d.N = N; d.H = Hi; d.W = Wi;
+        d.cout = bp.cin_tot[i];
+        d.weight = p->conv_w_flip[b][j];
+        d.out = T(i);
+        d.eps = 1e-5f;
+        d.path = 1;
+        d.nsrc = 1;
+        d.src[0].raw = G(i);
+        d.src[0].channels = C;
+        d.src[0].groups = 1;
+        d.src[0].xform = DG_X_SAME;
+        rc = conv3x3_generic_launch(d, st);
+        if (rc) return rc;
+        if (j == 1) {
+            rc = act_bwd(i - 1, T(i), C, 0, nullptr, 0, 0);
+        } else if (b < 5) {
+            // producer = skip tensor of level b-1: gradient from the decoder's concat (skip half) + this pooled path
+            const int lvl = b - 1, dconv = 2 * (8 - lvl);
+            rc = act_bwd(i - 1, T(dconv), 2 * pl.f[lvl], pl.f[lvl], T(i), pl.f[lvl], 0);
+        } else {
+            const int lvl = block_level(b), u = b - 5;
+            float* dlow = reinterpret_cast<float*>(bw + bp.low_off[u]);
+            rc = convt_bwd_launch(p->dtype, T(i), 2 * pl.f[lvl], p->up_w[u], raw(i - 1), stats(i - 1), p->gn_w[b - 1][1],
+                                  p->gn_b[b - 1][1], dlow, grads + gl.up_w[u], grads + gl.up_b[u],
+                                  reinterpret_cast<float*>(bw + bp.coef_off), N, Hi, Wi, pl.f[lvl + 1], pl.f[lvl],
+                                  p->groups[b - 1], 1e-5f, st);
+            if (rc) return rc;
+            rc = act_bwd(i - 1, dlow, pl.f[lvl + 1], 0, nullptr, 0, 0);
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 // ---- host-buffer pipeline state --------------------------------------------------------------
 struct HostPipe {
     bool ready = false;
@@ -288,6 +470,44 @@ int dg_lw_forward(const dg_lw_params* p, const float* x, float* y, int32_t N, in
                   size_t workspace_bytes, const float* target, double* l1_sum, dg_stream_t stream) {
     return lw_forward(p, x, y, N, H, W, workspace, workspace_bytes, target, l1_sum,
                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_lw_num_params(const dg_lw_params* p, size_t* count) {
+    LwPlan pl;
+    int rc = make_plan(p, 1, 16, 16, &pl);
+    if (rc) return rc;
+    GradLayout gl;
+    make_grad_layout(p, pl, &gl);
+    if (count) *count = gl.total;
+    return 0;
+}
+
+int dg_lw_backward_workspace_bytes(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, size_t* bytes) {
+    LwPlan pl;
+    int rc = make_plan(p, N, H, W, &pl);
+    if (rc) return rc;
+    BwdPlan bp;
+    make_bwd_plan(p, pl, N, &bp);
+    if (bytes) *bytes = bp.total;
+    return 0;
+}
+
+int dg_lw_backward(const dg_lw_params* p, const float* x, const float* grad_y, int32_t N, int32_t H, int32_t W,
+                   void* fwd_workspace, size_t fwd_bytes, void* bwd_workspace, size_t bwd_bytes, float* grads,
+                   dg_stream_t stream) {
+    return lw_backward(p, x, grad_y, N, H, W, fwd_workspace, fwd_bytes, bwd_workspace, bwd_bytes, grads,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t count, double* scratch,
+                  float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                  float grad_scale, dg_stream_t stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !scratch || count == 0 || step < 1) {
+        set_error("adamw: bad arguments");
+        return 2;
+    }
+    return adamw_launch(params, grads, exp_avg, exp_avg_sq, count, scratch, max_norm, lr, beta1, beta2, eps, weight_decay,
+                        step, grad_scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dg_lw_profile(const dg_lw_params* p, const float* x, float* y, int32_t N, int32_t H, int32_t W, void* workspace,

@@ -1,0 +1,440 @@
+// Backward of the UNet blocks (autograd of src/model.py:92-131 as driven by optimized_train.py:210/226) and the
+// fused optimizer tail (clip_grad_norm_ + AdamW, optimized_train.py:215-218,230-233,440-446).
+//
+// Gradient flow per conv i (raw output R_i, y_i = GN(R_i), A_i = SiLU(y_i)):
+//   G_i  = dL/dy_i = (sum of dL/dA_i contributions) * silu'(y_i)            -> act_bwd_kernel (+ per-(n,c) sums
+//          P1 = sum G, P2 = sum G*xhat, which are also dbeta / dgamma)
+//   dR_i = rstd*(gamma*G_i - m1_g - xhat*m2_g),  m1_g = mean_g(gamma*G), m2_g = mean_g(gamma*G*xhat)
+//                                                                             -> gn_bwd_apply_kernel (in place on G_i)
+//   dW_i = corr(A_in, dR_i)                                                   -> conv3x3_generic_kernel<WGRAD>
+//   dA_in = conv3x3(dR_i, flipped W_i)                                        -> the forward generic conv kernel itself
+//   ConvTranspose2d(2,2): dA_low, dW_t, dbias                                 -> convt_bwd_data / convt_bwd_weight
+//   head: dA_17 = dOut * w, dW_head, dbias                                    -> head_bwd_kernel
+// All gradient tensors are fp32 NHWC; the saved raw activations are read in their storage type.
+#include "common.cuh"
+
+namespace dg {
+
+namespace {
+constexpr int BW_THREADS = 256;
+
+__device__ __forceinline__ float silu_grad(float y) {
+    const float s = 1.f / (1.f + __expf(-y));
+    return s * (1.f + y * (1.f - s));
+}
+
+__device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, int n, int C, int groups, int c, double plane,
+                                             float eps, float& mean, float& rstd) {
+    const int cpg = C / groups;
+    const int g0 = (c / cpg) * cpg;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+        s1 += stats[(size_t)(n * C + g0 + k) * 2];
+        s2 += stats[(size_t)(n * C + g0 + k) * 2 + 1];
+    }
+    const double cnt = plane * cpg;
+    const double m = s1 / cnt;
+    double var = s2 / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    rstd = (float)rsqrt(var + (double)eps);
+}
+
+// ---- G = (dA_a + 0.25 * up2(dA_b)) * silu'(y);  P[n][c] += (sum G, sum G*xhat) -------------------------------------
+struct ActBwdArgs {
+    const void* raw; const double* stats; const float* gamma; const float* beta;
+    const float* dA_a; int stride_a, off_a;   // same-resolution gradient [N,H,W,stride_a], channels off_a..off_a+C
+    const float* dA_b; int stride_b, off_b;   // optional half-resolution gradient (AvgPool2d backward: /4, replicated)
+    float* G; double* P;
+    int N, H, W, C, groups; float eps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(BW_THREADS) act_bwd_kernel(const ActBwdArgs p) {
+    extern __shared__ double bsm[];
+    const int C = p.C;
+    double* psm = bsm;                                   // [C][2]
+    float* coef = reinterpret_cast<float*>(psm + 2 * C);  // [C][4] mean, rstd, gamma, beta
+    const int n = blockIdx.y;
+    const int HW = p.H * p.W;
+    for (int c = threadIdx.x; c < C; c += BW_THREADS) {
+        float m, r;
+        gn_mean_rstd(p.stats, n, C, p.groups, c, (double)HW, p.eps, m, r);
+        coef[4 * c] = m; coef[4 * c + 1] = r; coef[4 * c + 2] = p.gamma[c]; coef[4 * c + 3] = p.beta[c];
+        psm[2 * c] = 0.0; psm[2 * c + 1] = 0.0;
+    }
+    __syncthreads();
+    const T* raw = reinterpret_cast<const T*>(p.raw);
+    // thread -> fixed channel (needs BW_THREADS*gridDim.x to be a multiple of C when C < total threads: enforced by host)
+    const size_t total = (size_t)HW * C;
+    const size_t stride = (size_t)gridDim.x * BW_THREADS;
+    double a1 = 0.0, a2 = 0.0;
+    int cur_c = -1;
+    for (size_t e = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; e < total; e += stride) {
+        const int c = (int)(e % C);
+        const int pix = (int)(e / C);
+        if (c != cur_c) {
+            if (cur_c >= 0) { atomicAdd(&psm[2 * cur_c], a1); atomicAdd(&psm[2 * cur_c + 1], a2); }
+            cur_c = c; a1 = 0.0; a2 = 0.0;
+        }
+        const float r = Store<T>::to_f(raw[(size_t)n * total + e]);
+        const float xh = (r - coef[4 * c]) * coef[4 * c + 1];
+        const float y = xh * coef[4 * c + 2] + coef[4 * c + 3];
+        float d = 0.f;
+        if (p.dA_a) d = p.dA_a[((size_t)n * HW + pix) * p.stride_a + p.off_a + c];
+        if (p.dA_b) {
+            const int yy = pix / p.W, xx = pix % p.W;
+            d += 0.25f * p.dA_b[((size_t)(n * (p.H / 2) + yy / 2) * (p.W / 2) + xx / 2) * p.stride_b + p.off_b + c];
+        }
+        const float g = d * silu_grad(y);
+        p.G[(size_t)n * total + e] = g;
+        a1 += (double)g;
+        a2 += (double)(g * xh);
+    }
+    if (cur_c >= 0) { atomicAdd(&psm[2 * cur_c], a1); atomicAdd(&psm[2 * cur_c + 1], a2); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += BW_THREADS) atomicAdd(p.P + (size_t)n * C * 2 + i, psm[i]);
+}
+
+// ---- dR = rstd*(gamma*G - m1 - xhat*m2) in place; block (0,0) also reduces dgamma/dbeta over the batch -----------------
+struct GnBwdArgs {
+    const void* raw; const double* stats; const float* gamma; const double* P;
+    float* G;  // in: G, out: dR
+    float* dgamma; float* dbeta;
+    int N, H, W, C, groups; float eps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(BW_THREADS) gn_bwd_apply_kernel(const GnBwdArgs p) {
+    extern __shared__ float gsm[];  // [C][5] mean, rstd, gamma, m1, m2
+    const int C = p.C, n = blockIdx.y, HW = p.H * p.W;
+    const int cpg = C / p.groups;
+    for (int c = threadIdx.x; c < C; c += BW_THREADS) {
+        float m, r;
+        gn_mean_rstd(p.stats, n, C, p.groups, c, (double)HW, p.eps, m, r);
+        const int g0 = (c / cpg) * cpg;
+        double m1 = 0.0, m2 = 0.0;
+        for (int k = 0; k < cpg; ++k) {
+            m1 += (double)p.gamma[g0 + k] * p.P[((size_t)n * C + g0 + k) * 2];
+            m2 += (double)p.gamma[g0 + k] * p.P[((size_t)n * C + g0 + k) * 2 + 1];
+        }
+        const double cnt = (double)HW * cpg;
+        gsm[5 * c] = m; gsm[5 * c + 1] = r; gsm[5 * c + 2] = p.gamma[c];
+        gsm[5 * c + 3] = (float)(m1 / cnt); gsm[5 * c + 4] = (float)(m2 / cnt);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && p.dgamma != nullptr) {
+        for (int c = threadIdx.x; c < C; c += BW_THREADS) {
+            double dg = 0.0, db = 0.0;
+            for (int i = 0; i < p.N; ++i) {
+                db += p.P[((size_t)i * C + c) * 2];
+                dg += p.P[((size_t)i * C + c) * 2 + 1];
+            }
+            p.dgamma[c] = (float)dg;
+            p.dbeta[c] = (float)db;
+        }
+    }
+    __syncthreads();
+    const T* raw = reinterpret_cast<const T*>(p.raw);
+    const size_t total = (size_t)HW * C;
+    for (size_t e = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * BW_THREADS) {
+        const int c = (int)(e % C);
+        const float r = Store<T>::to_f(raw[(size_t)n * total + e]);
+        const float xh = (r - gsm[5 * c]) * gsm[5 * c + 1];
+        const float g = p.G[(size_t)n * total + e];
+        p.G[(size_t)n * total + e] = gsm[5 * c + 1] * (gsm[5 * c + 2] * g - gsm[5 * c + 3] - xh * gsm[5 * c + 4]);
+    }
+}
+
+// ---- head backward: dA = dOut * w -> G_last, P_last; dW_head, dbias -----------------------------------------------------
+struct HeadBwdArgs {
+    const void* raw; const double* stats; const float* gamma; const float* beta;
+    const float* dOut;    // [N,OC,H,W]
+    const float* w;       // [OC][C]
+    float* G; double* P;  // [N,H,W,C], [N,C,2]
+    float* dW; float* dB; // [OC][C], [OC] accumulated atomically (zero on entry)
+    int N, H, W, C, OC, groups; float eps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(BW_THREADS) head_bwd_kernel(const HeadBwdArgs p) {
+    extern __shared__ double hbs[];
+    const int C = p.C, OC = p.OC, n = blockIdx.y, HW = p.H * p.W;
+    double* psm = hbs;                                        // [C][2]
+    double* wacc = psm + 2 * C;                               // [OC][C] + [OC]
+    float* coef = reinterpret_cast<float*>(wacc + OC * C + OC);  // [C][4]
+    float* wsm = coef + 4 * C;                                // [OC][C]
+    for (int c = threadIdx.x; c < C; c += BW_THREADS) {
+        float m, r;
+        gn_mean_rstd(p.stats, n, C, p.groups, c, (double)HW, p.eps, m, r);
+        coef[4 * c] = m; coef[4 * c + 1] = r; coef[4 * c + 2] = p.gamma[c]; coef[4 * c + 3] = p.beta[c];
+        psm[2 * c] = 0.0; psm[2 * c + 1] = 0.0;
+    }
+    for (int i = threadIdx.x; i < OC * C + OC; i += BW_THREADS) wacc[i] = 0.0;
+    for (int i = threadIdx.x; i < OC * C; i += BW_THREADS) wsm[i] = p.w[i];
+    __syncthreads();
+    const T* raw = reinterpret_cast<const T*>(p.raw);
+    const int lane = threadIdx.x & 31;
+    // whole warps iterate together (inactive lanes contribute zeros) so the per-channel sums reduce with shuffles
+    const int npix_round = (HW + 31) & ~31;
+    for (int pix = blockIdx.x * BW_THREADS + threadIdx.x; pix < npix_round; pix += gridDim.x * BW_THREADS) {
+        const bool live = pix < HW;
+        float dO[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < OC; ++j) {
+            if (live) dO[j] = p.dOut[((size_t)n * OC + j) * HW + pix];
+            const float t = warp_sum(dO[j]);
+            if (lane == 0) atomicAdd(&wacc[OC * C + j], (double)t);
+        }
+        for (int c = 0; c < C; ++c) {
+            float g = 0.f, gx = 0.f, a = 0.f;
+            if (live) {
+                const float r = Store<T>::to_f(raw[((size_t)n * HW + pix) * C + c]);
+                const float xh = (r - coef[4 * c]) * coef[4 * c + 1];
+                const float y = xh * coef[4 * c + 2] + coef[4 * c + 3];
+                a = silu_f(y);
+                float d = 0.f;
+                for (int j = 0; j < OC; ++j) d = fmaf(dO[j], wsm[j * C + c], d);
+                g = d * silu_grad(y);
+                gx = g * xh;
+                p.G[((size_t)n * HW + pix) * C + c] = g;
+            }
+            const float t1 = warp_sum(g), t2 = warp_sum(gx);
+            if (lane == 0) { atomicAdd(&psm[2 * c], (double)t1); atomicAdd(&psm[2 * c + 1], (double)t2); }
+            for (int j = 0; j < OC; ++j) {
+                const float t3 = warp_sum(dO[j] * a);
+                if (lane == 0) atomicAdd(&wacc[j * C + c], (double)t3);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += BW_THREADS) atomicAdd(p.P + (size_t)n * C * 2 + i, psm[i]);
+    for (int i = threadIdx.x; i < OC * C; i += BW_THREADS) atomicAdd(p.dW + i, (float)wacc[i]);
+    for (int i = threadIdx.x; i < OC; i += BW_THREADS) atomicAdd(p.dB + i, (float)wacc[OC * C + i]);
+}
+
+// ---- ConvTranspose2d(k=2,s=2) backward ---------------------------------------------------------------------------------
+//   up[n, 2i+a, 2j+b, co] = bias[co] + sum_ci Alow[n,i,j,ci] * Wt[ab][ci][co]       (src/model.py:47-53)
+struct ConvtBwdArgs {
+    const float* dCat; int stride;      // gradient of the concat [N,H,W,stride]; the up half is channels 0..Cu
+    const float* wt;                    // [2][2][Cl][Cu]
+    const void* raw_low; const double* stats; const float* gamma; const float* beta;  // low-res producer (for A_low)
+    float* dAlow;                       // [N,H/2,W/2,Cl]
+    float* dWt; float* dBias;           // accumulated atomically
+    float* coefbuf;                     // scratch [N][Cl][2] (mean, rstd) of the low-res producer
+    int N, H, W, Cl, Cu, groups; float eps;
+};
+
+__global__ void __launch_bounds__(BW_THREADS) convt_bwd_data_kernel(const ConvtBwdArgs p) {
+    // one thread per (low pixel, ci): dAlow = sum_{ab,co} dUp[2i+a, 2j+b, co] * Wt[ab][ci][co]
+    const int Hl = p.H / 2, Wl = p.W / 2;
+    const size_t total = (size_t)p.N * Hl * Wl * p.Cl;
+    for (size_t e = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; e < total; e += (size_t)gridDim.x * BW_THREADS) {
+        const int ci = (int)(e % p.Cl);
+        const size_t lp = e / p.Cl;
+        const int j = (int)(lp % Wl);
+        const int i = (int)((lp / Wl) % Hl);
+        const int n = (int)(lp / ((size_t)Wl * Hl));
+        float acc = 0.f;
+        for (int ab = 0; ab < 4; ++ab) {
+            const float* d = p.dCat + ((size_t)(n * p.H + 2 * i + (ab >> 1)) * p.W + 2 * j + (ab & 1)) * p.stride;
+            const float* w = p.wt + ((size_t)ab * p.Cl + ci) * p.Cu;
+            for (int co = 0; co < p.Cu; ++co) acc = fmaf(__ldg(d + co), __ldg(w + co), acc);
+        }
+        p.dAlow[e] = acc;
+    }
+}
+
+__global__ void gn_mean_rstd_kernel(const double* stats, float* out, int C, int groups, double plane, float eps) {
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float m, r;
+        gn_mean_rstd(stats, n, C, groups, c, plane, eps, m, r);
+        out[((size_t)n * C + c) * 2] = m;
+        out[((size_t)n * C + c) * 2 + 1] = r;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BW_THREADS) convt_bwd_weight_kernel(const ConvtBwdArgs p) {
+    // grid.x: groups of 256 (ab, ci, co) combos; grid.y: slabs of low pixels.  One accumulator per thread.
+    constexpr int SLAB = 32;  // low pixels staged per iteration
+    extern __shared__ float csm[];
+    const int Cl = p.Cl, Cu = p.Cu;
+    float* alow = csm;                    // [SLAB][Cl]
+    float* dup = alow + SLAB * Cl;        // [SLAB][4][Cu]
+    const int Hl = p.H / 2, Wl = p.W / 2;
+    const int npix = p.N * Hl * Wl;
+    const int combo = blockIdx.x * BW_THREADS + threadIdx.x;
+    const int ncombo = 4 * Cl * Cu;
+    const int co = combo % Cu, ci = (combo / Cu) % Cl, ab = combo / (Cu * Cl);
+    const T* raw = reinterpret_cast<const T*>(p.raw_low);
+    float acc = 0.f, bacc = 0.f;
+    const bool do_bias = blockIdx.x == 0 && threadIdx.x < 4 * Cu;  // thread -> (ab', co') partial of dbias
+    for (int base = blockIdx.y * SLAB; base < npix; base += gridDim.y * SLAB) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < SLAB * Cl; idx += BW_THREADS) {
+            const int c = idx % Cl, lp = base + idx / Cl;
+            float v = 0.f;
+            if (lp < npix) {
+                const int n = lp / (Hl * Wl);
+                const float m = p.coefbuf[((size_t)n * Cl + c) * 2], r = p.coefbuf[((size_t)n * Cl + c) * 2 + 1];
+                const float y = (Store<T>::to_f(raw[(size_t)lp * Cl + c]) - m) * r * p.gamma[c] + p.beta[c];
+                v = silu_f(y);
+            }
+            alow[idx] = v;
+        }
+        for (int idx = threadIdx.x; idx < SLAB * 4 * Cu; idx += BW_THREADS) {
+            const int c = idx % Cu, q = (idx / Cu) % 4, lp = base + idx / (4 * Cu);
+            float v = 0.f;
+            if (lp < npix) {
+                const int j = lp % Wl, i = (lp / Wl) % Hl, n = lp / (Hl * Wl);
+                v = p.dCat[((size_t)(n * p.H + 2 * i + (q >> 1)) * p.W + 2 * j + (q & 1)) * p.stride + c];
+            }
+            dup[idx] = v;
+        }
+        __syncthreads();
+        if (combo < ncombo)
+            for (int s = 0; s < SLAB; ++s) acc = fmaf(alow[s * Cl + ci], dup[(s * 4 + ab) * Cu + co], acc);
+        if (do_bias)
+            for (int s = 0; s < SLAB; ++s) bacc += dup[s * 4 * Cu + threadIdx.x];
+    }
+    if (combo < ncombo) atomicAdd(p.dWt + ((size_t)ci * Cu + co) * 4 + ab, acc);  // parameter layout [Cl][Cu][2][2]
+    if (do_bias) atomicAdd(p.dBias + threadIdx.x % Cu, bacc);
+}
+
+// ---- optimizer tail over the flat parameter / gradient buffers -------------------------------------------------------------
+__global__ void __launch_bounds__(BW_THREADS) sumsq_kernel(const float* __restrict__ g, size_t n, double* out) {
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * BW_THREADS)
+        acc += (double)g[i] * (double)g[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double red[BW_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < BW_THREADS / 32; ++i) t += red[i];
+        atomicAdd(out, t);
+    }
+}
+
+struct AdamwArgs {
+    float* p; const float* g; float* m; float* v; size_t n;
+    const double* sumsq;  // global grad sum of squares (device), for clip_grad_norm_
+    float max_norm, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale;
+};
+
+__global__ void __launch_bounds__(BW_THREADS) adamw_kernel(const AdamwArgs a) {
+    // torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (total_norm + 1e-6)); torch.optim.AdamW (decoupled decay)
+    float coef = a.grad_scale;
+    if (a.max_norm > 0.f) {
+        const float total = (float)sqrt(*a.sumsq) * a.grad_scale;
+        coef *= fminf(1.f, a.max_norm / (total + 1e-6f));
+    }
+    for (size_t i = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; i < a.n; i += (size_t)gridDim.x * BW_THREADS) {
+        const float g = a.g[i] * coef;
+        float p = a.p[i] * (1.f - a.lr * a.weight_decay);
+        const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+        const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+        a.m[i] = m;
+        a.v[i] = v;
+        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+        a.p[i] = p - (a.lr / a.bc1) * (m / denom);
+    }
+}
+
+inline int ew_blocks(size_t elems, int C) {
+    // element-wise kernels keep a thread on one channel across its stride loop only if the stride is a multiple of C
+    size_t b = (elems + BW_THREADS - 1) / BW_THREADS;
+    if (b > 2048) b = 2048;
+    if (b < 1) b = 1;
+    (void)C;
+    return (int)b;
+}
+}  // namespace
+
+#define DG_BY_DTYPE(dt, CALL)                                          \
+    switch (dt) {                                                      \
+        case DG_F32: { using T = float; CALL; break; }                 \
+        case DG_F16: { using T = __half; CALL; break; }                \
+        case DG_BF16: { using T = __nv_bfloat16; CALL; break; }        \
+        default: set_error("bad dtype %d", dt); return 2;             \
+    }
+
+int act_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dA_a,
+                   int stride_a, int off_a, const float* dA_b, int stride_b, int off_b, float* G, double* P, int N, int H,
+                   int W, int C, int groups, float eps, cudaStream_t st) {
+    ActBwdArgs a{raw, stats, gamma, beta, dA_a, stride_a, off_a, dA_b, stride_b, off_b, G, P, N, H, W, C, groups, eps};
+    dim3 grid(ew_blocks((size_t)H * W * C, C), N);
+    const size_t smem = (size_t)C * 2 * sizeof(double) + (size_t)C * 4 * sizeof(float);
+    DG_BY_DTYPE(dtype, (act_bwd_kernel<T><<<grid, BW_THREADS, smem, st>>>(a)));
+    count_launch();
+    return check_launch("act_bwd");
+}
+
+int gn_bwd_apply_launch(int dtype, const void* raw, const double* stats, const float* gamma, const double* P, float* G,
+                        float* dgamma, float* dbeta, int N, int H, int W, int C, int groups, float eps, cudaStream_t st) {
+    GnBwdArgs a{raw, stats, gamma, P, G, dgamma, dbeta, N, H, W, C, groups, eps};
+    dim3 grid(ew_blocks((size_t)H * W * C, C), N);
+    const size_t smem = (size_t)C * 5 * sizeof(float);
+    DG_BY_DTYPE(dtype, (gn_bwd_apply_kernel<T><<<grid, BW_THREADS, smem, st>>>(a)));
+    count_launch();
+    return check_launch("gn_bwd_apply");
+}
+
+int head_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dOut,
+                    const float* w, float* G, double* P, float* dW, float* dB, int N, int H, int W, int C, int OC, int groups,
+                    float eps, cudaStream_t st) {
+    if (OC > 4) { set_error("head backward: out_channels %d > 4", OC); return 3; }
+    HeadBwdArgs a{raw, stats, gamma, beta, dOut, w, G, P, dW, dB, N, H, W, C, OC, groups, eps};
+    int bx = (H * W + BW_THREADS * 4 - 1) / (BW_THREADS * 4);
+    if (bx > 512) bx = 512;
+    dim3 grid(bx, N);
+    const size_t smem = (size_t)(2 * C + OC * C + OC) * sizeof(double) + (size_t)(4 * C + OC * C) * sizeof(float);
+    DG_BY_DTYPE(dtype, (head_bwd_kernel<T><<<grid, BW_THREADS, smem, st>>>(a)));
+    count_launch();
+    return check_launch("head_bwd");
+}
+
+int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const void* raw_low, const double* stats,
+                     const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias, float* coefbuf, int N,
+                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st) {
+    ConvtBwdArgs a{dCat, stride, wt, raw_low, stats, gamma, beta, dAlow, dWt, dBias, coefbuf, N, H, W, Cl, Cu, groups, eps};
+    gn_mean_rstd_kernel<<<N, 128, 0, st>>>(stats, coefbuf, Cl, groups, (double)(H / 2) * (W / 2), eps);
+    count_launch();
+    const size_t total = (size_t)N * (H / 2) * (W / 2) * Cl;
+    convt_bwd_data_kernel<<<ew_blocks(total, Cl), BW_THREADS, 0, st>>>(a);
+    count_launch();
+    int rc = check_launch("convt_bwd_data");
+    if (rc) return rc;
+    const int ncombo = 4 * Cl * Cu;
+    if (4 * Cu > BW_THREADS) { set_error("convT backward: %d up channels unsupported", Cu); return 3; }
+    const int npix = N * (H / 2) * (W / 2);
+    int slabs = (npix + 31) / 32;
+    if (slabs > 128) slabs = 128;
+    dim3 grid((ncombo + BW_THREADS - 1) / BW_THREADS, slabs);
+    const size_t smem = (size_t)32 * (Cl + 4 * Cu) * sizeof(float);
+    if (smem > 48 * 1024) {
+        set_error("convT backward: %zu B of shared memory (channels too large for this kernel)", smem);
+        return 3;
+    }
+    DG_BY_DTYPE(dtype, (convt_bwd_weight_kernel<T><<<grid, BW_THREADS, smem, st>>>(a)));
+    count_launch();
+    return check_launch("convt_bwd_weight");
+}
+
+int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), st);
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 10; }
+    int blocks = (int)((n + BW_THREADS - 1) / BW_THREADS);
+    if (blocks > 592) blocks = 592;
+    sumsq_kernel<<<blocks, BW_THREADS, 0, st>>>(g, n, sumsq_scratch);
+    count_launch();
+    AdamwArgs a{p, g, m, v, n, sumsq_scratch, max_norm, lr, beta1, beta2, eps, weight_decay,
+                (float)(1.0 - pow((double)beta1, step)), (float)sqrt(1.0 - pow((double)beta2, step)), grad_scale};
+    adamw_kernel<<<blocks, BW_THREADS, 0, st>>>(a);
+    count_launch();
+    return check_launch("adamw");
+}
+
+}  // namespace dg

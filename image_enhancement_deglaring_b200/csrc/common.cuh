@@ -114,6 +114,21 @@ int conv3x3_generic_launch(const dg_conv3x3_args& a, cudaStream_t stream);
 int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int conv_first_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int head_launch(const dg_head_args& a, cudaStream_t stream);
+int conv3x3_wgrad_launch(const dg_conv3x3_args& a, const float* dR, float* dW, int s_tap, int s_ci, int s_co,
+                         cudaStream_t stream);
+int act_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dA_a,
+                   int stride_a, int off_a, const float* dA_b, int stride_b, int off_b, float* G, double* P, int N, int H,
+                   int W, int C, int groups, float eps, cudaStream_t st);
+int gn_bwd_apply_launch(int dtype, const void* raw, const double* stats, const float* gamma, const double* P, float* G,
+                        float* dgamma, float* dbeta, int N, int H, int W, int C, int groups, float eps, cudaStream_t st);
+int head_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dOut,
+                    const float* w, float* G, double* P, float* dW, float* dB, int N, int H, int W, int C, int OC, int groups,
+                    float eps, cudaStream_t st);
+int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const void* raw_low, const double* stats,
+                     const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias, float* coefbuf, int N,
+                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st);
+int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t st);
 int tc_conv3x3_bytes(int cin, int cout, size_t* bytes);
 int tc_convt_bytes(int cl, int cu, size_t* bytes);
 int pack_conv3x3_tc(const float* w, void* out, int cin, int cout, int dtype, cudaStream_t st);

@@ -29,9 +29,15 @@ struct GenericCfg {
     int coef_off;   // float offsets into dynamic smem
     int low_off;
     int cobatches;
+    // WGRAD mode (backward of the conv weights, autograd of src/model.py:93,96): the same staging prologue rebuilds the
+    // activated input tile, and instead of the convolution the CTA correlates it with the output-gradient tile:
+    //   dW[tap][ci][co] += sum_pixels act[pixel + tap][ci] * dR[pixel][co]
+    const float* dR;  // [N,H,W,cout] fp32 gradient w.r.t. the raw conv output
+    float* dW;        // fp32, accumulated atomically at dW[tap*s_tap + ci*s_ci + co*s_co]
+    int s_tap, s_ci, s_co;
 };
 
-template <typename T, int NTY, int NCOG>
+template <typename T, int NTY, int NCOG, bool WGRAD>
 __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv3x3_args p, const GenericCfg cfg) {
     constexpr int TH = 4 * NTY;
     constexpr int AH = TH + 2;
@@ -79,6 +85,18 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
             cf += 3 * S.channels;
         }
         if (tid < 2 * COB) statsm[tid] = 0.0;
+        if constexpr (WGRAD) {
+            // output-gradient tile dRs[(r*32 + c)*COB + co] (aliases the weight-chunk region), zero outside the image
+            for (int idx = tid; idx < TH * TW * COB; idx += NTHREADS) {
+                const int co = idx % COB;
+                const int pix = idx / COB;
+                const int gy = y0 + pix / TW, gx = x0 + pix % TW;
+                float v = 0.f;
+                if (gy < H && gx < W && co_cta + co < Cout)
+                    v = __ldg(cfg.dR + ((size_t)(n * H + gy) * W + gx) * Cout + co_cta + co);
+                wsm[idx] = v;
+            }
+        }
     }
     __syncthreads();
 
@@ -238,6 +256,23 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
                     }
                 }
             }
+            if constexpr (WGRAD) {
+                __syncthreads();
+                for (int combo = tid; combo < 9 * CK * COB; combo += NTHREADS) {
+                    const int co = combo % COB;
+                    const int ck = (combo / COB) % CK;
+                    const int tap = combo / (COB * CK);
+                    if (ck >= cn || co_cta + co >= Cout) continue;
+                    const float* a0 = act + (ck * AH + tap / 3) * AW + tap % 3;
+                    float sum = 0.f;
+                    for (int r = 0; r < TH; ++r)
+#pragma unroll 8
+                        for (int c = 0; c < TW; ++c) sum = fmaf(a0[r * AW + c], wsm[(r * TW + c) * COB + co], sum);
+                    atomicAdd(cfg.dW + (size_t)tap * cfg.s_tap + (size_t)(ci_base + c0 + ck) * cfg.s_ci + (size_t)(co_cta + co) * cfg.s_co, sum);
+                }
+                __syncthreads();
+                continue;
+            }
             // ---- (2) stage the weight chunk wsm[tap][ck][co] ---------------------------------
             for (int idx = tid; idx < 9 * CK * COB; idx += NTHREADS) {
                 const int co = idx % COB;
@@ -282,6 +317,7 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
         cf += 3 * Cs;
     }
 
+    if constexpr (WGRAD) return;
     // ---- epilogue: store raw output (rounded to T) + GroupNorm statistics of the stored values
     const int co0 = co_cta + cog * 8;
     const int con = min(8, Cout - co0);  // may be <= 0 for padded channel groups
@@ -322,8 +358,8 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
     }
 }
 
-template <typename T, int NTY, int NCOG>
-static int launch_cfg(const dg_conv3x3_args& a, cudaStream_t stream) {
+template <typename T, int NTY, int NCOG, bool WGRAD>
+static int launch_cfg(const dg_conv3x3_args& a, cudaStream_t stream, const float* dR, float* dW, const int* strides) {
     constexpr int TH = 4 * NTY;
     constexpr int AH = TH + 2;
     constexpr int LH = TH / 2 + 2;
@@ -335,7 +371,11 @@ static int launch_cfg(const dg_conv3x3_args& a, cudaStream_t stream) {
         ncoef += 3 * a.src[s].channels;
         if (a.src[s].xform == DG_X_CONVT2) low_c = a.src[s].channels > low_c ? a.src[s].channels : low_c;
     }
-    size_t floats = (size_t)(2 * COB) * 2 + (size_t)CK * AH * AW + (size_t)9 * CK * COB;
+    cfg.dR = dR;
+    cfg.dW = dW;
+    if (strides) { cfg.s_tap = strides[0]; cfg.s_ci = strides[1]; cfg.s_co = strides[2]; }
+    const size_t wregion = WGRAD ? (size_t)TH * TW * COB : (size_t)9 * CK * COB;  // weight chunk or dR tile
+    size_t floats = (size_t)(2 * COB) * 2 + (size_t)CK * AH * AW + wregion;
     cfg.coef_off = (int)floats;
     floats += ncoef;
     cfg.low_off = (int)floats;
@@ -350,7 +390,7 @@ static int launch_cfg(const dg_conv3x3_args& a, cudaStream_t stream) {
         set_error("conv3x3 generic: %zu bytes of shared memory needed (channels too large)", smem);
         return 3;
     }
-    auto kern = conv3x3_generic_kernel<T, NTY, NCOG>;
+    auto kern = conv3x3_generic_kernel<T, NTY, NCOG, WGRAD>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -368,20 +408,32 @@ static int launch_cfg(const dg_conv3x3_args& a, cudaStream_t stream) {
     return check_launch("conv3x3_generic");
 }
 
-template <typename T>
-static int launch_T(const dg_conv3x3_args& a, cudaStream_t stream) {
-    if (a.cout <= 8) return launch_cfg<T, 8, 1>(a, stream);
-    if (a.cout <= 16) return launch_cfg<T, 4, 2>(a, stream);
-    if (a.cout <= 32) return launch_cfg<T, 2, 4>(a, stream);
-    return launch_cfg<T, 1, 8>(a, stream);
+template <typename T, bool WGRAD>
+static int launch_T(const dg_conv3x3_args& a, cudaStream_t stream, const float* dR, float* dW, const int* strides) {
+    if (a.cout <= 8) return launch_cfg<T, 8, 1, WGRAD>(a, stream, dR, dW, strides);
+    if (a.cout <= 16) return launch_cfg<T, 4, 2, WGRAD>(a, stream, dR, dW, strides);
+    if (a.cout <= 32) return launch_cfg<T, 2, 4, WGRAD>(a, stream, dR, dW, strides);
+    return launch_cfg<T, 1, 8, WGRAD>(a, stream, dR, dW, strides);
 }
 
 int conv3x3_generic_launch(const dg_conv3x3_args& a, cudaStream_t stream) {
     switch (a.dtype) {
-        case DG_F32: return launch_T<float>(a, stream);
-        case DG_F16: return launch_T<__half>(a, stream);
-        case DG_BF16: return launch_T<__nv_bfloat16>(a, stream);
+        case DG_F32: return launch_T<float, false>(a, stream, nullptr, nullptr, nullptr);
+        case DG_F16: return launch_T<__half, false>(a, stream, nullptr, nullptr, nullptr);
+        case DG_BF16: return launch_T<__nv_bfloat16, false>(a, stream, nullptr, nullptr, nullptr);
         default: set_error("conv3x3: bad dtype %d", a.dtype); return 2;
+    }
+}
+
+// dW += correlation of the activated input (rebuilt by the forward prologue from a.src) with dR; a.weight/a.out unused
+int conv3x3_wgrad_launch(const dg_conv3x3_args& a, const float* dR, float* dW, int s_tap, int s_ci, int s_co,
+                         cudaStream_t stream) {
+    const int strides[3] = {s_tap, s_ci, s_co};
+    switch (a.dtype) {
+        case DG_F32: return launch_T<float, true>(a, stream, dR, dW, strides);
+        case DG_F16: return launch_T<__half, true>(a, stream, dR, dW, strides);
+        case DG_BF16: return launch_T<__nv_bfloat16, true>(a, stream, dR, dW, strides);
+        default: set_error("conv3x3 wgrad: bad dtype %d", a.dtype); return 2;
     }
 }
 

@@ -85,11 +85,12 @@ class LightweightUNet(nn.Module):
         )
 
     # ---- packed-parameter cache (derived from the fp32 nn.Parameters; refreshed when they change) -----
-    def _key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.storage, self.path)
+    def _key(self, train):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.storage, self.path, train,
+                                                                               _lib.generation())
 
-    def _refresh(self):
-        key = self._key()
+    def _refresh(self, train=False):
+        key = self._key(train)
         if key == self._pack_key:
             return self._params_c
         dev = self.output_conv.weight.device
@@ -110,7 +111,10 @@ class LightweightUNet(nn.Module):
                 g = blk[gi].weight.detach().float().contiguous()
                 bt = blk[gi].bias.detach().float().contiguous()
                 wtc = ops.pack_conv3x3_tc(w, pc.dtype) if self.path != 1 else None
-                keep += [w, g, bt, wtc]
+                # backward only: dgrad runs as a forward conv with the taps flipped and Cin/Cout swapped
+                wfl = blk[ci].weight.detach().float().flip(2, 3).permute(2, 3, 0, 1).contiguous() if train else None
+                pc.conv_w_flip[b][j] = None if wfl is None else wfl.data_ptr()
+                keep += [w, g, bt, wtc, wfl]
                 pc.conv_w_tc[b][j] = None if wtc is None else wtc.data_ptr()
                 pc.conv_w[b][j] = w.data_ptr()
                 pc.gn_w[b][j] = g.data_ptr()

@@ -129,6 +129,8 @@ typedef struct {
     const float* up_b[4];
     const void* conv_w_tc[DG_MAX_BLOCKS][2];/* optional tensor-core packings (16-bit dtypes) */
     const void* up_w_tc[4];
+    const float* conv_w_flip[DG_MAX_BLOCKS][2]; /* backward only: [3][3][Cout][Cin] with taps flipped
+                                               (w.flip(2,3).permute(2,3,0,1)): dgrad is a forward conv */
     const float* head_w;                    /* output_conv.weight [out][f0]                */
     const float* head_b;
     int32_t path;                           /* 0 auto, 1 generic, 2 tensor-core            */
@@ -149,6 +151,27 @@ int dg_lw_forward(const dg_lw_params* p, const float* x, float* y, int32_t N, in
  * its statistics; for tests and for backward. */
 int dg_lw_layout(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, int32_t idx,
                  size_t* raw_offset, size_t* stats_offset, int32_t* channels, int32_t* h, int32_t* w);
+
+/* ---- training (autograd of src/model.py:101-133 as driven by optimized_train.py:206-233) -------
+ * dg_lw_backward consumes the workspace a dg_lw_forward of the same batch left behind (raw activations and
+ * GroupNorm statistics) and writes EVERY parameter gradient into `grads`, a flat fp32 buffer in the module's
+ * parameters() order and the parameters' own layouts (dg_lw_num_params elements, 486,409 for the shipped model):
+ *   enc1.0.weight, enc1.1.weight, enc1.1.bias, enc1.3.weight, enc1.4.weight, enc1.4.bias, enc2..., bottleneck...,
+ *   upconv4.weight, upconv4.bias, dec4..., upconv3..., dec3..., upconv2..., dec2..., upconv1..., dec1...,
+ *   output_conv.weight, output_conv.bias.
+ * grad_y is dL/d(output) fp32 [N,out,H,W] (nn.L1Loss backward = sign(o-t)/numel comes from the caller's autograd). */
+int dg_lw_num_params(const dg_lw_params* p, size_t* count);
+int dg_lw_backward_workspace_bytes(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, size_t* bytes);
+int dg_lw_backward(const dg_lw_params* p, const float* x, const float* grad_y, int32_t N, int32_t H, int32_t W,
+                   void* fwd_workspace, size_t fwd_bytes, void* bwd_workspace, size_t bwd_bytes, float* grads,
+                   dg_stream_t stream);
+
+/* Fused optimizer tail over flat buffers: torch.nn.utils.clip_grad_norm_(max_norm) (skipped if max_norm <= 0) followed by
+ * torch.optim.AdamW (optimized_train.py:215-218,230-233,440-446).  grads are first multiplied by grad_scale (1/world after a
+ * sum all-reduce).  `scratch` = one device double.  `step` counts from 1. */
+int dg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t count, double* scratch,
+                  float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                  float grad_scale, dg_stream_t stream);
 
 /* One forward with a CUDA-event pair around each of its 19 kernels (18 fused convs + head), recorded on
  * `stream`; synchronises the stream and writes the per-kernel milliseconds to ms19[19].  For bench.py's

@@ -1,0 +1,111 @@
+"""GPU parity of one training step (forward, L1, backward of all 64 parameters, clip 1.0, AdamW) against the golden
+step produced by the reference's own call sequence (tests/golden/make_golden.py section 3) and the autograd oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_unet as tpo
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden import TRAIN_LR, TRAIN_WD  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+dg = pytest.importorskip("image_enhancement_deglaring_b200")
+
+
+def _rand(shape, seed):
+    return torch.rand(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _net(sd, **kw):
+    net = dg.LightweightUNet(**kw)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().train()
+
+
+def test_gradients_match_golden_step(best_sd, golden):
+    g = golden("lw_train.npz")
+    net = _net(best_sd, path=1)
+    x, t = _rand((2, 1, 64, 64), 0).cuda(), _rand((2, 1, 64, 64), 1).cuda()
+    loss = torch.nn.L1Loss()(net(x), t)      # optimized_train.py:222-223
+    loss.backward()                           # :226
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5
+    bad = []
+    for k, p in net.named_parameters():
+        ref = g["grad/" + k]
+        assert p.grad is not None and tuple(p.grad.shape) == ref.shape, k
+        err = float(np.abs(p.grad.cpu().numpy() - ref).max())
+        if err > 2e-5 + 2e-4 * float(np.abs(ref).max()):
+            bad.append((k, err, float(np.abs(ref).max())))
+    assert not bad, bad
+    total = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in net.parameters()))
+    assert abs(float(total) - float(g["total_norm"])) <= 1e-3
+
+
+def test_fused_clip_adamw_matches_golden_step(best_sd, golden):
+    from image_enhancement_deglaring_b200.train import FusedAdamW
+    g = golden("lw_train.npz")
+    net = _net(best_sd, path=1)
+    opt = FusedAdamW(net.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD, max_grad_norm=1.0)   # :440-446 + clip :230
+    x, t = _rand((2, 1, 64, 64), 0).cuda(), _rand((2, 1, 64, 64), 1).cuda()
+    opt.zero_grad(set_to_none=True)
+    loss = torch.nn.L1Loss()(net(x), t)
+    loss.backward()
+    opt.step()
+    assert abs(opt.grad_norm() - float(g["total_norm"])) <= 1e-3
+    for k, p in net.named_parameters():
+        err = float(np.abs(p.detach().cpu().numpy() - g["new/" + k]).max())
+        assert err <= 5e-6, (k, err)
+    # the packed-weight caches must see the update: a second forward differs from the first and matches the oracle
+    with torch.no_grad():
+        y2 = net(x).cpu()
+        new_sd = {k: torch.from_numpy(g["new/" + k]) for k in best_sd}
+        ref2 = tpo.lightweight_forward(x.cpu(), new_sd)
+    assert float((y2 - ref2).abs().max()) <= 2e-4
+
+
+def test_separate_clip_then_step_like_the_reference_loop(best_sd, golden):
+    """optimized_train.py:226-233 verbatim: backward, torch clip_grad_norm_, optimizer.step()."""
+    from image_enhancement_deglaring_b200.train import FusedAdamW
+    g = golden("lw_train.npz")
+    net = _net(best_sd, path=1)
+    opt = FusedAdamW(net.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    x, t = _rand((2, 1, 64, 64), 0).cuda(), _rand((2, 1, 64, 64), 1).cuda()
+    opt.zero_grad(set_to_none=True)
+    torch.nn.L1Loss()(net(x), t).backward()
+    total = torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+    opt.step()
+    assert abs(float(total) - float(g["total_norm"])) <= 1e-3
+    for k, p in net.named_parameters():
+        assert float(np.abs(p.detach().cpu().numpy() - g["new/" + k]).max()) <= 5e-6, k
+
+
+def test_backward_against_autograd_oracle_other_shape(best_sd):
+    net = _net(best_sd, path=1)
+    x, t = _rand((3, 1, 48, 80), 5), _rand((3, 1, 48, 80), 6)
+    r = tpo.train_step(best_sd, x, t, max_norm=0.0)
+    loss = torch.nn.L1Loss()(net(x.cuda()), t.cuda())
+    loss.backward()
+    assert abs(float(loss) - r["loss"]) <= 1e-5
+    for k, p in net.named_parameters():
+        ref = r["grads"][k].numpy()
+        err = float(np.abs(p.grad.cpu().numpy() - ref).max())
+        assert err <= 2e-5 + 2e-4 * float(np.abs(ref).max()), (k, err)
+
+
+def test_training_forward_with_16bit_storage_runs_and_is_close(best_sd):
+    """fp16 storage of the saved activations: gradients stay within a few percent of the fp32 oracle."""
+    net = _net(best_sd, storage="fp16")
+    x, t = _rand((2, 1, 64, 64), 0), _rand((2, 1, 64, 64), 1)
+    r = tpo.train_step(best_sd, x, t, max_norm=0.0)
+    torch.nn.L1Loss()(net(x.cuda()), t.cuda()).backward()
+    num = den = 0.0
+    for k, p in net.named_parameters():
+        ref = r["grads"][k]
+        num += float(((p.grad.cpu() - ref) ** 2).sum())
+        den += float((ref ** 2).sum())
+    assert (num / den) ** 0.5 <= 5e-2
