@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
     double* statsm = smem_d;                                   // [COB][2]
     float* act = reinterpret_cast<float*>(statsm + 2 * COB);   // [CK][AH][AW]
     float* wsm = act + CK * AH * AW;                           // [9][CK][COB]
-    float* coef = wsm + 9 * CK * COB;                          // per source [C][3] (a, b, scale)
+    float* coef = reinterpret_cast<float*>(smem_d) + cfg.coef_off;  // per source [C][3] (a, b, scale)
     float* low = reinterpret_cast<float*>(smem_d) + cfg.low_off;  // [LH][LW][lch+1]
 
     const int tid = threadIdx.x;
