@@ -61,9 +61,7 @@ class LightweightUNet(nn.Module):
         self.dec1 = self._block(f[0] * 2, f[0])
         self.output_conv = nn.Conv2d(f[0], out_channels, kernel_size=1)
 
-        self._pack_key = None
-        self._packed = None
-        self._params_c = None
+        self._cache = {}   # train flag -> (key, tensors kept alive, dg_lw_params); both variants stay valid side by side
         self._ws = {}
 
     def _block(self, in_channels, features):
@@ -91,8 +89,9 @@ class LightweightUNet(nn.Module):
 
     def _refresh(self, train=False):
         key = self._key(train)
-        if key == self._pack_key:
-            return self._params_c
+        hit = self._cache.get(train)
+        if hit is not None and hit[0] == key:
+            return hit[2]
         dev = self.output_conv.weight.device
         if dev.type != "cuda":
             raise RuntimeError("LightweightUNet (B200) needs its parameters on a CUDA device: call .to('cuda'); "
@@ -132,7 +131,7 @@ class LightweightUNet(nn.Module):
         hb = self.output_conv.bias.detach().float().contiguous()
         keep += [hw, hb]
         pc.head_w, pc.head_b = hw.data_ptr(), hb.data_ptr()
-        self._packed, self._params_c, self._pack_key = keep, pc, key
+        self._cache[train] = (key, keep, pc)
         return pc
 
     def c_params(self):

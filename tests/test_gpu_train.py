@@ -27,6 +27,23 @@ def _net(sd, **kw):
     return net.cuda().train()
 
 
+def _check_updated_params(net, sd, grads, g):
+    """(1) exact: the fused clip + AdamW kernel vs the oracle's AdamW restatement fed OUR gradients (<= 1e-6);
+    (2) vs the reference's own step: the first AdamW update is lr*g/(|g|+eps), so entries with |g| ~ eps=1e-8 turn a 1e-9
+    gradient difference into ~1e-4; everything else must agree to 2e-5 and nothing may move by more than lr."""
+    clipped, _ = tpo.clip_grad_norm(grads, 1.0)
+    want = tpo.adamw_step({k: v.clone() for k, v in sd.items()}, clipped, {}, TRAIN_LR, TRAIN_WD)
+    loose = total = 0
+    for k, p in net.named_parameters():
+        got = p.detach().cpu()
+        assert float((got - want[k]).abs().max()) <= 1e-6, k
+        err = np.abs(got.numpy() - g["new/" + k])
+        assert err.max() <= 2 * TRAIN_LR, k
+        loose += int((err > 2e-5).sum())
+        total += err.size
+    assert loose <= 1e-4 * total, (loose, total)
+
+
 def test_gradients_match_golden_step(best_sd, golden):
     g = golden("lw_train.npz")
     net = _net(best_sd, path=1)
@@ -55,12 +72,10 @@ def test_fused_clip_adamw_matches_golden_step(best_sd, golden):
     opt.zero_grad(set_to_none=True)
     loss = torch.nn.L1Loss()(net(x), t)
     loss.backward()
+    grads = {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()}
     opt.step()
     assert abs(opt.grad_norm() - float(g["total_norm"])) <= 1e-3
-    for k, p in net.named_parameters():
-        err = float(np.abs(p.detach().cpu().numpy() - g["new/" + k]).max())
-        # first AdamW step is lr*g/(|g|+eps): entries with |g| ~ eps amplify 1e-9 gradient differences to ~1e-5
-        assert err <= 2e-5, (k, err)
+    _check_updated_params(net, best_sd, grads, g)
     # the packed-weight caches must see the update: a second forward differs from the first and matches the oracle
     with torch.no_grad():
         y2 = net(x).cpu()
@@ -78,11 +93,11 @@ def test_separate_clip_then_step_like_the_reference_loop(best_sd, golden):
     x, t = _rand((2, 1, 64, 64), 0).cuda(), _rand((2, 1, 64, 64), 1).cuda()
     opt.zero_grad(set_to_none=True)
     torch.nn.L1Loss()(net(x), t).backward()
+    grads = {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()}
     total = torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
     opt.step()
     assert abs(float(total) - float(g["total_norm"])) <= 1e-3
-    for k, p in net.named_parameters():
-        assert float(np.abs(p.detach().cpu().numpy() - g["new/" + k]).max()) <= 2e-5, k
+    _check_updated_params(net, best_sd, grads, g)
 
 
 def test_backward_against_autograd_oracle_other_shape(best_sd):

@@ -16,7 +16,7 @@ shape = tuple(int(v) for v in (sys.argv[1:5] or (2, 1, 64, 64)))
 x = torch.rand(*shape, generator=torch.Generator().manual_seed(0))
 t = torch.rand(*shape, generator=torch.Generator().manual_seed(1))
 r = tpo.train_step(sd, x, t, max_norm=0.0)
-net = dg.LightweightUNet(path=1)
+net = dg.LightweightUNet(path=int(os.environ.get("DG_PATH", "1")), storage=os.environ.get("DG_STORAGE", "fp32"))
 net.load_state_dict(sd, strict=True)
 net = net.cuda().train()
 loss = torch.nn.L1Loss()(net(x.cuda()), t.cuda())
