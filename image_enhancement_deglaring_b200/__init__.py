@@ -2,3 +2,6 @@
 from .model import LightweightUNet, count_parameters, get_model_size_mb  # noqa: F401
 
 __all__ = ["LightweightUNet", "count_parameters", "get_model_size_mb"]
+from .model_optimized import OptimizedUNet  # noqa: E402,F401
+
+__all__.append("OptimizedUNet")

@@ -472,6 +472,15 @@ int dg_lw_forward(const dg_lw_params* p, const float* x, float* y, int32_t N, in
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
+int dg_channel_attention(const double* act_sum, double plane, const float* w1, const float* w2, int32_t N, int32_t C,
+                         int32_t hidden, float* scale, dg_stream_t stream) {
+    if (!act_sum || !w1 || !w2 || !scale || N < 1 || C < 1 || hidden < 1 || plane <= 0) {
+        set_error("channel_attention: bad arguments");
+        return 2;
+    }
+    return se_scale_launch(act_sum, plane, w1, w2, N, C, hidden, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int dg_lw_num_params(const dg_lw_params* p, size_t* count) {
     LwPlan pl;
     int rc = make_plan(p, 1, 16, 16, &pl);

@@ -113,6 +113,12 @@ typedef struct {
 
 int dg_head1x1(const dg_head_args* args, dg_stream_t stream);
 
+/* ChannelAttention of OptimizedUNet (src/optimized_model.py:161-202): scale[n][c] = sigmoid(W2 . silu(W1 . mean)),
+ * mean[n][c] = act_sum[n][c] / plane, with act_sum the `act_sum` output of the conv that pools the same tensor.
+ * w1 [hidden][C], w2 [C][hidden] (the nn.Linear weights as they are).  The result feeds dg_src.scale. */
+int dg_channel_attention(const double* act_sum, double plane, const float* w1, const float* w2, int32_t N, int32_t C,
+                         int32_t hidden, float* scale, dg_stream_t stream);
+
 /* ---- whole-network entry points (native orchestrator) ------------------------------- */
 
 #define DG_MAX_BLOCKS 10  /* enc1-4, bottleneck, dec4-1 */

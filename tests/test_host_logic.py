@@ -55,6 +55,18 @@ def test_module_surface_matches_reference_contract(best_sd, golden):
     assert "GroupNorm(8, 8" in str(net) and "ConvTranspose2d(128, 64" in str(net)
 
 
+def test_optimized_surface_matches_reference_contract(golden):
+    import image_enhancement_deglaring_b200 as dg
+    g = golden("opt_rand.npz")
+    net = dg.OptimizedUNet()
+    assert list(net.state_dict().keys()) == list(g["keys"])                       # 76 keys, same order
+    assert [",".join(map(str, v.shape)) for v in net.state_dict().values()] == list(g["shapes"])
+    assert dg.count_parameters(net) == int(g["n_params"]) == 2163969
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            net(torch.zeros(1, 1, 16, 16))
+
+
 def test_no_cpu_fallback():
     import image_enhancement_deglaring_b200 as dg
     net = dg.LightweightUNet()
