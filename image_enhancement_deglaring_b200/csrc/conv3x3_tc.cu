@@ -71,7 +71,7 @@ struct Geo {
     static constexpr int ACT_BYTES = NC8 * PLANE * 16;
     static constexpr int WGT_BYTES = (STREAM ? 2 : 1) * STAGE_CHUNKS * COUT * 32;
     static constexpr int COEF_BYTES = NCOEF * 8;
-    static constexpr int STAT_BYTES = COUT * 2 * 8;  // double: shared atomics stay order-insensitive after rounding to float
+    static constexpr int STAT_BYTES = WM * COUT * 2 * 4;  // one float (sum, sumsq) slot per (m-warp, channel)
     static constexpr int LOW_BYTES = MODE == M_UPCAT ? NCL8 * LPLANE * 16 : 0;
     static constexpr int CTW_BYTES = MODE == M_UPCAT ? CT_CHUNKS * 2 * CT_N * 16 : 0;
     static constexpr int CTB_BYTES = MODE == M_UPCAT ? CU * 4 : 0;
@@ -94,11 +94,11 @@ struct Geo {
 
 // Stage a same-resolution (or 2x2-average-pooled) activated source into planes [plane0, plane0 + C/8).
 // Items are (pixel, 8-channel chunk), pixel-major so a warp's global loads are contiguous; 256 % (C/8) == 0, so a
-// thread always owns the same chunk and keeps its 8 (a, b) pairs in registers.  The item slots of a thread are split
-// into ITERS batches of BATCH; all loads of a batch are issued before any math (several 128-bit requests in flight
-// per thread), and the slot count is matched to the tile so few slots are wasted on index arithmetic (profile r1b:
-// 44% of the staging instructions were addressing).  `src` points at image n; offsets are 32-bit.
-template <typename T, typename G, int C, bool POOL, bool TANH>
+// thread always owns the same chunk and keeps its coefficients in registers.  The item slots of a thread are split into
+// ITERS batches of BATCH; all loads of a batch are issued before any math, the slot count is matched to the tile, the
+// (row, column) of a slot advances incrementally, and tiles whose halo lies inside the image skip every bounds test
+// (profiles r1b/r1c: addressing was ~1/3 of the instructions).  `src` points at image n; offsets are 32-bit.
+template <typename T, typename G, int C, bool POOL, int ACT>
 __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned char* __restrict__ src,
                                              const float2* __restrict__ cfs, int plane0, int y0, int x0, int H, int W) {
     constexpr int NC = C / 8;
@@ -108,70 +108,99 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
     constexpr int MAXB = POOL ? 2 : 5;
     constexpr int ITERS = (NSLOT + MAXB - 1) / MAXB;
     constexpr int BATCH = (NSLOT + ITERS - 1) / ITERS;
+    constexpr int DR = PSTRIDE / G::PW, DC = PSTRIDE % G::PW;      // slot-to-slot advance of (row, column)
+    constexpr bool H2 = (ACT == ACT_HALF2) && !POOL && std::is_same<T, __half>::value;
+    constexpr int FACT = H2 ? ACT_TANH : ACT;                      // float flavour used when half2 does not apply
     static_assert(TC_THREADS % NC == 0, "chunk ownership");
     const int c8 = threadIdx.x % NC;
     const int p0 = threadIdx.x / NC;
-    float2 cf[8];
+    float2 cf[H2 ? 1 : 8];
+    uint32_t ah[H2 ? 4 : 1], bh[H2 ? 4 : 1];
+    if constexpr (H2) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cf[k] = cfs[c8 * 8 + k];
+        for (int k = 0; k < 4; ++k) {
+            const float2 c0 = cfs[c8 * 8 + 2 * k], c1 = cfs[c8 * 8 + 2 * k + 1];
+            ah[k] = pack2<__half>(c0.x, c1.x);
+            bh[k] = pack2<__half>(c0.y, c1.y);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cf[k] = cfs[c8 * 8 + k];
+    }
     unsigned char* dst = act + (size_t)(plane0 + c8) * G::PLANE * 16;
     const uint32_t rowb = (uint32_t)(POOL ? 2 * W : W) * C * 2;    // source row pitch in bytes
+    const unsigned char* srcc = src + c8 * 16;
+    const bool interior = y0 >= 1 && x0 >= 1 && y0 + G::TH + 1 <= H && x0 + G::TW + 1 <= W;
+
+    auto run = [&](auto interior_c) {
+        constexpr bool INTERIOR = decltype(interior_c)::value;
+        int r = p0 / G::PW, c = p0 - (p0 / G::PW) * G::PW;
+        int pix = p0;
 #pragma unroll 1
-    for (int it = 0; it < ITERS; ++it) {
-        uint4 q[BATCH][POOL ? 4 : 1];
-        int pixs[BATCH];
-        bool ok[BATCH];
+        for (int it = 0; it < ITERS; ++it) {
+            uint4 q[BATCH][POOL ? 4 : 1];
+            int pixs[BATCH];
+            bool ok[BATCH];
 #pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-            const int pix = p0 + (it * BATCH + b) * PSTRIDE;
-            const int r = pix / G::PW, c = pix - r * G::PW;
-            const int gy = y0 + r - 1, gx = x0 + c - 1;
-            pixs[b] = pix;
-            ok[b] = pix < NPIX && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-            if (ok[b]) {
-                if constexpr (POOL) {
-                    const unsigned char* base = src + ((uint32_t)(2 * gy) * rowb + (uint32_t)(2 * gx * C + c8 * 8) * 2);
-                    q[b][0] = __ldg(reinterpret_cast<const uint4*>(base));
-                    q[b][1] = __ldg(reinterpret_cast<const uint4*>(base + C * 2));
-                    q[b][2] = __ldg(reinterpret_cast<const uint4*>(base + rowb));
-                    q[b][3] = __ldg(reinterpret_cast<const uint4*>(base + rowb + C * 2));
-                } else {
-                    q[b][0] = __ldg(reinterpret_cast<const uint4*>(src + ((uint32_t)gy * rowb + (uint32_t)(gx * C + c8 * 8) * 2)));
-                }
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-            if (pixs[b] >= NPIX) continue;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (ok[b]) {
-                float y[8];
-                act8<T, TANH>(q[b][0], cf, y);
-                if constexpr (POOL) {
-                    float t[8];
-#pragma unroll
-                    for (int j = 1; j < 4; ++j) {
-                        act8<T, TANH>(q[b][j], cf, t);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) y[k] += t[k];
+            for (int b = 0; b < BATCH; ++b) {
+                const int gy = y0 + r - 1, gx = x0 + c - 1;
+                pixs[b] = pix;
+                ok[b] = pix < NPIX && (INTERIOR || ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W));
+                if (ok[b]) {
+                    if constexpr (POOL) {
+                        const unsigned char* base = srcc + ((uint32_t)(2 * gy) * rowb + (uint32_t)(2 * gx) * (C * 2));
+                        q[b][0] = __ldg(reinterpret_cast<const uint4*>(base));
+                        q[b][1] = __ldg(reinterpret_cast<const uint4*>(base + C * 2));
+                        q[b][2] = __ldg(reinterpret_cast<const uint4*>(base + rowb));
+                        q[b][3] = __ldg(reinterpret_cast<const uint4*>(base + rowb + C * 2));
+                    } else {
+                        q[b][0] = __ldg(reinterpret_cast<const uint4*>(srcc + ((uint32_t)gy * rowb + (uint32_t)gx * (C * 2))));
                     }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) y[k] *= 0.25f;
                 }
-                o = pack8<T>(y);
+                pix += PSTRIDE;
+                r += DR;
+                c += DC;
+                if (c >= G::PW) { c -= G::PW; r += 1; }
             }
-            *reinterpret_cast<uint4*>(dst + (uint32_t)pixs[b] * 16) = o;
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                if (pixs[b] >= NPIX) continue;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[b]) {
+                    if constexpr (H2) {
+                        o = act8_h2(q[b][0], ah, bh);
+                    } else {
+                        float y[8];
+                        act8<T, FACT>(q[b][0], cf, y);
+                        if constexpr (POOL) {
+                            float t[8];
+#pragma unroll
+                            for (int j = 1; j < 4; ++j) {
+                                act8<T, FACT>(q[b][j], cf, t);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) y[k] += t[k];
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) y[k] *= 0.25f;
+                        }
+                        o = pack8<T>(y);
+                    }
+                }
+                *reinterpret_cast<uint4*>(dst + (uint32_t)pixs[b] * 16) = o;
+            }
         }
-    }
+    };
+    if (interior) run(std::true_type{});
+    else run(std::false_type{});
 }
 
-template <typename T, typename G, bool TANH>
+template <typename T, typename G, int ACT>
 __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* act = smem + G::OFF_ACT;
     unsigned char* wgt = smem + G::OFF_WGT;
     float2* coef = reinterpret_cast<float2*>(smem + G::OFF_COEF);
-    double* statf = reinterpret_cast<double*>(smem + G::OFF_STAT);
+    float* statf = reinterpret_cast<float*>(smem + G::OFF_STAT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % G::WM, wn = warp / G::WM;
@@ -202,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
                 gn_coef(p.st0, p.g0, p.b0, n, G::CL, p.groups0, c, (double)(H / 2) * (W / 2), p.eps, a, b);
             else
                 gn_coef(p.st1, p.g1, p.b1, n, G::CU, p.groups1, c - G::CL, (double)H * W, p.eps, a, b);
-            if constexpr (TANH) { a *= 0.5f; b *= 0.5f; }  // silu(y) = h + h*tanh(h), h = y/2
+            if constexpr (ACT != ACT_EXACT) { a *= 0.5f; b *= 0.5f; }  // silu(y) = h + h*tanh(h), h = y/2
             coef[c] = make_float2(a, b);
         }
         float* ctb = reinterpret_cast<float*>(smem + G::OFF_CTB);
@@ -212,23 +241,22 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
         for (int c = tid; c < G::CIN; c += TC_THREADS) {
             float a, b;
             gn_coef(p.st0, p.g0, p.b0, n, G::CIN, p.groups0, c, plane, p.eps, a, b);
-            if constexpr (TANH) { a *= 0.5f; b *= 0.5f; }
+            if constexpr (ACT != ACT_EXACT) { a *= 0.5f; b *= 0.5f; }
             coef[c] = make_float2(a, b);
         }
     }
-    for (int c = tid; c < 2 * G::COUT; c += TC_THREADS) statf[c] = 0.0;
     __syncthreads();
 
     // ---- (2) stage the activated halo tile ------------------------------------------------------------
     if constexpr (G::MODE == M_SAME) {
-        stage_planes<T, G, G::CIN, false, TANH>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 2,
+        stage_planes<T, G, G::CIN, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 2,
                                                 coef, 0, y0, x0, H, W);
     } else if constexpr (G::MODE == M_POOL) {
-        stage_planes<T, G, G::CIN, true, TANH>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 8,
+        stage_planes<T, G, G::CIN, true, ACT>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 8,
                                                coef, 0, y0, x0, H, W);
     } else {
         // skip -> planes [CU/8, 2CU/8)
-        stage_planes<T, G, G::CU, false, TANH>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::CU * 2,
+        stage_planes<T, G, G::CU, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::CU * 2,
                                                coef + G::CL, G::CU / 8, y0, x0, H, W);
         // activated low-res tile -> low planes
         unsigned char* low = smem + G::OFF_LOW;
@@ -250,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
                 if (gi >= 0 && gi < Hl && gj >= 0 && gj < Wl) {
                     float y[8];
                     const uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * Hl + gi) * Wl + gj) * G::CL + c8 * 8));
-                    act8<T, TANH>(q, cf, y);
+                    act8<T, (ACT == ACT_HALF2 ? ACT_TANH : ACT)>(q, cf, y);
                     o = pack8<T>(y);
                 }
                 *reinterpret_cast<uint4*>(low + ((size_t)c8 * G::LPLANE + lp) * 16) = o;
@@ -405,15 +433,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
         // by ~2^-12/sqrt(n) relative -- far below the rounding noise itself) so no unpack is needed; full tiles
         // take a branch-free path with one address computation per m-tile.
         const bool full = (y0 + G::TH <= H) && (x0 + G::TW <= W);
+        constexpr int RSTEP = G::WM / G::SEGS;
+        static_assert(G::WM % G::SEGS == 0, "a warp's m-tiles share one 16-pixel segment");
+        const int gx = x0 + (wm % G::SEGS) * 16 + (lane >> 2);
+        const uint32_t orow = (uint32_t)W * G::COUT;  // elements per output row
+        T* obase = outp + ((size_t)(n * H + y0 + wm / G::SEGS) * W + gx) * G::COUT + nt0 * 8 + 2 * (lane & 3);
         auto epilogue = [&](auto full_c) {
             constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
             for (int m = 0; m < G::MG; ++m) {
-                const int mt = wm + G::WM * (g + m);
-                const int row = mt / G::SEGS, seg = mt % G::SEGS;
-                const int gy = y0 + row;
-                const int gx = x0 + seg * 16 + (lane >> 2);
-                T* o = outp + ((size_t)(n * H + gy) * W + gx) * G::COUT + nt0 * 8 + 2 * (lane & 3);
+                // m-tile wm + WM*k sits RSTEP*k rows below the warp's first one, same 16-pixel segment
+                const int gy = y0 + wm / G::SEGS + RSTEP * (g + m);
+                T* o = obase + (uint32_t)((g + m) * RSTEP) * orow;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     const bool ok = FULL || (gy < H && gx + 8 * hf < W);
@@ -442,15 +473,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
                 b += __shfl_xor_sync(0xffffffffu, b, o);
             }
             if (lane < 4) {
+                // one slot per (m-warp, channel): no shared atomics, and the cross-warp sum below has a fixed order
                 const int ch = (nt0 + i) * 8 + 2 * lane + k;
-                atomicAdd(&statf[2 * ch], (double)a);
-                atomicAdd(&statf[2 * ch + 1], (double)b);
+                statf[(wm * G::COUT + ch) * 2] = a;
+                statf[(wm * G::COUT + ch) * 2 + 1] = b;
             }
         }
     __syncthreads();
     if (p.out_stats != nullptr)
-        for (int c = tid; c < 2 * G::COUT; c += TC_THREADS)
-            atomicAdd(p.out_stats + (size_t)n * G::COUT * 2 + c, statf[c]);
+        for (int c = tid; c < 2 * G::COUT; c += TC_THREADS) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < G::WM; ++w) t += (double)statf[w * G::COUT * 2 + c];
+            atomicAdd(p.out_stats + (size_t)n * G::COUT * 2 + c, t);
+        }
 }
 
 // ---- weight packing kernels ------------------------------------------------------------------------------
@@ -531,9 +567,9 @@ int pack_convt_tc(const float* w, void* out, int cl, int cu, int dtype, cudaStre
 }
 
 // ---- dispatch -----------------------------------------------------------------------------------------------
-template <typename T, typename G, bool TANH>
+template <typename T, typename G, int ACT>
 static int launch_geo(const TcArgs& t, cudaStream_t st) {
-    auto kern = conv3x3_tc_kernel<T, G, TANH>;
+    auto kern = conv3x3_tc_kernel<T, G, ACT>;
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
@@ -546,12 +582,12 @@ static int launch_geo(const TcArgs& t, cudaStream_t st) {
     return check_launch("conv3x3_tc");
 }
 
-template <typename T, bool TANH>
+template <typename T, int ACT>
 static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin, cudaStream_t st, bool* handled) {
     *handled = true;
     const int cout = a.cout;
 #define DG_TC(CI, CO, MD, TH, TW, WM, WN, ST) \
-    if (cin == CI && cout == CO && mode == MD) return launch_geo<T, Geo<CI, CO, MD, TH, TW, WM, WN, ST>, TANH>(t, st);
+    if (cin == CI && cout == CO && mode == MD) return launch_geo<T, Geo<CI, CO, MD, TH, TW, WM, WN, ST>, ACT>(t, st);
     DG_TC(8, 8, M_SAME, 16, 64, 8, 1, false)      // enc1.3, dec1.3
     DG_TC(8, 16, M_POOL, 16, 64, 8, 1, false)     // enc2.0
     DG_TC(16, 16, M_SAME, 16, 64, 8, 1, false)    // enc2.3, dec2.3
@@ -603,12 +639,15 @@ int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handl
     t.wgt = a.weight_tc;
     t.out = a.out; t.out_stats = a.out_stats;
     t.N = a.N; t.H = a.H; t.W = a.W; t.eps = a.eps;
-    const bool exact = (a.path & 4) != 0;  // path bit 2: exact ex2/rcp SiLU instead of tanh.approx
-    if (a.dtype == DG_F16)
-        return exact ? dispatch<__half, false>(a, t, mode, cin, stream, handled)
-                     : dispatch<__half, true>(a, t, mode, cin, stream, handled);
-    return exact ? dispatch<__nv_bfloat16, false>(a, t, mode, cin, stream, handled)
-                 : dispatch<__nv_bfloat16, true>(a, t, mode, cin, stream, handled);
+    // path bits 2-3 pick the prologue flavour: 0 = tanh.approx.f32 (default), 4 = exact ex2/rcp, 8 = packed half2 (fp16 only)
+    const int flavour = (a.path >> 2) & 3;
+    if (a.dtype == DG_F16) {
+        if (flavour == 1) return dispatch<__half, ACT_EXACT>(a, t, mode, cin, stream, handled);
+        if (flavour == 2) return dispatch<__half, ACT_HALF2>(a, t, mode, cin, stream, handled);
+        return dispatch<__half, ACT_TANH>(a, t, mode, cin, stream, handled);
+    }
+    if (flavour == 1) return dispatch<__nv_bfloat16, ACT_EXACT>(a, t, mode, cin, stream, handled);
+    return dispatch<__nv_bfloat16, ACT_TANH>(a, t, mode, cin, stream, handled);
 }
 
 }  // namespace dg

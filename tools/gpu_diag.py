@@ -43,12 +43,12 @@ def main():
         ref_r = tpo.lightweight_forward(xr, sd, taps=taps).numpy()
     print("== whole-net error vs oracle (max-abs / PSNR dB) ==")
     for storage in ("fp32", "fp16", "bf16"):
-        for path in ((1,) if storage == "fp32" else (1, 0, 4)):
+        for path in ((1,) if storage == "fp32" else ((1, 0, 4, 8) if storage == "fp16" else (1, 0, 4))):
             net = net_for(sd, storage, path)
             with torch.no_grad():
                 yp = net(xs.cuda()).cpu().numpy()
                 yr = net(xr.cuda()).cpu().numpy()
-            print(f"{storage:5s} path={ {1: 'generic     ', 0: 'tensor/tanh ', 4: 'tensor/exact'}[path]}: png {np.abs(yp - refs).max():.3e} / "
+            print(f"{storage:5s} path={ {1: 'generic     ', 0: 'tensor/tanh ', 4: 'tensor/exact', 8: 'tensor/half2'}[path]}: png {np.abs(yp - refs).max():.3e} / "
                   f"{psnr(yp, refs):.1f} dB   random4 {np.abs(yr - ref_r).max():.3e} / {psnr(yr, ref_r):.1f} dB")
             if storage != "fp32":
                 errs = []
