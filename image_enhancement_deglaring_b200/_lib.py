@@ -21,6 +21,7 @@ class DgSrc(C.Structure):
     _fields_ = [
         ("raw", C.c_void_p), ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("scale", C.c_void_p), ("ct_w", C.c_void_p), ("ct_b", C.c_void_p), ("ct_w_tc", C.c_void_p),
+        ("coef", C.c_void_p),
         ("channels", C.c_int32), ("groups", C.c_int32), ("xform", C.c_int32), ("silu", C.c_int32),
         ("ct_cout", C.c_int32), ("reserved", C.c_int32),
     ]
@@ -31,7 +32,9 @@ class DgConv3x3Args(C.Structure):
         ("src", DgSrc * 2), ("nsrc", C.c_int32), ("dtype", C.c_int32),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("cout", C.c_int32),
         ("weight", C.c_void_p), ("weight_tc", C.c_void_p), ("out", C.c_void_p), ("out_stats", C.c_void_p),
-        ("act_sum", C.c_void_p), ("eps", C.c_float), ("path", C.c_int32),
+        ("act_sum", C.c_void_p), ("out_coef", C.c_void_p), ("out_counter", C.c_void_p), ("out_gamma", C.c_void_p),
+        ("out_beta", C.c_void_p), ("out_groups", C.c_int32), ("reserved", C.c_int32), ("eps", C.c_float),
+        ("path", C.c_int32),
     ]
 
 

@@ -49,8 +49,8 @@ static int validate_src(const dg_src& s, const char* who) {
 struct LwPlan {
     int f[5];
     int conv_c[18], conv_h[18], conv_w[18];
-    size_t raw_off[18], stats_off[18];
-    size_t stats_bytes, total_bytes;
+    size_t raw_off[18], stats_off[18], counter_off[18], coef_off[18];
+    size_t stats_bytes, total_bytes;  // stats_bytes = the zero-initialised prefix (statistics + arrival counters)
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -76,8 +76,16 @@ static int make_plan(const dg_lw_params* p, int N, int H, int W, LwPlan* pl) {
         pl->stats_off[i] = off;
         off += (size_t)N * pl->conv_c[i] * 2 * sizeof(double);
     }
+    for (int i = 0; i < 18; ++i) {
+        pl->counter_off[i] = off;
+        off += align_up((size_t)N * sizeof(int32_t), 8);
+    }
     pl->stats_bytes = off;
     off = align_up(off, 256);
+    for (int i = 0; i < 18; ++i) {
+        pl->coef_off[i] = off;
+        off += align_up((size_t)N * pl->conv_c[i] * 2 * sizeof(float), 256);
+    }
     for (int i = 0; i < 18; ++i) {
         pl->raw_off[i] = off;
         off += align_up((size_t)N * pl->conv_h[i] * pl->conv_w[i] * pl->conv_c[i] * dtype_size(p->dtype), 256);
@@ -92,6 +100,7 @@ static dg_src gn_src(const dg_lw_params* p, const LwPlan& pl, char* ws, int conv
     const int b = conv_idx / 2, j = conv_idx % 2;
     s.raw = ws + pl.raw_off[conv_idx];
     s.stats = reinterpret_cast<const double*>(ws + pl.stats_off[conv_idx]);
+    s.coef = reinterpret_cast<const float*>(ws + pl.coef_off[conv_idx]);
     s.gamma = p->gn_w[b][j];
     s.beta = p->gn_b[b][j];
     s.channels = pl.conv_c[conv_idx];
@@ -128,6 +137,11 @@ static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, in
         a.weight_tc = p->conv_w_tc[b][i % 2];
         a.out = ws + pl.raw_off[i];
         a.out_stats = reinterpret_cast<double*>(ws + pl.stats_off[i]);
+        a.out_coef = reinterpret_cast<float*>(ws + pl.coef_off[i]);
+        a.out_counter = reinterpret_cast<int32_t*>(ws + pl.counter_off[i]);
+        a.out_gamma = p->gn_w[b][i % 2];
+        a.out_beta = p->gn_b[b][i % 2];
+        a.out_groups = p->groups[b];
         a.eps = 1e-5f;
         a.path = p->path;
         a.nsrc = 1;

@@ -76,8 +76,12 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
             if (S.xform == DG_X_UP2 || S.xform == DG_X_CONVT2) { Hs = H / 2; Ws = W / 2; }
             for (int c = tid; c < S.channels; c += NTHREADS) {
                 float a = 1.f, b = 0.f;
-                if (S.stats != nullptr)
+                if (S.coef != nullptr) {
+                    a = __ldg(S.coef + (size_t)(n * S.channels + c) * 2);
+                    b = __ldg(S.coef + (size_t)(n * S.channels + c) * 2 + 1);
+                } else if (S.stats != nullptr) {
                     gn_coef(S.stats, S.gamma, S.beta, n, S.channels, S.groups, c, (double)Hs * Ws, p.eps, a, b);
+                }
                 cf[3 * c] = a;
                 cf[3 * c + 1] = b;
                 cf[3 * c + 2] = S.scale ? S.scale[(size_t)n * S.channels + c] : 1.f;
@@ -354,6 +358,10 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
         if (tid < 2 * COB) {
             const int co = co_cta + (tid >> 1);
             if (co < Cout) atomicAdd(p.out_stats + ((size_t)n * Cout + co) * 2 + (tid & 1), statsm[tid]);
+        }
+        if (p.out_coef != nullptr && p.out_counter != nullptr && p.out_gamma != nullptr && p.out_groups > 0) {
+            if (last_cta_of_image(p.out_counter + n, gridDim.x * gridDim.y * cfg.cobatches))
+                gn_finalize(p.out_stats, p.out_gamma, p.out_beta, n, Cout, p.out_groups, (double)H * W, p.eps, p.out_coef);
         }
     }
 }

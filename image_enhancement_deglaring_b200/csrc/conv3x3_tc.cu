@@ -32,6 +32,8 @@ struct TcArgs {
     const void* wgt; const void* ctw; const float* ctb;
     void* out; double* out_stats;
     int N, H, W; float eps;
+    const float* cf0; const float* cf1;   // optional finished (a, b) of src0 / src1 ([N,C,2]), else computed from st0 / st1
+    float* out_coef; int* out_counter; const float* out_gamma; const float* out_beta; int out_groups;
 };
 
 // ---- compile-time geometry -------------------------------------------------------------------------
@@ -227,10 +229,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
     if constexpr (G::MODE == M_UPCAT) {
         for (int c = tid; c < G::CL + G::CU; c += TC_THREADS) {
             float a, b;
-            if (c < G::CL)
-                gn_coef(p.st0, p.g0, p.b0, n, G::CL, p.groups0, c, (double)(H / 2) * (W / 2), p.eps, a, b);
-            else
-                gn_coef(p.st1, p.g1, p.b1, n, G::CU, p.groups1, c - G::CL, (double)H * W, p.eps, a, b);
+            if (c < G::CL) {
+                if (p.cf0) { a = __ldg(p.cf0 + (size_t)(n * G::CL + c) * 2); b = __ldg(p.cf0 + (size_t)(n * G::CL + c) * 2 + 1); }
+                else gn_coef(p.st0, p.g0, p.b0, n, G::CL, p.groups0, c, (double)(H / 2) * (W / 2), p.eps, a, b);
+            } else {
+                const int cc = c - G::CL;
+                if (p.cf1) { a = __ldg(p.cf1 + (size_t)(n * G::CU + cc) * 2); b = __ldg(p.cf1 + (size_t)(n * G::CU + cc) * 2 + 1); }
+                else gn_coef(p.st1, p.g1, p.b1, n, G::CU, p.groups1, cc, (double)H * W, p.eps, a, b);
+            }
             if constexpr (ACT != ACT_EXACT) { a *= 0.5f; b *= 0.5f; }  // silu(y) = h + h*tanh(h), h = y/2
             coef[c] = make_float2(a, b);
         }
@@ -240,7 +246,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
         const double plane = G::MODE == M_POOL ? (double)(2 * H) * (2 * W) : (double)H * W;
         for (int c = tid; c < G::CIN; c += TC_THREADS) {
             float a, b;
-            gn_coef(p.st0, p.g0, p.b0, n, G::CIN, p.groups0, c, plane, p.eps, a, b);
+            if (p.cf0) { a = __ldg(p.cf0 + (size_t)(n * G::CIN + c) * 2); b = __ldg(p.cf0 + (size_t)(n * G::CIN + c) * 2 + 1); }
+            else gn_coef(p.st0, p.g0, p.b0, n, G::CIN, p.groups0, c, plane, p.eps, a, b);
             if constexpr (ACT != ACT_EXACT) { a *= 0.5f; b *= 0.5f; }
             coef[c] = make_float2(a, b);
         }
@@ -487,6 +494,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
             for (int w = 0; w < G::WM; ++w) t += (double)statf[w * G::COUT * 2 + c];
             atomicAdd(p.out_stats + (size_t)n * G::COUT * 2 + c, t);
         }
+    if (p.out_coef != nullptr && p.out_stats != nullptr) {
+        if (last_cta_of_image(p.out_counter + n, gridDim.x * gridDim.y))
+            gn_finalize(p.out_stats, p.out_gamma, p.out_beta, n, G::COUT, p.out_groups, (double)H * W, p.eps, p.out_coef);
+    }
 }
 
 // ---- weight packing kernels ------------------------------------------------------------------------------
@@ -636,6 +647,12 @@ int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handl
         return 0;
     if (a.N > 65535) return 0;
     t.src0 = s0.raw; t.st0 = s0.stats; t.g0 = s0.gamma; t.b0 = s0.beta; t.groups0 = s0.groups;
+    t.cf0 = s0.coef;
+    if (a.nsrc == 2) t.cf1 = a.src[1].coef;
+    if (a.out_coef && a.out_counter && a.out_gamma && a.out_beta && a.out_groups > 0) {
+        t.out_coef = a.out_coef; t.out_counter = a.out_counter; t.out_gamma = a.out_gamma; t.out_beta = a.out_beta;
+        t.out_groups = a.out_groups;
+    }
     t.wgt = a.weight_tc;
     t.out = a.out; t.out_stats = a.out_stats;
     t.N = a.N; t.H = a.H; t.W = a.W; t.eps = a.eps;

@@ -20,8 +20,12 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const dg_head_args p
     const int HW = p.H * p.W;
     for (int c = threadIdx.x; c < C; c += HEAD_THREADS) {
         float a = 1.f, b = 0.f;
-        if (p.src.stats != nullptr)
+        if (p.src.coef != nullptr) {
+            a = __ldg(p.src.coef + (size_t)(n * C + c) * 2);
+            b = __ldg(p.src.coef + (size_t)(n * C + c) * 2 + 1);
+        } else if (p.src.stats != nullptr) {
             gn_coef(p.src.stats, p.src.gamma, p.src.beta, n, C, p.src.groups, c, (double)HW, p.eps, a, b);
+        }
         coef[2 * c] = a;
         coef[2 * c + 1] = b;
     }

@@ -62,6 +62,8 @@ typedef struct {
     const float* ct_w;    /* DG_X_CONVT2: weights packed [2][2][channels][ct_cout] fp32    */
     const float* ct_b;    /* DG_X_CONVT2: bias [ct_cout]                                   */
     const void* ct_w_tc;  /* DG_X_CONVT2: optional tensor-core packing (dg_pack_convt2x2_tc) */
+    const float* coef;    /* optional [N,channels,2] finished GroupNorm affine (a, b) written by the producer's
+                             last CTA (dg_conv3x3_args.out_coef); consumers prefer it over `stats`   */
     int32_t channels;
     int32_t groups;       /* GroupNorm groups over `channels`                              */
     int32_t xform;        /* DG_X_*                                                        */
@@ -88,6 +90,14 @@ typedef struct {
     double* out_stats;    /* [N,cout,2], must be zero on entry; accumulated atomically     */
     double* act_sum;      /* optional [N,src[0].channels]: sum over pixels of the ACTIVATED
                              src[0] (for ChannelAttention's global average); zero on entry  */
+    /* optional: the LAST CTA to finish an image turns its statistics into the GroupNorm affine of the norm that
+       follows this conv, so consumers load two floats per channel instead of redoing double-precision math per CTA */
+    float* out_coef;          /* [N,cout,2] (a = rstd*gamma, b = beta - mean*a)                  */
+    int32_t* out_counter;     /* [N] arrival counters, zero on entry                              */
+    const float* out_gamma;   /* [cout] weight / bias / groups of the GroupNorm applied to `out`  */
+    const float* out_beta;
+    int32_t out_groups;
+    int32_t reserved;
     float eps;            /* GroupNorm eps of the sources (1e-5)                           */
     int32_t path;         /* 0 = auto, 1 = force generic CUDA-core path, 2 = force tensor-core path */
 } dg_conv3x3_args;

@@ -30,8 +30,8 @@ def test_struct_layouts_match_header_sizes():
     import ctypes as C
     from image_enhancement_deglaring_b200 import _lib
     # 8 pointers + 6 int32; 2 srcs + 6 int32 + 5 pointers + float + int32; ...
-    assert C.sizeof(_lib.DgSrc) == 8 * 8 + 6 * 4
-    assert C.sizeof(_lib.DgConv3x3Args) == 2 * C.sizeof(_lib.DgSrc) + 6 * 4 + 5 * 8 + 8
+    assert C.sizeof(_lib.DgSrc) == 9 * 8 + 6 * 4
+    assert C.sizeof(_lib.DgConv3x3Args) == 2 * C.sizeof(_lib.DgSrc) + 6 * 4 + 9 * 8 + 8 + 8
     assert C.sizeof(_lib.DgHeadArgs) == C.sizeof(_lib.DgSrc) + 5 * 4 + 4 + 5 * 8 + 8
 
 
