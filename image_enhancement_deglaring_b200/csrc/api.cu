@@ -100,7 +100,10 @@ static dg_src gn_src(const dg_lw_params* p, const LwPlan& pl, char* ws, int conv
     const int b = conv_idx / 2, j = conv_idx % 2;
     s.raw = ws + pl.raw_off[conv_idx];
     s.stats = reinterpret_cast<const double*>(ws + pl.stats_off[conv_idx]);
-    s.coef = reinterpret_cast<const float*>(ws + pl.coef_off[conv_idx]);
+    // path bit 4: producer-side GroupNorm finalisation.  Measured SLOWER on B200 (2.87 vs 2.74 ms/batch-64 forward): the
+    // threadfence + ticket keeps every producer CTA resident until its statistics atomics have landed, which costs more
+    // than the consumers' double-precision prologue saves.  Kept selectable for experiments; off by default.
+    s.coef = (p->path & 16) ? reinterpret_cast<const float*>(ws + pl.coef_off[conv_idx]) : nullptr;
     s.gamma = p->gn_w[b][j];
     s.beta = p->gn_b[b][j];
     s.channels = pl.conv_c[conv_idx];
@@ -137,7 +140,7 @@ static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, in
         a.weight_tc = p->conv_w_tc[b][i % 2];
         a.out = ws + pl.raw_off[i];
         a.out_stats = reinterpret_cast<double*>(ws + pl.stats_off[i]);
-        a.out_coef = reinterpret_cast<float*>(ws + pl.coef_off[i]);
+        a.out_coef = (p->path & 16) ? reinterpret_cast<float*>(ws + pl.coef_off[i]) : nullptr;
         a.out_counter = reinterpret_cast<int32_t*>(ws + pl.counter_off[i]);
         a.out_gamma = p->gn_w[b][i % 2];
         a.out_beta = p->gn_b[b][i % 2];
