@@ -34,7 +34,6 @@ struct TcArgs {
     int N, H, W; float eps;
     const float* cf0; const float* cf1;   // optional finished (a, b) of src0 / src1 ([N,C,2]), else computed from st0 / st1
     float* out_coef; int* out_counter; const float* out_gamma; const float* out_beta; int out_groups;
-    int tiles_x, tiles_y, total_tiles;    // persistent CTAs walk contiguous ranges of the (n, tile_y, tile_x) order
 };
 
 // ---- compile-time geometry -------------------------------------------------------------------------
@@ -207,14 +206,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % G::WM, wn = warp / G::WM;
+    const int n = blockIdx.z;
+    const int y0 = blockIdx.y * G::TH, x0 = blockIdx.x * G::TW;
     const int H = p.H, W = p.W;
-    // Persistent CTA: a contiguous slice of the tile order, so the image index changes at most a few times per CTA and the
-    // per-image work (GroupNorm coefficients in double precision, statistics flush with global atomics) and the per-CTA
-    // work (weight load) are amortised over many tiles instead of being paid by every 16x64 tile.
-    const int tile_first = (int)((long long)blockIdx.x * p.total_tiles / gridDim.x);
-    const int tile_last = (int)((long long)(blockIdx.x + 1) * p.total_tiles / gridDim.x);
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
-    int cur_n = -1;
 
     // ---- (0) start the weight traffic ----------------------------------------------------------------
     auto load_stage = [&](int stage, int buf) {
@@ -223,7 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
         const uint32_t dst = smem_u32(wgt) + buf * BYTES;
         for (int i = tid * 16; i < BYTES; i += TC_THREADS * 16) cp_async16(dst + i, src + i);
     };
-    if constexpr (!G::STREAM) load_stage(0, 0);
+    load_stage(0, 0);
     if constexpr (G::MODE == M_UPCAT) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.ctw);
         const uint32_t dst = smem_u32(smem + G::OFF_CTW);
@@ -231,12 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
     }
     cp_async_commit();
 
-    if constexpr (G::MODE == M_UPCAT) {
-        float* ctb = reinterpret_cast<float*>(smem + G::OFF_CTB);
-        for (int c = tid; c < G::CU; c += TC_THREADS) ctb[c] = p.ctb[c];
-    }
-    // ---- (1) GroupNorm coefficients (a, b) per source channel, recomputed when the image changes -----------
-    auto compute_coefs = [&](int n) {
+    // ---- (1) GroupNorm coefficients (a, b) per source channel ---------------------------------------
     if constexpr (G::MODE == M_UPCAT) {
         for (int c = tid; c < G::CL + G::CU; c += TC_THREADS) {
             float a, b;
@@ -251,6 +240,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
             if constexpr (ACT != ACT_EXACT) { a *= 0.5f; b *= 0.5f; }  // silu(y) = h + h*tanh(h), h = y/2
             coef[c] = make_float2(a, b);
         }
+        float* ctb = reinterpret_cast<float*>(smem + G::OFF_CTB);
+        for (int c = tid; c < G::CU; c += TC_THREADS) ctb[c] = p.ctb[c];
     } else {
         const double plane = G::MODE == M_POOL ? (double)(2 * H) * (2 * W) : (double)H * W;
         for (int c = tid; c < G::CIN; c += TC_THREADS) {
@@ -261,67 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
             coef[c] = make_float2(a, b);
         }
     }
-    };
-
-    const uint32_t act_u = smem_u32(act);
-    const uint32_t wgt_u = smem_u32(wgt);
-    const int nt0 = wn * G::NT;
-    // per-lane B row offset inside a chunk (bytes): matrix = lane>>3 -> (k-half, n-tile of the pair)
-    const uint32_t b_lane = G::NT == 1 ? (uint32_t)(((((lane >> 3) & 1) * G::COUT) + nt0 * 8 + (lane & 7)) * 16)
-                                       : (uint32_t)(((((lane >> 3) & 1) * G::COUT) + (nt0 + (lane >> 4)) * 8 + (lane & 7)) * 16);
-    float s1[G::NT][2], s2[G::NT][2];
-#pragma unroll
-    for (int i = 0; i < G::NT; ++i) s1[i][0] = s1[i][1] = s2[i][0] = s2[i][1] = 0.f;
-    T* outp = reinterpret_cast<T*>(p.out);
-
-    // ---- (5) GroupNorm statistics of image n_flush: lanes with equal lane&3 hold the same channels ----------------
-    auto flush_stats = [&](int n_flush) {
-#pragma unroll
-        for (int i = 0; i < G::NT; ++i)
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                float a = s1[i][k], b = s2[i][k];
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    a += __shfl_xor_sync(0xffffffffu, a, o);
-                    b += __shfl_xor_sync(0xffffffffu, b, o);
-                }
-                if (lane < 4) {
-                    // one slot per (m-warp, channel): no shared atomics, and the cross-warp sum below has a fixed order
-                    const int ch = (nt0 + i) * 8 + 2 * lane + k;
-                    statf[(wm * G::COUT + ch) * 2] = a;
-                    statf[(wm * G::COUT + ch) * 2 + 1] = b;
-                }
-                s1[i][k] = 0.f;
-                s2[i][k] = 0.f;
-            }
-        __syncthreads();
-        if (p.out_stats != nullptr)
-            for (int c = tid; c < 2 * G::COUT; c += TC_THREADS) {
-                double t = 0.0;
-#pragma unroll
-                for (int w = 0; w < G::WM; ++w) t += (double)statf[w * G::COUT * 2 + c];
-                atomicAdd(p.out_stats + (size_t)n_flush * G::COUT * 2 + c, t);
-            }
-        __syncthreads();
-    };
-
-#pragma unroll 1
-    for (int tile = tile_first; tile < tile_last; ++tile) {
-    const int n = tile / tiles_per_img;
-    const int trem = tile - n * tiles_per_img;
-    const int y0 = (trem / p.tiles_x) * G::TH, x0 = (trem % p.tiles_x) * G::TW;
-    __syncthreads();  // every warp is done with the previous tile's shared-memory operands
-    if (n != cur_n) {
-        if (cur_n >= 0) flush_stats(cur_n);
-        compute_coefs(n);
-        cur_n = n;
-        __syncthreads();
-    }
-    if constexpr (G::STREAM) {
-        load_stage(0, 0);
-        cp_async_commit();
-    }
+    __syncthreads();
 
     // ---- (2) stage the activated halo tile ------------------------------------------------------------
     if constexpr (G::MODE == M_SAME) {
@@ -431,6 +362,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
     }
 
     // ---- (3) main loop: 9 shifted GEMMs ------------------------------------------------------------------
+    const uint32_t act_u = smem_u32(act);
+    const uint32_t wgt_u = smem_u32(wgt);
+    const int nt0 = wn * G::NT;
+    // per-lane B row offset inside a chunk (bytes): matrix = lane>>3 -> (k-half, n-tile of the pair)
+    const uint32_t b_lane = G::NT == 1 ? (uint32_t)(((((lane >> 3) & 1) * G::COUT) + nt0 * 8 + (lane & 7)) * 16)
+                                       : (uint32_t)(((((lane >> 3) & 1) * G::COUT) + (nt0 + (lane >> 4)) * 8 + (lane & 7)) * 16);
+    float s1[G::NT][2], s2[G::NT][2];
+#pragma unroll
+    for (int i = 0; i < G::NT; ++i) s1[i][0] = s1[i][1] = s2[i][0] = s2[i][1] = 0.f;
+    T* outp = reinterpret_cast<T*>(p.out);
+
 #pragma unroll 1
     for (int g = 0; g < G::MPW; g += G::MG) {
         float acc[G::MG][G::NT][4];
@@ -526,8 +468,36 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
         if (full) epilogue(std::true_type{});
         else epilogue(std::false_type{});
     }
-    }  // tile loop
-    if (cur_n >= 0) flush_stats(cur_n);
+    // ---- (5) GroupNorm statistics: lanes with equal lane&3 hold the same channels -------------------------
+#pragma unroll
+    for (int i = 0; i < G::NT; ++i)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            float a = s1[i][k], b = s2[i][k];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane < 4) {
+                // one slot per (m-warp, channel): no shared atomics, and the cross-warp sum below has a fixed order
+                const int ch = (nt0 + i) * 8 + 2 * lane + k;
+                statf[(wm * G::COUT + ch) * 2] = a;
+                statf[(wm * G::COUT + ch) * 2 + 1] = b;
+            }
+        }
+    __syncthreads();
+    if (p.out_stats != nullptr)
+        for (int c = tid; c < 2 * G::COUT; c += TC_THREADS) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < G::WM; ++w) t += (double)statf[w * G::COUT * 2 + c];
+            atomicAdd(p.out_stats + (size_t)n * G::COUT * 2 + c, t);
+        }
+    if (p.out_coef != nullptr && p.out_stats != nullptr) {
+        if (last_cta_of_image(p.out_counter + n, gridDim.x * gridDim.y))
+            gn_finalize(p.out_stats, p.out_gamma, p.out_beta, n, G::COUT, p.out_groups, (double)H * W, p.eps, p.out_coef);
+    }
 }
 
 // ---- weight packing kernels ------------------------------------------------------------------------------
@@ -617,22 +587,8 @@ static int launch_geo(const TcArgs& t, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%d B): %s", G::SMEM_BYTES, cudaGetErrorString(e)); return 4; }
         attr_done = true;
     }
-    static int max_ctas = 0;  // resident CTAs on this device for this instantiation
-    if (max_ctas == 0) {
-        int dev = 0, sms = 0, occ = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TC_THREADS, G::SMEM_BYTES);
-        max_ctas = sms * (occ > 0 ? occ : 1);
-    }
-    TcArgs ta = t;
-    ta.tiles_x = (t.W + G::TW - 1) / G::TW;
-    ta.tiles_y = (t.H + G::TH - 1) / G::TH;
-    const long long total = (long long)ta.tiles_x * ta.tiles_y * t.N;
-    if (total > 0x7fffffffLL) { set_error("conv3x3 tc: too many tiles"); return 3; }
-    ta.total_tiles = (int)total;
-    const int grid = ta.total_tiles < max_ctas ? ta.total_tiles : max_ctas;
-    kern<<<grid, TC_THREADS, G::SMEM_BYTES, st>>>(ta);
+    dim3 grid((t.W + G::TW - 1) / G::TW, (t.H + G::TH - 1) / G::TH, t.N);
+    kern<<<grid, TC_THREADS, G::SMEM_BYTES, st>>>(t);
     count_launch();
     return check_launch("conv3x3_tc");
 }
@@ -693,7 +649,10 @@ int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handl
     t.src0 = s0.raw; t.st0 = s0.stats; t.g0 = s0.gamma; t.b0 = s0.beta; t.groups0 = s0.groups;
     t.cf0 = s0.coef;
     if (a.nsrc == 2) t.cf1 = a.src[1].coef;
-    // (producer-side finalisation is not offered by the persistent kernel: CTAs per image are not a fixed count)
+    if (a.out_coef && a.out_counter && a.out_gamma && a.out_beta && a.out_groups > 0) {
+        t.out_coef = a.out_coef; t.out_counter = a.out_counter; t.out_gamma = a.out_gamma; t.out_beta = a.out_beta;
+        t.out_groups = a.out_groups;
+    }
     t.wgt = a.weight_tc;
     t.out = a.out; t.out_stats = a.out_stats;
     t.N = a.N; t.H = a.H; t.W = a.W; t.eps = a.eps;
