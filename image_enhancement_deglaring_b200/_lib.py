@@ -69,6 +69,8 @@ SYMBOLS = {
     "dg_lw_layout": (C.c_int, [C.POINTER(DgLwParams), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_int32),
                                C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dg_convt2x2_fused": (C.c_int, [C.POINTER(DgSrc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
+                                    C.c_int32, C.c_void_p]),
     "dg_channel_attention": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
     "dg_lw_num_params": (C.c_int, [C.POINTER(DgLwParams), C.POINTER(C.c_size_t)]),

@@ -50,6 +50,7 @@ struct LwPlan {
     int f[5];
     int conv_c[18], conv_h[18], conv_w[18];
     size_t raw_off[18], stats_off[18], counter_off[18], coef_off[18];
+    size_t up_off[4];  // scratch for a materialised upconvK output (deep decoder levels, 16-bit storage)
     size_t stats_bytes, total_bytes;  // stats_bytes = the zero-initialised prefix (statistics + arrival counters)
 };
 
@@ -89,6 +90,12 @@ static int make_plan(const dg_lw_params* p, int N, int H, int W, LwPlan* pl) {
     for (int i = 0; i < 18; ++i) {
         pl->raw_off[i] = off;
         off += align_up((size_t)N * pl->conv_h[i] * pl->conv_w[i] * pl->conv_c[i] * dtype_size(p->dtype), 256);
+    }
+    for (int u = 0; u < 4; ++u) {
+        const int lvl = 3 - u;
+        pl->up_off[u] = off;
+        if (p->dtype != DG_F32 && u < 3)
+            off += align_up((size_t)N * (H >> lvl) * (W >> lvl) * pl->f[lvl] * dtype_size(p->dtype), 256);
     }
     pl->total_bytes = off;
     return 0;
@@ -167,6 +174,22 @@ static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, in
             a.src[0].ct_cout = pl.f[lvl];
             a.src[1] = gn_src(p, pl, ws, 2 * lvl + 1, DG_X_SAME);  // skip: torch.cat((up, skip), 1)
             a.nsrc = 2;
+            // deep levels (upconv4, upconv3; upconv2 with path bit 5): run the transposed conv as its own tensor-core GEMM and
+            // feed its output as an identity source -- see convt_tc.cu for why this beats fusing there
+            const bool unfuse = p->dtype != DG_F32 && (p->path & 3) != 1 && (u < 2 || (u == 2 && (p->path & 32)));
+            if (unfuse) {
+                bool handled = false;
+                void* up = ws + pl.up_off[u];
+                rc = convt_tc_launch(a.src[0], p->dtype, N, a.H, a.W, up, 1e-5f, p->path, stream, &handled);
+                if (rc) return rc;
+                if (handled) {
+                    memset(&a.src[0], 0, sizeof(dg_src));
+                    a.src[0].raw = up;
+                    a.src[0].channels = pl.f[lvl];
+                    a.src[0].groups = 1;
+                    a.src[0].xform = DG_X_SAME;
+                }
+            }
         }
         rc = dg_conv3x3_fused(&a, reinterpret_cast<dg_stream_t>(stream));
         if (rc) return rc;
@@ -487,6 +510,18 @@ int dg_lw_forward(const dg_lw_params* p, const float* x, float* y, int32_t N, in
                   size_t workspace_bytes, const float* target, double* l1_sum, dg_stream_t stream) {
     return lw_forward(p, x, y, N, H, W, workspace, workspace_bytes, target, l1_sum,
                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_convt2x2_fused(const dg_src* src, int32_t dtype, int32_t N, int32_t H, int32_t W, void* out, float eps, int32_t path,
+                      dg_stream_t stream) {
+    if (src == nullptr || out == nullptr || N < 1 || H < 2 || W < 2) { set_error("convt2x2: bad arguments"); return 2; }
+    int rc = validate_src(*src, "convt2x2");
+    if (rc) return rc;
+    bool handled = false;
+    rc = convt_tc_launch(*src, dtype, N, H, W, out, eps, path, reinterpret_cast<cudaStream_t>(stream), &handled);
+    if (rc) return rc;
+    if (!handled) { set_error("convt2x2: configuration not covered by the tensor-core kernel (use the fused DG_X_CONVT2 source)"); return 3; }
+    return 0;
 }
 
 int dg_channel_attention(const double* act_sum, double plane, const float* w1, const float* w2, int32_t N, int32_t C,

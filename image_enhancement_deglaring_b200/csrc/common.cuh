@@ -149,6 +149,8 @@ int conv3x3_generic_launch(const dg_conv3x3_args& a, cudaStream_t stream);
 int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int conv_first_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int head_launch(const dg_head_args& a, cudaStream_t stream);
+int convt_tc_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, float eps, int path, cudaStream_t st,
+                    bool* handled);
 int se_scale_launch(const double* act_sum, double plane, const float* w1, const float* w2, int N, int C, int hidden,
                     float* scale, cudaStream_t st);
 int conv3x3_wgrad_launch(const dg_conv3x3_args& a, const float* dR, float* dW, int s_tap, int s_ci, int s_co,

@@ -23,7 +23,10 @@
 
 namespace dg {
 
-enum { M_SAME = 0, M_POOL = 1, M_UPCAT = 2 };
+// M_CAT2: torch.cat((up, skip)) where `up` is an already materialised ConvTranspose output (identity source, planes
+// [0, C/8)) and `skip` is activated on load -- used for the deep decoder levels, where running the transposed conv as its own
+// small GEMM kernel (convt_tc_kernel) beats fusing it (profile r1c: 1 CTA/SM, 65 KB of ConvTranspose weights per CTA).
+enum { M_SAME = 0, M_POOL = 1, M_UPCAT = 2, M_CAT2 = 3 };
 constexpr int TC_THREADS = 256;
 
 struct TcArgs {
@@ -68,7 +71,7 @@ struct Geo {
     static constexpr int LPLANE = pad_plane(LM, NCL8);
     static constexpr int LMT = (LM + 15) / 16;
     static constexpr int CT_CHUNKS = CL / 16, CT_N = 4 * CU, CT_NT = CT_N / 8, CT_NTG = CT_NT < 8 ? CT_NT : 8;
-    static constexpr int NCOEF = MODE == M_UPCAT ? (CL + CU) : CIN;
+    static constexpr int NCOEF = MODE == M_UPCAT ? (CL + CU) : (MODE == M_CAT2 ? COUT : CIN);
     // shared memory carve-up (bytes)
     static constexpr int ACT_BYTES = NC8 * PLANE * 16;
     static constexpr int WGT_BYTES = (STREAM ? 2 : 1) * STAGE_CHUNKS * COUT * 32;
@@ -90,7 +93,7 @@ struct Geo {
     static_assert(MPW % MG == 0, "m-tile groups");
     static_assert(!STREAM || (MG == MPW && CIN >= 16), "streamed weights need all accumulators live");
     static_assert(NT == 1 || NT % 2 == 0, "n-tiles come in ldmatrix.x4 pairs");
-    static_assert(MODE != M_UPCAT || CIN == 2 * COUT, "UPCAT: ConvTranspose 2C->C + skip C");
+    static_assert((MODE != M_UPCAT && MODE != M_CAT2) || CIN == 2 * COUT, "UPCAT/CAT2: (up C, skip C) -> C");
     static_assert(CIN % 8 == 0 && COUT % 8 == 0 && TW % 16 == 0 && TH % 2 == 0, "shape");
 };
 
@@ -100,7 +103,7 @@ struct Geo {
 // ITERS batches of BATCH; all loads of a batch are issued before any math, the slot count is matched to the tile, the
 // (row, column) of a slot advances incrementally, and tiles whose halo lies inside the image skip every bounds test
 // (profiles r1b/r1c: addressing was ~1/3 of the instructions).  `src` points at image n; offsets are 32-bit.
-template <typename T, typename G, int C, bool POOL, int ACT>
+template <typename T, typename G, int C, bool POOL, int ACT, bool IDENT = false>
 __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned char* __restrict__ src,
                                              const float2* __restrict__ cfs, int plane0, int y0, int x0, int H, int W) {
     constexpr int NC = C / 8;
@@ -169,7 +172,9 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
                 if (pixs[b] >= NPIX) continue;
                 uint4 o = make_uint4(0u, 0u, 0u, 0u);
                 if (ok[b]) {
-                    if constexpr (H2) {
+                    if constexpr (IDENT) {
+                        o = q[b][0];  // already-final values (materialised ConvTranspose output): plain copy
+                    } else if constexpr (H2) {
                         o = act8_h2(q[b][0], ah, bh);
                     } else {
                         float y[8];
@@ -242,6 +247,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
         }
         float* ctb = reinterpret_cast<float*>(smem + G::OFF_CTB);
         for (int c = tid; c < G::CU; c += TC_THREADS) ctb[c] = p.ctb[c];
+    } else if constexpr (G::MODE == M_CAT2) {
+        for (int c = tid; c < G::COUT; c += TC_THREADS) {
+            float a, b;
+            if (p.cf1) { a = __ldg(p.cf1 + (size_t)(n * G::COUT + c) * 2); b = __ldg(p.cf1 + (size_t)(n * G::COUT + c) * 2 + 1); }
+            else gn_coef(p.st1, p.g1, p.b1, n, G::COUT, p.groups1, c, (double)H * W, p.eps, a, b);
+            if constexpr (ACT != ACT_EXACT) { a *= 0.5f; b *= 0.5f; }
+            coef[c] = make_float2(a, b);
+        }
     } else {
         const double plane = G::MODE == M_POOL ? (double)(2 * H) * (2 * W) : (double)H * W;
         for (int c = tid; c < G::CIN; c += TC_THREADS) {
@@ -258,6 +271,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) 
     if constexpr (G::MODE == M_SAME) {
         stage_planes<T, G, G::CIN, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 2,
                                                 coef, 0, y0, x0, H, W);
+    } else if constexpr (G::MODE == M_CAT2) {
+        stage_planes<T, G, G::COUT, false, ACT, true>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::COUT * 2,
+                                                      coef, 0, y0, x0, H, W);
+        stage_planes<T, G, G::COUT, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::COUT * 2,
+                                                 coef, G::COUT / 8, y0, x0, H, W);
     } else if constexpr (G::MODE == M_POOL) {
         stage_planes<T, G, G::CIN, true, ACT>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 8,
                                                coef, 0, y0, x0, H, W);
@@ -608,6 +626,9 @@ static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin
     DG_TC(64, 64, M_SAME, 8, 32, 4, 2, true)      // enc4.3, dec4.3
     DG_TC(64, 128, M_POOL, 4, 32, 2, 4, true)     // bottleneck.0
     DG_TC(128, 128, M_SAME, 4, 32, 2, 4, true)    // bottleneck.3
+    DG_TC(128, 64, M_CAT2, 8, 16, 4, 2, true)     // dec4.0 on a materialised upconv4
+    DG_TC(64, 32, M_CAT2, 8, 32, 4, 2, true)      // dec3.0 on a materialised upconv3
+    DG_TC(32, 16, M_CAT2, 8, 64, 8, 1, false)     // dec2.0 on a materialised upconv2
     DG_TC(128, 64, M_UPCAT, 8, 16, 4, 2, true)    // upconv4 + dec4.0
     DG_TC(64, 32, M_UPCAT, 8, 32, 4, 2, true)     // upconv3 + dec3.0
     DG_TC(32, 16, M_UPCAT, 8, 64, 8, 1, false)    // upconv2 + dec2.0
@@ -629,6 +650,13 @@ int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handl
         if (s0.stats == nullptr || !s0.silu || s0.scale != nullptr) return 0;
         mode = s0.xform == DG_X_SAME ? M_SAME : M_POOL;
         cin = s0.channels;
+    } else if (a.nsrc == 2 && s0.xform == DG_X_SAME && a.src[1].xform == DG_X_SAME && s0.stats == nullptr && !s0.silu &&
+               s0.scale == nullptr) {
+        const dg_src& s1 = a.src[1];
+        if (s1.stats == nullptr || !s1.silu || s1.scale || s0.channels != a.cout || s1.channels != a.cout) return 0;
+        mode = M_CAT2;
+        cin = 2 * a.cout;
+        t.src1 = s1.raw; t.st1 = s1.stats; t.g1 = s1.gamma; t.b1 = s1.beta; t.groups1 = s1.groups;
     } else if (a.nsrc == 2 && s0.xform == DG_X_CONVT2 && a.src[1].xform == DG_X_SAME) {
         const dg_src& s1 = a.src[1];
         if (s0.stats == nullptr || s1.stats == nullptr || !s0.silu || !s1.silu || s0.scale || s1.scale) return 0;

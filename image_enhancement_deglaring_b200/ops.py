@@ -129,3 +129,12 @@ def head1x1(src, weight, bias, N, H, W, dtype, out=None, target=None, l1_sum=Non
     a.eps = eps
     _lib.check(lib.dg_head1x1(C.byref(a), _stream(stream)))
     return out
+
+
+def convt2x2_fused(src, N, H, W, dtype, out=None, path=0, stream=None, eps=1e-5):
+    """Stand-alone tensor-core ConvTranspose2d(2,2)+bias of the activated low-res source -> NHWC [N,H,W,ct_cout]."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((N, H, W, src.ct_cout), dtype=TORCH_DTYPE[dtype], device=src._keep[0].device)
+    _lib.check(lib.dg_convt2x2_fused(C.byref(src), dtype, N, H, W, _ptr(out), eps, path, _stream(stream)))
+    return out

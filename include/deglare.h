@@ -123,6 +123,14 @@ typedef struct {
 
 int dg_head1x1(const dg_head_args* args, dg_stream_t stream);
 
+/* Stand-alone nn.ConvTranspose2d(k=2, s=2) + bias (src/model.py:47-53) of the ACTIVATED low-resolution tensor described by
+ * `src` (xform DG_X_CONVT2 with ct_w_tc / ct_b / ct_cout; GroupNorm + SiLU applied on load), on the tensor cores, 16-bit
+ * storage only.  out: NHWC [N,H,W,ct_cout] (H, W = the up-sampled size).  The result is consumed by dg_conv3x3_fused as an
+ * identity source (stats = NULL, silu = 0) next to the skip source.  Returns 3 for configurations it does not cover --
+ * the fused DG_X_CONVT2 source of dg_conv3x3_fused covers everything. */
+int dg_convt2x2_fused(const dg_src* src, int32_t dtype, int32_t N, int32_t H, int32_t W, void* out, float eps, int32_t path,
+                      dg_stream_t stream);
+
 /* ChannelAttention of OptimizedUNet (src/optimized_model.py:161-202): scale[n][c] = sigmoid(W2 . silu(W1 . mean)),
  * mean[n][c] = act_sum[n][c] / plane, with act_sum the `act_sum` output of the conv that pools the same tensor.
  * w1 [hidden][C], w2 [C][hidden] (the nn.Linear weights as they are).  The result feeds dg_src.scale. */

@@ -319,6 +319,41 @@ def test_tc_exact_and_tanh_silu_agree(dtype):
         assert float((o.float().cpu().permute(0, 3, 1, 2) - ref).abs().max()) <= tol
 
 
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("c,H,W", [(64, 16, 32), (32, 16, 32), (16, 32, 64), (64, 2, 2), (32, 6, 10)])
+def test_tc_standalone_convt_then_cat2(dtype, c, H, W):
+    """Deep decoder levels: ConvTranspose as its own tensor-core GEMM, then the conv over (identity up, activated skip)."""
+    rs = _rs(16)
+    N = 2
+    low = torch.from_numpy((rs.standard_normal((N, 2 * c, H // 2, W // 2)) * 2).astype(np.float32))
+    skip = torch.from_numpy((rs.standard_normal((N, c, H, W)) * 2 + 0.3).astype(np.float32))
+    ql, seen_l = _nhwc(low, dtype)
+    qs, seen_s = _nhwc(skip, dtype)
+    g1, b1 = _gn_params(rs, 2 * c)
+    g2, b2 = _gn_params(rs, c)
+    ctw = torch.from_numpy((rs.standard_normal((2 * c, c, 2, 2)) * (1.0 / np.sqrt(2 * c))).astype(np.float32))
+    ctb = torch.from_numpy((rs.standard_normal(c) * 0.2).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((c, 2 * c, 3, 3)) * (1.0 / np.sqrt(18 * c))).astype(np.float32))
+    wp = ops.pack_conv3x3(w.cuda())
+    ctp = ops.pack_convt2x2(ctw.cuda())
+    s0 = ops.make_src(ql, 2 * c, xform=ops.DG_X_CONVT2, stats=_stats(seen_l), gamma=g1.cuda(), beta=b1.cuda(),
+                      groups=8, ct_w=ctp, ct_b=ctb.cuda(), ct_cout=c, ct_w_tc=ops.pack_convt2x2_tc(ctp, dtype))
+    up = ops.convt2x2_fused(s0, N, H, W, dtype)
+    torch.cuda.synchronize()
+    up_ref = F.conv_transpose2d(tpo.gn_silu(seen_l, 8, g1, b1), ctw, ctb, stride=2)
+    tol = (6e-3 if dtype == ops.DG_F16 else 4e-2) * max(1.0, float(up_ref.abs().max()))
+    assert float((up.float().cpu().permute(0, 3, 1, 2) - up_ref).abs().max()) <= tol
+    su = ops.make_src(up, c, silu=False)
+    s1 = ops.make_src(qs, c, stats=_stats(seen_s), gamma=g2.cuda(), beta=b2.cuda(), groups=8)
+    o_ref, st_ref = ops.conv3x3_fused([su, s1], wp, c, N, H, W, dtype, path=1)
+    o_tc, st_tc = ops.conv3x3_fused([su, s1], wp, c, N, H, W, dtype, path=2, weight_tc=ops.pack_conv3x3_tc(wp, dtype))
+    torch.cuda.synchronize()
+    _tc_check(o_tc, st_tc, o_ref, st_ref, dtype, f"tc cat2 {2 * c}->{c}")
+    ref = F.conv2d(torch.cat((up.float().cpu().permute(0, 3, 1, 2), tpo.gn_silu(seen_s, 8, g2, b2)), 1), w, None, 1, 1)
+    assert float((o_tc.float().cpu().permute(0, 3, 1, 2) - ref).abs().max()) <= (6e-3 if dtype == ops.DG_F16 else 4e-2) * max(
+        1.0, float(ref.abs().max()))
+
+
 def test_tc_path_refuses_unsupported():
     w = torch.zeros(3, 3, 24, 24, device="cuda")
     raw = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.float16)
