@@ -88,6 +88,12 @@ struct Geo {
     static constexpr int OFF_STAT = OFF_COEF + COEF_BYTES;
     static constexpr int OFF_CTB = OFF_STAT + STAT_BYTES;
     static constexpr int SMEM_BYTES = OFF_CTB + CTB_BYTES;
+    // Resident CTAs per SM the register allocator must leave room for (__launch_bounds__): the narrow memory-bound layers
+    // live on inter-CTA overlap of their staging / MMA phases (4 CTAs = 64 registers; a 74-register build ran 12 % slower),
+    // the compute-heavy ones need ~100 registers for 64 accumulators.
+    static constexpr int CTA_TARGET = ACC_REGS == 32 ? (MODE == M_POOL ? 3 : 4) : 2;
+    static constexpr int CTA_SMEM = (227 * 1024) / (SMEM_BYTES + 1024);
+    static constexpr int MIN_CTAS = CTA_SMEM < 1 ? 1 : (CTA_SMEM < CTA_TARGET ? CTA_SMEM : CTA_TARGET);
     static_assert(WM * WN == 8, "8 warps");
     static_assert(MTILES % WM == 0 && (COUT / 8) % WN == 0, "tile split");
     static_assert(MPW % MG == 0, "m-tile groups");
@@ -202,7 +208,7 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
 }
 
 template <typename T, typename G, int ACT>
-__global__ void __launch_bounds__(TC_THREADS) conv3x3_tc_kernel(const TcArgs p) {
+__global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(const TcArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* act = smem + G::OFF_ACT;
     unsigned char* wgt = smem + G::OFF_WGT;
