@@ -91,7 +91,7 @@ struct Geo {
     // Resident CTAs per SM the register allocator must leave room for (__launch_bounds__): the narrow memory-bound layers
     // live on inter-CTA overlap of their staging / MMA phases (4 CTAs = 64 registers; a 74-register build ran 12 % slower),
     // the compute-heavy ones need ~100 registers for 64 accumulators.
-    static constexpr int CTA_TARGET = ACC_REGS == 32 ? (MODE == M_POOL ? 3 : 4) : 2;
+    static constexpr int CTA_TARGET = (MG * NT * 4 <= 32) ? (MODE == M_POOL ? 3 : 4) : 2;
     static constexpr int CTA_SMEM = (227 * 1024) / (SMEM_BYTES + 1024);
     static constexpr int MIN_CTAS = CTA_SMEM < 1 ? 1 : (CTA_SMEM < CTA_TARGET ? CTA_SMEM : CTA_TARGET);
     static_assert(WM * WN == 8, "8 warps");
