@@ -16,7 +16,7 @@
 namespace dg {
 
 namespace {
-constexpr int F_TH = 16, F_TW = 64, F_PH = F_TH + 2, F_PW = F_TW + 2, F_PA = 68;  // PA: even row pitch (elements)
+constexpr int F_TH = 32, F_TW = 64, F_PH = F_TH + 2, F_PW = F_TW + 2, F_PA = 68;  // PA: even row pitch (elements)
 constexpr int F_THREADS = 256;
 
 struct FirstArgs {
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
     constexpr int COUT = 8 * NT;
     __shared__ __align__(16) T tileA[F_PH * F_PA];
     __shared__ __align__(16) T tileB[F_PH * F_PA];  // tileB[r][c] = tile(r, c + 1)
-    __shared__ double statd[2 * COUT];
+    __shared__ float statw[8][2 * COUT];  // per-warp (sum, sumsq) slots, summed in a fixed order
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = lane & 3, g = lane >> 2;
@@ -78,7 +78,6 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
             if (c >= 1) rb[c - 1] = h;
         }
     }
-    if (tid < 2 * COUT) statd[tid] = 0.0;
 
     // ---- B fragments: b0 = k-slot pair q, b1 = pair 4+q, column (output channel) g of each n-tile -------
     uint32_t bfr[NT][2];
@@ -159,12 +158,17 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
             }
             if (lane < 4) {
                 const int ch = i * 8 + 2 * lane + k;
-                atomicAdd(&statd[2 * ch], (double)a);
-                atomicAdd(&statd[2 * ch + 1], (double)b);
+                statw[warp][2 * ch] = a;
+                statw[warp][2 * ch + 1] = b;
             }
         }
     __syncthreads();
-    if (p.out_stats != nullptr && tid < 2 * COUT) atomicAdd(p.out_stats + (size_t)n * COUT * 2 + tid, statd[tid]);
+    if (p.out_stats != nullptr && tid < 2 * COUT) {
+        double t = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) t += (double)statw[w8][tid];
+        atomicAdd(p.out_stats + (size_t)n * COUT * 2 + tid, t);
+    }
     if (p.out_coef != nullptr && p.out_stats != nullptr) {
         if (last_cta_of_image(p.out_counter + n, gridDim.x * gridDim.y))
             gn_finalize(p.out_stats, p.out_gamma, p.out_beta, n, COUT, p.out_groups, (double)H * W, p.eps, p.out_coef);
