@@ -79,7 +79,7 @@ struct Geo {
     static constexpr int STAT_BYTES = WM * COUT * 2 * 4;  // one float (sum, sumsq) slot per (m-warp, channel)
     static constexpr int LOW_BYTES = MODE == M_UPCAT ? NCL8 * LPLANE * 16 : 0;
     static constexpr int CTW_BYTES = MODE == M_UPCAT ? CT_CHUNKS * 2 * CT_N * 16 : 0;
-    static constexpr int CTB_BYTES = MODE == M_UPCAT ? CU * 4 : 0;
+    static constexpr int CTB_BYTES = MODE == M_UPCAT ? (CU * 4 + ((LM + 15) / 16) * 16) : 0;  // bias + scatter mask table
     static constexpr int OFF_ACT = 0;
     static constexpr int OFF_WGT = OFF_ACT + ACT_BYTES;
     static constexpr int OFF_LOW = OFF_WGT + WGT_BYTES;
@@ -253,6 +253,23 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
         }
         float* ctb = reinterpret_cast<float*>(smem + G::OFF_CTB);
         for (int c = tid; c < G::CU; c += TC_THREADS) ctb[c] = p.ctb[c];
+        // scatter mask of every low pixel (li, lj): it feeds the 2x2 block at tile (2li-1+a, 2lj-1+b); bit (2a+b) = that
+        // position lies inside the staged tile, bit 4+(2a+b) = it also lies inside the image (else the concat is zero there)
+        unsigned char* okt = smem + G::OFF_CTB + G::CU * 4;
+        for (int lp = tid; lp < G::LM; lp += TC_THREADS) {
+            const int li = lp / G::LPW, lj = lp - li * G::LPW;
+            const int r0 = 2 * li - 1, c0 = 2 * lj - 1;
+            uint32_t m = 0;
+#pragma unroll
+            for (int ab = 0; ab < 4; ++ab) {
+                const int r = r0 + (ab >> 1), c = c0 + (ab & 1);
+                const bool in_tile = (unsigned)r < (unsigned)G::PH && (unsigned)c < (unsigned)G::PW;
+                const bool in_img = (unsigned)(y0 - 1 + r) < (unsigned)H && (unsigned)(x0 - 1 + c) < (unsigned)W;
+                m |= (in_tile ? 1u : 0u) << ab;
+                m |= ((in_tile && in_img) ? 1u : 0u) << (4 + ab);
+            }
+            okt[lp] = (unsigned char)m;
+        }
     } else if constexpr (G::MODE == M_CAT2) {
         for (int c = tid; c < G::COUT; c += TC_THREADS) {
             float a, b;
@@ -300,19 +317,34 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
             float2 cf[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) cf[k] = coef[c8 * 8 + k];
-#pragma unroll 2
-            for (int idx = tid; idx < G::LM * G::NCL8; idx += TC_THREADS) {
-                const int lp = idx / G::NCL8;
-                const int li = lp / G::LPW;
-                const int gi = li0 + li, gj = lj0 + lp - li * G::LPW;
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (gi >= 0 && gi < Hl && gj >= 0 && gj < Wl) {
-                    float y[8];
-                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(n * Hl + gi) * Wl + gj) * G::CL + c8 * 8));
-                    act8<T, (ACT == ACT_HALF2 ? ACT_TANH : ACT)>(q, cf, y);
-                    o = pack8<T>(y);
+            constexpr int LITEMS = G::LM * G::NCL8;
+            constexpr int LSLOTS = (LITEMS + TC_THREADS - 1) / TC_THREADS;
+            constexpr int LB = LSLOTS < 4 ? LSLOTS : 4;  // loads in flight per thread
+            const unsigned char* rawn = reinterpret_cast<const unsigned char*>(raw) + (size_t)n * Hl * Wl * G::CL * 2 + c8 * 16;
+#pragma unroll 1
+            for (int idx0 = tid; idx0 < LITEMS; idx0 += TC_THREADS * LB) {
+                uint4 q[LB];
+                bool ok[LB];
+#pragma unroll
+                for (int b = 0; b < LB; ++b) {
+                    const int lp = (idx0 + b * TC_THREADS) / G::NCL8;
+                    const int li = lp / G::LPW;
+                    const int gi = li0 + li, gj = lj0 + lp - li * G::LPW;
+                    ok[b] = lp < G::LM && (unsigned)gi < (unsigned)Hl && (unsigned)gj < (unsigned)Wl;
+                    if (ok[b]) q[b] = __ldg(reinterpret_cast<const uint4*>(rawn + (uint32_t)(gi * Wl + gj) * (G::CL * 2)));
                 }
-                *reinterpret_cast<uint4*>(low + ((size_t)c8 * G::LPLANE + lp) * 16) = o;
+#pragma unroll
+                for (int b = 0; b < LB; ++b) {
+                    const int lp = (idx0 + b * TC_THREADS) / G::NCL8;
+                    if (lp >= G::LM) continue;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok[b]) {
+                        float y[8];
+                        act8<T, (ACT == ACT_HALF2 ? ACT_TANH : ACT)>(q[b], cf, y);
+                        o = pack8<T>(y);
+                    }
+                    *reinterpret_cast<uint4*>(low + ((size_t)c8 * G::LPLANE + lp) * 16) = o;
+                }
             }
         }
         cp_async_wait<0>();  // ConvTranspose weights (and conv stage 0) have landed
@@ -349,22 +381,13 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
                 // Geometry of the two accumulator rows is n-tile independent: low pixel (li, lj) feeds the 2x2 block at
                 // tile (2li-1+a, 2lj-1+b); bit (2a+b) of `okm` = inside the staged tile, bit 4+(2a+b) = inside the image.
                 uint32_t boff[2], okm[2];
+                const unsigned char* okt = smem + G::OFF_CTB + G::CU * 4;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     const int lp = mt * 16 + (lane >> 2) + 8 * hf;
                     const int li = lp / G::LPW, lj = lp - li * G::LPW;
-                    const int r0 = 2 * li - 1, c0 = 2 * lj - 1;
-                    boff[hf] = (uint32_t)((r0 * G::PW + c0) * 16);
-                    uint32_t m = 0;
-#pragma unroll
-                    for (int ab = 0; ab < 4; ++ab) {
-                        const int r = r0 + (ab >> 1), c = c0 + (ab & 1);
-                        const bool in_tile = lp < G::LM && (unsigned)r < (unsigned)G::PH && (unsigned)c < (unsigned)G::PW;
-                        const bool in_img = (unsigned)(y0 - 1 + r) < (unsigned)H && (unsigned)(x0 - 1 + c) < (unsigned)W;
-                        m |= (in_tile ? 1u : 0u) << ab;
-                        m |= ((in_tile && in_img) ? 1u : 0u) << (4 + ab);
-                    }
-                    okm[hf] = m;
+                    boff[hf] = (uint32_t)(((2 * li - 1) * G::PW + (2 * lj - 1)) * 16);
+                    okm[hf] = lp < G::LM ? (uint32_t)okt[lp] : 0u;
                 }
 #pragma unroll
                 for (int i = 0; i < G::CT_NTG; ++i) {
