@@ -450,6 +450,9 @@ int dg_conv3x3_fused(const dg_conv3x3_args* a, dg_stream_t stream) {
         int rc = conv_first_tc_launch(*a, st, &handled);
         if (rc) return rc;
         if (handled) return 0;
+        rc = conv3x3_umma_launch(*a, st, &handled);   // tcgen05 + TMEM for the deep layers it covers
+        if (rc) return rc;
+        if (handled) return 0;
         rc = conv3x3_tc_launch(*a, st, &handled);
         if (rc) return rc;
         if (handled) return 0;

@@ -1,0 +1,369 @@
+// tcgen05 implicit-GEMM 3x3 conv for the DEEP layers (C_out >= 32..64, K = 9*C_in >= 288): 5th-generation tensor cores with
+// the accumulator in tensor memory.  Same fusion contract as conv3x3_tc.cu (GroupNorm apply + SiLU [+ AvgPool | identity
+// `up` half of a concat] on load, raw NHWC output + GroupNorm statistics in the epilogue).
+//
+// Why here and not on the narrow layers: a UMMA reads its 128 x 16 A tile from shared memory for every instruction, so
+// with N = C_out = 8..16 it is shared-memory-bound at 1/8..1/4 of the tensor rate, while from N = 64 on the 4 KB A tile is
+// amortised over 64+ output channels and the measured HMMA ceiling of the legacy path (990 MAC/clk/SM, tools/mma_bench.cu)
+// becomes the limit instead (these layers ran at 38-47 % tensor-pipe utilisation on mma.sync, profiles/r01_ncu_full_summary).
+//
+// Implicit GEMM without im2col: the activated haloed tile lives in shared memory as 16-bit channel planes
+// [C/8][rows*32 pixels][8 ch]; 8 consecutive pixels of a plane are one contiguous 128-byte core matrix, so a no-swizzle
+// K-major descriptor (LBO = plane stride, SBO = 128 B) describes 128 output pixels x 16 channels, and a vertical tap is a
+// start-address offset (validated by tools/umma_test.cu).  M-rows must be consecutive pixels, so horizontal taps use three
+// copies of the tile, pre-shifted by kx (copy_k[r][c] = tile(r, c + k)); tiles are TH x 32 pixels = TH/4 accumulators of
+// 128 lanes x C_out fp32 columns in TMEM.  Weights use the HMMA path's packing ([chunk][k-half][C_out][8]) unchanged:
+// it is exactly the K-major no-swizzle B layout (LBO = C_out*16, SBO = 128).
+//
+// One elected thread issues all 9 * C_in/16 UMMAs per accumulator and commits them to an mbarrier; all warps then read
+// their TMEM lanes (tcgen05.ld 32x32b), round, store, and reduce the statistics with a halving butterfly.
+#include "tc_common.cuh"
+
+namespace dg {
+
+namespace {
+constexpr int UM_THREADS = 256;
+constexpr int UM_TW = 32;
+enum { UM_SAME = 0, UM_POOL = 1, UM_CAT2 = 3 };
+
+struct UmArgs {
+    const void* src0; const double* st0; const float* g0; const float* b0; const float* cf0; int groups0;
+    const void* src1; const double* st1; const float* g1; const float* b1; const float* cf1; int groups1;
+    const void* wgt;
+    void* out; double* out_stats;
+    int N, H, W; float eps;
+};
+
+constexpr int um_pow2_cols(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512))); }
+
+template <int CIN_, int COUT_, int MODE_, int TH_>
+struct UGeo {
+    static constexpr int CIN = CIN_, COUT = COUT_, MODE = MODE_, TH = TH_;
+    static constexpr int MB = TH * UM_TW / 128;               // accumulators (128-pixel M blocks)
+    static constexpr int NC8 = CIN / 8, ROWS = TH + 2, HW = UM_TW + 2;
+    static constexpr int PLANE_BYTES = ROWS * UM_TW * 16;      // one channel plane of one shifted copy
+    static constexpr int COPY_BYTES = NC8 * PLANE_BYTES;
+    static constexpr int ACT_BYTES = 3 * COPY_BYTES;
+    static constexpr int KSTEPS = CIN / 16, NCHUNK = 9 * KSTEPS;
+    static constexpr int WGT_BYTES = NCHUNK * COUT * 32;
+    static constexpr int NCOEF = MODE == UM_CAT2 ? COUT : CIN;
+    static constexpr int TMEM_COLS = um_pow2_cols(MB * COUT);
+    static constexpr int OFF_ACT = 0;
+    static constexpr int OFF_WGT = OFF_ACT + ACT_BYTES;
+    static constexpr int OFF_COEF = OFF_WGT + WGT_BYTES;
+    static constexpr int OFF_STAT = OFF_COEF + NCOEF * 8;
+    static constexpr int OFF_BAR = OFF_STAT + 8 * COUT * 2 * 4;
+    static constexpr int SMEM_BYTES = OFF_BAR + 16;
+    static_assert(TH % 4 == 0 && (MB == 1 || MB == 2), "tile = 1 or 2 accumulators of 4 rows x 32 pixels");
+    static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "UMMA shape");
+    static_assert(UM_THREADS % NC8 == 0, "chunk ownership");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+    static_assert(MODE != UM_CAT2 || CIN == 2 * COUT, "CAT2: (up C, skip C) -> C");
+};
+
+__device__ __forceinline__ uint64_t um_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+
+// halving butterfly: 16 per-lane values -> every lane ends with the 32-lane total of ONE of them (index from lane bits 4..1)
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool hi = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = hi ? v[i + half] : v[i];
+            const float give = hi ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, give, bit);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <typename T, typename G, int ACT>
+__global__ void __launch_bounds__(UM_THREADS, 1) conv3x3_umma_kernel(const UmArgs p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* act = smem + G::OFF_ACT;
+    unsigned char* wgt = smem + G::OFF_WGT;
+    float2* coef = reinterpret_cast<float2*>(smem + G::OFF_COEF);
+    float* statw = reinterpret_cast<float*>(smem + G::OFF_STAT);   // [8 warps][COUT][2]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + G::OFF_BAR + 8);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z;
+    const int y0 = blockIdx.y * G::TH, x0 = blockIdx.x * UM_TW;
+    const int H = p.H, W = p.W;
+    constexpr int FACT = ACT == ACT_HALF2 ? ACT_TANH : ACT;
+
+    // ---- (0) weights -> shared memory (cp.async), TMEM allocation, barrier init -------------------------------------
+    {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wgt);
+        const uint32_t dst = smem_u32(wgt);
+        for (int i = tid * 16; i < G::WGT_BYTES; i += UM_THREADS * 16) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(G::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // ---- (1) GroupNorm coefficients ---------------------------------------------------------------------------------------
+    {
+        const bool cat = G::MODE == UM_CAT2;
+        const double plane = G::MODE == UM_POOL ? (double)(2 * H) * (2 * W) : (double)H * W;
+        for (int c = tid; c < G::NCOEF; c += UM_THREADS) {
+            float a, b;
+            const float* cf = cat ? p.cf1 : p.cf0;
+            if (cf) { a = __ldg(cf + (size_t)(n * G::NCOEF + c) * 2); b = __ldg(cf + (size_t)(n * G::NCOEF + c) * 2 + 1); }
+            else if (cat) gn_coef(p.st1, p.g1, p.b1, n, G::NCOEF, p.groups1, c, plane, p.eps, a, b);
+            else gn_coef(p.st0, p.g0, p.b0, n, G::NCOEF, p.groups0, c, plane, p.eps, a, b);
+            if constexpr (FACT != ACT_EXACT) { a *= 0.5f; b *= 0.5f; }
+            coef[c] = make_float2(a, b);
+        }
+    }
+    __syncthreads();
+
+    // ---- (2) stage the activated haloed tile into the three kx-shifted copies ----------------------------------------------
+    {
+        const int c8 = tid % G::NC8;
+        const bool ident = G::MODE == UM_CAT2 && c8 < G::COUT / 8;              // `up` half of the concat: plain copy
+        const int cc8 = (G::MODE == UM_CAT2 && !ident) ? c8 - G::COUT / 8 : c8;  // chunk index inside its source
+        const int Cs = G::MODE == UM_CAT2 ? G::COUT : G::CIN;                    // channels of the source tensor
+        float2 cf[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cf[k] = ident ? make_float2(0.f, 0.f) : coef[cc8 * 8 + k];
+        const unsigned char* srcb = reinterpret_cast<const unsigned char*>((G::MODE == UM_CAT2 && !ident) ? p.src1 : p.src0);
+        const int Hs = G::MODE == UM_POOL ? 2 * H : H, Ws = G::MODE == UM_POOL ? 2 * W : W;
+        srcb += (size_t)n * Hs * Ws * Cs * 2 + cc8 * 16;
+        const uint32_t rowb = (uint32_t)Ws * Cs * 2;
+        constexpr int NPIX = G::ROWS * G::HW;
+        constexpr int PSTRIDE = UM_THREADS / G::NC8;
+        constexpr int NSLOT = (NPIX + PSTRIDE - 1) / PSTRIDE;
+        constexpr int MAXB = G::MODE == UM_POOL ? 2 : 4;
+        constexpr int ITERS = (NSLOT + MAXB - 1) / MAXB;
+        constexpr int BATCH = (NSLOT + ITERS - 1) / ITERS;
+        unsigned char* dstp = act + (size_t)c8 * G::PLANE_BYTES;
+        int hp = tid / G::NC8;
+#pragma unroll 1
+        for (int it = 0; it < ITERS; ++it) {
+            uint4 q[BATCH][G::MODE == UM_POOL ? 4 : 1];
+            int hps[BATCH];
+            bool ok[BATCH];
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                const int r = hp / G::HW, c = hp - r * G::HW;
+                const int gy = y0 + r - 1, gx = x0 + c - 1;
+                hps[b] = hp;
+                ok[b] = hp < NPIX && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+                if (ok[b]) {
+                    if constexpr (G::MODE == UM_POOL) {
+                        const unsigned char* base = srcb + ((uint32_t)(2 * gy) * rowb + (uint32_t)(2 * gx) * (Cs * 2));
+                        q[b][0] = __ldg(reinterpret_cast<const uint4*>(base));
+                        q[b][1] = __ldg(reinterpret_cast<const uint4*>(base + Cs * 2));
+                        q[b][2] = __ldg(reinterpret_cast<const uint4*>(base + rowb));
+                        q[b][3] = __ldg(reinterpret_cast<const uint4*>(base + rowb + Cs * 2));
+                    } else {
+                        q[b][0] = __ldg(reinterpret_cast<const uint4*>(srcb + ((uint32_t)gy * rowb + (uint32_t)gx * (Cs * 2))));
+                    }
+                }
+                hp += PSTRIDE;
+            }
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                if (hps[b] >= NPIX) continue;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[b]) {
+                    if (ident) {
+                        o = q[b][0];
+                    } else {
+                        float y[8];
+                        act8<T, FACT>(q[b][0], cf, y);
+                        if constexpr (G::MODE == UM_POOL) {
+                            float t[8];
+#pragma unroll
+                            for (int j = 1; j < 4; ++j) {
+                                act8<T, FACT>(q[b][j], cf, t);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) y[k] += t[k];
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) y[k] *= 0.25f;
+                        }
+                        o = pack8<T>(y);
+                    }
+                }
+                // haloed column c (tile x = c - 1) lands in copy k at column c - k, for the copies where that is inside [0, 32)
+                const int r = hps[b] / G::HW, c = hps[b] - r * G::HW;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int col = c - k;
+                    if ((unsigned)col < (unsigned)UM_TW)
+                        *reinterpret_cast<uint4*>(dstp + (size_t)k * G::COPY_BYTES + (uint32_t)(r * UM_TW + col) * 16) = o;
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    // generic-proxy writes (st.shared, cp.async) must be visible to the tensor core's async-proxy reads
+    asm volatile("fence.proxy.async.shared::cta;");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t taddr = *tmem_slot;
+
+    // ---- (3) one thread issues the whole K loop of every accumulator -----------------------------------------------------
+    if (tid == 0) {
+        constexpr uint32_t IDESC = (1u << 4) | ((std::is_same<T, __half>::value ? 0u : 1u) << 7) |
+                                   ((std::is_same<T, __half>::value ? 0u : 1u) << 10) | ((uint32_t)(G::COUT >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+        const uint32_t act_u = smem_u32(act), wgt_u = smem_u32(wgt);
+#pragma unroll 1
+        for (int mb = 0; mb < G::MB; ++mb) {
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const uint32_t a_tap = act_u + kx * G::COPY_BYTES + (uint32_t)((mb * 4 + ky) * UM_TW) * 16;
+#pragma unroll
+                for (int j = 0; j < G::KSTEPS; ++j) {
+                    const uint64_t da = um_desc(a_tap + 2 * j * G::PLANE_BYTES, G::PLANE_BYTES, 128);
+                    const uint64_t db = um_desc(wgt_u + (uint32_t)((tap * G::KSTEPS + j) * G::COUT * 32), G::COUT * 16, 128);
+                    const uint32_t accum = (tap | j) ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(taddr + mb * G::COUT), "l"(da), "l"(db), "r"(IDESC), "r"(accum));
+                }
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)));
+    }
+    // ---- (4) wait for the tensor core, then TMEM -> registers -> HBM + statistics ---------------------------------------------
+    {
+        uint32_t done = 0;
+        for (int spin = 0; spin < (1 << 26) && !done; ++spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(bar)));
+        if (!done) __trap();  // never observed; a bounded wait keeps a broken descriptor from hanging the device
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const int mb = warp >> 2;           // warps 0-3 read accumulator 0, warps 4-7 accumulator 1 (same TMEM lanes)
+    const bool active = mb < G::MB;
+    if (active) {
+        const int row = mb * 4 + (warp & 3);
+        const int gy = y0 + row, gx = x0 + lane;
+        const bool valid = gy < H && gx < W;
+        T* o = reinterpret_cast<T*>(p.out) + ((size_t)(n * H + gy) * W + gx) * G::COUT;
+#pragma unroll 1
+        for (int c0 = 0; c0 < G::COUT; c0 += 16) {
+            uint32_t r[16];
+            const uint32_t ta = taddr + ((uint32_t)((warp & 3) * 32) << 16) + mb * G::COUT + c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(ta));
+            asm volatile("tcgen05.wait::ld.sync.aligned;");
+            float v[16], s[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+                s[j] = v[j] * v[j];
+            }
+            if (valid) {
+                uint4 lo = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
+                uint4 hi = make_uint4(pack2<T>(v[8], v[9]), pack2<T>(v[10], v[11]), pack2<T>(v[12], v[13]), pack2<T>(v[14], v[15]));
+                *reinterpret_cast<uint4*>(o + c0) = lo;
+                *reinterpret_cast<uint4*>(o + c0 + 8) = hi;
+            }
+            const float tsum = butterfly16(v, lane);
+            const float tsq = butterfly16(s, lane);
+            if ((lane & 1) == 0) {
+                // after the butterfly lane bits 4..1 select the channel: bit 4 -> +8, bit 3 -> +4, bit 2 -> +2, bit 1 -> +1
+                const int ch = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                statw[(warp * G::COUT + ch) * 2] = tsum;
+                statw[(warp * G::COUT + ch) * 2 + 1] = tsq;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (p.out_stats != nullptr)
+        for (int c = tid; c < 2 * G::COUT; c += UM_THREADS) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 4 * G::MB; ++w) t += (double)statw[w * G::COUT * 2 + c];
+            atomicAdd(p.out_stats + (size_t)n * G::COUT * 2 + c, t);
+        }
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(G::TMEM_COLS));
+    }
+}
+
+template <typename T, typename G, int ACT>
+int launch_um(const UmArgs& a, cudaStream_t st) {
+    auto kern = conv3x3_umma_kernel<T, G, ACT>;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%d B): %s", G::SMEM_BYTES, cudaGetErrorString(e)); return 4; }
+        done = true;
+    }
+    dim3 grid((a.W + UM_TW - 1) / UM_TW, (a.H + G::TH - 1) / G::TH, a.N);
+    kern<<<grid, UM_THREADS, G::SMEM_BYTES, st>>>(a);
+    count_launch();
+    return check_launch("conv3x3_umma");
+}
+
+template <typename T, int ACT>
+int dispatch_um(const UmArgs& a, int mode, int cin, int cout, cudaStream_t st, bool* handled) {
+    *handled = true;
+    if (mode == UM_SAME && cin == 64 && cout == 64) return launch_um<T, UGeo<64, 64, UM_SAME, 8>, ACT>(a, st);   // enc4.3, dec4.3
+    if (mode == UM_POOL && cin == 32 && cout == 64) return launch_um<T, UGeo<32, 64, UM_POOL, 8>, ACT>(a, st);   // enc4.0
+    if (mode == UM_CAT2 && cin == 64 && cout == 32) return launch_um<T, UGeo<64, 32, UM_CAT2, 8>, ACT>(a, st);   // dec3.0
+    *handled = false;
+    return 0;
+}
+}  // namespace
+
+int conv3x3_umma_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (a.dtype != DG_F16 && a.dtype != DG_BF16) return 0;
+    if (a.weight_tc == nullptr || a.act_sum != nullptr || a.N > 65535 || (a.path & 64)) return 0;  // path bit 6: HMMA only
+    const dg_src& s0 = a.src[0];
+    UmArgs u;
+    memset(&u, 0, sizeof(u));
+    int mode, cin;
+    if (a.nsrc == 1 && (s0.xform == DG_X_SAME || s0.xform == DG_X_POOL2)) {
+        if (s0.stats == nullptr || !s0.silu || s0.scale != nullptr) return 0;
+        mode = s0.xform == DG_X_SAME ? UM_SAME : UM_POOL;
+        cin = s0.channels;
+    } else if (a.nsrc == 2 && s0.xform == DG_X_SAME && a.src[1].xform == DG_X_SAME && s0.stats == nullptr && !s0.silu &&
+               s0.scale == nullptr) {
+        const dg_src& s1 = a.src[1];
+        if (s1.stats == nullptr || !s1.silu || s1.scale || s0.channels != a.cout || s1.channels != a.cout) return 0;
+        mode = UM_CAT2;
+        cin = 2 * a.cout;
+        u.src1 = s1.raw; u.st1 = s1.stats; u.g1 = s1.gamma; u.b1 = s1.beta; u.cf1 = s1.coef; u.groups1 = s1.groups;
+    } else {
+        return 0;
+    }
+    if ((reinterpret_cast<uintptr_t>(s0.raw) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.weight_tc) |
+         reinterpret_cast<uintptr_t>(u.src1)) & 15)
+        return 0;
+    u.src0 = s0.raw; u.st0 = s0.stats; u.g0 = s0.gamma; u.b0 = s0.beta; u.cf0 = s0.coef; u.groups0 = s0.groups;
+    u.wgt = a.weight_tc;
+    u.out = a.out; u.out_stats = a.out_stats;
+    u.N = a.N; u.H = a.H; u.W = a.W; u.eps = a.eps;
+    const int flavour = (a.path >> 2) & 3;
+    if (a.dtype == DG_F16)
+        return flavour == 1 ? dispatch_um<__half, ACT_EXACT>(u, mode, cin, a.cout, stream, handled)
+                            : dispatch_um<__half, ACT_TANH>(u, mode, cin, a.cout, stream, handled);
+    return flavour == 1 ? dispatch_um<__nv_bfloat16, ACT_EXACT>(u, mode, cin, a.cout, stream, handled)
+                        : dispatch_um<__nv_bfloat16, ACT_TANH>(u, mode, cin, a.cout, stream, handled);
+}
+
+}  // namespace dg

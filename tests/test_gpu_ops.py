@@ -354,6 +354,42 @@ def test_tc_standalone_convt_then_cat2(dtype, c, H, W):
         1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("mode,cin,cout,H,W", [("same", 64, 64, 16, 64), ("same", 64, 64, 8, 32), ("same", 64, 64, 12, 40),
+                                                 ("pool", 32, 64, 16, 32), ("pool", 32, 64, 6, 10), ("cat2", 64, 32, 16, 64),
+                                                 ("cat2", 64, 32, 10, 36)])
+def test_umma_matches_hmma_and_generic(dtype, mode, cin, cout, H, W):
+    """tcgen05/TMEM kernel (path 2) vs the mma.sync kernel (path 2 | 64) vs the generic kernel on identical inputs."""
+    rs = _rs(17)
+    N = 3
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
+    wp = ops.pack_conv3x3(w.cuda())
+    wtc = ops.pack_conv3x3_tc(wp, dtype)
+    if mode == "cat2":
+        up = torch.from_numpy((rs.standard_normal((N, cout, H, W)) * 1.5).astype(np.float32))
+        skip = torch.from_numpy((rs.standard_normal((N, cout, H, W)) * 2 + 0.3).astype(np.float32))
+        qu, _ = _nhwc(up, dtype)
+        qs, seen = _nhwc(skip, dtype)
+        g, b = _gn_params(rs, cout)
+        srcs = [ops.make_src(qu, cout, silu=False), ops.make_src(qs, cout, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=8)]
+    else:
+        f = 2 if mode == "pool" else 1
+        raw = torch.from_numpy((rs.standard_normal((N, cin, f * H, f * W)) * 3 + 1).astype(np.float32))
+        q, seen = _nhwc(raw, dtype)
+        g, b = _gn_params(rs, cin)
+        srcs = [ops.make_src(q, cin, xform=ops.DG_X_POOL2 if mode == "pool" else ops.DG_X_SAME, stats=_stats(seen),
+                             gamma=g.cuda(), beta=b.cuda(), groups=8)]
+    o_gen, s_gen = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=1)
+    o_um, s_um = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2, weight_tc=wtc)
+    o_hm, s_hm = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2 | 64, weight_tc=wtc)
+    torch.cuda.synchronize()
+    _tc_check(o_um, s_um, o_gen, s_gen, dtype, f"umma {mode} {cin}->{cout}")
+    _tc_check(o_hm, s_hm, o_gen, s_gen, dtype, f"hmma {mode} {cin}->{cout}")
+    # both tensor paths round the same fp16 operands: they agree far tighter than either does with the fp32-staged generic path
+    scale = max(1.0, float(o_gen.float().abs().max()))
+    assert float((o_um.float() - o_hm.float()).abs().max()) <= (2e-3 if dtype == ops.DG_F16 else 1.6e-2) * scale
+
+
 def test_tc_path_refuses_unsupported():
     w = torch.zeros(3, 3, 24, 24, device="cuda")
     raw = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.float16)
