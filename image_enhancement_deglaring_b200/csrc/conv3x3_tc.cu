@@ -61,7 +61,7 @@ struct Geo {
     static constexpr int SEGS = TW / 16, MTILES = TH * SEGS, MPW = MTILES / WM, NT = COUT / 8 / WN;
     // accumulator budget per thread: 32 registers for the narrow memory-bound layers (more CTAs per SM), 64 for the
     // compute-heavy ones (B-fragment reuse; with streamed weights all m-tiles of a warp stay live across tap stages)
-    static constexpr int ACC_REGS = (STREAM || COUT > 16) ? 64 : 32;
+    static constexpr int ACC_REGS = STREAM ? 64 : 32;
     static constexpr int MG = (MPW * NT * 4 <= ACC_REGS) ? MPW : (ACC_REGS / (NT * 4));
     static constexpr int STAGE_CHUNKS = STREAM ? KC : NCHUNK;
     static constexpr int NSTAGE = STREAM ? 9 : 1;
@@ -652,7 +652,7 @@ static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin
     DG_TC(16, 32, M_POOL, 16, 32, 8, 1, false)    // enc3.0
     DG_TC(32, 32, M_SAME, 16, 32, 8, 1, false)    // enc3.3, dec3.3
     DG_TC(32, 64, M_POOL, 8, 32, 4, 2, false)     // enc4.0
-    DG_TC(64, 64, M_SAME, 8, 32, 4, 2, true)      // enc4.3, dec4.3
+    DG_TC(64, 64, M_SAME, 4, 32, 4, 2, true)      // enc4.3, dec4.3 (4x32 tiles: 32 accumulators -> 4 CTAs/SM)
     DG_TC(64, 128, M_POOL, 4, 32, 2, 4, true)     // bottleneck.0
     DG_TC(128, 128, M_SAME, 4, 32, 2, 4, true)    // bottleneck.3
     DG_TC(128, 64, M_CAT2, 8, 16, 4, 2, true)     // dec4.0 on a materialised upconv4

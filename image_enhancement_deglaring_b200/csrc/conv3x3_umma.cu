@@ -40,7 +40,9 @@ template <int CIN_, int COUT_, int MODE_>
 struct UGeo {
     static constexpr int CIN = CIN_, COUT = COUT_, MODE = MODE_, TH = 4;   // tile = 4 rows x 32 pixels = one 128-lane accumulator
     static constexpr int NC8 = CIN / 8, ROWS = TH + 2, HW = UM_TW + 2;
-    static constexpr int PLANE_BYTES = ROWS * UM_TW * 16;      // one channel plane of one shifted copy
+    // one channel plane of one shifted copy, +16 B so that the NC8 planes a warp writes for one pixel land in different
+    // bank groups (a 128-byte-multiple stride made every staging store an 8-way bank conflict)
+    static constexpr int PLANE_BYTES = ROWS * UM_TW * 16 + 16;
     static constexpr int COPY_BYTES = NC8 * PLANE_BYTES;
     static constexpr int ACT_BYTES = 3 * COPY_BYTES;           // one staged tile (three kx-shifted copies)
     static constexpr int KSTEPS = CIN / 16, NCHUNK = 9 * KSTEPS;
@@ -396,7 +398,12 @@ int dispatch_um(const UmArgs& a, int mode, int cin, int cout, cudaStream_t st, b
 int conv3x3_umma_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled) {
     *handled = false;
     if (a.dtype != DG_F16 && a.dtype != DG_BF16) return 0;
-    if (a.weight_tc == nullptr || a.act_sum != nullptr || a.N > 65535 || (a.path & 64)) return 0;  // path bit 6: HMMA only
+    // Opt-in (path bit 6).  Measured on B200 (profiles/r01_ncu_umma.txt): correct, but for THIS 486k-parameter net it only
+    // ties the mma.sync kernel on 64->64 (74 vs 76 us) and loses on 64->32 (322 vs 208 us): with C <= 128 the per-pixel
+    // CUDA-core work of the fused prologue/epilogue (activation, three shifted tile copies, statistics butterfly) at 8 warps
+    // per SM bounds the kernel while the tensor pipe idles at 12 %.  It is the template for the wide (features_start=64)
+    // variant, where MMA work grows with C^2 and prologue work with C.
+    if (a.weight_tc == nullptr || a.act_sum != nullptr || a.N > 65535 || !(a.path & 64)) return 0;
     const dg_src& s0 = a.src[0];
     UmArgs u;
     memset(&u, 0, sizeof(u));

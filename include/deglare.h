@@ -102,7 +102,7 @@ typedef struct {
     int32_t path;         /* bits 0-1: 0 = auto, 1 = force generic CUDA-core path, 2 = force tensor-core path;
                              bits 2-3: SiLU flavour of the tensor-core prologue (0 tanh.approx, 1 exact ex2/rcp, 2 half2);
                              bit 4: producer-side GroupNorm finalisation; bit 5: un-fuse upconv2 as well;
-                             bit 6: mma.sync kernels only (skip the tcgen05 kernel)                      */
+                             bit 6: use the tcgen05/TMEM kernel where it exists (deep 64-channel layers; measured at parity)                      */
 } dg_conv3x3_args;
 
 int dg_conv3x3_fused(const dg_conv3x3_args* args, dg_stream_t stream);

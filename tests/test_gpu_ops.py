@@ -359,7 +359,7 @@ def test_tc_standalone_convt_then_cat2(dtype, c, H, W):
                                                  ("pool", 32, 64, 16, 32), ("pool", 32, 64, 6, 10), ("cat2", 64, 32, 16, 64),
                                                  ("cat2", 64, 32, 10, 36)])
 def test_umma_matches_hmma_and_generic(dtype, mode, cin, cout, H, W):
-    """tcgen05/TMEM kernel (path 2) vs the mma.sync kernel (path 2 | 64) vs the generic kernel on identical inputs."""
+    """tcgen05/TMEM kernel (path 2 | 64) vs the mma.sync kernel (path 2) vs the generic kernel on identical inputs."""
     rs = _rs(17)
     N = 3
     w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
@@ -380,8 +380,8 @@ def test_umma_matches_hmma_and_generic(dtype, mode, cin, cout, H, W):
         srcs = [ops.make_src(q, cin, xform=ops.DG_X_POOL2 if mode == "pool" else ops.DG_X_SAME, stats=_stats(seen),
                              gamma=g.cuda(), beta=b.cuda(), groups=8)]
     o_gen, s_gen = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=1)
-    o_um, s_um = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2, weight_tc=wtc)
-    o_hm, s_hm = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2 | 64, weight_tc=wtc)
+    o_um, s_um = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2 | 64, weight_tc=wtc)
+    o_hm, s_hm = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2, weight_tc=wtc)
     torch.cuda.synchronize()
     _tc_check(o_um, s_um, o_gen, s_gen, dtype, f"umma {mode} {cin}->{cout}")
     _tc_check(o_hm, s_hm, o_gen, s_gen, dtype, f"hmma {mode} {cin}->{cout}")
