@@ -59,9 +59,10 @@ struct Geo {
     static constexpr int KC = CIN >= 16 ? CIN / 16 : 1;
     static constexpr int NCHUNK = CIN == 8 ? 5 : 9 * KC;
     static constexpr int SEGS = TW / 16, MTILES = TH * SEGS, MPW = MTILES / WM, NT = COUT / 8 / WN;
-    // accumulator budget per thread: 32 registers for the narrow memory-bound layers (more CTAs per SM), 64 for the
-    // compute-heavy ones (B-fragment reuse; with streamed weights all m-tiles of a warp stay live across tap stages)
-    static constexpr int ACC_REGS = STREAM ? 64 : 32;
+    // accumulator budget per thread: 32 registers everywhere.  These kernels are latency-bound on the CUDA-core prologue /
+    // epilogue, so more resident CTAs beat B-fragment reuse (measured: 64 -> 32 accumulators gave ~10 % on levels 3-4);
+    // with streamed weights a second group of m-tiles simply streams the (L2-resident) taps again.
+    static constexpr int ACC_REGS = 32;
     static constexpr int MG = (MPW * NT * 4 <= ACC_REGS) ? MPW : (ACC_REGS / (NT * 4));
     static constexpr int STAGE_CHUNKS = STREAM ? KC : NCHUNK;
     static constexpr int NSTAGE = STREAM ? 9 : 1;
@@ -97,7 +98,7 @@ struct Geo {
     static_assert(WM * WN == 8, "8 warps");
     static_assert(MTILES % WM == 0 && (COUT / 8) % WN == 0, "tile split");
     static_assert(MPW % MG == 0, "m-tile groups");
-    static_assert(!STREAM || (MG == MPW && CIN >= 16), "streamed weights need all accumulators live");
+    static_assert(!STREAM || CIN >= 16, "streamed weights: one tap per stage");
     static_assert(NT == 1 || NT % 2 == 0, "n-tiles come in ldmatrix.x4 pairs");
     static_assert((MODE != M_UPCAT && MODE != M_CAT2) || CIN == 2 * COUT, "UPCAT/CAT2: (up C, skip C) -> C");
     static_assert(CIN % 8 == 0 && COUT % 8 == 0 && TW % 16 == 0 && TH % 2 == 0, "shape");
@@ -432,6 +433,12 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
 #pragma unroll
             for (int i = 0; i < G::NT; ++i) acc[m][i][0] = acc[m][i][1] = acc[m][i][2] = acc[m][i][3] = 0.f;
         }
+        if constexpr (G::STREAM) {
+            if (g > 0) {  // next group of m-tiles: stream the taps again (the trailing barrier of the last stage freed buffer 0)
+                load_stage(0, 0);
+                cp_async_commit();
+            }
+        }
 #pragma unroll 1
         for (int stage = 0; stage < G::NSTAGE; ++stage) {
             if constexpr (G::STREAM) {
@@ -652,7 +659,7 @@ static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin
     DG_TC(16, 32, M_POOL, 16, 32, 8, 1, false)    // enc3.0
     DG_TC(32, 32, M_SAME, 16, 32, 8, 1, false)    // enc3.3, dec3.3
     DG_TC(32, 64, M_POOL, 8, 32, 4, 2, false)     // enc4.0
-    DG_TC(64, 64, M_SAME, 4, 32, 4, 2, true)      // enc4.3, dec4.3 (4x32 tiles: 32 accumulators -> 4 CTAs/SM)
+    DG_TC(64, 64, M_SAME, 8, 32, 4, 2, true)      // enc4.3, dec4.3
     DG_TC(64, 128, M_POOL, 4, 32, 2, 4, true)     // bottleneck.0
     DG_TC(128, 128, M_SAME, 4, 32, 2, 4, true)    // bottleneck.3
     DG_TC(128, 64, M_CAT2, 8, 16, 4, 2, true)     // dec4.0 on a materialised upconv4
