@@ -59,10 +59,10 @@ struct Geo {
     static constexpr int KC = CIN >= 16 ? CIN / 16 : 1;
     static constexpr int NCHUNK = CIN == 8 ? 5 : 9 * KC;
     static constexpr int SEGS = TW / 16, MTILES = TH * SEGS, MPW = MTILES / WM, NT = COUT / 8 / WN;
-    // accumulator budget per thread: 32 registers everywhere.  These kernels are latency-bound on the CUDA-core prologue /
-    // epilogue, so more resident CTAs beat B-fragment reuse (measured: 64 -> 32 accumulators gave ~10 % on levels 3-4);
-    // with streamed weights a second group of m-tiles simply streams the (L2-resident) taps again.
-    static constexpr int ACC_REGS = 32;
+    // accumulator budget per thread: 32 registers when the weights are resident -- those kernels are latency-bound on the
+    // CUDA-core prologue / epilogue, so more resident CTAs beat B-fragment reuse (measured ~10 % on levels 3-4); 64 when the
+    // taps stream (a second m-tile group would stream them again: measured 8-15 % slower on the 128-channel layers).
+    static constexpr int ACC_REGS = STREAM ? 64 : 32;
     static constexpr int MG = (MPW * NT * 4 <= ACC_REGS) ? MPW : (ACC_REGS / (NT * 4));
     static constexpr int STAGE_CHUNKS = STREAM ? KC : NCHUNK;
     static constexpr int NSTAGE = STREAM ? 9 : 1;
