@@ -92,6 +92,7 @@ SYMBOLS = {
     "dg_pack_convt2x2_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_last_error_string": (C.c_char_p, []),
     "dg_version": (C.c_int, []),
+    "dg_set_pdl": (C.c_int, [C.c_int]),
     "dg_launch_count": (C.c_uint64, []),
 }
 
@@ -111,6 +112,8 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("DG_PDL") == "0":   # A/B switch for programmatic dependent launch
+            lib.dg_set_pdl(0)
         _lib = lib
     return _lib
 

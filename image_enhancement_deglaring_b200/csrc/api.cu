@@ -17,6 +17,8 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -428,6 +430,10 @@ extern "C" {
 
 const char* dg_last_error_string(void) { return g_err; }
 int dg_version(void) { return 100; }
+int dg_set_pdl(int enabled) {
+    const int old = g_pdl.exchange(enabled ? 1 : 0);
+    return old;
+}
 uint64_t dg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int dg_conv3x3_fused(const dg_conv3x3_args* a, dg_stream_t stream) {

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "deglare.h"
 
 namespace dg {
@@ -103,6 +105,14 @@ __device__ __forceinline__ void gn_coef(const double* __restrict__ stats, const 
     b = (float)((double)beta[c] - mean * rstd * (double)gamma[c]);
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// The forward is a chain of ~20 short kernels, each consuming its predecessor's output.  With the stream-serialisation
+// attribute a kernel may start while the previous one drains its last wave; everything before pdl_wait() (weight
+// cp.async, index setup, TMEM / barrier init) overlaps that tail, and pdl_wait() blocks until the predecessor's memory
+// operations are complete and visible.  pdl_launch_dependents() lets the successor begin as soon as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // ---- producer-side GroupNorm finalisation --------------------------------------------------------------------------
 // Every CTA of a conv adds its partial (sum, sumsq) to stats[n] with double atomics; the CTA that arrives last at the
 // per-image counter (threadfence + atomic ticket) sees the complete sums and writes the affine (a, b) of the GroupNorm
@@ -143,6 +153,22 @@ __device__ __forceinline__ void gn_finalize(const double* stats, const float* __
 // ---- host side ---------------------------------------------------------------------------
 namespace dg {
 void set_error(const char* fmt, ...);
+bool pdl_enabled();
+// <<<>>> replacement that adds the programmatic-stream-serialisation attribute when PDL is on
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 void count_launch();
 int check_launch(const char* what);
 int conv3x3_generic_launch(const dg_conv3x3_args& a, cudaStream_t stream);

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
     const int y0 = blockIdx.y * G::TH, x0 = blockIdx.x * G::TW;
     const int H = p.H, W = p.W;
 
+    pdl_launch_dependents();
     // ---- (0) start the weight traffic ----------------------------------------------------------------
     auto load_stage = [&](int stage, int buf) {
         constexpr int BYTES = G::STAGE_CHUNKS * G::COUT * 32;
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
     }
     cp_async_commit();
 
+    pdl_wait();  // everything above overlapped the producer's tail; its activations / statistics are complete from here on
     // ---- (1) GroupNorm coefficients (a, b) per source channel ---------------------------------------
     if constexpr (G::MODE == M_UPCAT) {
         for (int c = tid; c < G::CL + G::CU; c += TC_THREADS) {
@@ -642,7 +644,8 @@ static int launch_geo(const TcArgs& t, cudaStream_t st) {
         attr_done = true;
     }
     dim3 grid((t.W + G::TW - 1) / G::TW, (t.H + G::TH - 1) / G::TH, t.N);
-    kern<<<grid, TC_THREADS, G::SMEM_BYTES, st>>>(t);
+    cudaError_t le = launch_kernel(kern, grid, dim3(TC_THREADS), (size_t)G::SMEM_BYTES, st, t);
+    if (le != cudaSuccess) { set_error("conv3x3_tc launch: %s", cudaGetErrorString(le)); return 10; }
     count_launch();
     return check_launch("conv3x3_tc");
 }

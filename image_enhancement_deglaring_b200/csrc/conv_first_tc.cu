@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
     const int y0 = blockIdx.y * F_TH, x0 = blockIdx.x * F_TW;
     const int H = p.H, W = p.W;
 
+    pdl_launch_dependents();
+    pdl_wait();  // the statistics buffer is zeroed by a memset / reused from the previous forward's consumers
     // ---- stage the haloed input tile (fp32 -> T), zero outside the image ------------------------------
     // Per tile row: 16 aligned float4 groups (the 64 interior pixels; tile column = 1 + 4j..4 + 4j) and the two halo
     // columns.  In tileB (shifted copy) a group is one aligned 8-byte store; in tileA it straddles 4-byte words.
@@ -191,14 +193,16 @@ int conv_first_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* ha
         f.out_groups = a.out_groups;
     }
     dim3 grid((a.W + F_TW - 1) / F_TW, (a.H + F_TH - 1) / F_TH, a.N);
+    cudaError_t le = cudaSuccess;
     if (a.dtype == DG_F16) {
-        if (a.cout == 8) conv_first_tc_kernel<__half, 1><<<grid, F_THREADS, 0, stream>>>(f);
-        else conv_first_tc_kernel<__half, 2><<<grid, F_THREADS, 0, stream>>>(f);
+        if (a.cout == 8) le = launch_kernel(conv_first_tc_kernel<__half, 1>, grid, dim3(F_THREADS), (size_t)0, stream, f);
+        else le = launch_kernel(conv_first_tc_kernel<__half, 2>, grid, dim3(F_THREADS), (size_t)0, stream, f);
     } else {
-        if (a.cout == 8) conv_first_tc_kernel<__nv_bfloat16, 1><<<grid, F_THREADS, 0, stream>>>(f);
-        else conv_first_tc_kernel<__nv_bfloat16, 2><<<grid, F_THREADS, 0, stream>>>(f);
+        if (a.cout == 8) le = launch_kernel(conv_first_tc_kernel<__nv_bfloat16, 1>, grid, dim3(F_THREADS), (size_t)0, stream, f);
+        else le = launch_kernel(conv_first_tc_kernel<__nv_bfloat16, 2>, grid, dim3(F_THREADS), (size_t)0, stream, f);
     }
     *handled = true;
+    if (le != cudaSuccess) { set_error("conv_first_tc launch: %s", cudaGetErrorString(le)); return 10; }
     count_launch();
     return check_launch("conv_first_tc");
 }

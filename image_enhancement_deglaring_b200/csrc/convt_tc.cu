@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(CT_THREADS) convt_tc_kernel(const ConvtArgs p)
         for (int i = tid * 16; i < CTW_BYTES; i += CT_THREADS * 16) cp_async16(dst + i, src + i);
         cp_async_commit();
     }
+    pdl_launch_dependents();
+    pdl_wait();
     for (int c = tid; c < CL; c += CT_THREADS) {
         float a, b;
         if (p.coef) { a = __ldg(p.coef + (size_t)(n * CL + c) * 2); b = __ldg(p.coef + (size_t)(n * CL + c) * 2 + 1); }
@@ -146,7 +148,8 @@ int launch_convt(const ConvtArgs& a, cudaStream_t st) {
         done = true;
     }
     dim3 grid((a.h * a.w + CT_MP - 1) / CT_MP, a.N);
-    kern<<<grid, CT_THREADS, SMEM, st>>>(a);
+    cudaError_t le = launch_kernel(kern, grid, dim3(CT_THREADS), (size_t)SMEM, st, a);
+    if (le != cudaSuccess) { set_error("convt_tc launch: %s", cudaGetErrorString(le)); return 10; }
     count_launch();
     return check_launch("convt_tc");
 }

@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fast_kernel(const dg_head_a
     __shared__ float ws[C];
     const int n = blockIdx.y;
     const int HW = p.H * p.W;
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x < C) {
         float a, b;
         if (p.src.coef != nullptr) {
@@ -156,8 +158,8 @@ static bool head_fast(const dg_head_args& a, cudaStream_t stream) {
     int bx = (HW + HEAD_THREADS * 8 - 1) / (HEAD_THREADS * 8);
     if (bx < 1) bx = 1;
     dim3 grid(bx, a.N);
-    if (C == 8) head_fast_kernel<T, 8><<<grid, HEAD_THREADS, 0, stream>>>(a);
-    else head_fast_kernel<T, 16><<<grid, HEAD_THREADS, 0, stream>>>(a);
+    if (C == 8) launch_kernel(head_fast_kernel<T, 8>, grid, dim3(HEAD_THREADS), (size_t)0, stream, a);
+    else launch_kernel(head_fast_kernel<T, 16>, grid, dim3(HEAD_THREADS), (size_t)0, stream, a);
     return true;
 }
 

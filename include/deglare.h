@@ -228,6 +228,8 @@ int dg_pack_convt2x2_tc(const float* w, void* out, int32_t cin, int32_t cout, in
 /* ---- misc --------------------------------------------------------------------------- */
 const char* dg_last_error_string(void);
 int dg_version(void);
+/* Programmatic dependent launch for the library's kernel chain (default on); returns the previous setting. */
+int dg_set_pdl(int enabled);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t dg_launch_count(void);
 
