@@ -276,10 +276,19 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = abytes[top] / (per_kernel_ms[top] * 1e-3) / 1e9
+        # DRAM bytes of the same kernel from one `ncu --set full` capture at this batch size (profiles/ncu_traffic.json)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f).get(LAYERS[top])
+            if tr and B == 64 and H == 512 and args.storage == "fp16":
+                traffic = tr["traffic"]
+        except (OSError, ValueError):
+            pass
         net_bytes = sum(abytes)
         roofline = {
             "bound": "hbm", "kernel": LAYERS[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None,
+            "frac": achieved / peak, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
             "kernel_ms": per_kernel_ms[top], "kernel_share_of_step": per_kernel_ms[top] / sum(per_kernel_ms),
             "whole_net": {"algorithmic_bytes_per_step": net_bytes, "achieved": net_bytes / (ms_max / args.steps * 1e-3) / 1e9,
