@@ -85,6 +85,21 @@ def test_odd_shapes(best_sd, golden, shape, seed, key):
     assert np.abs(y - g[key]).max() <= 1e-4
 
 
+@pytest.mark.parametrize("shape,seed", [((1, 1, 96, 80), 1), ((3, 1, 16, 16), 2), ((2, 1, 528, 32), 7), ((2, 1, 48, 1040), 8)])
+def test_odd_shapes_16bit_tensor_core_path(best_sd, shape, seed):
+    """Partial tiles, images smaller than a tile, and very wide / tall images through the tensor-core kernels."""
+    x = _rand(shape, seed)
+    with torch.no_grad():
+        ref = tpo.lightweight_forward(x, best_sd).numpy()
+    net = _net(best_sd, storage="fp16")
+    with torch.no_grad():
+        y = net(x.cuda()).cpu().numpy()
+        y1 = _net(best_sd, storage="fp16", path=1)(x.cuda()).cpu().numpy()   # generic kernels, same storage
+    assert np.abs(y - ref).max() <= 5e-3, shape
+    assert psnr(y, ref) >= 50.0
+    assert np.abs(y - y1).max() <= 5e-3
+
+
 def test_full_size_batch_row_and_checksum(best_sd, golden):
     g = golden("lw_rand.npz")
     net = _net(best_sd)

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Per-kernel time of one training step (torch profiler, CUDA activities) to rank the backward kernels."""
+import os, sys, collections
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import image_enhancement_deglaring_b200 as dg
+from image_enhancement_deglaring_b200.train import FusedAdamW
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+storage = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+sd = torch.load(os.path.join(ROOT, "weights", "best_model.pth"))
+net = dg.LightweightUNet(storage=storage); net.load_state_dict(sd, strict=True); net = net.cuda().train()
+opt = FusedAdamW(net.parameters(), lr=2e-3, weight_decay=6e-5, max_grad_norm=1.0)
+x = torch.rand(B, 1, 512, 512).cuda(); t = torch.rand(B, 1, 512, 512).cuda()
+def step():
+    opt.zero_grad(); loss = torch.nn.L1Loss()(net(x), t); loss.backward(); opt.step()
+step(); torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    step(); torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0.0, 0])
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        k = e.name.split("<")[0].replace("void dg::", "").replace("(anonymous namespace)::", "")[:48]
+        agg[k][0] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+        agg[k][1] += 1
+tot = sum(v[0] for v in agg.values())
+print(f"batch {B} storage {storage}: total device time {tot/1e3:.2f} ms")
+for k, (t_us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
+    print(f"  {k:50s} {t_us/1e3:8.2f} ms  x{n:3d}  {t_us/tot*100:5.1f}%")
