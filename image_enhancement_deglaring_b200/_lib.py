@@ -53,7 +53,7 @@ class DgLwParams(C.Structure):
         ("conv_w", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("gn_w", (C.c_void_p * 2) * DG_MAX_BLOCKS),
         ("gn_b", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w", C.c_void_p * 4), ("up_b", C.c_void_p * 4),
         ("conv_w_tc", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w_tc", C.c_void_p * 4),
-        ("conv_w_flip", (C.c_void_p * 2) * DG_MAX_BLOCKS),
+        ("conv_w_flip", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w_t", C.c_void_p * 4),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("path", C.c_int32), ("reserved", C.c_int32),
     ]
 

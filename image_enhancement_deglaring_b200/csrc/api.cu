@@ -328,6 +328,8 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
     for (int b = 0; b < 9; ++b)
         for (int j = 0; j < 2; ++j)
             if ((2 * b + j) > 0 && p->conv_w_flip[b][j] == nullptr) { set_error("backward: flipped weights missing"); return 2; }
+    for (int u = 0; u < 4; ++u)
+        if (p->up_w_t[u] == nullptr) { set_error("backward: transposed ConvTranspose weights missing"); return 2; }
     char* fw = static_cast<char*>(fwd_ws);
     char* bw = static_cast<char*>(bwd_ws);
     cudaError_t e = cudaMemsetAsync(bw, 0, bp.p_bytes, st);
@@ -384,7 +386,7 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
         } else {
             const int lvl = block_level(b), u = b - 5;
             float* dlow = reinterpret_cast<float*>(bw + bp.low_off[u]);
-            rc = convt_bwd_launch(p->dtype, T(i), 2 * pl.f[lvl], p->up_w[u], raw(i - 1), stats(i - 1), p->gn_w[b - 1][1],
+            rc = convt_bwd_launch(p->dtype, T(i), 2 * pl.f[lvl], p->up_w[u], p->up_w_t[u], raw(i - 1), stats(i - 1), p->gn_w[b - 1][1],
                                   p->gn_b[b - 1][1], dlow, grads + gl.up_w[u], grads + gl.up_b[u],
                                   reinterpret_cast<float*>(bw + bp.coef_off), N, Hi, Wi, pl.f[lvl + 1], pl.f[lvl],
                                   p->groups[b - 1], 1e-5f, st);

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(BW_THREADS) head_bwd_kernel(const HeadBwdArgs 
 struct ConvtBwdArgs {
     const float* dCat; int stride;      // gradient of the concat [N,H,W,stride]; the up half is channels 0..Cu
     const float* wt;                    // [2][2][Cl][Cu]
+    const float* wt_t;                  // [2][2][Cu][Cl] (transposed copy: the data-gradient kernel reads it coalesced over ci)
     const void* raw_low; const double* stats; const float* gamma; const float* beta;  // low-res producer (for A_low)
     float* dAlow;                       // [N,H/2,W/2,Cl]
     float* dWt; float* dBias;           // accumulated atomically
@@ -235,9 +236,16 @@ __global__ void __launch_bounds__(BW_THREADS) convt_bwd_data_kernel(const ConvtB
         const int n = (int)(lp / ((size_t)Wl * Hl));
         float acc = 0.f;
         for (int ab = 0; ab < 4; ++ab) {
-            const float* d = p.dCat + ((size_t)(n * p.H + 2 * i + (ab >> 1)) * p.W + 2 * j + (ab & 1)) * p.stride;
-            const float* w = p.wt + ((size_t)ab * p.Cl + ci) * p.Cu;
-            for (int co = 0; co < p.Cu; ++co) acc = fmaf(__ldg(d + co), __ldg(w + co), acc);
+            // all ci-threads of a pixel read the same gradient (broadcast); the weights are coalesced over ci
+            const float4* d = reinterpret_cast<const float4*>(p.dCat + ((size_t)(n * p.H + 2 * i + (ab >> 1)) * p.W + 2 * j + (ab & 1)) * p.stride);
+            const float* w = p.wt_t + (size_t)ab * p.Cu * p.Cl + ci;
+            for (int co = 0; co < p.Cu; co += 4) {
+                const float4 g = __ldg(d + (co >> 2));
+                acc = fmaf(g.x, __ldg(w + (size_t)co * p.Cl), acc);
+                acc = fmaf(g.y, __ldg(w + (size_t)(co + 1) * p.Cl), acc);
+                acc = fmaf(g.z, __ldg(w + (size_t)(co + 2) * p.Cl), acc);
+                acc = fmaf(g.w, __ldg(w + (size_t)(co + 3) * p.Cl), acc);
+            }
         }
         p.dAlow[e] = acc;
     }
@@ -254,25 +262,31 @@ __global__ void gn_mean_rstd_kernel(const double* stats, float* out, int C, int 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BW_THREADS) convt_bwd_weight_kernel(const ConvtBwdArgs p) {
-    // grid.x: groups of 256 (ab, ci, co) combos; grid.y: slabs of low pixels.  One accumulator per thread.
-    constexpr int SLAB = 32;  // low pixels staged per iteration
+__global__ void __launch_bounds__(BW_THREADS) convt_bwd_weight_kernel(const ConvtBwdArgs p, int slab) {
+    // grid.x: groups of 256 consecutive (ab, ci, co) combos (co fastest); grid.y: strided slabs of low pixels.  A CTA stages
+    // only the activated input channels [ci_lo, ci_hi] and the gradient positions [ab_lo, ab_hi] its combos touch.
     extern __shared__ float csm[];
     const int Cl = p.Cl, Cu = p.Cu;
-    float* alow = csm;                    // [SLAB][Cl]
-    float* dup = alow + SLAB * Cl;        // [SLAB][4][Cu]
     const int Hl = p.H / 2, Wl = p.W / 2;
     const int npix = p.N * Hl * Wl;
-    const int combo = blockIdx.x * BW_THREADS + threadIdx.x;
     const int ncombo = 4 * Cl * Cu;
+    const int c_first = blockIdx.x * BW_THREADS;
+    const int c_last = min(c_first + BW_THREADS, ncombo) - 1;
+    const int ab_lo = c_first / (Cl * Cu), ab_hi = c_last / (Cl * Cu);
+    int ci_lo = (c_first / Cu) % Cl, ci_hi = (c_last / Cu) % Cl;
+    if (ab_hi > ab_lo) { ci_lo = 0; ci_hi = Cl - 1; }
+    const int nci = ci_hi - ci_lo + 1, nab = ab_hi - ab_lo + 1;
+    float* alow = csm;                    // [slab][nci]
+    float* dup = alow + slab * nci;       // [slab][nab][Cu]
+    const int combo = c_first + threadIdx.x;
     const int co = combo % Cu, ci = (combo / Cu) % Cl, ab = combo / (Cu * Cl);
     const T* raw = reinterpret_cast<const T*>(p.raw_low);
     float acc = 0.f, bacc = 0.f;
-    const bool do_bias = blockIdx.x == 0 && threadIdx.x < 4 * Cu;  // thread -> (ab', co') partial of dbias
-    for (int base = blockIdx.y * SLAB; base < npix; base += gridDim.y * SLAB) {
+    const bool do_bias = blockIdx.x == 0 && threadIdx.x < 4 * Cu && p.dBias != nullptr;  // needs all four positions: see host
+    for (int base = blockIdx.y * slab; base < npix; base += gridDim.y * slab) {
         __syncthreads();
-        for (int idx = threadIdx.x; idx < SLAB * Cl; idx += BW_THREADS) {
-            const int c = idx % Cl, lp = base + idx / Cl;
+        for (int idx = threadIdx.x; idx < slab * nci; idx += BW_THREADS) {
+            const int c = ci_lo + idx % nci, lp = base + idx / nci;
             float v = 0.f;
             if (lp < npix) {
                 const int n = lp / (Hl * Wl);
@@ -282,8 +296,8 @@ __global__ void __launch_bounds__(BW_THREADS) convt_bwd_weight_kernel(const Conv
             }
             alow[idx] = v;
         }
-        for (int idx = threadIdx.x; idx < SLAB * 4 * Cu; idx += BW_THREADS) {
-            const int c = idx % Cu, q = (idx / Cu) % 4, lp = base + idx / (4 * Cu);
+        for (int idx = threadIdx.x; idx < slab * nab * Cu; idx += BW_THREADS) {
+            const int c = idx % Cu, q = ab_lo + (idx / Cu) % nab, lp = base + idx / (nab * Cu);
             float v = 0.f;
             if (lp < npix) {
                 const int j = lp % Wl, i = (lp / Wl) % Hl, n = lp / (Hl * Wl);
@@ -292,13 +306,42 @@ __global__ void __launch_bounds__(BW_THREADS) convt_bwd_weight_kernel(const Conv
             dup[idx] = v;
         }
         __syncthreads();
-        if (combo < ncombo)
-            for (int s = 0; s < SLAB; ++s) acc = fmaf(alow[s * Cl + ci], dup[(s * 4 + ab) * Cu + co], acc);
-        if (do_bias)
-            for (int s = 0; s < SLAB; ++s) bacc += dup[s * 4 * Cu + threadIdx.x];
+        if (combo < ncombo) {
+            const float* ap = alow + (ci - ci_lo);
+            const float* dp = dup + (ab - ab_lo) * Cu + co;
+#pragma unroll 4
+            for (int s = 0; s < slab; ++s) acc = fmaf(ap[s * nci], dp[s * nab * Cu], acc);
+        }
+        if (do_bias) {
+            const float* dp = dup + threadIdx.x;   // block 0 covers ab 0..nab-1; (ab', co') = thread index
+            if ((int)threadIdx.x < nab * Cu)
+                for (int s = 0; s < slab; ++s) bacc += dp[s * nab * Cu];
+        }
     }
     if (combo < ncombo) atomicAdd(p.dWt + ((size_t)ci * Cu + co) * 4 + ab, acc);  // parameter layout [Cl][Cu][2][2]
-    if (do_bias) atomicAdd(p.dBias + threadIdx.x % Cu, bacc);
+    if (do_bias && (int)threadIdx.x < nab * Cu) atomicAdd(p.dBias + threadIdx.x % Cu, bacc);
+}
+
+// dbias[co] = sum over every up-sampled pixel of the gradient (separate, trivially parallel reduction)
+__global__ void __launch_bounds__(BW_THREADS) convt_bwd_bias_kernel(const ConvtBwdArgs p) {
+    extern __shared__ float bsum[];  // [Cu]
+    for (int c = threadIdx.x; c < p.Cu; c += BW_THREADS) bsum[c] = 0.f;
+    __syncthreads();
+    const size_t total = (size_t)p.N * p.H * p.W * p.Cu;
+    const size_t stride = (size_t)gridDim.x * BW_THREADS;   // multiple of Cu for power-of-two Cu <= 256
+    float acc = 0.f;
+    int cur = -1;
+    for (size_t e = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; e < total; e += stride) {
+        const int c = (int)(e % p.Cu);
+        if (c != cur) {
+            if (cur >= 0) atomicAdd(&bsum[cur], acc);
+            cur = c; acc = 0.f;
+        }
+        acc += p.dCat[(e / p.Cu) * p.stride + c];
+    }
+    if (cur >= 0) atomicAdd(&bsum[cur], acc);
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.Cu; c += BW_THREADS) atomicAdd(p.dBias + c, bsum[c]);
 }
 
 // ---- optimizer tail over the flat parameter / gradient buffers -------------------------------------------------------------
@@ -395,10 +438,11 @@ int head_bwd_launch(int dtype, const void* raw, const double* stats, const float
     return check_launch("head_bwd");
 }
 
-int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const void* raw_low, const double* stats,
-                     const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias, float* coefbuf, int N,
-                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st) {
-    ConvtBwdArgs a{dCat, stride, wt, raw_low, stats, gamma, beta, dAlow, dWt, dBias, coefbuf, N, H, W, Cl, Cu, groups, eps};
+int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low,
+                     const double* stats, const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias,
+                     float* coefbuf, int N, int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st) {
+    if (Cu % 4 || (stride % 4) || (reinterpret_cast<uintptr_t>(dCat) & 15)) { set_error("convT backward: unaligned gradient"); return 3; }
+    ConvtBwdArgs a{dCat, stride, wt, wt_t, raw_low, stats, gamma, beta, dAlow, dWt, nullptr, coefbuf, N, H, W, Cl, Cu, groups, eps};
     gn_mean_rstd_kernel<<<N, 128, 0, st>>>(stats, coefbuf, Cl, groups, (double)(H / 2) * (W / 2), eps);
     count_launch();
     const size_t total = (size_t)N * (H / 2) * (W / 2) * Cl;
@@ -406,18 +450,37 @@ int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, 
     count_launch();
     int rc = check_launch("convt_bwd_data");
     if (rc) return rc;
+    // bias gradient
+    ConvtBwdArgs ab = a;
+    ab.dBias = dBias;
+    int bb = (int)(((size_t)N * H * W * Cu + BW_THREADS * 16 - 1) / (BW_THREADS * 16));
+    if (bb > 1024) bb = 1024;
+    if (bb < 1) bb = 1;
+    convt_bwd_bias_kernel<<<bb, BW_THREADS, (size_t)Cu * sizeof(float), st>>>(ab);
+    count_launch();
+    // weight gradient: 256 combos per CTA; slab sized for ~32 KB of staged operands
     const int ncombo = 4 * Cl * Cu;
-    if (4 * Cu > BW_THREADS) { set_error("convT backward: %d up channels unsupported", Cu); return 3; }
+    const int per_cta_ci = (BW_THREADS / Cu) < 1 ? 1 : (BW_THREADS / Cu) + 1;
+    const int width = (Cl * Cu >= BW_THREADS) ? (per_cta_ci + Cu) : (Cl + 4 * Cu);  // floats staged per low pixel (upper bound)
+    int slab = 8192 / width;
+    if (slab > 128) slab = 128;
+    if (slab < 8) slab = 8;
     const int npix = N * (H / 2) * (W / 2);
-    int slabs = (npix + 31) / 32;
-    if (slabs > 128) slabs = 128;
-    dim3 grid((ncombo + BW_THREADS - 1) / BW_THREADS, slabs);
-    const size_t smem = (size_t)32 * (Cl + 4 * Cu) * sizeof(float);
-    if (smem > 48 * 1024) {
-        set_error("convT backward: %zu B of shared memory (channels too large for this kernel)", smem);
-        return 3;
+    int slabs = (npix + slab - 1) / slab;
+    const int gx = (ncombo + BW_THREADS - 1) / BW_THREADS;
+    int gy = 2048 / gx;
+    if (gy < 1) gy = 1;
+    if (gy > slabs) gy = slabs;
+    dim3 grid(gx, gy);
+    const size_t smem = (size_t)slab * (size_t)width * sizeof(float);
+    if (smem > 96 * 1024) { set_error("convT backward: %zu B of shared memory", smem); return 3; }
+    static bool attr[3] = {false, false, false};
+    const int di = dtype == DG_F32 ? 0 : (dtype == DG_F16 ? 1 : 2);
+    if (!attr[di]) {
+        DG_BY_DTYPE(dtype, (cudaFuncSetAttribute(convt_bwd_weight_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)));
+        attr[di] = true;
     }
-    DG_BY_DTYPE(dtype, (convt_bwd_weight_kernel<T><<<grid, BW_THREADS, smem, st>>>(a)));
+    DG_BY_DTYPE(dtype, (convt_bwd_weight_kernel<T><<<grid, BW_THREADS, smem, st>>>(a, slab)));
     count_launch();
     return check_launch("convt_bwd_weight");
 }

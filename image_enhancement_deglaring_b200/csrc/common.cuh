@@ -190,7 +190,7 @@ int gn_bwd_apply_launch(int dtype, const void* raw, const double* stats, const f
 int head_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dOut,
                     const float* w, float* G, double* P, float* dW, float* dB, int N, int H, int W, int C, int OC, int groups,
                     float eps, cudaStream_t st);
-int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const void* raw_low, const double* stats,
+int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low, const double* stats,
                      const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias, float* coefbuf, int N,
                      int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st);
 int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, float lr,

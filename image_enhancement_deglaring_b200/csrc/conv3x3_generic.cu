@@ -262,17 +262,38 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
             }
             if constexpr (WGRAD) {
                 __syncthreads();
-                for (int combo = tid; combo < 9 * CK * COB; combo += NTHREADS) {
-                    const int co = combo % COB;
-                    const int ck = (combo / COB) % CK;
-                    const int tap = combo / (COB * CK);
-                    if (ck >= cn || co_cta + co >= Cout) continue;
+                // task = (tap, input channel of the chunk, group of 8 output channels, pixel split): 8 accumulators in
+                // registers, one activation load + two broadcast 128-bit gradient loads per 8 FMAs
+                constexpr int COG = COB / 8;
+                constexpr int NTASK = 9 * CK * COG;
+                constexpr int SPLIT = NTASK >= NTHREADS ? 1 : NTHREADS / NTASK;   // spare threads split the tile rows
+                for (int task = tid; task < NTASK * SPLIT; task += NTHREADS) {
+                    const int sp = task / NTASK;
+                    const int t2 = task - sp * NTASK;
+                    const int cg = t2 % COG;
+                    const int ck = (t2 / COG) % CK;
+                    const int tap = t2 / (COG * CK);
+                    if (ck >= cn || co_cta + cg * 8 >= Cout) continue;
                     const float* a0 = act + (ck * AH + tap / 3) * AW + tap % 3;
-                    float sum = 0.f;
-                    for (int r = 0; r < TH; ++r)
-#pragma unroll 8
-                        for (int c = 0; c < TW; ++c) sum = fmaf(a0[r * AW + c], wsm[(r * TW + c) * COB + co], sum);
-                    atomicAdd(cfg.dW + (size_t)tap * cfg.s_tap + (size_t)(ci_base + c0 + ck) * cfg.s_ci + (size_t)(co_cta + co) * cfg.s_co, sum);
+                    const float* d0 = wsm + cg * 8;
+                    float sum[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) sum[k] = 0.f;
+                    for (int r = sp; r < TH; r += SPLIT)
+#pragma unroll 4
+                        for (int c = 0; c < TW; ++c) {
+                            const float xv = a0[r * AW + c];
+                            const float4 g0 = *reinterpret_cast<const float4*>(d0 + (r * TW + c) * COB);
+                            const float4 g1 = *reinterpret_cast<const float4*>(d0 + (r * TW + c) * COB + 4);
+                            sum[0] = fmaf(xv, g0.x, sum[0]); sum[1] = fmaf(xv, g0.y, sum[1]);
+                            sum[2] = fmaf(xv, g0.z, sum[2]); sum[3] = fmaf(xv, g0.w, sum[3]);
+                            sum[4] = fmaf(xv, g1.x, sum[4]); sum[5] = fmaf(xv, g1.y, sum[5]);
+                            sum[6] = fmaf(xv, g1.z, sum[6]); sum[7] = fmaf(xv, g1.w, sum[7]);
+                        }
+                    float* dst = cfg.dW + (size_t)tap * cfg.s_tap + (size_t)(ci_base + c0 + ck) * cfg.s_ci;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (co_cta + cg * 8 + k < Cout) atomicAdd(dst + (size_t)(co_cta + cg * 8 + k) * cfg.s_co, sum[k]);
                 }
                 __syncthreads();
                 continue;

@@ -123,7 +123,9 @@ class LightweightUNet(nn.Module):
             w = ops.pack_convt2x2(m.weight)
             bt = m.bias.detach().float().contiguous()
             wtc = ops.pack_convt2x2_tc(w, pc.dtype) if self.path != 1 else None
-            keep += [w, bt, wtc]
+            wtt = m.weight.detach().float().permute(2, 3, 1, 0).contiguous() if train else None   # [2,2,Co,Ci]
+            pc.up_w_t[u] = None if wtt is None else wtt.data_ptr()
+            keep += [w, bt, wtc, wtt]
             pc.up_w_tc[u] = None if wtc is None else wtc.data_ptr()
             pc.up_w[u] = w.data_ptr()
             pc.up_b[u] = bt.data_ptr()

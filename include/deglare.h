@@ -158,6 +158,7 @@ typedef struct {
     const void* up_w_tc[4];
     const float* conv_w_flip[DG_MAX_BLOCKS][2]; /* backward only: [3][3][Cout][Cin] with taps flipped
                                                (w.flip(2,3).permute(2,3,0,1)): dgrad is a forward conv */
+    const float* up_w_t[4];                 /* backward only: ConvTranspose weights as [2][2][Cout][Cin]   */
     const float* head_w;                    /* output_conv.weight [out][f0]                */
     const float* head_b;
     int32_t path;                           /* 0 auto, 1 generic, 2 tensor-core            */

@@ -21,7 +21,12 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 agg = collections.defaultdict(lambda: [0.0, 0])
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
-        k = e.name.split("<")[0].replace("void dg::", "").replace("(anonymous namespace)::", "")[:48]
+        k = e.name.replace("void dg::", "").replace("(anonymous namespace)::", "")
+        if "conv3x3_generic_kernel" in k:
+            k = "conv3x3_generic " + ("WGRAD" if "true" in k.split(">(")[0].split(",")[-1] or "(bool)1" in k else "fwd/dgrad") + " " + k.split("<")[1].split(",")[0]
+        else:
+            k = k.split("<")[0]
+        k = k[:56]
         agg[k][0] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
         agg[k][1] += 1
 tot = sum(v[0] for v in agg.values())
