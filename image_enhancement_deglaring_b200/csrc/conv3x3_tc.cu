@@ -54,6 +54,7 @@ template <int CIN_, int COUT_, int MODE_, int TH_, int TW_, int WM_, int WN_, bo
 struct Geo {
     static constexpr int CIN = CIN_, COUT = COUT_, MODE = MODE_, TH = TH_, TW = TW_, WM = WM_, WN = WN_;
     static constexpr bool STREAM = STREAM_;
+    static constexpr int THREADS = 32 * WM * WN;  // 8 warps, or 4 for the narrow layers (more, smaller CTAs per SM)
     static constexpr int PH = TH + 2, PW = TW + 2, NC8 = CIN / 8;
     static constexpr int PLANE = pad_plane(PH * PW, NC8);
     static constexpr int KC = CIN >= 16 ? CIN / 16 : 1;
@@ -92,10 +93,10 @@ struct Geo {
     // Resident CTAs per SM the register allocator must leave room for (__launch_bounds__): the narrow memory-bound layers
     // live on inter-CTA overlap of their staging / MMA phases (4 CTAs = 64 registers; a 74-register build ran 12 % slower),
     // the compute-heavy ones need ~100 registers for 64 accumulators.
-    static constexpr int CTA_TARGET = (MG * NT * 4 <= 32) ? (MODE == M_POOL ? 3 : 4) : 2;
+    static constexpr int CTA_TARGET = ((MG * NT * 4 <= 32) ? (MODE == M_POOL ? 3 : 4) : 2) * (256 / THREADS);
     static constexpr int CTA_SMEM = (227 * 1024) / (SMEM_BYTES + 1024);
     static constexpr int MIN_CTAS = CTA_SMEM < 1 ? 1 : (CTA_SMEM < CTA_TARGET ? CTA_SMEM : CTA_TARGET);
-    static_assert(WM * WN == 8, "8 warps");
+    static_assert(WM * WN == 8 || WM * WN == 4, "4 or 8 warps");
     static_assert(MTILES % WM == 0 && (COUT / 8) % WN == 0, "tile split");
     static_assert(MPW % MG == 0, "m-tile groups");
     static_assert(!STREAM || CIN >= 16, "streamed weights: one tap per stage");
@@ -115,7 +116,7 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
                                              const float2* __restrict__ cfs, int plane0, int y0, int x0, int H, int W) {
     constexpr int NC = C / 8;
     constexpr int NPIX = G::PH * G::PW;
-    constexpr int PSTRIDE = TC_THREADS / NC;                       // pixels between two slots of a thread
+    constexpr int PSTRIDE = G::THREADS / NC;                       // pixels between two slots of a thread
     constexpr int NSLOT = (NPIX + PSTRIDE - 1) / PSTRIDE;
     constexpr int MAXB = POOL ? 2 : 5;
     constexpr int ITERS = (NSLOT + MAXB - 1) / MAXB;
@@ -123,7 +124,7 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
     constexpr int DR = PSTRIDE / G::PW, DC = PSTRIDE % G::PW;      // slot-to-slot advance of (row, column)
     constexpr bool H2 = (ACT == ACT_HALF2) && !POOL && std::is_same<T, __half>::value;
     constexpr int FACT = H2 ? ACT_TANH : ACT;                      // float flavour used when half2 does not apply
-    static_assert(TC_THREADS % NC == 0, "chunk ownership");
+    static_assert(G::THREADS % NC == 0, "chunk ownership");
     const int c8 = threadIdx.x % NC;
     const int p0 = threadIdx.x / NC;
     float2 cf[H2 ? 1 : 8];
@@ -209,7 +210,7 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
 }
 
 template <typename T, typename G, int ACT>
-__global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(const TcArgs p) {
+__global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) conv3x3_tc_kernel(const TcArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* act = smem + G::OFF_ACT;
     unsigned char* wgt = smem + G::OFF_WGT;
@@ -228,20 +229,20 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
         constexpr int BYTES = G::STAGE_CHUNKS * G::COUT * 32;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wgt) + (size_t)stage * BYTES;
         const uint32_t dst = smem_u32(wgt) + buf * BYTES;
-        for (int i = tid * 16; i < BYTES; i += TC_THREADS * 16) cp_async16(dst + i, src + i);
+        for (int i = tid * 16; i < BYTES; i += G::THREADS * 16) cp_async16(dst + i, src + i);
     };
     load_stage(0, 0);
     if constexpr (G::MODE == M_UPCAT) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.ctw);
         const uint32_t dst = smem_u32(smem + G::OFF_CTW);
-        for (int i = tid * 16; i < G::CTW_BYTES; i += TC_THREADS * 16) cp_async16(dst + i, src + i);
+        for (int i = tid * 16; i < G::CTW_BYTES; i += G::THREADS * 16) cp_async16(dst + i, src + i);
     }
     cp_async_commit();
 
     pdl_wait();  // everything above overlapped the producer's tail; its activations / statistics are complete from here on
     // ---- (1) GroupNorm coefficients (a, b) per source channel ---------------------------------------
     if constexpr (G::MODE == M_UPCAT) {
-        for (int c = tid; c < G::CL + G::CU; c += TC_THREADS) {
+        for (int c = tid; c < G::CL + G::CU; c += G::THREADS) {
             float a, b;
             if (c < G::CL) {
                 if (p.cf0) { a = __ldg(p.cf0 + (size_t)(n * G::CL + c) * 2); b = __ldg(p.cf0 + (size_t)(n * G::CL + c) * 2 + 1); }
@@ -255,11 +256,11 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
             coef[c] = make_float2(a, b);
         }
         float* ctb = reinterpret_cast<float*>(smem + G::OFF_CTB);
-        for (int c = tid; c < G::CU; c += TC_THREADS) ctb[c] = p.ctb[c];
+        for (int c = tid; c < G::CU; c += G::THREADS) ctb[c] = p.ctb[c];
         // scatter mask of every low pixel (li, lj): it feeds the 2x2 block at tile (2li-1+a, 2lj-1+b); bit (2a+b) = that
         // position lies inside the staged tile, bit 4+(2a+b) = it also lies inside the image (else the concat is zero there)
         unsigned char* okt = smem + G::OFF_CTB + G::CU * 4;
-        for (int lp = tid; lp < G::LM; lp += TC_THREADS) {
+        for (int lp = tid; lp < G::LM; lp += G::THREADS) {
             const int li = lp / G::LPW, lj = lp - li * G::LPW;
             const int r0 = 2 * li - 1, c0 = 2 * lj - 1;
             uint32_t m = 0;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
             okt[lp] = (unsigned char)m;
         }
     } else if constexpr (G::MODE == M_CAT2) {
-        for (int c = tid; c < G::COUT; c += TC_THREADS) {
+        for (int c = tid; c < G::COUT; c += G::THREADS) {
             float a, b;
             if (p.cf1) { a = __ldg(p.cf1 + (size_t)(n * G::COUT + c) * 2); b = __ldg(p.cf1 + (size_t)(n * G::COUT + c) * 2 + 1); }
             else gn_coef(p.st1, p.g1, p.b1, n, G::COUT, p.groups1, c, (double)H * W, p.eps, a, b);
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
         }
     } else {
         const double plane = G::MODE == M_POOL ? (double)(2 * H) * (2 * W) : (double)H * W;
-        for (int c = tid; c < G::CIN; c += TC_THREADS) {
+        for (int c = tid; c < G::CIN; c += G::THREADS) {
             float a, b;
             if (p.cf0) { a = __ldg(p.cf0 + (size_t)(n * G::CIN + c) * 2); b = __ldg(p.cf0 + (size_t)(n * G::CIN + c) * 2 + 1); }
             else gn_coef(p.st0, p.g0, p.b0, n, G::CIN, p.groups0, c, plane, p.eps, a, b);
@@ -315,22 +316,22 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
         const int Hl = H / 2, Wl = W / 2;
         const int li0 = (y0 >> 1) - 1, lj0 = (x0 >> 1) - 1;
         {
-            static_assert(TC_THREADS % G::NCL8 == 0, "chunk ownership");
+            static_assert(G::THREADS % G::NCL8 == 0, "chunk ownership");
             const int c8 = tid % G::NCL8;
             float2 cf[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) cf[k] = coef[c8 * 8 + k];
             constexpr int LITEMS = G::LM * G::NCL8;
-            constexpr int LSLOTS = (LITEMS + TC_THREADS - 1) / TC_THREADS;
+            constexpr int LSLOTS = (LITEMS + G::THREADS - 1) / G::THREADS;
             constexpr int LB = LSLOTS < 4 ? LSLOTS : 4;  // loads in flight per thread
             const unsigned char* rawn = reinterpret_cast<const unsigned char*>(raw) + (size_t)n * Hl * Wl * G::CL * 2 + c8 * 16;
 #pragma unroll 1
-            for (int idx0 = tid; idx0 < LITEMS; idx0 += TC_THREADS * LB) {
+            for (int idx0 = tid; idx0 < LITEMS; idx0 += G::THREADS * LB) {
                 uint4 q[LB];
                 bool ok[LB];
 #pragma unroll
                 for (int b = 0; b < LB; ++b) {
-                    const int lp = (idx0 + b * TC_THREADS) / G::NCL8;
+                    const int lp = (idx0 + b * G::THREADS) / G::NCL8;
                     const int li = lp / G::LPW;
                     const int gi = li0 + li, gj = lj0 + lp - li * G::LPW;
                     ok[b] = lp < G::LM && (unsigned)gi < (unsigned)Hl && (unsigned)gj < (unsigned)Wl;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
                 }
 #pragma unroll
                 for (int b = 0; b < LB; ++b) {
-                    const int lp = (idx0 + b * TC_THREADS) / G::NCL8;
+                    const int lp = (idx0 + b * G::THREADS) / G::NCL8;
                     if (lp >= G::LM) continue;
                     uint4 o = make_uint4(0u, 0u, 0u, 0u);
                     if (ok[b]) {
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
         const float* ctb = reinterpret_cast<const float*>(smem + G::OFF_CTB);
         constexpr int NG = G::CT_NT / G::CT_NTG;  // work item = (16 low pixels, CT_NTG n-tiles), round-robin over warps
 #pragma unroll 1
-        for (int item = warp; item < G::LMT * NG; item += 8) {
+        for (int item = warp; item < G::LMT * NG; item += G::WM * G::WN) {
             const int mt = item / NG;
             const int ng = (item % NG) * G::CT_NTG;
             int lp_lane = mt * 16 + (lane & 15);
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
         }
     __syncthreads();
     if (p.out_stats != nullptr)
-        for (int c = tid; c < 2 * G::COUT; c += TC_THREADS) {
+        for (int c = tid; c < 2 * G::COUT; c += G::THREADS) {
             double t = 0.0;
 #pragma unroll
             for (int w = 0; w < G::WM; ++w) t += (double)statf[w * G::COUT * 2 + c];
@@ -644,7 +645,7 @@ static int launch_geo(const TcArgs& t, cudaStream_t st) {
         attr_done = true;
     }
     dim3 grid((t.W + G::TW - 1) / G::TW, (t.H + G::TH - 1) / G::TH, t.N);
-    cudaError_t le = launch_kernel(kern, grid, dim3(TC_THREADS), (size_t)G::SMEM_BYTES, st, t);
+    cudaError_t le = launch_kernel(kern, grid, dim3(G::THREADS), (size_t)G::SMEM_BYTES, st, t);
     if (le != cudaSuccess) { set_error("conv3x3_tc launch: %s", cudaGetErrorString(le)); return 10; }
     count_launch();
     return check_launch("conv3x3_tc");
@@ -656,7 +657,7 @@ static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin
     const int cout = a.cout;
 #define DG_TC(CI, CO, MD, TH, TW, WM, WN, ST) \
     if (cin == CI && cout == CO && mode == MD) return launch_geo<T, Geo<CI, CO, MD, TH, TW, WM, WN, ST>, ACT>(t, st);
-    DG_TC(8, 8, M_SAME, 16, 64, 8, 1, false)      // enc1.3, dec1.3
+    DG_TC(8, 8, M_SAME, 16, 32, 4, 1, false)      // enc1.3, dec1.3 (128-thread CTAs: 8 independent phase streams per SM)
     DG_TC(8, 16, M_POOL, 16, 64, 8, 1, false)     // enc2.0
     DG_TC(16, 16, M_SAME, 16, 64, 8, 1, false)    // enc2.3, dec2.3
     DG_TC(16, 32, M_POOL, 16, 32, 8, 1, false)    // enc3.0
