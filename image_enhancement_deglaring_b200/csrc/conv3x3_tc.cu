@@ -54,7 +54,13 @@ template <int CIN_, int COUT_, int MODE_, int TH_, int TW_, int WM_, int WN_, bo
 struct Geo {
     static constexpr int CIN = CIN_, COUT = COUT_, MODE = MODE_, TH = TH_, TW = TW_, WM = WM_, WN = WN_;
     static constexpr bool STREAM = STREAM_;
-    static constexpr int THREADS = 32 * WM * WN;  // 8 warps, or 4 for the narrow layers (more, smaller CTAs per SM)
+    static constexpr int THREADS = 32 * WM * WN;
+    // ROLL: the narrow layers are bound by the shared-memory data pipe (profile r1c: l1tex LSU wavefronts at ~70 % of peak,
+    // ~3/4 of them the ldmatrix re-reads of the same pixels for the 9 taps).  There a warp owns a COLUMN of consecutive
+    // output rows of one 16-pixel segment, loads each (input row, kx) fragment once and feeds it to the three output rows
+    // that use it (ky = 0, 1, 2); the weights live in registers.  ldmatrix traffic drops from 9 to ~3.75 reads per pixel.
+    static constexpr bool ROLL = !STREAM_ && CIN_ <= 16 && (COUT_ / 8 / WN_) <= 2 && (WM_ % (TW_ / 16)) == 0;
+    static constexpr int RW = TH_ / (WM_ / (TW_ / 16) > 0 ? WM_ / (TW_ / 16) : 1);  // rows per warp in ROLL mode  // 8 warps, or 4 for the narrow layers (more, smaller CTAs per SM)
     static constexpr int PH = TH + 2, PW = TW + 2, NC8 = CIN / 8;
     static constexpr int PLANE = pad_plane(PH * PW, NC8);
     static constexpr int KC = CIN >= 16 ? CIN / 16 : 1;
@@ -424,6 +430,92 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
     for (int i = 0; i < G::NT; ++i) s1[i][0] = s1[i][1] = s2[i][0] = s2[i][1] = 0.f;
     T* outp = reinterpret_cast<T*>(p.out);
 
+    if constexpr (G::ROLL) {
+        static_assert(G::RW * (G::WM / G::SEGS) == G::TH && G::RW * G::NT * 4 <= 32, "ROLL: rows per warp / accumulator budget");
+        cp_async_wait<0>();
+        __syncthreads();  // weights + staged tile visible to every warp
+        // B fragments of all 9 taps in registers: b[tap][nt][kh] = W[tap][ci = 8*kh + 2*(lane&3) (+1)][co = nt*8 + lane>>2]
+        constexpr int KH = G::CIN == 8 ? 1 : 2;
+        uint32_t bw[9][G::NT][KH];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int i = 0; i < G::NT; ++i)
+#pragma unroll
+                for (int kh = 0; kh < KH; ++kh) {
+                    const int chunk = G::CIN == 8 ? t / 2 : t, khh = G::CIN == 8 ? (t & 1) : kh;
+                    bw[t][i][kh] = *reinterpret_cast<const uint32_t*>(
+                        wgt + ((size_t)(chunk * 2 + khh) * G::COUT + (nt0 + i) * 8 + (lane >> 2)) * 16 + (lane & 3) * 4);
+                }
+        const int seg = wm % G::SEGS, rb = wm / G::SEGS;
+        float acc[G::RW][G::NT][4];
+#pragma unroll
+        for (int y = 0; y < G::RW; ++y)
+#pragma unroll
+            for (int i = 0; i < G::NT; ++i) acc[y][i][0] = acc[y][i][1] = acc[y][i][2] = acc[y][i][3] = 0.f;
+        // lane's pixel of the m-tile in the haloed tile, input row 0 of this warp's block, kx = 0
+        const uint32_t a_base = act_u + (uint32_t)(((rb * G::RW) * G::PW + seg * 16 + (lane & 15)) * 16);
+#pragma unroll
+        for (int r = 0; r < G::RW + 2; ++r) {  // input row r of the block feeds output rows r-2 .. r (ky = r - y)
+            const uint32_t a_row = a_base + (uint32_t)(r * G::PW * 16);
+            if constexpr (G::CIN == 8) {
+                uint32_t f0, f1, f2, f3, g0, g1;
+                ldsm_x4(a_row + (lane >> 4) * 16, f0, f1, f2, f3);   // lanes 0-15: kx = 0, lanes 16-31: kx = 1 (next pixel)
+                ldsm_x2(a_row + 32, g0, g1);                          // kx = 2
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int y = r - ky;
+                    if (y < 0 || y >= G::RW) continue;
+#pragma unroll
+                    for (int i = 0; i < G::NT; ++i) {
+                        mma16816<T>(acc[y][i], f0, f1, f2, f3, bw[ky * 3][i][0], bw[ky * 3 + 1][i][0]);
+                        mma16808<T>(acc[y][i], g0, g1, bw[ky * 3 + 2][i][0]);
+                    }
+                }
+            } else {
+                uint32_t f[3][4];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)   // lanes 0-15: channels 0-7 (plane 0), lanes 16-31: channels 8-15 (plane 1)
+                    ldsm_x4(a_row + kx * 16 + (lane >> 4) * (G::PLANE * 16), f[kx][0], f[kx][1], f[kx][2], f[kx][3]);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int y = r - ky;
+                    if (y < 0 || y >= G::RW) continue;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int i = 0; i < G::NT; ++i)
+                            mma16816<T>(acc[y][i], f[kx][0], f[kx][1], f[kx][2], f[kx][3], bw[ky * 3 + kx][i][0], bw[ky * 3 + kx][i][KH - 1]);
+                }
+            }
+        }
+        // epilogue: this warp's RW consecutive rows of one 16-pixel segment
+        const bool full = (y0 + G::TH <= H) && (x0 + G::TW <= W);
+        const int gx = x0 + seg * 16 + (lane >> 2);
+        const uint32_t orow = (uint32_t)W * G::COUT;
+        T* obase = outp + ((size_t)(n * H + y0 + rb * G::RW) * W + gx) * G::COUT + nt0 * 8 + 2 * (lane & 3);
+        auto epilogue = [&](auto full_c) {
+            constexpr bool FULL = decltype(full_c)::value;
+#pragma unroll
+            for (int y = 0; y < G::RW; ++y) {
+                const int gy = y0 + rb * G::RW + y;
+                T* o = obase + (uint32_t)y * orow;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const bool ok = FULL || (gy < H && gx + 8 * hf < W);
+#pragma unroll
+                    for (int i = 0; i < G::NT; ++i) {
+                        const float v0 = ok ? acc[y][i][2 * hf] : 0.f, v1 = ok ? acc[y][i][2 * hf + 1] : 0.f;
+                        if (ok) *reinterpret_cast<uint32_t*>(o + hf * 8 * G::COUT + i * 8) = pack2<T>(v0, v1);
+                        s1[i][0] += v0; s2[i][0] = fmaf(v0, v0, s2[i][0]);
+                        s1[i][1] += v1; s2[i][1] = fmaf(v1, v1, s2[i][1]);
+                    }
+                }
+            }
+        };
+        if (full) epilogue(std::true_type{});
+        else epilogue(std::false_type{});
+    } else
 #pragma unroll 1
     for (int g = 0; g < G::MPW; g += G::MG) {
         float acc[G::MG][G::NT][4];
@@ -658,8 +750,8 @@ static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin
 #define DG_TC(CI, CO, MD, TH, TW, WM, WN, ST) \
     if (cin == CI && cout == CO && mode == MD) return launch_geo<T, Geo<CI, CO, MD, TH, TW, WM, WN, ST>, ACT>(t, st);
     DG_TC(8, 8, M_SAME, 16, 32, 4, 1, false)      // enc1.3, dec1.3 (128-thread CTAs: 8 independent phase streams per SM)
-    DG_TC(8, 16, M_POOL, 16, 64, 8, 1, false)     // enc2.0
-    DG_TC(16, 16, M_SAME, 16, 64, 8, 1, false)    // enc2.3, dec2.3
+    DG_TC(8, 16, M_POOL, 16, 32, 8, 1, false)     // enc2.0 (ROLL: 4 rows per warp)
+    DG_TC(16, 16, M_SAME, 16, 32, 8, 1, false)    // enc2.3, dec2.3 (ROLL: 4 row blocks x 2 segments, 4 rows per warp)
     DG_TC(16, 32, M_POOL, 16, 32, 8, 1, false)    // enc3.0
     DG_TC(32, 32, M_SAME, 16, 32, 8, 1, false)    // enc3.3, dec3.3
     DG_TC(32, 64, M_POOL, 8, 32, 4, 2, false)     // enc4.0
