@@ -59,8 +59,8 @@ struct Geo {
     // ~3/4 of them the ldmatrix re-reads of the same pixels for the 9 taps).  There a warp owns a COLUMN of consecutive
     // output rows of one 16-pixel segment, loads each (input row, kx) fragment once and feeds it to the three output rows
     // that use it (ky = 0, 1, 2); the weights live in registers.  ldmatrix traffic drops from 9 to ~3.75 reads per pixel.
-    static constexpr bool ROLL = !STREAM_ && CIN_ <= 16 && (COUT_ / 8 / WN_) <= 2 && (WM_ % (TW_ / 16)) == 0;
-    static constexpr int RW = TH_ / (WM_ / (TW_ / 16) > 0 ? WM_ / (TW_ / 16) : 1);  // rows per warp in ROLL mode  // 8 warps, or 4 for the narrow layers (more, smaller CTAs per SM)
+    static constexpr int RW = TH_ / (WM_ / (TW_ / 16) > 0 ? WM_ / (TW_ / 16) : 1);  // rows per warp in ROLL mode
+    static constexpr bool ROLL = !STREAM_ && CIN_ <= 16 && (WM_ % (TW_ / 16)) == 0 && RW * (COUT_ / 8 / WN_) * 4 <= 32;
     static constexpr int PH = TH + 2, PW = TW + 2, NC8 = CIN / 8;
     static constexpr int PLANE = pad_plane(PH * PW, NC8);
     static constexpr int KC = CIN >= 16 ? CIN / 16 : 1;
@@ -99,7 +99,7 @@ struct Geo {
     // Resident CTAs per SM the register allocator must leave room for (__launch_bounds__): the narrow memory-bound layers
     // live on inter-CTA overlap of their staging / MMA phases (4 CTAs = 64 registers; a 74-register build ran 12 % slower),
     // the compute-heavy ones need ~100 registers for 64 accumulators.
-    static constexpr int CTA_TARGET = ((MG * NT * 4 <= 32) ? (MODE == M_POOL ? 3 : 4) : 2) * (256 / THREADS);
+    static constexpr int CTA_TARGET = ((MG * NT * 4 <= 32) ? ((MODE == M_POOL || (ROLL && CIN == 16 && NT == 2)) ? 3 : 4) : 2) * (256 / THREADS);
     static constexpr int CTA_SMEM = (227 * 1024) / (SMEM_BYTES + 1024);
     static constexpr int MIN_CTAS = CTA_SMEM < 1 ? 1 : (CTA_SMEM < CTA_TARGET ? CTA_SMEM : CTA_TARGET);
     static_assert(WM * WN == 8 || WM * WN == 4, "4 or 8 warps");
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
         };
         if (full) epilogue(std::true_type{});
         else epilogue(std::false_type{});
-    } else
+    } else {  // (braces: a bare `else` followed by `#pragma unroll` made nvcc drop the statement after the loop)
 #pragma unroll 1
     for (int g = 0; g < G::MPW; g += G::MG) {
         float acc[G::MG][G::NT][4];
@@ -616,6 +616,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
         };
         if (full) epilogue(std::true_type{});
         else epilogue(std::false_type{});
+    }
     }
     // ---- (5) GroupNorm statistics: lanes with equal lane&3 hold the same channels -------------------------
 #pragma unroll
@@ -750,8 +751,8 @@ static int dispatch(const dg_conv3x3_args& a, const TcArgs& t, int mode, int cin
 #define DG_TC(CI, CO, MD, TH, TW, WM, WN, ST) \
     if (cin == CI && cout == CO && mode == MD) return launch_geo<T, Geo<CI, CO, MD, TH, TW, WM, WN, ST>, ACT>(t, st);
     DG_TC(8, 8, M_SAME, 16, 32, 4, 1, false)      // enc1.3, dec1.3 (128-thread CTAs: 8 independent phase streams per SM)
-    DG_TC(8, 16, M_POOL, 16, 32, 8, 1, false)     // enc2.0 (ROLL: 4 rows per warp)
-    DG_TC(16, 16, M_SAME, 16, 32, 8, 1, false)    // enc2.3, dec2.3 (ROLL: 4 row blocks x 2 segments, 4 rows per warp)
+    DG_TC(8, 16, M_POOL, 16, 64, 8, 1, false)     // enc2.0 (ROLL measured slower: .135 vs .112 ms, pooled staging wants the wide tile)
+    DG_TC(16, 16, M_SAME, 16, 64, 8, 1, false)    // enc2.3, dec2.3 (ROLL at 16x32 measured slower: .117 vs .099 ms)
     DG_TC(16, 32, M_POOL, 16, 32, 8, 1, false)    // enc3.0
     DG_TC(32, 32, M_SAME, 16, 32, 8, 1, false)    // enc3.3, dec3.3
     DG_TC(32, 64, M_POOL, 8, 32, 4, 2, false)     // enc4.0
