@@ -251,6 +251,21 @@ def main():
     e2e_value = world * B * e2e_steps / float(t.item())
     e2e_err = float((hy.to(dev) - y).abs().max())
 
+    # ---- the same, uint8 images in / uint8 images out (api/app.py:153,190-193 folded into the kernels)
+    hx8 = (hx * 255).to(torch.uint8).pin_memory()
+    hy8 = torch.empty((B, 1, H, W), dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        sess.run_pinned_u8(hx8, hy8)
+    barrier()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        sess.run_pinned_u8(hx8, hy8)
+    barrier()
+    t = torch.tensor([time.perf_counter() - te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * B * e2e_steps / float(t.item())
+
     # ---- per-kernel device times (CUDA events on the launching stream) -> roofline of the dominant kernel
     roofline = None
     if rank == 0:
@@ -318,6 +333,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 4, "d2h_bytes_per_step": B * H * W * 4,
                     "steps": e2e_steps, "api": "InferenceSession.run_pinned -> dg_lw_infer_host (pinned host buffers)",
                     "max_abs_vs_device_path": e2e_err},
+            "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": B * H * W,
+                       "steps": e2e_steps, "api": "InferenceSession.run_pinned_u8 -> dg_lw_infer_host_u8 (uint8 pixels in and out, "
+                                                  "/255 and clip*255 on the GPU as api/app.py:153,190-193 do on the host)"},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

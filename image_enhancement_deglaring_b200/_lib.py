@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdeglare.so")
 
 DG_F32, DG_F16, DG_BF16 = 0, 1, 2
-DG_X_SAME, DG_X_POOL2, DG_X_UP2, DG_X_CONVT2, DG_X_IMAGE = 0, 1, 2, 3, 4
+DG_X_SAME, DG_X_POOL2, DG_X_UP2, DG_X_CONVT2, DG_X_IMAGE, DG_X_IMAGE_U8 = 0, 1, 2, 3, 4, 5
 DG_MAX_BLOCKS = 10
 
 DTYPE_CODES = {"fp32": DG_F32, "fp16": DG_F16, "bf16": DG_BF16}
@@ -42,7 +42,7 @@ class DgHeadArgs(C.Structure):
     _fields_ = [
         ("src", DgSrc), ("dtype", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("cout", C.c_int32), ("weight", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
-        ("target", C.c_void_p), ("l1_sum", C.c_void_p), ("eps", C.c_float), ("reserved", C.c_int32),
+        ("target", C.c_void_p), ("l1_sum", C.c_void_p), ("eps", C.c_float), ("out_kind", C.c_int32),
     ]
 
 
@@ -86,6 +86,10 @@ SYMBOLS = {
                                            C.POINTER(C.c_size_t)]),
     "dg_lw_infer_host": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_size_t]),
+    "dg_lw_forward_u8": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dg_lw_infer_host_u8": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p, C.c_size_t]),
     "dg_tc_conv3x3_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "dg_pack_conv3x3_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_tc_convt2x2_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),

@@ -43,7 +43,7 @@ static int validate_src(const dg_src& s, const char* who) {
         set_error("%s: ConvTranspose parameters missing", who);
         return 2;
     }
-    if (s.xform < DG_X_SAME || s.xform > DG_X_IMAGE) { set_error("%s: bad xform %d", who, s.xform); return 2; }
+    if (s.xform < DG_X_SAME || s.xform > DG_X_IMAGE_U8) { set_error("%s: bad xform %d", who, s.xform); return 2; }
     return 0;
 }
 
@@ -122,9 +122,10 @@ static dg_src gn_src(const dg_lw_params* p, const LwPlan& pl, char* ws, int conv
     return s;
 }
 
-static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, int H, int W, void* workspace,
+// io: bit 0 = x is uint8 (normalised by 1/255 on load), bit 1 = y is uint8 (clip + quantise in the head)
+static int lw_forward(const dg_lw_params* p, const void* x, void* y, int N, int H, int W, void* workspace,
                       size_t ws_bytes, const float* target, double* l1_sum, cudaStream_t stream,
-                      cudaEvent_t* evs = nullptr) {
+                      cudaEvent_t* evs = nullptr, int io = 0) {
     LwPlan pl;
     int rc = make_plan(p, N, H, W, &pl);
     if (rc) return rc;
@@ -162,7 +163,7 @@ static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, in
             a.src[0].raw = x;
             a.src[0].channels = p->in_channels;
             a.src[0].groups = 1;
-            a.src[0].xform = DG_X_IMAGE;
+            a.src[0].xform = (io & 1) ? DG_X_IMAGE_U8 : DG_X_IMAGE;
         } else if (i % 2 == 1) {
             a.src[0] = gn_src(p, pl, ws, i - 1, DG_X_SAME);
         } else if (b < 5) {
@@ -209,6 +210,7 @@ static int lw_forward(const dg_lw_params* p, const float* x, float* y, int N, in
     h.target = target;
     h.l1_sum = l1_sum;
     h.eps = 1e-5f;
+    h.out_kind = (io & 2) ? 1 : 0;
     rc = dg_head1x1(&h, reinterpret_cast<dg_stream_t>(stream));
     if (evs) cudaEventRecord(evs[19], stream);
     return rc;
@@ -401,7 +403,7 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
 // ---- host-buffer pipeline state --------------------------------------------------------------
 struct HostPipe {
     bool ready = false;
-    cudaStream_t s_in, s_cmp, s_out;
+    cudaStream_t s_in, s_cmp[2], s_out;
     cudaEvent_t in_done[2], cmp_done[2], out_done[2];
 };
 static HostPipe g_pipe;
@@ -410,7 +412,8 @@ static int pipe_init() {
     if (g_pipe.ready) return 0;
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&g_pipe.s_in, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&g_pipe.s_cmp, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&g_pipe.s_cmp[0], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&g_pipe.s_cmp[1], cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&g_pipe.s_out, cudaStreamNonBlocking)) != cudaSuccess) {
         set_error("stream create: %s", cudaGetErrorString(e));
         return 10;
@@ -603,12 +606,14 @@ int dg_lw_host_scratch_bytes(const dg_lw_params* p, int32_t chunk, int32_t H, in
     if (rc) return rc;
     const size_t in_b = align_up((size_t)chunk * p->in_channels * H * W * sizeof(float), 256);
     const size_t out_b = align_up((size_t)chunk * p->out_channels * H * W * sizeof(float), 256);
-    if (bytes) *bytes = 2 * in_b + 2 * out_b + pl.total_bytes;
+    if (bytes) *bytes = 2 * in_b + 2 * out_b + 2 * align_up(pl.total_bytes, 256);
     return 0;
 }
 
-int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, int32_t N, int32_t H, int32_t W,
-                     int32_t chunk, void* dev_ws, size_t dev_ws_bytes) {
+// Chunk i: H2D on s_in -> forward on s_cmp[i & 1] with workspace i & 1 -> D2H on s_out.  Two compute streams let the
+// under-filled deep layers of one chunk (16 images x 8 tiles < 148 SMs) overlap the next chunk's wide layers.
+static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host_y, int N, int H, int W, int chunk,
+                           void* dev_ws, size_t dev_ws_bytes, int io) {
     if (chunk < 1) { set_error("infer_host: chunk %d", chunk); return 2; }
     if (chunk > N) chunk = N;
     LwPlan pl;
@@ -618,36 +623,57 @@ int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, 
     dg_lw_host_scratch_bytes(p, chunk, H, W, &need);
     if (dev_ws == nullptr || dev_ws_bytes < need) { set_error("infer_host: scratch %zu < %zu", dev_ws_bytes, need); return 4; }
     if (host_x == nullptr || host_y == nullptr) { set_error("infer_host: null host buffer"); return 2; }
-    if ((rc = pipe_init())) return rc;
+    if ((rc = dg::pipe_init())) return rc;
+    const size_t esz_in = (io & 1) ? 1 : sizeof(float), esz_out = (io & 2) ? 1 : sizeof(float);
     const size_t in_img = (size_t)p->in_channels * H * W, out_img = (size_t)p->out_channels * H * W;
     const size_t in_b = align_up(chunk * in_img * sizeof(float), 256);
     const size_t out_b = align_up(chunk * out_img * sizeof(float), 256);
+    const size_t ws_b = align_up(pl.total_bytes, 256);
     char* base = static_cast<char*>(dev_ws);
-    float* dx[2] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + in_b)};
-    float* dy[2] = {reinterpret_cast<float*>(base + 2 * in_b), reinterpret_cast<float*>(base + 2 * in_b + out_b)};
-    void* ws = base + 2 * in_b + 2 * out_b;
-    HostPipe& P = g_pipe;
+    char* dx[2] = {base, base + in_b};
+    char* dy[2] = {base + 2 * in_b, base + 2 * in_b + out_b};
+    char* ws[2] = {base + 2 * in_b + 2 * out_b, base + 2 * in_b + 2 * out_b + ws_b};
+    dg::HostPipe& P = dg::g_pipe;
+    const char* hx = static_cast<const char*>(host_x);
+    char* hy = static_cast<char*>(host_y);
     const int nchunks = (N + chunk - 1) / chunk;
     for (int i = 0; i < nchunks; ++i) {
         const int b = i & 1;
         const int n0 = i * chunk;
         const int nn = (N - n0 < chunk) ? (N - n0) : chunk;
         if (i >= 2) cudaStreamWaitEvent(P.s_in, P.cmp_done[b], 0);  // dx[b] consumed by chunk i-2
-        cudaMemcpyAsync(dx[b], host_x + (size_t)n0 * in_img, nn * in_img * sizeof(float), cudaMemcpyHostToDevice, P.s_in);
+        cudaMemcpyAsync(dx[b], hx + (size_t)n0 * in_img * esz_in, nn * in_img * esz_in, cudaMemcpyHostToDevice, P.s_in);
         cudaEventRecord(P.in_done[b], P.s_in);
-        cudaStreamWaitEvent(P.s_cmp, P.in_done[b], 0);
-        if (i >= 2) cudaStreamWaitEvent(P.s_cmp, P.out_done[b], 0);  // dy[b] drained by chunk i-2
-        rc = lw_forward(p, dx[b], dy[b], nn, H, W, ws, pl.total_bytes, nullptr, nullptr, P.s_cmp);
+        cudaStreamWaitEvent(P.s_cmp[b], P.in_done[b], 0);
+        if (i >= 2) cudaStreamWaitEvent(P.s_cmp[b], P.out_done[b], 0);  // dy[b] drained by chunk i-2
+        rc = dg::lw_forward(p, dx[b], dy[b], nn, H, W, ws[b], pl.total_bytes, nullptr, nullptr, P.s_cmp[b], nullptr, io);
         if (rc) { cudaDeviceSynchronize(); return rc; }
-        cudaEventRecord(P.cmp_done[b], P.s_cmp);
+        cudaEventRecord(P.cmp_done[b], P.s_cmp[b]);
         cudaStreamWaitEvent(P.s_out, P.cmp_done[b], 0);
-        cudaMemcpyAsync(host_y + (size_t)n0 * out_img, dy[b], nn * out_img * sizeof(float), cudaMemcpyDeviceToHost, P.s_out);
+        cudaMemcpyAsync(hy + (size_t)n0 * out_img * esz_out, dy[b], nn * out_img * esz_out, cudaMemcpyDeviceToHost, P.s_out);
         cudaEventRecord(P.out_done[b], P.s_out);
     }
     cudaError_t e = cudaStreamSynchronize(P.s_out);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(P.s_cmp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(P.s_cmp[0]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(P.s_cmp[1]);
     if (e != cudaSuccess) { set_error("infer_host: %s", cudaGetErrorString(e)); return 10; }
     return 0;
+}
+
+int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, int32_t N, int32_t H, int32_t W,
+                     int32_t chunk, void* dev_ws, size_t dev_ws_bytes) {
+    return infer_host_impl(p, host_x, host_y, N, H, W, chunk, dev_ws, dev_ws_bytes, 0);
+}
+
+int dg_lw_infer_host_u8(const dg_lw_params* p, const uint8_t* host_x, uint8_t* host_y, int32_t N, int32_t H, int32_t W,
+                        int32_t chunk, void* dev_ws, size_t dev_ws_bytes) {
+    return infer_host_impl(p, host_x, host_y, N, H, W, chunk, dev_ws, dev_ws_bytes, 3);
+}
+
+int dg_lw_forward_u8(const dg_lw_params* p, const uint8_t* x, uint8_t* y, int32_t N, int32_t H, int32_t W, void* workspace,
+                     size_t workspace_bytes, dg_stream_t stream) {
+    return dg::lw_forward(p, x, y, N, H, W, workspace, workspace_bytes, nullptr, nullptr,
+                          reinterpret_cast<cudaStream_t>(stream), nullptr, 3);
 }
 
 }  // extern "C"

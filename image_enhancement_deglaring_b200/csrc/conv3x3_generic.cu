@@ -210,6 +210,11 @@ __global__ void __launch_bounds__(NTHREADS) conv3x3_generic_kernel(const dg_conv
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
                                 if (k < cn) v[k] = __ldg(img + ((size_t)(n * Cs + c0 + k) * H + gy) * W + gx);
+                        } else if (S.xform == DG_X_IMAGE_U8) {  // float32(u) / 255.0f, api/app.py:153
+                            const unsigned char* img = reinterpret_cast<const unsigned char*>(S.raw);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                if (k < cn) v[k] = __fdiv_rn((float)__ldg(img + ((size_t)(n * Cs + c0 + k) * H + gy) * W + gx), 255.f);
                         } else if (S.xform == DG_X_POOL2) {
                             const int Hs = 2 * H, Ws = 2 * W;
 #pragma unroll

@@ -23,7 +23,10 @@ struct FirstArgs {
     const float* x; const float* w; void* out; double* out_stats;
     int N, H, W;
     float* out_coef; int* out_counter; const float* out_gamma; const float* out_beta; int out_groups; float eps;
+    int x_u8;  // x points at uint8 pixels, normalised as float32(u) / 255.0f (api/app.py:153) -- IEEE divide, bit-exact
 };
+
+__device__ __forceinline__ float u8_norm(unsigned int u) { return __fdiv_rn((float)u, 255.f); }
 
 template <typename T, int NT>
 __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArgs p) {
@@ -44,7 +47,10 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
     // Per tile row: 16 aligned float4 groups (the 64 interior pixels; tile column = 1 + 4j..4 + 4j) and the two halo
     // columns.  In tileB (shifted copy) a group is one aligned 8-byte store; in tileA it straddles 4-byte words.
     const float* img = p.x + (size_t)n * H * W;
-    const bool vec_ok = (x0 + F_TW <= W) && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    const unsigned char* img8 = reinterpret_cast<const unsigned char*>(p.x) + (size_t)n * H * W;
+    const bool u8 = p.x_u8 != 0;
+    const bool vec_ok = (x0 + F_TW <= W) && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & (u8 ? 3 : 15)) == 0);
+    auto px = [&](size_t off) -> float { return u8 ? u8_norm(__ldg(img8 + off)) : __ldg(img + off); };
     for (int idx = tid; idx < F_PH * 18; idx += F_THREADS) {
         const int r = idx / 18, j = idx - r * 18;
         const int gy = y0 + r - 1;
@@ -56,12 +62,17 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
             const int gx = x0 + 4 * j;
             if (rowok) {
                 if (vec_ok) {
-                    v = __ldg(reinterpret_cast<const float4*>(img + (size_t)gy * W + gx));
+                    if (u8) {
+                        const uchar4 q4 = __ldg(reinterpret_cast<const uchar4*>(img8 + (size_t)gy * W + gx));
+                        v = make_float4(u8_norm(q4.x), u8_norm(q4.y), u8_norm(q4.z), u8_norm(q4.w));
+                    } else {
+                        v = __ldg(reinterpret_cast<const float4*>(img + (size_t)gy * W + gx));
+                    }
                 } else {
-                    if (gx < W) v.x = __ldg(img + (size_t)gy * W + gx);
-                    if (gx + 1 < W) v.y = __ldg(img + (size_t)gy * W + gx + 1);
-                    if (gx + 2 < W) v.z = __ldg(img + (size_t)gy * W + gx + 2);
-                    if (gx + 3 < W) v.w = __ldg(img + (size_t)gy * W + gx + 3);
+                    if (gx < W) v.x = px((size_t)gy * W + gx);
+                    if (gx + 1 < W) v.y = px((size_t)gy * W + gx + 1);
+                    if (gx + 2 < W) v.z = px((size_t)gy * W + gx + 2);
+                    if (gx + 3 < W) v.w = px((size_t)gy * W + gx + 3);
                 }
             }
             const uint32_t lo = pack2<T>(v.x, v.y), hi = pack2<T>(v.z, v.w);
@@ -74,7 +85,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
             const int c = j == 16 ? 0 : F_PW - 1;
             const int gx = x0 + c - 1;
             float v = 0.f;
-            if (rowok && (unsigned)gx < (unsigned)W) v = __ldg(img + (size_t)gy * W + gx);
+            if (rowok && (unsigned)gx < (unsigned)W) v = px((size_t)gy * W + gx);
             const T h = Store<T>::from_f(v);
             ra[c] = h;
             if (c >= 1) rb[c - 1] = h;
@@ -181,13 +192,13 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_tc_kernel(const FirstArg
 int conv_first_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled) {
     *handled = false;
     const dg_src& s = a.src[0];
-    if (a.nsrc != 1 || s.xform != DG_X_IMAGE || s.channels != 1 || s.stats != nullptr || s.silu || s.scale) return 0;
+    if (a.nsrc != 1 || (s.xform != DG_X_IMAGE && s.xform != DG_X_IMAGE_U8) || s.channels != 1 || s.stats != nullptr || s.silu || s.scale) return 0;
     if (a.dtype != DG_F16 && a.dtype != DG_BF16) return 0;
     if (a.cout != 8 && a.cout != 16) return 0;
     if (a.act_sum != nullptr || a.N > 65535) return 0;
     if (reinterpret_cast<uintptr_t>(a.out) & 3) return 0;
     FirstArgs f{reinterpret_cast<const float*>(s.raw), a.weight, a.out, a.out_stats, a.N, a.H, a.W,
-                nullptr, nullptr, nullptr, nullptr, 0, a.eps};
+                nullptr, nullptr, nullptr, nullptr, 0, a.eps, s.xform == DG_X_IMAGE_U8 ? 1 : 0};
     if (a.out_coef && a.out_counter && a.out_gamma && a.out_beta && a.out_groups > 0) {
         f.out_coef = a.out_coef; f.out_counter = a.out_counter; f.out_gamma = a.out_gamma; f.out_beta = a.out_beta;
         f.out_groups = a.out_groups;

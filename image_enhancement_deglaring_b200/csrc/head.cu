@@ -12,6 +12,11 @@ namespace dg {
 constexpr int HEAD_THREADS = 256;
 constexpr int HEAD_MAX_OC = 4;
 
+// out_kind 1: the /infer post-processing `(np.clip(y, 0, 1) * 255).astype(np.uint8)` (api/app.py:190-193): fp32 multiply, truncation
+__device__ __forceinline__ unsigned char quant_u8(float y) {
+    return (unsigned char)__float2uint_rz(__fmul_rn(fminf(fmaxf(y, 0.f), 1.f), 255.f));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const dg_head_args p) {
     extern __shared__ float hsm[];
@@ -60,7 +65,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const dg_head_args p
         for (int j = 0; j < HEAD_MAX_OC; ++j) {
             if (j < p.cout) {
                 const size_t oi = ((size_t)n * p.cout + j) * HW + pix;
-                p.out[oi] = o[j];
+                if (p.out_kind == 1) reinterpret_cast<unsigned char*>(p.out)[oi] = quant_u8(o[j]);
+                else reinterpret_cast<float*>(p.out)[oi] = o[j];
                 if (p.target != nullptr) l1 += (double)fabsf(o[j] - p.target[oi]);
             }
         }
@@ -109,7 +115,9 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fast_kernel(const dg_head_a
     for (int c = 0; c < C; ++c) { cf[c] = cfs[c]; w[c] = ws[c]; }
     const float bias = p.bias[0];
     const uint4* raw = reinterpret_cast<const uint4*>(p.src.raw) + (size_t)n * HW * NC8;
-    float* out = p.out + (size_t)n * HW;
+    float* out = reinterpret_cast<float*>(p.out) + (size_t)n * HW;
+    unsigned char* out8 = reinterpret_cast<unsigned char*>(p.out) + (size_t)n * HW;
+    const bool u8 = p.out_kind == 1;
     constexpr int PB = 4;  // pixels in flight per thread
     for (int pix0 = blockIdx.x * HEAD_THREADS * PB + threadIdx.x; pix0 < HW; pix0 += gridDim.x * HEAD_THREADS * PB) {
         uint4 q[PB][NC8];
@@ -143,7 +151,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fast_kernel(const dg_head_a
                         o = fmaf(fmaf(h1, t1, h1), w[c + 1], o);
                     }
                 }
-                out[pix] = o;
+                if (u8) out8[pix] = quant_u8(o);
+                else out[pix] = o;
             }
         }
     }
@@ -168,6 +177,8 @@ int head_launch(const dg_head_args& a, cudaStream_t stream) {
         set_error("head: out_channels %d not in 1..%d", a.cout, HEAD_MAX_OC);
         return 3;
     }
+    if (a.out_kind != 0 && a.out_kind != 1) { set_error("head: bad out_kind %d", a.out_kind); return 2; }
+    if (a.out_kind == 1 && a.target != nullptr) { set_error("head: the fused L1 sum needs the fp32 output"); return 2; }
     // >= 8 pixels per thread when the image allows it: the per-block prologue (GroupNorm coefficients in double,
     // weights to shared memory) was most of the kernel at one pixel per thread (profile r1b: 11.6 warp-inst/pixel)
     const int HW = a.H * a.W;

@@ -173,6 +173,24 @@ class LightweightUNet(nn.Module):
                                      None, None, torch.cuda.current_stream().cuda_stream))
         return y
 
+    def forward_u8(self, x):
+        """uint8 in, uint8 out: the /infer pre/post-processing of api/app.py:153,190-193 folded into the first and last
+        kernel -- `x.float() / 255.0` on load, `(clip(y, 0, 1) * 255).to(uint8)` on store.  x: uint8 [N,in,H,W] on CUDA.
+        Bit-identical to quantising `forward(x.float() / 255.0)`; inference only."""
+        lib = _lib.load()
+        if not x.is_cuda or x.dtype != torch.uint8:
+            raise RuntimeError("forward_u8 expects a uint8 CUDA tensor")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise RuntimeError(f"expected input [N,{self.in_channels},H,W], got {tuple(x.shape)}")
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        pc = self._refresh()
+        ws = self._workspace(N, H, W, x.device)
+        y = torch.empty((N, self.out_channels, H, W), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.dg_lw_forward_u8(C.byref(pc), x.data_ptr(), y.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream))
+        return y
+
     # ---- debugging / test hooks ----------------------------------------------------------------------
     def raw_activation(self, idx, N, H, W):
         """View of the raw output of conv `idx` (0..17) from the last forward at this shape, as NCHW fp32."""

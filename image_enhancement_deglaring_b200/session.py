@@ -41,6 +41,7 @@ class InferenceSession:
         self._scratch_key = None
         self._pin_in = None
         self._pin_out = None
+        self._pin8 = None
 
     def get_inputs(self):
         return [self._in]
@@ -79,6 +80,33 @@ class InferenceSession:
             _lib.check(_lib.load().dg_lw_infer_host(C.byref(self.model.c_params()), x_host.data_ptr(), y_host.data_ptr(),
                                                     N, H, W, chunk, scratch.data_ptr(), scratch.numel()))
         return y_host
+
+    def run_pinned_u8(self, x_host, y_host):
+        """uint8 twin of run_pinned (dg_lw_infer_host_u8): /255 on load and clip*255 -> uint8 on store happen on the GPU
+        (api/app.py:153,190-193), a quarter of the PCIe bytes each way."""
+        N, _, H, W = x_host.shape
+        if x_host.dtype != torch.uint8 or y_host.dtype != torch.uint8:
+            raise RuntimeError("run_pinned_u8 expects uint8 host tensors")
+        chunk = min(self.chunk, N)
+        scratch = self._scratch_for(chunk, H, W)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dg_lw_infer_host_u8(C.byref(self.model.c_params()), x_host.data_ptr(), y_host.data_ptr(),
+                                                       N, H, W, chunk, scratch.data_ptr(), scratch.numel()))
+        return y_host
+
+    def run_u8(self, images):
+        """images: uint8 ndarray [N,in,H,W] (grayscale pixels as api/app.py:150 produces them) -> uint8 ndarray
+        [N,out,H,W], the array api/app.py:193 hands to PIL."""
+        x = np.ascontiguousarray(images)
+        if x.dtype != np.uint8 or x.ndim != 4 or x.shape[1] != self.model.in_channels:
+            raise RuntimeError(f"expected uint8 input [N,{self.model.in_channels},H,W], got {x.dtype} {x.shape}")
+        N, _, H, W = x.shape
+        if self._pin8 is None or tuple(self._pin8[0].shape) != (N, self.model.in_channels, H, W):
+            self._pin8 = (torch.empty((N, self.model.in_channels, H, W), dtype=torch.uint8).pin_memory(),
+                          torch.empty((N, self.model.out_channels, H, W), dtype=torch.uint8).pin_memory())
+        self._pin8[0].copy_(torch.from_numpy(x))
+        self.run_pinned_u8(*self._pin8)
+        return self._pin8[1].numpy().copy()
 
     def run(self, output_names, input_feed, run_options=None):
         x = input_feed[self._in.name]

@@ -43,7 +43,8 @@ enum {
     DG_X_POOL2 = 1,  /* nn.AvgPool2d(2,2) of the activated source   src/model.py:35-41   */
     DG_X_UP2 = 2,    /* nn.Upsample(x2, nearest)          src/optimized_model.py:112     */
     DG_X_CONVT2 = 3, /* nn.ConvTranspose2d(k=2,s=2)+bias  src/model.py:47-53             */
-    DG_X_IMAGE = 4   /* network input: fp32 NCHW, no norm, no activation                 */
+    DG_X_IMAGE = 4,  /* network input: fp32 NCHW, no norm, no activation                 */
+    DG_X_IMAGE_U8 = 5 /* network input: uint8 NCHW, value / 255.0f on load (the /infer normalisation, api/app.py:153) */
 };
 
 /* One input of a fused 3x3 conv.  The consumer applies, while staging its halo tile:
@@ -108,7 +109,7 @@ typedef struct {
 int dg_conv3x3_fused(const dg_conv3x3_args* args, dg_stream_t stream);
 
 /* Output head: GroupNorm+SiLU of the last block, then nn.Conv2d(C, out_channels, 1) + bias
- * (src/model.py:57,131; src/optimized_model.py:74,158).  fp32 NCHW output.  If `target` is
+ * (src/model.py:57,131; src/optimized_model.py:74,158).  fp32 (or quantised uint8) NCHW output.  If `target` is
  * given, also accumulates sum|out-target| into *l1_sum (nn.L1Loss forward, optimized_train.py:439). */
 typedef struct {
     dg_src src;
@@ -117,11 +118,11 @@ typedef struct {
     int32_t cout;
     const float* weight;  /* [cout][channels] */
     const float* bias;    /* [cout]           */
-    float* out;           /* [N,cout,H,W] fp32 */
+    void* out;            /* [N,cout,H,W] fp32 (out_kind 0) or uint8 (out_kind 1) */
     const float* target;  /* optional [N,cout,H,W] */
     double* l1_sum;       /* optional, zero on entry */
     float eps;
-    int32_t reserved;
+    int32_t out_kind;     /* 0: fp32.  1: uint8 = (uint8)(clip(y, 0, 1) * 255), the /infer post-processing (api/app.py:190-193) */
 } dg_head_args;
 
 int dg_head1x1(const dg_head_args* args, dg_stream_t stream);
@@ -209,12 +210,22 @@ int dg_lw_profile(const dg_lw_params* p, const float* x, float* y, int32_t N, in
 
 /* End-to-end inference from HOST buffers (what api/app.py:171 `ort_session.run` and
  * evaluate.py:245 do from the caller's point of view): pipelines H2D copy, forward and D2H
- * copy over `chunk`-image slices on private streams; returns when host_y is complete.
+ * copy over `chunk`-image slices on private streams (consecutive chunks run on two compute streams
+ * with a workspace each); returns when host_y is complete.
  * host_x/host_y should be pinned for full PCIe rate.  `dev_ws` is caller-owned device scratch of
  * dg_lw_host_scratch_bytes() bytes. */
 int dg_lw_host_scratch_bytes(const dg_lw_params* p, int32_t chunk, int32_t H, int32_t W, size_t* bytes);
 int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, int32_t N, int32_t H,
                      int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes);
+
+/* uint8 in / uint8 out: what api/app.py:153-193 does around `ort_session.run` -- `img.astype(float32) / 255.0`
+ * before, `(np.clip(y, 0, 1) * 255).astype(np.uint8)` after -- folded into the first and the last kernel, so a quarter of
+ * the bytes cross PCIe and HBM at both ends.  Bit-identical to running the fp32 entry points on u/255.0f and quantising
+ * their output on the host.  Same workspace / scratch sizes as the fp32 entry points. */
+int dg_lw_forward_u8(const dg_lw_params* p, const uint8_t* x, uint8_t* y, int32_t N, int32_t H, int32_t W,
+                     void* workspace, size_t workspace_bytes, dg_stream_t stream);
+int dg_lw_infer_host_u8(const dg_lw_params* p, const uint8_t* host_x, uint8_t* host_y, int32_t N, int32_t H,
+                        int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes);
 
 /* ---- tensor-core weight packing (16-bit storage types) ---------------------------------
  * The HMMA implicit-GEMM kernels read B operands as ldmatrix-ready tiles

@@ -183,3 +183,66 @@ def test_infer_host_matches_device_forward(best_sd):
         y = net(x.cuda()).cpu().numpy()
     assert out.shape == (5, 1, 64, 64) and out.dtype == np.float32
     assert np.abs(out - y).max() <= 1e-6
+
+
+def _quantise(y):
+    """api/app.py:190-193: clip to [0, 1], scale by 255 in float32, truncate to uint8."""
+    return (np.clip(y, 0, 1) * 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("storage", ["fp32", "fp16"])
+def test_u8_io_is_bit_identical_to_quantised_fp32_io(best_sd, storage):
+    """uint8 in / uint8 out folded into the first / last kernel must equal the host-side
+    `u.astype(float32) / 255.0` -> forward -> `(clip(y, 0, 1) * 255).astype(uint8)` of api/app.py:153-193 exactly."""
+    net = _net(best_sd, storage=storage)
+    rs = np.random.RandomState(5)
+    for shape in [(3, 1, 64, 96), (2, 1, 48, 80), (1, 1, 512, 512)]:
+        u = rs.randint(0, 256, size=shape).astype(np.uint8)
+        u[0, 0, :4, :8] = np.array([0, 255, 1, 254, 127, 128, 2, 253], dtype=np.uint8)
+        xf = torch.from_numpy(u.astype(np.float32) / 255.0).cuda()
+        with torch.no_grad():
+            want = _quantise(net(xf).cpu().numpy())
+            got = net.forward_u8(torch.from_numpy(u).cuda()).cpu().numpy()
+        assert got.dtype == np.uint8 and got.shape == shape
+        assert np.array_equal(got, want), f"{storage} {shape}: {int((got != want).sum())} pixels differ"
+
+
+def test_u8_png_golden_within_one_level(best_sd, golden):
+    """The reference's /infer output image for the two shipped PNGs: fp32 storage differs from the quantised reference
+    output only where 255*y sits within float noise of an integer (<= 1 level, a handful of pixels); fp16 storage <= 2 levels."""
+    g = golden("lw_png.npz")
+    for storage, max_levels, max_frac in [("fp32", 1, 1e-3), ("fp16", 2, 0.5)]:
+        net = _net(best_sd, storage=storage)
+        for i in (1, 2):
+            want = _quantise(g[f"y{i}"])
+            got = net.forward_u8(torch.from_numpy(g[f"x{i}_u8"])[None, None].cuda())[0, 0].cpu().numpy()
+            d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert d.max() <= max_levels, f"{storage} png{i}: {d.max()} levels"
+            assert (d > 0).mean() <= max_frac, f"{storage} png{i}: {(d > 0).mean():.4f} of the pixels differ"
+
+
+def test_u8_session_matches_device_forward(best_sd):
+    from image_enhancement_deglaring_b200.session import InferenceSession
+    net = _net(best_sd, storage="fp16")
+    sess = InferenceSession(net, chunk=2)
+    u = np.random.RandomState(6).randint(0, 256, size=(5, 1, 64, 64)).astype(np.uint8)
+    out = sess.run_u8(u)
+    want = net.forward_u8(torch.from_numpy(u).cuda()).cpu().numpy()
+    assert out.dtype == np.uint8 and np.array_equal(out, want)
+    with pytest.raises(RuntimeError):
+        sess.run_u8(u.astype(np.float32))
+    with pytest.raises(RuntimeError):
+        net.forward_u8(torch.from_numpy(u))  # CPU tensor
+
+
+def test_infer_host_many_chunks_two_compute_streams(best_sd):
+    """dg_lw_infer_host alternates two compute streams / workspaces over the chunks: every chunk count parity."""
+    from image_enhancement_deglaring_b200.session import InferenceSession
+    net = _net(best_sd, storage="fp16")
+    x = _rand((7, 1, 64, 64), 22)
+    with torch.no_grad():
+        y = net(x.cuda()).cpu().numpy()
+    for chunk in (1, 2, 3, 7, 16):
+        sess = InferenceSession(net, chunk=chunk)
+        out = sess.run(["output"], {"input": x.numpy()})[0]
+        assert np.array_equal(out, y), f"chunk {chunk}"
