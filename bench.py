@@ -233,7 +233,7 @@ def main():
     value = world * B * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the reference-facing session API, host buffers in and out ------------
-    sess = InferenceSession(net, chunk=16)
+    sess = InferenceSession(net, chunk=8)
     hx, hy = sess.pinned_buffers(B, H, W)
     hx.copy_(x.cpu())
     for _ in range(2):

@@ -22,7 +22,7 @@ NodeArg = namedtuple("NodeArg", "name shape type")
 
 
 class InferenceSession:
-    def __init__(self, model, providers=None, *, storage="fp32", chunk=16, device="cuda:0"):
+    def __init__(self, model, providers=None, *, storage="fp32", chunk=8, device="cuda:0"):
         if isinstance(model, (str, bytes)):
             ckpt = torch.load(model, map_location="cpu")
             if "model_state_dict" in ckpt:  # optimized_train.py:63-73 checkpoint layout

@@ -210,7 +210,7 @@ int dg_lw_profile(const dg_lw_params* p, const float* x, float* y, int32_t N, in
 
 /* End-to-end inference from HOST buffers (what api/app.py:171 `ort_session.run` and
  * evaluate.py:245 do from the caller's point of view): pipelines H2D copy, forward and D2H
- * copy over `chunk`-image slices on private streams (consecutive chunks run on two compute streams
+ * copy over `chunk`-image slices on private streams (up to four chunks in flight on their own compute streams,
  * with a workspace each); returns when host_y is complete.
  * host_x/host_y should be pinned for full PCIe rate.  `dev_ws` is caller-owned device scratch of
  * dg_lw_host_scratch_bytes() bytes. */

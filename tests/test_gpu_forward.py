@@ -246,3 +246,22 @@ def test_infer_host_many_chunks_two_compute_streams(best_sd):
         sess = InferenceSession(net, chunk=chunk)
         out = sess.run(["output"], {"input": x.numpy()})[0]
         assert np.array_equal(out, y), f"chunk {chunk}"
+
+
+def test_tiled_high_resolution_equals_per_tile_forward(best_sd):
+    """BASELINE.json configs[2] (definition A of SURVEY 8e): a 1024x1536 image as six independent 512x512 tiles equals the
+    module applied to each tile on its own -- float and uint8 entry points."""
+    from image_enhancement_deglaring_b200.tiling import infer_tiled, split_tiles
+    net = _net(best_sd, storage="fp16")
+    img = _rand((1024, 1536), 31).cuda()
+    with torch.no_grad():
+        full = infer_tiled(net, img, tile=512, batch=4)
+        tiles, grid = split_tiles(img, 512)
+        assert grid == (2, 3)
+        for t in (0, 4):
+            r, c = divmod(t, 3)
+            one = net(tiles[t:t + 1])[0]
+            assert torch.equal(full[:, 512 * r:512 * (r + 1), 512 * c:512 * (c + 1)], one)
+        u = (img * 255).to(torch.uint8)
+        full8 = infer_tiled(net.forward_u8, u, tile=512)
+        assert full8.dtype == torch.uint8 and torch.equal(full8[:, :512, 1024:], net.forward_u8(split_tiles(u, 512)[0][2:3])[0])

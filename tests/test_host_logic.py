@@ -134,3 +134,51 @@ def test_gradient_bucket_allreduce_world2(tmp_path):
     lin(x).abs().mean().backward()
     want = torch.cat([p.grad.flatten() for p in lin.parameters()])
     assert torch.allclose(got, want, atol=1e-6)
+
+
+# ---- 4096^2-style tiling (BASELINE.json configs[2]): tiles are independent units sharded over ranks --------------
+def _fake_forward(t):
+    """Stands in for the CUDA module on CPU: per-tile, position-dependent, so a misplaced tile cannot cancel out."""
+    ramp = torch.arange(t.shape[-1], dtype=t.dtype)
+    return t * 2.0 + ramp + t.mean(dim=(1, 2, 3), keepdim=True)
+
+
+def test_tiles_roundtrip_and_order():
+    from image_enhancement_deglaring_b200.tiling import infer_tiled, merge_tiles, split_tiles
+    img = torch.arange(3 * 8 * 12, dtype=torch.float32).reshape(3, 8, 12)
+    tiles, grid = split_tiles(img, tile=4)
+    assert tiles.shape == (6, 3, 4, 4) and grid == (2, 3)
+    assert torch.equal(tiles[4], img[:, 4:8, 4:8])            # row-major: tile 4 = (row 1, col 1)
+    assert torch.equal(merge_tiles(tiles, grid), img)
+    single = infer_tiled(_fake_forward, img[0], tile=4, batch=4)  # 2-D input -> one channel; 6 tiles in calls of 4 + 2
+    want = merge_tiles(_fake_forward(split_tiles(img[0], 4)[0]), grid)
+    assert torch.equal(single, want)
+    with pytest.raises(RuntimeError):
+        split_tiles(torch.zeros(10, 12), tile=4)
+
+
+def _tile_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from image_enhancement_deglaring_b200.tiling import infer_tiled
+    res = {}
+    for name, (h, w) in {"even": (8, 16), "ragged": (12, 4), "fewer_tiles_than_ranks": (4, 4)}.items():
+        img = torch.arange(h * w, dtype=torch.float32).reshape(h, w) / 7.0
+        res[name] = infer_tiled(_fake_forward, img, tile=4, rank=rank, world=world)
+        part, span, _ = infer_tiled(_fake_forward, img, tile=4, rank=rank, world=world, gather=False)
+        assert part.shape[0] == span[1] - span[0]
+    torch.save(res, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_tiled_inference_sharded_world2(tmp_path):
+    from image_enhancement_deglaring_b200.tiling import infer_tiled
+    port = 31500 + (os.getpid() % 2000)
+    out = str(tmp_path / "tiles.pt")
+    mp.spawn(_tile_worker, args=(2, port, out), nprocs=2, join=True)
+    r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    for name, (h, w) in {"even": (8, 16), "ragged": (12, 4), "fewer_tiles_than_ranks": (4, 4)}.items():
+        img = torch.arange(h * w, dtype=torch.float32).reshape(h, w) / 7.0
+        want = infer_tiled(_fake_forward, img, tile=4)
+        assert torch.equal(r0[name], want) and torch.equal(r1[name], want), name
