@@ -61,6 +61,8 @@ class DgLwParams(C.Structure):
 # every symbol include/deglare.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "dg_conv3x3_fused": (C.c_int, [C.POINTER(DgConv3x3Args), C.c_void_p]),
+    "dg_conv3x3_wgrad": (C.c_int, [C.POINTER(DgConv3x3Args), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p]),
     "dg_head1x1": (C.c_int, [C.POINTER(DgHeadArgs), C.c_void_p]),
     "dg_lw_workspace_bytes": (C.c_int, [C.POINTER(DgLwParams), C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_size_t)]),

@@ -96,7 +96,7 @@ static int make_plan(const dg_lw_params* p, int N, int H, int W, LwPlan* pl) {
     for (int u = 0; u < 4; ++u) {
         const int lvl = 3 - u;
         pl->up_off[u] = off;
-        if (p->dtype != DG_F32 && u < 3)
+        if (p->dtype != DG_F32)   // all four: inference materialises the deep ones, the tensor-core wgrad wants every `up`
             off += align_up((size_t)N * (H >> lvl) * (W >> lvl) * pl->f[lvl] * dtype_size(p->dtype), 256);
     }
     pl->total_bytes = off;
@@ -359,8 +359,37 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
         // dW_i: same sources as the forward conv, correlated with dR_i; written in the parameter's [Co][Ci][3][3] layout
         dg_conv3x3_args a;
         fwd_conv_args(p, pl, fw, x, N, i, &a);
-        rc = conv3x3_wgrad_launch(a, G(i), grads + gl.conv_w[b][j], /*tap*/ 1, /*ci*/ 9, /*co*/ 9 * bp.cin_tot[i], st);
-        if (rc) return rc;
+        bool wg_done = false;
+        if (p->dtype != DG_F32 && (p->path & 3) != 1 && i > 0) {
+            // tensor-core wgrad (wgrad_tc.cu); a decoder conv reads the MATERIALISED ConvTranspose output: the forward left it
+            // in the workspace for the deep levels, for the fused levels it is rebuilt here by the same stand-alone kernel
+            bool ok = true;
+            if (a.nsrc == 2) {
+                const int lvl = block_level(b), u = b - 5;
+                void* up = fw + pl.up_off[u];
+                const bool have_up = (u < 2 || (u == 2 && (p->path & 32)));
+                if (!have_up) {
+                    rc = convt_tc_launch(a.src[0], p->dtype, N, Hi, Wi, up, 1e-5f, p->path, st, &ok);
+                    if (rc) return rc;
+                }
+                if (ok) {
+                    memset(&a.src[0], 0, sizeof(dg_src));
+                    a.src[0].raw = up;
+                    a.src[0].channels = pl.f[lvl];
+                    a.src[0].groups = 1;
+                    a.src[0].xform = DG_X_SAME;
+                }
+            }
+            if (ok) {
+                rc = conv3x3_wgrad_tc_launch(a, G(i), grads + gl.conv_w[b][j], 1, 9, 9 * bp.cin_tot[i], st, &wg_done);
+                if (rc) return rc;
+            }
+            if (!wg_done) fwd_conv_args(p, pl, fw, x, N, i, &a);  // restore the fused description for the generic kernel
+        }
+        if (!wg_done) {
+            rc = conv3x3_wgrad_launch(a, G(i), grads + gl.conv_w[b][j], /*tap*/ 1, /*ci*/ 9, /*co*/ 9 * bp.cin_tot[i], st);
+            if (rc) return rc;
+        }
         if (i == 0) break;
         // dA_in = conv3x3(dR_i, flipped weights): the forward kernel on an identity fp32 source
         dg_conv3x3_args d;
@@ -473,6 +502,24 @@ int dg_conv3x3_fused(const dg_conv3x3_args* a, dg_stream_t stream) {
         if ((a->path & 3) == 2) { set_error("conv3x3: tensor-core path does not cover this configuration"); return 3; }
     }
     return conv3x3_generic_launch(*a, st);
+}
+
+int dg_conv3x3_wgrad(const dg_conv3x3_args* a, const float* dR, float* dW, int32_t s_tap, int32_t s_ci, int32_t s_co,
+                     dg_stream_t stream) {
+    if (a == nullptr || dR == nullptr || dW == nullptr) { set_error("wgrad: null pointer"); return 2; }
+    if (a->nsrc < 1 || a->nsrc > 2) { set_error("wgrad: nsrc %d", a->nsrc); return 2; }
+    for (int s = 0; s < a->nsrc; ++s) {
+        int rc = validate_src(a->src[s], "wgrad");
+        if (rc) return rc;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((a->path & 3) != 1) {
+        bool handled = false;
+        int rc = conv3x3_wgrad_tc_launch(*a, dR, dW, s_tap, s_ci, s_co, st, &handled);
+        if (rc || handled) return rc;
+        if ((a->path & 3) == 2) { set_error("wgrad: no tensor-core kernel for this configuration"); return 3; }
+    }
+    return conv3x3_wgrad_launch(*a, dR, dW, s_tap, s_ci, s_co, st);
 }
 
 int dg_head1x1(const dg_head_args* a, dg_stream_t stream) {

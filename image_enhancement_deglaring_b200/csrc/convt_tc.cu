@@ -32,7 +32,7 @@ struct ConvtArgs {
 template <typename T, int CL, int CU, int ACT>
 __global__ void __launch_bounds__(CT_THREADS) convt_tc_kernel(const ConvtArgs p) {
     constexpr int NCL8 = CL / 8, LPLANE = ct_pad_plane(CT_MP, NCL8);
-    constexpr int CHUNKS = CL / 16, CT_N = 4 * CU, CT_NT = CT_N / 8, NTG = 8;
+    constexpr int CHUNKS = CL / 16, CT_N = 4 * CU, CT_NT = CT_N / 8, NTG = CT_NT < 8 ? CT_NT : 8;
     static_assert(CT_NT % NTG == 0, "n-tile groups");
     constexpr int LOW_BYTES = NCL8 * LPLANE * 16, CTW_BYTES = CHUNKS * 2 * CT_N * 16;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -160,6 +160,7 @@ int dispatch_convt(const ConvtArgs& a, int cl, int cu, cudaStream_t st, bool* ha
     if (cl == 128 && cu == 64) return launch_convt<T, 128, 64, ACT>(a, st);   // upconv4
     if (cl == 64 && cu == 32) return launch_convt<T, 64, 32, ACT>(a, st);     // upconv3
     if (cl == 32 && cu == 16) return launch_convt<T, 32, 16, ACT>(a, st);     // upconv2
+    if (cl == 16 && cu == 8) return launch_convt<T, 16, 8, ACT>(a, st);       // upconv1 (training: wgrad of dec1.0 reads `up`)
     *handled = false;
     return 0;
 }

@@ -1,0 +1,367 @@
+// Weight gradient of the fused 3x3 convs on the tensor cores (16-bit storage tiers).
+//
+//   dW[co][ci][ky][kx] = sum over (n, y, x) of  A[n, y+ky-1, x+kx-1, ci] * dR[n, y, x, co]
+// with A the ACTIVATED conv input (GroupNorm + SiLU (+ 2x2 average pool / channel concat) of the saved raw tensors,
+// rebuilt on load exactly as the forward prologue does: src/model.py:92-99,107-128) and dR the gradient at the raw conv
+// output (backward.cu).  Per tap this is a GEMM with M = ci, N = co and K = pixels -- the long dimension is K, so a CTA
+// walks spatial tiles, keeps its [taps x ci x co] block of dW in mma.sync accumulators across all of them, and issues one
+// fp32 atomicAdd per element at the very end.  Both operands are pixel-major in shared memory (the forward kernels'
+// channel-plane layout: 16 bytes = 8 channels of one pixel), which is the TRANSPOSE of what the MMA wants for an
+// M x K / K x N operand pair -- ldmatrix.trans delivers the fragments directly, with the 3x3 tap again a +16 B/pixel shift.
+// Operands are bf16 whatever the storage type (dR ~ 1/numel underflows fp16; bf16 keeps fp32's exponent), accumulation
+// fp32.  The generic CUDA-core WGRAD mode (conv3x3_generic.cu) stays the fp32-tier and any-shape path: 20.7 ms of a
+// 39 ms training step at batch 32 before this kernel (torch profiler).
+#include <type_traits>
+
+#include "tc_common.cuh"
+
+namespace dg {
+
+namespace {
+
+constexpr int WG_THREADS = 256;
+enum { WG_SAME = 0, WG_POOL = 1, WG_CAT2 = 2 };
+
+constexpr int wg_pad_plane(int pix, int nc8) {
+    const int want = nc8 >= 8 ? 1 : (nc8 <= 1 ? 0 : 8 / nc8);
+    if (nc8 <= 1) return pix;
+    int p = pix;
+    while (p % 8 != want) ++p;
+    return p;
+}
+
+struct WgArgs {
+    const void* src0; const double* st0; const float* g0; const float* b0; int groups0;   // SAME/POOL source, or `up` (CAT2)
+    const void* src1; const double* st1; const float* g1; const float* b1; int groups1;   // CAT2: skip
+    const float* dR; float* dW;
+    int N, H, W;
+    int s_tap, s_ci, s_co;
+    float eps;
+    int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 to_bf16x8(const uint4& q) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        return q;
+    } else {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 v = unpack2<T>(w[k]);
+            o[k] = pack2<__nv_bfloat16>(v.x, v.y);
+        }
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// CI: input channels of the conv (both concat halves), CO: output channels, NTW: n-tiles (8 co) per CTA,
+// TAPS: taps per CTA (9, 3 = one kernel row, 1); grid = (persistent CTAs, 9 / TAPS tap groups, CO / (8 NTW) co blocks)
+template <typename T, int CI, int CO, int MODE, int TH, int TW, int TAPS, int NTW>
+struct WgGeo {
+    static constexpr int PH = TH + 2, PW = TW + 2, NC8 = CI / 8;
+    static constexpr int APLANE = wg_pad_plane(PH * PW, NC8);
+    static constexpr int DPLANE = wg_pad_plane(TH * TW, NTW);
+    static constexpr bool PAIR = CI == 8;                       // 8 input channels: an m-tile is a PAIR of taps
+    static constexpr int MT = PAIR ? 1 : CI / 16;
+    static constexpr int ITEMS = PAIR ? 5 : TAPS * MT;          // (tap or tap pair, m-tile) work items of a CTA
+    static constexpr int IPW = (ITEMS + 7) / 8;                 // per warp
+    static constexpr int SEGS = TW / 16;
+    static constexpr int A_BYTES = NC8 * APLANE * 16, D_BYTES = NTW * DPLANE * 16;
+    static constexpr int NCOEF = MODE == WG_CAT2 ? CI / 2 : CI;
+    static constexpr int SMEM = A_BYTES + D_BYTES + NCOEF * 8;
+    static_assert(!PAIR || TAPS == 9, "tap pairs need all nine taps in one CTA");
+    static_assert(TAPS == 9 || TAPS == 3 || TAPS == 1, "taps per CTA");
+    static_assert(CI % 8 == 0 && (PAIR || CI % 16 == 0) && CO % (8 * NTW) == 0 && TW % 16 == 0, "shape");
+    static_assert(IPW * NTW * 4 <= 64, "accumulator budget");
+    static_assert(NTW == 1 || NTW % 2 == 0, "n-tiles come in ldmatrix.x4 pairs");
+    static_assert(WG_THREADS % NC8 == 0 && WG_THREADS % NTW == 0, "chunk ownership");
+};
+
+template <typename T, int CI, int CO, int MODE, int TH, int TW, int TAPS, int NTW>
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
+    using G = WgGeo<T, CI, CO, MODE, TH, TW, TAPS, NTW>;
+    using BF = __nv_bfloat16;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* act = smem;
+    unsigned char* dsm = smem + G::A_BYTES;
+    float2* coef = reinterpret_cast<float2*>(smem + G::A_BYTES + G::D_BYTES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tap0 = blockIdx.y * TAPS;          // first tap of this CTA
+    const int co0 = blockIdx.z * NTW * 8;        // first output channel of this CTA
+    const int H = p.H, W = p.W;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int ntiles = tiles_per_img * p.N;
+
+    float acc[G::IPW][NTW][4];
+#pragma unroll
+    for (int s = 0; s < G::IPW; ++s)
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) acc[s][j][0] = acc[s][j][1] = acc[s][j][2] = acc[s][j][3] = 0.f;
+
+    const uint32_t act_u = smem_u32(act), dsm_u = smem_u32(dsm);
+    int cur_n = -1;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img;
+        const int tr = tile - n * tiles_per_img;
+        const int y0 = (tr / p.tiles_x) * TH, x0 = (tr % p.tiles_x) * TW;
+        __syncthreads();  // everyone is done reading the previous tile (and the previous image's coefficients)
+        if (n != cur_n) {
+            cur_n = n;
+            // GroupNorm affine (a, b) per activated source channel, pre-halved for silu(y) = h + h tanh(h)
+            for (int c = tid; c < G::NCOEF; c += WG_THREADS) {
+                float a, b;
+                if constexpr (MODE == WG_CAT2) {
+                    gn_coef(p.st1, p.g1, p.b1, n, CI / 2, p.groups1, c, (double)H * W, p.eps, a, b);
+                } else {
+                    const double plane = MODE == WG_POOL ? (double)(2 * H) * (2 * W) : (double)H * W;
+                    gn_coef(p.st0, p.g0, p.b0, n, CI, p.groups0, c, plane, p.eps, a, b);
+                }
+                coef[c] = make_float2(0.5f * a, 0.5f * b);
+            }
+            __syncthreads();
+        }
+        // ---- stage the activated haloed input tile as bf16 channel planes ------------------------------------------
+        {
+            constexpr int NPIX = G::PH * G::PW;
+            const int c8 = tid % G::NC8;
+            constexpr bool HAS_IDENT = MODE == WG_CAT2;
+            const bool ident = HAS_IDENT && c8 < G::NC8 / 2;       // CAT2: planes [0, CI/16) = materialised `up`, copied
+            constexpr int CS = MODE == WG_CAT2 ? CI / 2 : CI;       // channels of the tensor a chunk is read from
+            const int cc8 = (MODE == WG_CAT2 && !ident) ? c8 - G::NC8 / 2 : c8;
+            float2 cf[8];
+            if (!ident) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cf[k] = coef[cc8 * 8 + k];
+            }
+            const unsigned char* base;
+            if constexpr (MODE == WG_CAT2) base = reinterpret_cast<const unsigned char*>(ident ? p.src0 : p.src1) + (size_t)n * H * W * CS * 2;
+            else if constexpr (MODE == WG_POOL) base = reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * CS * 8;
+            else base = reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * CS * 2;
+            base += cc8 * 16;
+            unsigned char* dst = act + (size_t)c8 * G::APLANE * 16;
+            for (int pix = tid / G::NC8; pix < NPIX; pix += WG_THREADS / G::NC8) {
+                const int r = pix / G::PW, c = pix - r * G::PW;
+                const int gy = y0 + r - 1, gx = x0 + c - 1;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
+                    if constexpr (MODE == WG_POOL) {
+                        const size_t rowb = (size_t)(2 * W) * CS * 2;
+                        const unsigned char* q0 = base + (size_t)(2 * gy) * rowb + (size_t)(2 * gx) * CS * 2;
+                        float y[8], t[8];
+                        act8<T, ACT_TANH>(__ldg(reinterpret_cast<const uint4*>(q0)), cf, y);
+                        act8<T, ACT_TANH>(__ldg(reinterpret_cast<const uint4*>(q0 + CS * 2)), cf, t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) y[k] += t[k];
+                        act8<T, ACT_TANH>(__ldg(reinterpret_cast<const uint4*>(q0 + rowb)), cf, t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) y[k] += t[k];
+                        act8<T, ACT_TANH>(__ldg(reinterpret_cast<const uint4*>(q0 + rowb + CS * 2)), cf, t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) y[k] = 0.25f * (y[k] + t[k]);
+                        o = pack8<BF>(y);
+                    } else {
+                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)gy * W + gx) * CS * 2));
+                        if (ident) {
+                            o = to_bf16x8<T>(q);
+                        } else {
+                            float y[8];
+                            act8<T, ACT_TANH>(q, cf, y);
+                            o = pack8<BF>(y);
+                        }
+                    }
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)pix * 16) = o;
+            }
+        }
+        // ---- stage dR (fp32 NHWC) for this CTA's output channels as bf16 planes, zero outside the image -------------
+        {
+            const int j8 = tid % NTW;
+            const float* gsrc = p.dR + (size_t)n * H * W * CO + co0 + j8 * 8;
+            unsigned char* dst = dsm + (size_t)j8 * G::DPLANE * 16;
+            for (int pix = tid / NTW; pix < TH * TW; pix += WG_THREADS / NTW) {
+                const int r = pix / TW, c = pix - r * TW;
+                const int gy = y0 + r, gx = x0 + c;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (gy < H && gx < W) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CO));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CO) + 1);
+                    o = make_uint4(pack2<BF>(a.x, a.y), pack2<BF>(a.z, a.w), pack2<BF>(b.x, b.y), pack2<BF>(b.z, b.w));
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)pix * 16) = o;
+            }
+        }
+        __syncthreads();
+        // ---- K loop over the tile's 16-pixel row segments ----------------------------------------------------------
+#pragma unroll
+        for (int s = 0; s < G::IPW; ++s) {
+            const int item = warp + 8 * s;
+            if (item >= G::ITEMS) continue;  // warp-uniform
+            // A address of this lane for pixel (row 0, segment 0): matrices = (plane lo, px 0-7), (plane hi, px 0-7),
+            // (plane lo, px 8-15), (plane hi, px 8-15); "plane hi" is the second TAP of the pair when CI == 8
+            uint32_t a_lane;
+            if constexpr (G::PAIR) {
+                const int t_lo = 2 * item, t_hi = (2 * item + 1 < 9) ? 2 * item + 1 : 2 * item;
+                const int t = ((lane >> 3) & 1) ? t_hi : t_lo;
+                a_lane = (uint32_t)((((t / 3) * G::PW + (t % 3)) + (lane & 7) + 8 * (lane >> 4)) * 16);
+            } else {
+                const int tap = tap0 + item / G::MT, mt = item % G::MT;
+                a_lane = (uint32_t)((((2 * mt + ((lane >> 3) & 1)) * G::APLANE) + (tap / 3) * G::PW + (tap % 3) + (lane & 7) +
+                                     8 * (lane >> 4)) * 16);
+            }
+            // B address: matrices = (plane j, px 0-7), (plane j, px 8-15), (plane j+1, px 0-7), (plane j+1, px 8-15)
+            const uint32_t b_lane = NTW == 1 ? (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 16)
+                                             : (uint32_t)((((lane >> 4) * G::DPLANE) + (lane & 7) + 8 * ((lane >> 3) & 1)) * 16);
+#pragma unroll 1
+            for (int r = 0; r < TH; ++r) {
+#pragma unroll
+                for (int sg = 0; sg < G::SEGS; ++sg) {
+                    uint32_t a0, a1, a2, a3;
+                    ldsm_x4_t(act_u + a_lane + (uint32_t)((r * G::PW + sg * 16) * 16), a0, a1, a2, a3);
+                    const uint32_t boff = dsm_u + b_lane + (uint32_t)((r * TW + sg * 16) * 16);
+                    if constexpr (NTW == 1) {
+                        uint32_t b0, b1;
+                        ldsm_x2_t(boff, b0, b1);
+                        mma16816<BF>(acc[s][0], a0, a1, a2, a3, b0, b1);
+                    } else {
+#pragma unroll
+                        for (int jp = 0; jp < NTW / 2; ++jp) {
+                            uint32_t b0, b1, b2, b3;
+                            ldsm_x4_t(boff + (uint32_t)(2 * jp * G::DPLANE * 16), b0, b1, b2, b3);
+                            mma16816<BF>(acc[s][2 * jp], a0, a1, a2, a3, b0, b1);
+                            mma16816<BF>(acc[s][2 * jp + 1], a0, a1, a2, a3, b2, b3);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---- one atomicAdd per element of this CTA's dW block ---------------------------------------------------------------
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int s = 0; s < G::IPW; ++s) {
+        const int item = warp + 8 * s;
+        if (item >= G::ITEMS) continue;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {   // accumulator rows g and g + 8
+            int tap, ci;
+            if constexpr (G::PAIR) {
+                tap = 2 * item + hf;
+                ci = g;
+                if (tap > 8) continue;
+            } else {
+                tap = tap0 + item / G::MT;
+                ci = (item % G::MT) * 16 + g + 8 * hf;
+            }
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                const int co = co0 + j * 8 + 2 * q;
+                float* d = p.dW + (size_t)tap * p.s_tap + (size_t)ci * p.s_ci;
+                atomicAdd(d + (size_t)co * p.s_co, acc[s][j][2 * hf]);
+                atomicAdd(d + (size_t)(co + 1) * p.s_co, acc[s][j][2 * hf + 1]);
+            }
+        }
+    }
+}
+
+template <typename T, int CI, int CO, int MODE, int TH, int TW, int TAPS, int NTW>
+int launch_wg(WgArgs a, cudaStream_t st) {
+    using G = WgGeo<T, CI, CO, MODE, TH, TW, TAPS, NTW>;
+    auto kern = wgrad_tc_kernel<T, CI, CO, MODE, TH, TW, TAPS, NTW>;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute(%d B): %s", G::SMEM, cudaGetErrorString(e)); return 4; }
+        done = true;
+    }
+    a.tiles_x = (a.W + TW - 1) / TW;
+    a.tiles_y = (a.H + TH - 1) / TH;
+    const int ntiles = a.tiles_x * a.tiles_y * a.N;
+    constexpr int GY = 9 / TAPS, GZ = CO / (8 * NTW);
+    // persistent CTAs: about two waves of (148 SMs x resident CTAs) over all tap groups / co blocks, so the end-of-kernel
+    // atomics (one per dW element per CTA) stay a small fraction of the work
+    constexpr int RES = (227 * 1024) / (G::SMEM + 1024) > 4 ? 4 : ((227 * 1024) / (G::SMEM + 1024) < 1 ? 1 : (227 * 1024) / (G::SMEM + 1024));
+    int gx = (148 * RES * 2 + GY * GZ - 1) / (GY * GZ);
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    kern<<<dim3(gx, GY, GZ), WG_THREADS, G::SMEM, st>>>(a);
+    count_launch();
+    return check_launch("wgrad_tc");
+}
+
+template <typename T>
+int dispatch_wg(const WgArgs& a, int ci, int co, int mode, cudaStream_t st, bool* handled) {
+    *handled = true;
+#define DG_WG(CI_, CO_, MODE_, TH_, TW_, TAPS_, NTW_) \
+    if (ci == CI_ && co == CO_ && mode == MODE_) return launch_wg<T, CI_, CO_, MODE_, TH_, TW_, TAPS_, NTW_>(a, st);
+    DG_WG(8, 8, WG_SAME, 16, 64, 9, 1)       // enc1.3, dec1.3
+    DG_WG(8, 16, WG_POOL, 16, 64, 9, 2)      // enc2.0
+    DG_WG(16, 16, WG_SAME, 16, 64, 9, 2)     // enc2.3, dec2.3
+    DG_WG(16, 32, WG_POOL, 16, 32, 9, 4)     // enc3.0
+    DG_WG(32, 32, WG_SAME, 16, 32, 9, 4)     // enc3.3, dec3.3
+    DG_WG(32, 64, WG_POOL, 8, 32, 3, 8)      // enc4.0
+    DG_WG(64, 64, WG_SAME, 8, 32, 3, 8)      // enc4.3, dec4.3
+    DG_WG(64, 128, WG_POOL, 8, 32, 3, 8)     // bottleneck.0
+    DG_WG(128, 128, WG_SAME, 8, 32, 1, 8)    // bottleneck.3
+    DG_WG(128, 64, WG_CAT2, 8, 32, 1, 8)     // dec4.0
+    DG_WG(64, 32, WG_CAT2, 8, 32, 3, 4)      // dec3.0
+    DG_WG(32, 16, WG_CAT2, 16, 32, 9, 2)     // dec2.0
+    DG_WG(16, 8, WG_CAT2, 16, 64, 9, 1)      // dec1.0
+#undef DG_WG
+    *handled = false;
+    return 0;
+}
+
+}  // namespace
+
+// Sources as dg_conv3x3_fused describes them, except that a ConvTranspose source must already be MATERIALISED: src[0] =
+// identity 16-bit NHWC `up` (stats == NULL, silu == 0), src[1] = the skip.  dW element (tap, ci, co) lives at
+// dW[tap*s_tap + ci*s_ci + co*s_co] and is accumulated atomically (zero it first).
+int conv3x3_wgrad_tc_launch(const dg_conv3x3_args& a, const float* dR, float* dW, int s_tap, int s_ci, int s_co,
+                            cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (a.dtype != DG_F16 && a.dtype != DG_BF16) return 0;
+    if (a.N < 1 || (reinterpret_cast<uintptr_t>(dR) & 15)) return 0;
+    WgArgs w;
+    memset(&w, 0, sizeof(w));
+    int mode, ci;
+    const dg_src& s0 = a.src[0];
+    if (a.nsrc == 1) {
+        if (s0.stats == nullptr || !s0.silu || s0.scale || s0.coef) return 0;
+        if (s0.xform == DG_X_SAME) mode = WG_SAME;
+        else if (s0.xform == DG_X_POOL2) mode = WG_POOL;
+        else return 0;
+        ci = s0.channels;
+        w.src0 = s0.raw; w.st0 = s0.stats; w.g0 = s0.gamma; w.b0 = s0.beta; w.groups0 = s0.groups;
+        if (reinterpret_cast<uintptr_t>(s0.raw) & 15) return 0;
+    } else if (a.nsrc == 2) {
+        const dg_src& s1 = a.src[1];
+        if (s0.xform != DG_X_SAME || s0.stats != nullptr || s0.silu || s0.scale) return 0;   // materialised up
+        if (s1.xform != DG_X_SAME || s1.stats == nullptr || !s1.silu || s1.scale || s1.coef) return 0;
+        if (s0.channels != s1.channels) return 0;
+        mode = WG_CAT2;
+        ci = 2 * s0.channels;
+        w.src0 = s0.raw;
+        w.src1 = s1.raw; w.st1 = s1.stats; w.g1 = s1.gamma; w.b1 = s1.beta; w.groups1 = s1.groups;
+        if ((reinterpret_cast<uintptr_t>(s0.raw) | reinterpret_cast<uintptr_t>(s1.raw)) & 15) return 0;
+    } else {
+        return 0;
+    }
+    w.dR = dR; w.dW = dW; w.N = a.N; w.H = a.H; w.W = a.W;
+    w.s_tap = s_tap; w.s_ci = s_ci; w.s_co = s_co; w.eps = a.eps;
+    if (a.dtype == DG_F16) return dispatch_wg<__half>(w, ci, a.cout, mode, st, handled);
+    return dispatch_wg<__nv_bfloat16>(w, ci, a.cout, mode, st, handled);
+}
+
+}  // namespace dg

@@ -112,6 +112,23 @@ def conv3x3_fused(srcs, weight, cout, N, H, W, dtype, out=None, out_stats=None, 
     return out, out_stats
 
 
+def conv3x3_wgrad(srcs, dR, cin_total, cout, N, H, W, dtype, path=0, stream=None, eps=1e-5):
+    """Weight gradient of conv3x3_fused's conv: dW [cout, cin_total, 3, 3] fp32 (the nn.Conv2d.weight layout) from the same
+    source descriptions and dR = fp32 NHWC [N,H,W,cout] gradient at the raw conv output."""
+    lib = _lib.load()
+    dW = torch.zeros((cout, cin_total, 3, 3), dtype=torch.float32, device=dR.device)
+    a = DgConv3x3Args()
+    for i, s in enumerate(srcs):
+        a.src[i] = s
+    a.nsrc = len(srcs)
+    a.dtype = dtype
+    a.N, a.H, a.W, a.cout = N, H, W, cout
+    a.eps = eps
+    a.path = path
+    _lib.check(lib.dg_conv3x3_wgrad(C.byref(a), _ptr(dR), _ptr(dW), 1, 9, 9 * cin_total, _stream(stream)))
+    return dW
+
+
 def head1x1(src, weight, bias, N, H, W, dtype, out=None, target=None, l1_sum=None, stream=None, eps=1e-5):
     lib = _lib.load()
     cout = weight.shape[0]

@@ -108,6 +108,15 @@ typedef struct {
 
 int dg_conv3x3_fused(const dg_conv3x3_args* args, dg_stream_t stream);
 
+/* Weight gradient of the same fused conv (autograd of src/model.py:93,96 as driven by optimized_train.py:210/226):
+ *   dW[tap*s_tap + ci*s_ci + co*s_co] += sum_{n,y,x} A[n, y+ky-1, x+kx-1, ci] * dR[n, y, x, co],   tap = 3*ky + kx,
+ * A = the ACTIVATED input rebuilt from args->src exactly as the forward does, dR = fp32 NHWC [N,H,W,cout] gradient at the raw
+ * conv output.  dW must be zero (or hold a running sum) on entry; args->weight / out / out_stats are ignored.
+ * path bits 0-1 as in dg_conv3x3_fused: the tensor-core kernel (16-bit storage, bf16 operands, fp32 accumulate) covers the
+ * LightweightUNet(features_start=8) layers with a ConvTranspose source given MATERIALISED (src[0] = identity `up`). */
+int dg_conv3x3_wgrad(const dg_conv3x3_args* args, const float* dR, float* dW, int32_t s_tap, int32_t s_ci, int32_t s_co,
+                     dg_stream_t stream);
+
 /* Output head: GroupNorm+SiLU of the last block, then nn.Conv2d(C, out_channels, 1) + bias
  * (src/model.py:57,131; src/optimized_model.py:74,158).  fp32 (or quantised uint8) NCHW output.  If `target` is
  * given, also accumulates sum|out-target| into *l1_sum (nn.L1Loss forward, optimized_train.py:439). */

@@ -398,3 +398,87 @@ def test_tc_path_refuses_unsupported():
     src = ops.make_src(raw, 24, stats=st, gamma=g, beta=g, groups=8)
     with pytest.raises(RuntimeError, match="tensor-core"):
         ops.conv3x3_fused([src], w, 24, 1, 8, 8, ops.DG_F16, path=2)
+
+
+# ---- weight gradient: tensor-core kernel (bf16 operands, fp32 accumulate) vs generic kernel vs torch autograd ----------
+def _wgrad_ref(act_in, dR_nchw, cout):
+    """d/dW of sum(conv2d(act_in, W) * dR): the reference's autograd on the ACTIVATED input."""
+    w = torch.zeros((cout, act_in.shape[1], 3, 3), dtype=torch.float64, requires_grad=True)
+    (F.conv2d(act_in.double(), w, None, 1, 1) * dR_nchw.double()).sum().backward()
+    return w.grad.float()
+
+
+def _wgrad_check(dw_tc, dw_gen, ref, what):
+    scale = float(ref.abs().max())
+    e_gen = float((dw_gen.cpu() - ref).abs().max()) / scale
+    e_tc = float((dw_tc.cpu() - ref).abs().max()) / scale
+    assert e_gen <= 2e-3, f"{what}: generic wgrad rel err {e_gen:.3e}"
+    # bf16 operands: 2^-9 relative rounding per factor, averaged over K = N*H*W products
+    assert e_tc <= 1e-2, f"{what}: tensor-core wgrad rel err {e_tc:.3e} (generic {e_gen:.3e})"
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 8, 64, 128), (16, 16, 32, 64), (32, 32, 32, 32), (64, 64, 16, 32),
+                                            (128, 128, 8, 32), (8, 8, 48, 80), (32, 32, 6, 10)])
+def test_wgrad_tc_same(dtype, cin, cout, H, W):
+    rs = _rs(41)
+    N = 3
+    raw = torch.from_numpy((rs.standard_normal((N, cin, H, W)) * 2 + 0.5).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, cin)
+    dR = torch.from_numpy((rs.standard_normal((N, H, W, cout)) * 1e-6).astype(np.float32)).cuda()   # ~1/numel: underflows fp16
+    src = ops.make_src(q, cin, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=8)
+    dw_gen = ops.conv3x3_wgrad([src], dR, cin, cout, N, H, W, dtype, path=1)
+    dw_tc = ops.conv3x3_wgrad([src], dR, cin, cout, N, H, W, dtype, path=2)
+    torch.cuda.synchronize()
+    ref = _wgrad_ref(tpo.gn_silu(seen, 8, g, b), dR.cpu().permute(0, 3, 1, 2), cout)
+    _wgrad_check(dw_tc, dw_gen, ref, f"wgrad same {cin}->{cout}")
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 16, 32, 64), (16, 32, 16, 32), (32, 64, 16, 32), (64, 128, 8, 32), (8, 16, 24, 40)])
+def test_wgrad_tc_pool(dtype, cin, cout, H, W):
+    rs = _rs(42)
+    N = 2
+    raw = torch.from_numpy((rs.standard_normal((N, cin, 2 * H, 2 * W)) * 2 - 0.5).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, cin)
+    dR = torch.from_numpy((rs.standard_normal((N, H, W, cout)) * 1e-6).astype(np.float32)).cuda()
+    src = ops.make_src(q, cin, xform=ops.DG_X_POOL2, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=8)
+    dw_gen = ops.conv3x3_wgrad([src], dR, cin, cout, N, H, W, dtype, path=1)
+    dw_tc = ops.conv3x3_wgrad([src], dR, cin, cout, N, H, W, dtype, path=2)
+    torch.cuda.synchronize()
+    ref = _wgrad_ref(F.avg_pool2d(tpo.gn_silu(seen, 8, g, b), 2), dR.cpu().permute(0, 3, 1, 2), cout)
+    _wgrad_check(dw_tc, dw_gen, ref, f"wgrad pool {cin}->{cout}")
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("c,H,W", [(8, 64, 128), (16, 32, 64), (32, 16, 32), (64, 16, 32), (8, 48, 80)])
+def test_wgrad_tc_cat(dtype, c, H, W):
+    """Decoder conv: input = cat(materialised ConvTranspose output, activated skip)."""
+    rs = _rs(43)
+    N = 2
+    up = torch.from_numpy((rs.standard_normal((N, c, H, W)) * 1.5).astype(np.float32))
+    skip = torch.from_numpy((rs.standard_normal((N, c, H, W)) * 2 + 0.3).astype(np.float32))
+    qu, seen_u = _nhwc(up, dtype)
+    qs, seen_s = _nhwc(skip, dtype)
+    g, b = _gn_params(rs, c)
+    dR = torch.from_numpy((rs.standard_normal((N, H, W, c)) * 1e-6).astype(np.float32)).cuda()
+    s0 = ops.make_src(qu, c, silu=False)
+    s1 = ops.make_src(qs, c, stats=_stats(seen_s), gamma=g.cuda(), beta=b.cuda(), groups=8)
+    dw_gen = ops.conv3x3_wgrad([s0, s1], dR, 2 * c, c, N, H, W, dtype, path=1)
+    dw_tc = ops.conv3x3_wgrad([s0, s1], dR, 2 * c, c, N, H, W, dtype, path=2)
+    torch.cuda.synchronize()
+    ref = _wgrad_ref(torch.cat((seen_u, tpo.gn_silu(seen_s, 8, g, b)), 1), dR.cpu().permute(0, 3, 1, 2), c)
+    _wgrad_check(dw_tc, dw_gen, ref, f"wgrad cat {2 * c}->{c}")
+
+
+def test_wgrad_tc_refuses_what_it_does_not_cover():
+    rs = _rs(44)
+    q, seen = _nhwc(torch.from_numpy(rs.standard_normal((1, 24, 16, 16)).astype(np.float32)), ops.DG_F16)
+    g, b = _gn_params(rs, 24)
+    src = ops.make_src(q, 24, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=8)
+    dR = torch.zeros((1, 16, 16, 24), device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.conv3x3_wgrad([src], dR, 24, 24, 1, 16, 16, ops.DG_F16, path=2)
+    ops.conv3x3_wgrad([src], dR, 24, 24, 1, 16, 16, ops.DG_F16, path=0)   # auto falls back to the generic kernel
