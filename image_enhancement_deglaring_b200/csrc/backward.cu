@@ -643,7 +643,13 @@ int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, 
     if (bb < 1) bb = 1;
     convt_bwd_bias_kernel<<<bb, BW_THREADS, (size_t)Cu * sizeof(float), st>>>(ab);
     count_launch();
-    // weight gradient: 256 combos per CTA; slab sized for ~32 KB of staged operands
+    // weight gradient: tensor cores where the configuration is covered (wgrad_tc.cu), else 256 combos per CTA on CUDA cores
+    {
+        bool handled = false;
+        rc = convt_wgrad_tc_launch(dtype, dCat, stride, raw_low, stats, gamma, beta, dWt, N, H, W, Cl, Cu, groups, eps, st, &handled);
+        if (rc || handled) return rc;
+    }
+    // slab sized for ~32 KB of staged operands
     const int ncombo = 4 * Cl * Cu;
     const int per_cta_ci = (BW_THREADS / Cu) < 1 ? 1 : (BW_THREADS / Cu) + 1;
     const int width = (Cl * Cu >= BW_THREADS) ? (per_cta_ci + Cu) : (Cl + 4 * Cu);  // floats staged per low pixel (upper bound)

@@ -323,6 +323,196 @@ int dispatch_wg(const WgArgs& a, int ci, int co, int mode, cudaStream_t st, bool
     return 0;
 }
 
+
+// ---- ConvTranspose2d(k=2, s=2) weight gradient (src/model.py:47-53 backward) -------------------------------------------
+//   dWt[ci][co][a][b] = sum over (n, i, j) of  A_low[n, i, j, ci] * dUp[n, 2i+a, 2j+b, co]
+// the same GEMM shape (M = ci, N = co, K = low pixels) once per kernel position (a, b): the "tap" is now the position, the A
+// tile needs no halo and the B tile of a position gathers every second pixel of the concat gradient's up half.
+struct CtWgArgs {
+    const void* raw_low; const double* stats; const float* gamma; const float* beta; int groups;
+    const float* dCat; int stride;   // [N, 2Hl, 2Wl, stride], up half = channels 0..CU
+    float* dWt;                      // [CL][CU][2][2], accumulated atomically
+    int N, Hl, Wl; float eps;
+    int tiles_x, tiles_y;
+};
+
+template <typename T, int CL, int CU, int TH, int TW, int POSG>
+__global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgArgs p) {
+    using BF = __nv_bfloat16;
+    constexpr int NC8 = CL / 8, NTW = CU / 8, MT = CL / 16, ITEMS = POSG * MT, IPW = (ITEMS + 7) / 8, SEGS = TW / 16;
+    constexpr int APLANE = wg_pad_plane(TH * TW, NC8), DPLANE = wg_pad_plane(TH * TW, NTW);
+    constexpr int A_BYTES = NC8 * APLANE * 16, D_BYTES = POSG * NTW * DPLANE * 16;
+    static_assert(IPW * NTW * 4 <= 64 && (NTW == 1 || NTW % 2 == 0) && TW % 16 == 0, "shape");
+    static_assert(WG_THREADS % NC8 == 0 && WG_THREADS % NTW == 0, "chunk ownership");
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* act = smem;
+    unsigned char* dsm = smem + A_BYTES;
+    float2* coef = reinterpret_cast<float2*>(smem + A_BYTES + D_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pos0 = blockIdx.y * POSG;
+    const int Hl = p.Hl, Wl = p.Wl, H = 2 * Hl, W = 2 * Wl;
+    const int tiles_per_img = p.tiles_x * p.tiles_y, ntiles = tiles_per_img * p.N;
+    float acc[IPW][NTW][4];
+#pragma unroll
+    for (int s = 0; s < IPW; ++s)
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) acc[s][j][0] = acc[s][j][1] = acc[s][j][2] = acc[s][j][3] = 0.f;
+    const uint32_t act_u = smem_u32(act), dsm_u = smem_u32(dsm);
+    int cur_n = -1;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img;
+        const int tr = tile - n * tiles_per_img;
+        const int y0 = (tr / p.tiles_x) * TH, x0 = (tr % p.tiles_x) * TW;   // low-resolution tile origin
+        __syncthreads();
+        if (n != cur_n) {
+            cur_n = n;
+            for (int c = tid; c < CL; c += WG_THREADS) {
+                float a, b;
+                gn_coef(p.stats, p.gamma, p.beta, n, CL, p.groups, c, (double)Hl * Wl, p.eps, a, b);
+                coef[c] = make_float2(0.5f * a, 0.5f * b);
+            }
+            __syncthreads();
+        }
+        {   // activated low tile
+            const int c8 = tid % NC8;
+            float2 cf[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cf[k] = coef[c8 * 8 + k];
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(p.raw_low) + (size_t)n * Hl * Wl * CL * 2 + c8 * 16;
+            unsigned char* dst = act + (size_t)c8 * APLANE * 16;
+            for (int pix = tid / NC8; pix < TH * TW; pix += WG_THREADS / NC8) {
+                const int r = pix / TW, c = pix - r * TW;
+                const int gy = y0 + r, gx = x0 + c;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (gy < Hl && gx < Wl) {
+                    float y[8];
+                    act8<T, ACT_TANH>(__ldg(reinterpret_cast<const uint4*>(base + ((size_t)gy * Wl + gx) * CL * 2)), cf, y);
+                    o = pack8<BF>(y);
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)pix * 16) = o;
+            }
+        }
+        {   // gradient of the up half, one plane set per kernel position
+            const int j8 = tid % NTW;
+            const float* gsrc = p.dCat + (size_t)n * H * W * p.stride + j8 * 8;
+            for (int it = tid / NTW; it < POSG * TH * TW; it += WG_THREADS / NTW) {
+                const int ps = it / (TH * TW), pix = it - ps * (TH * TW);
+                const int pos = pos0 + ps;
+                const int r = pix / TW, c = pix - r * TW;
+                const int gy = y0 + r, gx = x0 + c;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (gy < Hl && gx < Wl) {
+                    const float* q = gsrc + ((size_t)(2 * gy + (pos >> 1)) * W + 2 * gx + (pos & 1)) * p.stride;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(q));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(q) + 1);
+                    o = make_uint4(pack2<BF>(a.x, a.y), pack2<BF>(a.z, a.w), pack2<BF>(b.x, b.y), pack2<BF>(b.z, b.w));
+                }
+                *reinterpret_cast<uint4*>(dsm + ((size_t)(ps * NTW + j8) * DPLANE + pix) * 16) = o;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < IPW; ++s) {
+            const int item = warp + 8 * s;
+            if (item >= ITEMS) continue;
+            const int ps = item / MT, mt = item % MT;
+            const uint32_t a_lane = (uint32_t)((((2 * mt + ((lane >> 3) & 1)) * APLANE) + (lane & 7) + 8 * (lane >> 4)) * 16);
+            const uint32_t b_lane = (NTW == 1 ? (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 16)
+                                              : (uint32_t)((((lane >> 4) * DPLANE) + (lane & 7) + 8 * ((lane >> 3) & 1)) * 16)) +
+                                    (uint32_t)(ps * NTW * DPLANE * 16);
+#pragma unroll 2
+            for (int k16 = 0; k16 < TH * SEGS; ++k16) {
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4_t(act_u + a_lane + (uint32_t)(k16 * 256), a0, a1, a2, a3);
+                const uint32_t boff = dsm_u + b_lane + (uint32_t)(k16 * 256);
+                if constexpr (NTW == 1) {
+                    uint32_t b0, b1;
+                    ldsm_x2_t(boff, b0, b1);
+                    mma16816<BF>(acc[s][0], a0, a1, a2, a3, b0, b1);
+                } else {
+#pragma unroll
+                    for (int jp = 0; jp < NTW / 2; ++jp) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4_t(boff + (uint32_t)(2 * jp * DPLANE * 16), b0, b1, b2, b3);
+                        mma16816<BF>(acc[s][2 * jp], a0, a1, a2, a3, b0, b1);
+                        mma16816<BF>(acc[s][2 * jp + 1], a0, a1, a2, a3, b2, b3);
+                    }
+                }
+            }
+        }
+    }
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int s = 0; s < IPW; ++s) {
+        const int item = warp + 8 * s;
+        if (item >= ITEMS) continue;
+        const int pos = pos0 + item / MT, mt = item % MT;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int ci = mt * 16 + g + 8 * hf;
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                const int co = j * 8 + 2 * q;
+                atomicAdd(p.dWt + ((size_t)ci * CU + co) * 4 + pos, acc[s][j][2 * hf]);
+                atomicAdd(p.dWt + ((size_t)ci * CU + co + 1) * 4 + pos, acc[s][j][2 * hf + 1]);
+            }
+        }
+    }
+}
+
+template <typename T, int CL, int CU, int POSG>
+int launch_ctwg(CtWgArgs a, cudaStream_t st) {
+    constexpr int TH = 8, TW = 32;
+    constexpr int NC8 = CL / 8, NTW = CU / 8;
+    constexpr int SMEM = NC8 * wg_pad_plane(TH * TW, NC8) * 16 + POSG * NTW * wg_pad_plane(TH * TW, NTW) * 16 + CL * 8;
+    auto kern = convt_wgrad_tc_kernel<T, CL, CU, TH, TW, POSG>;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) { set_error("convt_wgrad_tc: cudaFuncSetAttribute(%d B): %s", SMEM, cudaGetErrorString(e)); return 4; }
+        done = true;
+    }
+    a.tiles_x = (a.Wl + TW - 1) / TW;
+    a.tiles_y = (a.Hl + TH - 1) / TH;
+    const int ntiles = a.tiles_x * a.tiles_y * a.N;
+    constexpr int GY = 4 / POSG;
+    constexpr int RES = (227 * 1024) / (SMEM + 1024) > 4 ? 4 : ((227 * 1024) / (SMEM + 1024) < 1 ? 1 : (227 * 1024) / (SMEM + 1024));
+    int gx = (148 * RES * 2 + GY - 1) / GY;
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    kern<<<dim3(gx, GY), WG_THREADS, SMEM, st>>>(a);
+    count_launch();
+    return check_launch("convt_wgrad_tc");
+}
+
+template <typename T>
+int dispatch_ctwg(const CtWgArgs& a, int cl, int cu, cudaStream_t st, bool* handled) {
+    *handled = true;
+    if (cl == 128 && cu == 64) return launch_ctwg<T, 128, 64, 1>(a, st);
+    if (cl == 64 && cu == 32) return launch_ctwg<T, 64, 32, 4>(a, st);
+    if (cl == 32 && cu == 16) return launch_ctwg<T, 32, 16, 4>(a, st);
+    if (cl == 16 && cu == 8) return launch_ctwg<T, 16, 8, 4>(a, st);
+    *handled = false;
+    return 0;
+}
+
+}  // namespace
+
+// dWt [Cl][Cu][2][2] += correlation of the activated low-resolution producer with the up half (channels 0..Cu of a
+// [N,H,W,stride] fp32 tensor) of the concat gradient.  16-bit storage, LightweightUNet(features_start=8) channel pairs.
+int convt_wgrad_tc_launch(int dtype, const float* dCat, int stride, const void* raw_low, const double* stats, const float* gamma,
+                          const float* beta, float* dWt, int N, int H, int W, int Cl, int Cu, int groups, float eps,
+                          cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (dtype != DG_F16 && dtype != DG_BF16) return 0;
+    if ((reinterpret_cast<uintptr_t>(dCat) & 15) || (stride & 3) || (reinterpret_cast<uintptr_t>(raw_low) & 15) || ((H | W) & 1)) return 0;
+    CtWgArgs a{raw_low, stats, gamma, beta, groups, dCat, stride, dWt, N, H / 2, W / 2, eps, 0, 0};
+    if (dtype == DG_F16) return dispatch_ctwg<__half>(a, Cl, Cu, st, handled);
+    return dispatch_ctwg<__nv_bfloat16>(a, Cl, Cu, st, handled);
+}
+
+namespace {
 }  // namespace
 
 // Sources as dg_conv3x3_fused describes them, except that a ConvTranspose source must already be MATERIALISED: src[0] =

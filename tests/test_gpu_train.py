@@ -113,15 +113,20 @@ def test_backward_against_autograd_oracle_other_shape(best_sd):
         assert err <= 2e-5 + 2e-4 * float(np.abs(ref).max()), (k, err)
 
 
-def test_training_forward_with_16bit_storage_runs_and_is_close(best_sd):
-    """fp16 storage of the saved activations: gradients stay within a few percent of the fp32 oracle."""
+@pytest.mark.parametrize("shape", [(2, 1, 64, 64), (2, 1, 128, 160)])
+def test_training_16bit_storage_tensor_core_backward_is_close(best_sd, shape):
+    """fp16 storage of the saved activations, tensor-core forward / wgrad / ConvTranspose wgrad (bf16 operands, fp32
+    accumulate): every parameter gradient within 2 % (measured <= 0.7 %) and the whole gradient within 0.5 % (measured
+    0.18 %) of the fp32 oracle step -- the same size as the CUDA-core backward on the same storage (0.07-0.11 %)."""
     net = _net(best_sd, storage="fp16")
-    x, t = _rand((2, 1, 64, 64), 0), _rand((2, 1, 64, 64), 1)
+    x, t = _rand(shape, 0), _rand(shape, 1)
     r = tpo.train_step(best_sd, x, t, max_norm=0.0)
     torch.nn.L1Loss()(net(x.cuda()), t.cuda()).backward()
     num = den = 0.0
     for k, p in net.named_parameters():
         ref = r["grads"][k]
-        num += float(((p.grad.cpu() - ref) ** 2).sum())
+        g = p.grad.cpu()
+        assert float((g - ref).norm()) <= 2e-2 * float(ref.norm()) + 1e-12, k
+        num += float(((g - ref) ** 2).sum())
         den += float((ref ** 2).sum())
-    assert (num / den) ** 0.5 <= 5e-2
+    assert (num / den) ** 0.5 <= 5e-3
