@@ -391,7 +391,13 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
             if (rc) return rc;
         }
         if (i == 0) break;
-        // dA_in = conv3x3(dR_i, flipped weights): the forward kernel on an identity fp32 source
+        // dA_in = conv3x3(dR_i, flipped weights): tensor cores where covered (dgrad_tc.cu) ...
+        bool dg_done = false;
+        if (p->dtype != DG_F32 && (p->path & 3) != 1 && p->conv_w_tc_bf16[b][j] != nullptr) {
+            rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], T(i), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done);
+            if (rc) return rc;
+        }
+        // ... else the forward generic kernel on an identity fp32 source
         dg_conv3x3_args d;
         memset(&d, 0, sizeof(d));
         d.dtype = DG_F32;
@@ -406,8 +412,10 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
         d.src[0].channels = C;
         d.src[0].groups = 1;
         d.src[0].xform = DG_X_SAME;
-        rc = conv3x3_generic_launch(d, st);
-        if (rc) return rc;
+        if (!dg_done) {
+            rc = conv3x3_generic_launch(d, st);
+            if (rc) return rc;
+        }
         if (j == 1) {
             rc = act_bwd(i - 1, T(i), C, 0, nullptr, 0, 0);
         } else if (b < 5) {

@@ -180,6 +180,8 @@ int convt_tc_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, 
                     bool* handled);
 int se_scale_launch(const double* act_sum, double plane, const float* w1, const float* w2, int N, int C, int hidden,
                     float* scale, cudaStream_t st);
+int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
+                            cudaStream_t st, bool* handled);
 int convt_wgrad_tc_launch(int dtype, const float* dCat, int stride, const void* raw_low, const double* stats, const float* gamma,
                           const float* beta, float* dWt, int N, int H, int W, int Cl, int Cu, int groups, float eps,
                           cudaStream_t st, bool* handled);

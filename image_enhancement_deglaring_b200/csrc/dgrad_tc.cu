@@ -1,0 +1,243 @@
+// Data gradient of the 3x3 convs on the tensor cores (16-bit storage tiers):
+//   dA[n, y, x, ci] = sum over (ky, kx, co) of  dR[n, y+1-ky, x+1-kx, co] * W[co][ci][ky][kx]
+// i.e. a 3x3 conv of dR (fp32 NHWC, identity source, zero padding) with the taps flipped and Cin / Cout swapped
+// (autograd of src/model.py:93,96).  As an implicit GEMM: M = pixels, K = (tap', co), N = ci.  A fragments come from the
+// haloed dR tile staged as bf16 channel planes (the forward kernels' layout, tap = +16 B/pixel shift); B fragments are read
+// with ldmatrix.trans straight from the FORWARD weights' tensor-core packing ([chunk][k-half][Cout][8], bf16): a matrix
+// there is 8 co rows x 8 ci columns, and transposed it is exactly the (k = co, n = ci) fragment of tap' = 8 - tap.
+// bf16 operands (dR ~ 1/numel underflows fp16), fp32 accumulate, fp32 NHWC output.  Replaces the generic CUDA-core conv
+// on flipped fp32 weights for these layers: 6.4 ms of an 18 ms batch-32 training step before this kernel.
+#include "tc_common.cuh"
+
+namespace dg {
+
+namespace {
+
+constexpr int DGR_THREADS = 256;
+
+constexpr int dgr_pad_plane(int pix, int nc8) {
+    const int want = nc8 >= 8 ? 1 : (nc8 <= 1 ? 0 : 8 / nc8);
+    if (nc8 <= 1) return pix;
+    int p = pix;
+    while (p % 8 != want) ++p;
+    return p;
+}
+
+struct DgradArgs {
+    const float* dR;   // [N,H,W,CK]
+    const void* wtc;   // forward packing of W [CK = Cout_fwd][CN = Cin_fwd][3][3] in bf16 (dg_pack_conv3x3_tc)
+    float* out;        // [N,H,W,CN]
+    int N, H, W;
+};
+
+__device__ __forceinline__ void dgr_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void dgr_ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+// CK: channels of dR (K side), CN: channels of the result, NB: result channels per CTA (grid.z = CN / NB)
+template <int CK, int CN, int NB, int TH, int TW>
+struct DgrGeo {
+    static constexpr int PH = TH + 2, PW = TW + 2, KC8 = CK / 8, NB8 = NB / 8;
+    static constexpr int PLANE = dgr_pad_plane(PH * PW, KC8);
+    static constexpr bool PAIR = CK == 8;                    // K chunk of 16 = two taps x 8 channels
+    static constexpr int KCH = PAIR ? 1 : CK / 16;           // K chunks per tap
+    static constexpr int SEGS = TW / 16, MTILES = TH * SEGS, MPW = MTILES / 8;  // 8 m-warps, every warp all NB8 n-tiles
+    static constexpr int A_BYTES = KC8 * PLANE * 16;
+    static constexpr int W_BYTES = 9 * NB8 * CK * 16;        // [tap_f][n8][co][8 ci]
+    static constexpr int SMEM = A_BYTES + W_BYTES;
+    static_assert(MTILES % 8 == 0 && MPW * NB8 * 4 <= 64, "accumulator budget");
+    static_assert(CK % 8 == 0 && (PAIR || CK % 16 == 0) && CN % NB == 0 && NB % 8 == 0 && TW % 16 == 0, "shape");
+    static_assert(NB8 == 1 || NB8 % 2 == 0, "n-tiles come in ldmatrix.x4 pairs");
+    static_assert(DGR_THREADS % KC8 == 0, "chunk ownership");
+};
+
+template <int CK, int CN, int NB, int TH, int TW>
+__global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p) {
+    using G = DgrGeo<CK, CN, NB, TH, TW>;
+    using BF = __nv_bfloat16;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* act = smem;
+    unsigned char* wsm = smem + G::A_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.y;
+    const int tiles_x = (p.W + TW - 1) / TW;
+    const int y0 = (blockIdx.x / tiles_x) * TH, x0 = (blockIdx.x % tiles_x) * TW;
+    const int nb8_0 = blockIdx.z * G::NB8;   // first 8-channel block of the result handled here
+    const int H = p.H, W = p.W;
+
+    // ---- weights of this CTA's result channels: for every forward tap and n8 block, CK rows of 16 bytes ----------------
+    {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wtc);
+        const uint32_t dst = smem_u32(wsm);
+        constexpr int PIECES = 9 * G::NB8 * CK;
+        for (int i = tid; i < PIECES; i += DGR_THREADS) {
+            const int co = i % CK, t2 = i / CK;
+            const int j8 = t2 % G::NB8, tap = t2 / G::NB8;
+            const int n8g = nb8_0 + j8;
+            int chunk, khalf;
+            if constexpr (CN >= 16) { chunk = tap * (CN / 16) + (n8g >> 1); khalf = n8g & 1; }
+            else { chunk = tap >> 1; khalf = tap & 1; }
+            cp_async16(dst + (uint32_t)i * 16, src + ((size_t)(chunk * 2 + khalf) * CK + co) * 16);
+        }
+        cp_async_commit();
+    }
+    // ---- haloed dR tile -> bf16 channel planes, zero outside the image -----------------------------------------------
+    {
+        const int c8 = tid % G::KC8;
+        const float* gsrc = p.dR + (size_t)n * H * W * CK + c8 * 8;
+        unsigned char* dst = act + (size_t)c8 * G::PLANE * 16;
+        for (int pix = tid / G::KC8; pix < G::PH * G::PW; pix += DGR_THREADS / G::KC8) {
+            const int r = pix / G::PW, c = pix - r * G::PW;
+            const int gy = y0 + r - 1, gx = x0 + c - 1;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CK));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CK) + 1);
+                o = make_uint4(pack2<BF>(a.x, a.y), pack2<BF>(a.z, a.w), pack2<BF>(b.x, b.y), pack2<BF>(b.z, b.w));
+            }
+            *reinterpret_cast<uint4*>(dst + (size_t)pix * 16) = o;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- main loop ---------------------------------------------------------------------------------------------------
+    const uint32_t act_u = smem_u32(act), wsm_u = smem_u32(wsm);
+    float acc[G::MPW][G::NB8][4];
+    uint32_t a_pix[G::MPW];
+#pragma unroll
+    for (int m = 0; m < G::MPW; ++m) {
+        const int mt = warp + 8 * m;
+        a_pix[m] = (uint32_t)(((mt / G::SEGS) * G::PW + (mt % G::SEGS) * 16 + (lane & 15)) * 16);
+#pragma unroll
+        for (int j = 0; j < G::NB8; ++j) acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f;
+    }
+    // B lane addressing inside one (tap, n8) block of CK rows: matrix = lane >> 3
+    //   regular: (rows +0..7, n8 j), (rows +8..15, n8 j), (rows +0..7, n8 j+1), (rows +8..15, n8 j+1)
+    //   PAIR:    (tap lo, n8 j), (tap hi, n8 j), (tap lo, n8 j+1), (tap hi, n8 j+1)   -- tap offset added per chunk
+    constexpr uint32_t BLK = CK * 16;  // bytes of one (tap, n8) block
+    if constexpr (G::PAIR) {
+#pragma unroll
+        for (int ch = 0; ch < 5; ++ch) {
+            const int tp_lo = 2 * ch, tp_hi = (2 * ch + 1 < 9) ? 2 * ch + 1 : 2 * ch;   // taps of the dgrad conv (shift of dR)
+            const int o_lo = ((tp_lo / 3) * G::PW + (tp_lo % 3)) * 16, o_hi = ((tp_hi / 3) * G::PW + (tp_hi % 3)) * 16;
+            const uint32_t a_off = (uint32_t)(o_lo + (lane >> 4) * (o_hi - o_lo));
+            const int tf = 8 - (((lane >> 3) & 1) ? tp_hi : tp_lo);   // forward tap whose weights multiply this shift
+            uint32_t bf[G::NB8][2];
+            if constexpr (G::NB8 == 1) {
+                dgr_ldsm_x2_t(wsm_u + (uint32_t)(tf * G::NB8) * BLK + (uint32_t)((lane & 7) * 16), bf[0][0], bf[0][1]);
+            } else {
+#pragma unroll
+                for (int jp = 0; jp < G::NB8 / 2; ++jp)
+                    dgr_ldsm_x4_t(wsm_u + (uint32_t)(tf * G::NB8 + 2 * jp + (lane >> 4)) * BLK + (uint32_t)((lane & 7) * 16),
+                                  bf[2 * jp][0], bf[2 * jp][1], bf[2 * jp + 1][0], bf[2 * jp + 1][1]);
+            }
+            if (ch == 4) {   // the last chunk holds tap 8 only: its upper K half must not contribute
+#pragma unroll
+                for (int j = 0; j < G::NB8; ++j) bf[j][1] = 0u;
+            }
+#pragma unroll
+            for (int m = 0; m < G::MPW; ++m) {
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(act_u + a_pix[m] + a_off, a0, a1, a2, a3);
+#pragma unroll
+                for (int j = 0; j < G::NB8; ++j) mma16816<BF>(acc[m][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int tp = 0; tp < 9; ++tp) {
+            const int tf = 8 - tp;
+            const uint32_t a_tap = (uint32_t)(((tp / 3) * G::PW + (tp % 3)) * 16);
+#pragma unroll
+            for (int kc = 0; kc < G::KCH; ++kc) {
+                const uint32_t a_off = a_tap + (uint32_t)((2 * kc + (lane >> 4)) * G::PLANE * 16);
+                uint32_t bf[G::NB8][2];
+                const uint32_t row = (uint32_t)((kc * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
+                if constexpr (G::NB8 == 1) {
+                    dgr_ldsm_x2_t(wsm_u + (uint32_t)(tf * G::NB8) * BLK + row, bf[0][0], bf[0][1]);
+                } else {
+#pragma unroll
+                    for (int jp = 0; jp < G::NB8 / 2; ++jp)
+                        dgr_ldsm_x4_t(wsm_u + (uint32_t)(tf * G::NB8 + 2 * jp + (lane >> 4)) * BLK + row, bf[2 * jp][0], bf[2 * jp][1],
+                                      bf[2 * jp + 1][0], bf[2 * jp + 1][1]);
+                }
+#pragma unroll
+                for (int m = 0; m < G::MPW; ++m) {
+                    uint32_t a0, a1, a2, a3;
+                    ldsm_x4(act_u + a_pix[m] + a_off, a0, a1, a2, a3);
+#pragma unroll
+                    for (int j = 0; j < G::NB8; ++j) mma16816<BF>(acc[m][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
+                }
+            }
+        }
+    }
+    // ---- epilogue: fp32 NHWC ------------------------------------------------------------------------------------------
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int m = 0; m < G::MPW; ++m) {
+        const int mt = warp + 8 * m;
+        const int gy = y0 + mt / G::SEGS;
+        if (gy >= H) continue;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int gx = x0 + (mt % G::SEGS) * 16 + g + 8 * hf;
+            if (gx >= W) continue;
+            float* o = p.out + ((size_t)(n * H + gy) * W + gx) * CN + nb8_0 * 8 + 2 * q;
+#pragma unroll
+            for (int j = 0; j < G::NB8; ++j)
+                *reinterpret_cast<float2*>(o + j * 8) = make_float2(acc[m][j][2 * hf], acc[m][j][2 * hf + 1]);
+        }
+    }
+}
+
+template <int CK, int CN, int NB, int TH, int TW>
+int launch_dgr(const DgradArgs& a, cudaStream_t st) {
+    using G = DgrGeo<CK, CN, NB, TH, TW>;
+    auto kern = dgrad_tc_kernel<CK, CN, NB, TH, TW>;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) { set_error("dgrad_tc: cudaFuncSetAttribute(%d B): %s", G::SMEM, cudaGetErrorString(e)); return 4; }
+        done = true;
+    }
+    dim3 grid(((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH), a.N, CN / NB);
+    kern<<<grid, DGR_THREADS, G::SMEM, st>>>(a);
+    count_launch();
+    return check_launch("dgrad_tc");
+}
+
+}  // namespace
+
+// out[N,H,W,cn] = conv3x3(dR[N,H,W,ck], flipped / transposed W); wtc_bf16 = dg_pack_conv3x3_tc(W packed, cin = cn, cout = ck, DG_BF16)
+int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
+                            cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (wtc_bf16 == nullptr || N < 1 || N > 65535) return 0;
+    if ((reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(wtc_bf16)) & 15) return 0;
+    DgradArgs a{dR, wtc_bf16, out, N, H, W};
+    *handled = true;
+#define DG_DGR(CK_, CN_, NB_, TH_, TW_) if (ck == CK_ && cn == CN_) return launch_dgr<CK_, CN_, NB_, TH_, TW_>(a, st);
+    DG_DGR(8, 8, 8, 16, 32)        // enc1.3, dec1.3
+    DG_DGR(16, 8, 8, 16, 32)       // enc2.0
+    DG_DGR(16, 16, 16, 16, 32)     // enc2.3, dec2.3
+    DG_DGR(32, 16, 16, 16, 32)     // enc3.0
+    DG_DGR(32, 32, 32, 8, 32)      // enc3.3, dec3.3
+    DG_DGR(64, 32, 32, 8, 32)      // enc4.0
+    DG_DGR(64, 64, 32, 8, 32)      // enc4.3, dec4.3
+    DG_DGR(128, 64, 32, 8, 32)     // bottleneck.0
+    DG_DGR(128, 128, 32, 8, 32)    // bottleneck.3
+    DG_DGR(64, 128, 32, 8, 32)     // dec4.0
+    DG_DGR(32, 64, 32, 8, 32)      // dec3.0
+    DG_DGR(16, 32, 32, 16, 32)     // dec2.0
+    DG_DGR(8, 16, 16, 16, 32)      // dec1.0
+#undef DG_DGR
+    *handled = false;
+    return 0;
+}
+
+}  // namespace dg

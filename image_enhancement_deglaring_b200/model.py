@@ -113,7 +113,12 @@ class LightweightUNet(nn.Module):
                 # backward only: dgrad runs as a forward conv with the taps flipped and Cin/Cout swapped
                 wfl = blk[ci].weight.detach().float().flip(2, 3).permute(2, 3, 0, 1).contiguous() if train else None
                 pc.conv_w_flip[b][j] = None if wfl is None else wfl.data_ptr()
-                keep += [w, g, bt, wtc, wfl]
+                # tensor-core dgrad: bf16 packing of the forward weights (read transposed; bf16 because dR underflows fp16)
+                wbf = None
+                if train and self.path != 1 and pc.dtype != ops.DG_F32:
+                    wbf = wtc if pc.dtype == ops.DG_BF16 else ops.pack_conv3x3_tc(w, ops.DG_BF16)
+                pc.conv_w_tc_bf16[b][j] = None if wbf is None else wbf.data_ptr()
+                keep += [w, g, bt, wtc, wfl, wbf]
                 pc.conv_w_tc[b][j] = None if wtc is None else wtc.data_ptr()
                 pc.conv_w[b][j] = w.data_ptr()
                 pc.gn_w[b][j] = g.data_ptr()
