@@ -64,32 +64,35 @@ __device__ __forceinline__ uint4 to_bf16x8(const uint4& q) {
     }
 }
 
-// CI: input channels of the conv (both concat halves), CO: output channels, NTW: n-tiles (8 co) per CTA,
-// TAPS: taps per CTA (9, 3 = one kernel row, 1); grid = (persistent CTAs, 9 / TAPS tap groups, CO / (8 NTW) co blocks)
-template <typename T, int CI, int CO, int MODE, int TH, int TW, int TAPS, int NTW>
+// CI: input channels of the conv (both concat halves), CO: output channels.  A CTA owns the dW block of ALL nine taps x
+// CIB input channels x (8 NTW) output channels: grid = (persistent CTAs, CI / CIB, CO / (8 NTW)).  Splitting over input
+// channels (not taps) means the expensive operand -- the activated tile -- is staged exactly once per tile over the whole grid
+// (a CTA stages only its CIB / 8 planes); only the cheap dR conversion repeats CI / CIB times.  Nine warps, one per tap, each
+// with CIB / 16 m-tiles (a tap-split version re-activated the tile up to 9x and left dec4.0 at 595 us; this one: see DESIGN).
+// CI == 8: an m-tile is a PAIR of taps (rows 0-7 / 8-15), five warps of eight work.
+template <typename T, int CI, int CO, int MODE, int TH, int TW, int CIB, int NTW>
 struct WgGeo {
-    static constexpr int PH = TH + 2, PW = TW + 2, NC8 = CI / 8;
+    static constexpr bool PAIR = CI == 8;
+    static constexpr int THREADS = PAIR ? 256 : 288;
+    static constexpr int PH = TH + 2, PW = TW + 2, NC8 = CIB / 8;
     static constexpr int APLANE = wg_pad_plane(PH * PW, NC8);
     static constexpr int DPLANE = wg_pad_plane(TH * TW, NTW);
-    static constexpr bool PAIR = CI == 8;                       // 8 input channels: an m-tile is a PAIR of taps
-    static constexpr int MT = PAIR ? 1 : CI / 16;
-    static constexpr int ITEMS = PAIR ? 5 : TAPS * MT;          // (tap or tap pair, m-tile) work items of a CTA
-    static constexpr int IPW = (ITEMS + 7) / 8;                 // per warp
+    static constexpr int IPW = PAIR ? 1 : CIB / 16;             // m-tiles per warp
     static constexpr int SEGS = TW / 16;
     static constexpr int A_BYTES = NC8 * APLANE * 16, D_BYTES = NTW * DPLANE * 16;
     static constexpr int NCOEF = MODE == WG_CAT2 ? CI / 2 : CI;
     static constexpr int SMEM = A_BYTES + D_BYTES + NCOEF * 8;
-    static_assert(!PAIR || TAPS == 9, "tap pairs need all nine taps in one CTA");
-    static_assert(TAPS == 9 || TAPS == 3 || TAPS == 1, "taps per CTA");
-    static_assert(CI % 8 == 0 && (PAIR || CI % 16 == 0) && CO % (8 * NTW) == 0 && TW % 16 == 0, "shape");
+    static_assert(!PAIR || CIB == 8, "8 input channels: one block");
+    static_assert(CI % CIB == 0 && (PAIR || CIB % 16 == 0) && CO % (8 * NTW) == 0 && TW % 16 == 0, "shape");
     static_assert(IPW * NTW * 4 <= 64, "accumulator budget");
     static_assert(NTW == 1 || NTW % 2 == 0, "n-tiles come in ldmatrix.x4 pairs");
-    static_assert(WG_THREADS % NC8 == 0 && WG_THREADS % NTW == 0, "chunk ownership");
+    static_assert(THREADS % NC8 == 0 && THREADS % NTW == 0, "chunk ownership");
 };
 
-template <typename T, int CI, int CO, int MODE, int TH, int TW, int TAPS, int NTW>
-__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
-    using G = WgGeo<T, CI, CO, MODE, TH, TW, TAPS, NTW>;
+template <typename T, int CI, int CO, int MODE, int TH, int TW, int CIB, int NTW>
+__global__ void __launch_bounds__(WgGeo<T, CI, CO, MODE, TH, TW, CIB, NTW>::THREADS) wgrad_tc_kernel(const WgArgs p) {
+    using G = WgGeo<T, CI, CO, MODE, TH, TW, CIB, NTW>;
+    constexpr int WG_THREADS = G::THREADS;
     using BF = __nv_bfloat16;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* act = smem;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
     float2* coef = reinterpret_cast<float2*>(smem + G::A_BYTES + G::D_BYTES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tap0 = blockIdx.y * TAPS;          // first tap of this CTA
+    const int ci0 = blockIdx.y * CIB;            // first input channel of this CTA
     const int co0 = blockIdx.z * NTW * 8;        // first output channel of this CTA
     const int H = p.H, W = p.W;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -135,11 +138,12 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
         // ---- stage the activated haloed input tile as bf16 channel planes ------------------------------------------
         {
             constexpr int NPIX = G::PH * G::PW;
-            const int c8 = tid % G::NC8;
+            const int c8 = tid % G::NC8;              // plane of this CTA's block
+            const int c8g = ci0 / 8 + c8;              // 8-channel chunk of the conv input
             constexpr bool HAS_IDENT = MODE == WG_CAT2;
-            const bool ident = HAS_IDENT && c8 < G::NC8 / 2;       // CAT2: planes [0, CI/16) = materialised `up`, copied
+            const bool ident = HAS_IDENT && c8g < CI / 16;          // CAT2: chunks [0, CI/16) = materialised `up`, copied
             constexpr int CS = MODE == WG_CAT2 ? CI / 2 : CI;       // channels of the tensor a chunk is read from
-            const int cc8 = (MODE == WG_CAT2 && !ident) ? c8 - G::NC8 / 2 : c8;
+            const int cc8 = (MODE == WG_CAT2 && !ident) ? c8g - CI / 16 : c8g;
             float2 cf[8];
             if (!ident) {
 #pragma unroll
@@ -151,6 +155,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
             else base = reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * CS * 2;
             base += cc8 * 16;
             unsigned char* dst = act + (size_t)c8 * G::APLANE * 16;
+#pragma unroll 4
             for (int pix = tid / G::NC8; pix < NPIX; pix += WG_THREADS / G::NC8) {
                 const int r = pix / G::PW, c = pix - r * G::PW;
                 const int gy = y0 + r - 1, gx = x0 + c - 1;
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
             const int j8 = tid % NTW;
             const float* gsrc = p.dR + (size_t)n * H * W * CO + co0 + j8 * 8;
             unsigned char* dst = dsm + (size_t)j8 * G::DPLANE * 16;
+#pragma unroll 4
             for (int pix = tid / NTW; pix < TH * TW; pix += WG_THREADS / NTW) {
                 const int r = pix / TW, c = pix - r * TW;
                 const int gy = y0 + r, gx = x0 + c;
@@ -204,44 +210,41 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
         }
         __syncthreads();
         // ---- K loop over the tile's 16-pixel row segments ----------------------------------------------------------
-#pragma unroll
-        for (int s = 0; s < G::IPW; ++s) {
-            const int item = warp + 8 * s;
-            if (item >= G::ITEMS) continue;  // warp-uniform
-            // A address of this lane for pixel (row 0, segment 0): matrices = (plane lo, px 0-7), (plane hi, px 0-7),
-            // (plane lo, px 8-15), (plane hi, px 8-15); "plane hi" is the second TAP of the pair when CI == 8
+        // A matrices of a lane: (plane lo, px 0-7), (plane hi, px 0-7), (plane lo, px 8-15), (plane hi, px 8-15); "plane hi"
+        // is the second TAP of the pair when CI == 8.  B: (plane j, px 0-7), (plane j, px 8-15), (plane j+1, ...), ...
+        const bool active = G::PAIR ? warp < 5 : true;
+        if (active) {
             uint32_t a_lane;
             if constexpr (G::PAIR) {
-                const int t_lo = 2 * item, t_hi = (2 * item + 1 < 9) ? 2 * item + 1 : 2 * item;
+                const int t_lo = 2 * warp, t_hi = (2 * warp + 1 < 9) ? 2 * warp + 1 : 2 * warp;
                 const int t = ((lane >> 3) & 1) ? t_hi : t_lo;
                 a_lane = (uint32_t)((((t / 3) * G::PW + (t % 3)) + (lane & 7) + 8 * (lane >> 4)) * 16);
             } else {
-                const int tap = tap0 + item / G::MT, mt = item % G::MT;
-                a_lane = (uint32_t)((((2 * mt + ((lane >> 3) & 1)) * G::APLANE) + (tap / 3) * G::PW + (tap % 3) + (lane & 7) +
-                                     8 * (lane >> 4)) * 16);
+                const int tap = warp;
+                a_lane = (uint32_t)(((((lane >> 3) & 1) * G::APLANE) + (tap / 3) * G::PW + (tap % 3) + (lane & 7) + 8 * (lane >> 4)) * 16);
             }
-            // B address: matrices = (plane j, px 0-7), (plane j, px 8-15), (plane j+1, px 0-7), (plane j+1, px 8-15)
             const uint32_t b_lane = NTW == 1 ? (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 16)
                                              : (uint32_t)((((lane >> 4) * G::DPLANE) + (lane & 7) + 8 * ((lane >> 3) & 1)) * 16);
 #pragma unroll 1
             for (int r = 0; r < TH; ++r) {
 #pragma unroll
                 for (int sg = 0; sg < G::SEGS; ++sg) {
-                    uint32_t a0, a1, a2, a3;
-                    ldsm_x4_t(act_u + a_lane + (uint32_t)((r * G::PW + sg * 16) * 16), a0, a1, a2, a3);
+                    uint32_t bf[NTW][2];
                     const uint32_t boff = dsm_u + b_lane + (uint32_t)((r * TW + sg * 16) * 16);
                     if constexpr (NTW == 1) {
-                        uint32_t b0, b1;
-                        ldsm_x2_t(boff, b0, b1);
-                        mma16816<BF>(acc[s][0], a0, a1, a2, a3, b0, b1);
+                        ldsm_x2_t(boff, bf[0][0], bf[0][1]);
                     } else {
 #pragma unroll
-                        for (int jp = 0; jp < NTW / 2; ++jp) {
-                            uint32_t b0, b1, b2, b3;
-                            ldsm_x4_t(boff + (uint32_t)(2 * jp * G::DPLANE * 16), b0, b1, b2, b3);
-                            mma16816<BF>(acc[s][2 * jp], a0, a1, a2, a3, b0, b1);
-                            mma16816<BF>(acc[s][2 * jp + 1], a0, a1, a2, a3, b2, b3);
-                        }
+                        for (int jp = 0; jp < NTW / 2; ++jp)
+                            ldsm_x4_t(boff + (uint32_t)(2 * jp * G::DPLANE * 16), bf[2 * jp][0], bf[2 * jp][1], bf[2 * jp + 1][0],
+                                      bf[2 * jp + 1][1]);
+                    }
+#pragma unroll
+                    for (int s = 0; s < G::IPW; ++s) {
+                        uint32_t a0, a1, a2, a3;
+                        ldsm_x4_t(act_u + a_lane + (uint32_t)((2 * s * G::APLANE + r * G::PW + sg * 16) * 16), a0, a1, a2, a3);
+#pragma unroll
+                        for (int j = 0; j < NTW; ++j) mma16816<BF>(acc[s][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
                     }
                 }
             }
@@ -249,20 +252,19 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
     }
     // ---- one atomicAdd per element of this CTA's dW block ---------------------------------------------------------------
     const int g = lane >> 2, q = lane & 3;
+    if (G::PAIR && warp >= 5) return;
 #pragma unroll
     for (int s = 0; s < G::IPW; ++s) {
-        const int item = warp + 8 * s;
-        if (item >= G::ITEMS) continue;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {   // accumulator rows g and g + 8
             int tap, ci;
             if constexpr (G::PAIR) {
-                tap = 2 * item + hf;
+                tap = 2 * warp + hf;
                 ci = g;
                 if (tap > 8) continue;
             } else {
-                tap = tap0 + item / G::MT;
-                ci = (item % G::MT) * 16 + g + 8 * hf;
+                tap = warp;
+                ci = ci0 + s * 16 + g + 8 * hf;
             }
 #pragma unroll
             for (int j = 0; j < NTW; ++j) {
@@ -275,10 +277,10 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs p) {
     }
 }
 
-template <typename T, int CI, int CO, int MODE, int TH, int TW, int TAPS, int NTW>
+template <typename T, int CI, int CO, int MODE, int TH, int TW, int CIB, int NTW>
 int launch_wg(WgArgs a, cudaStream_t st) {
-    using G = WgGeo<T, CI, CO, MODE, TH, TW, TAPS, NTW>;
-    auto kern = wgrad_tc_kernel<T, CI, CO, MODE, TH, TW, TAPS, NTW>;
+    using G = WgGeo<T, CI, CO, MODE, TH, TW, CIB, NTW>;
+    auto kern = wgrad_tc_kernel<T, CI, CO, MODE, TH, TW, CIB, NTW>;
     static bool done = false;
     if (!done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
@@ -288,14 +290,18 @@ int launch_wg(WgArgs a, cudaStream_t st) {
     a.tiles_x = (a.W + TW - 1) / TW;
     a.tiles_y = (a.H + TH - 1) / TH;
     const int ntiles = a.tiles_x * a.tiles_y * a.N;
-    constexpr int GY = 9 / TAPS, GZ = CO / (8 * NTW);
-    // persistent CTAs: about two waves of (148 SMs x resident CTAs) over all tap groups / co blocks, so the end-of-kernel
-    // atomics (one per dW element per CTA) stay a small fraction of the work
-    constexpr int RES = (227 * 1024) / (G::SMEM + 1024) > 4 ? 4 : ((227 * 1024) / (G::SMEM + 1024) < 1 ? 1 : (227 * 1024) / (G::SMEM + 1024));
-    int gx = (148 * RES * 2 + GY * GZ - 1) / (GY * GZ);
+    constexpr int GY = CI / CIB, GZ = CO / (8 * NTW);
+    // persistent CTAs: two per SM over all channel blocks.  Every CTA ends with one atomicAdd per element of its dW block, so
+    // CTAs must walk several tiles each: with one tile per CTA the 64-channel layers spent most of their time in 19 M atomics
+    // (measured: 64->64 189 -> 103 us, 128->128 218 -> 94 us).  The narrow layers are staging-latency bound and their dW
+    // blocks are tiny, so they keep two waves of four CTAs per SM (two per SM cost them 221 -> 269 us).
+    constexpr int FIT = (227 * 1024) / (G::SMEM + 1024);
+    constexpr bool SMALL = 9 * CIB * NTW * 8 <= 2304;
+    constexpr int RES = SMALL ? (FIT > 4 ? 8 : 2 * FIT) : (FIT >= 2 ? 2 : 1);
+    int gx = (148 * RES + GY * GZ - 1) / (GY * GZ);
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
-    kern<<<dim3(gx, GY, GZ), WG_THREADS, G::SMEM, st>>>(a);
+    kern<<<dim3(gx, GY, GZ), G::THREADS, G::SMEM, st>>>(a);
     count_launch();
     return check_launch("wgrad_tc");
 }
@@ -303,21 +309,21 @@ int launch_wg(WgArgs a, cudaStream_t st) {
 template <typename T>
 int dispatch_wg(const WgArgs& a, int ci, int co, int mode, cudaStream_t st, bool* handled) {
     *handled = true;
-#define DG_WG(CI_, CO_, MODE_, TH_, TW_, TAPS_, NTW_) \
-    if (ci == CI_ && co == CO_ && mode == MODE_) return launch_wg<T, CI_, CO_, MODE_, TH_, TW_, TAPS_, NTW_>(a, st);
-    DG_WG(8, 8, WG_SAME, 16, 64, 9, 1)       // enc1.3, dec1.3
-    DG_WG(8, 16, WG_POOL, 16, 64, 9, 2)      // enc2.0
-    DG_WG(16, 16, WG_SAME, 16, 64, 9, 2)     // enc2.3, dec2.3
-    DG_WG(16, 32, WG_POOL, 16, 32, 9, 4)     // enc3.0
-    DG_WG(32, 32, WG_SAME, 16, 32, 9, 4)     // enc3.3, dec3.3
-    DG_WG(32, 64, WG_POOL, 8, 32, 3, 8)      // enc4.0
-    DG_WG(64, 64, WG_SAME, 8, 32, 3, 8)      // enc4.3, dec4.3
-    DG_WG(64, 128, WG_POOL, 8, 32, 3, 8)     // bottleneck.0
-    DG_WG(128, 128, WG_SAME, 8, 32, 1, 8)    // bottleneck.3
-    DG_WG(128, 64, WG_CAT2, 8, 32, 1, 8)     // dec4.0
-    DG_WG(64, 32, WG_CAT2, 8, 32, 3, 4)      // dec3.0
-    DG_WG(32, 16, WG_CAT2, 16, 32, 9, 2)     // dec2.0
-    DG_WG(16, 8, WG_CAT2, 16, 64, 9, 1)      // dec1.0
+#define DG_WG(CI_, CO_, MODE_, TH_, TW_, CIB_, NTW_) \
+    if (ci == CI_ && co == CO_ && mode == MODE_) return launch_wg<T, CI_, CO_, MODE_, TH_, TW_, CIB_, NTW_>(a, st);
+    DG_WG(8, 8, WG_SAME, 16, 64, 8, 1)        // enc1.3, dec1.3
+    DG_WG(8, 16, WG_POOL, 16, 64, 8, 2)       // enc2.0
+    DG_WG(16, 16, WG_SAME, 16, 64, 16, 2)     // enc2.3, dec2.3
+    DG_WG(16, 32, WG_POOL, 16, 32, 16, 4)     // enc3.0
+    DG_WG(32, 32, WG_SAME, 16, 32, 32, 4)     // enc3.3, dec3.3
+    DG_WG(32, 64, WG_POOL, 8, 32, 32, 8)      // enc4.0
+    DG_WG(64, 64, WG_SAME, 8, 32, 32, 8)      // enc4.3, dec4.3
+    DG_WG(64, 128, WG_POOL, 8, 32, 16, 16)    // bottleneck.0 (pooled staging is the expensive side: never repeat it)
+    DG_WG(128, 128, WG_SAME, 8, 32, 32, 8)    // bottleneck.3
+    DG_WG(128, 64, WG_CAT2, 8, 32, 32, 8)     // dec4.0
+    DG_WG(64, 32, WG_CAT2, 8, 32, 32, 4)      // dec3.0
+    DG_WG(32, 16, WG_CAT2, 16, 32, 16, 2)     // dec2.0
+    DG_WG(16, 8, WG_CAT2, 16, 64, 16, 1)      // dec1.0
 #undef DG_WG
     *handled = false;
     return 0;
@@ -477,8 +483,8 @@ int launch_ctwg(CtWgArgs a, cudaStream_t st) {
     a.tiles_y = (a.Hl + TH - 1) / TH;
     const int ntiles = a.tiles_x * a.tiles_y * a.N;
     constexpr int GY = 4 / POSG;
-    constexpr int RES = (227 * 1024) / (SMEM + 1024) > 4 ? 4 : ((227 * 1024) / (SMEM + 1024) < 1 ? 1 : (227 * 1024) / (SMEM + 1024));
-    int gx = (148 * RES * 2 + GY - 1) / GY;
+    constexpr int RES = (227 * 1024) / (SMEM + 1024) >= 2 ? 2 : 1;
+    int gx = (148 * RES + GY - 1) / GY;
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     kern<<<dim3(gx, GY), WG_THREADS, SMEM, st>>>(a);

@@ -32,6 +32,10 @@ for e in prof.events():
 wg = [(e.name, (e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total)) for e in prof.events()
       if e.device_type == torch.autograd.DeviceType.CUDA and "conv3x3_generic_kernel" in e.name]
 print("generic conv launches in order (ms):", " ".join(("W" if ("true" in n.split(">(")[0].split(",")[-1] or "(bool)1" in n) else "f") + f"{t/1e3:.2f}" for n, t in wg))
+for pat in ("wgrad_tc_kernel", "dgrad_tc_kernel", "act_bwd_vec", "convt_bwd_data"):
+    seq = [(e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total) for e in prof.events()
+           if e.device_type == torch.autograd.DeviceType.CUDA and pat in e.name and "convt_wgrad" not in e.name]
+    print(pat, "in launch order (us):", " ".join(f"{t:.0f}" for t in seq))
 tot = sum(v[0] for v in agg.values())
 print(f"batch {B} storage {storage}: total device time {tot/1e3:.2f} ms")
 for k, (t_us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
