@@ -54,7 +54,7 @@ class DgLwParams(C.Structure):
         ("gn_b", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w", C.c_void_p * 4), ("up_b", C.c_void_p * 4),
         ("conv_w_tc", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w_tc", C.c_void_p * 4),
         ("conv_w_flip", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w_t", C.c_void_p * 4),
-        ("conv_w_tc_bf16", (C.c_void_p * 2) * DG_MAX_BLOCKS),
+        ("up_w_tc_bf16", C.c_void_p * 4), ("conv_w_tc_bf16", (C.c_void_p * 2) * DG_MAX_BLOCKS),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("path", C.c_int32), ("reserved", C.c_int32),
     ]
 

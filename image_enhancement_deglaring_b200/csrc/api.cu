@@ -428,7 +428,7 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
             rc = convt_bwd_launch(p->dtype, T(i), 2 * pl.f[lvl], p->up_w[u], p->up_w_t[u], raw(i - 1), stats(i - 1), p->gn_w[b - 1][1],
                                   p->gn_b[b - 1][1], dlow, grads + gl.up_w[u], grads + gl.up_b[u],
                                   reinterpret_cast<float*>(bw + bp.coef_off), N, Hi, Wi, pl.f[lvl + 1], pl.f[lvl],
-                                  p->groups[b - 1], 1e-5f, st);
+                                  p->groups[b - 1], 1e-5f, st, (p->path & 3) != 1 ? p->up_w_tc_bf16[u] : nullptr);
             if (rc) return rc;
             rc = act_bwd(i - 1, dlow, pl.f[lvl + 1], 0, nullptr, 0, 0);
         }

@@ -625,16 +625,25 @@ int head_bwd_launch(int dtype, const void* raw, const double* stats, const float
 
 int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low,
                      const double* stats, const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias,
-                     float* coefbuf, int N, int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st) {
+                     float* coefbuf, int N, int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st,
+                     const void* wtc_bf16) {
     if (Cu % 4 || (stride % 4) || (reinterpret_cast<uintptr_t>(dCat) & 15)) { set_error("convT backward: unaligned gradient"); return 3; }
     ConvtBwdArgs a{dCat, stride, wt, wt_t, raw_low, stats, gamma, beta, dAlow, dWt, nullptr, coefbuf, N, H, W, Cl, Cu, groups, eps};
     gn_mean_rstd_kernel<<<N, 128, 0, st>>>(stats, coefbuf, Cl, groups, (double)(H / 2) * (W / 2), eps);
     count_launch();
     const size_t total = (size_t)N * (H / 2) * (W / 2) * Cl;
-    convt_bwd_data_kernel<<<ew_blocks(total, Cl), BW_THREADS, 0, st>>>(a);
-    count_launch();
-    int rc = check_launch("convt_bwd_data");
-    if (rc) return rc;
+    int rc = 0;
+    bool data_done = false;
+    if (dtype != DG_F32 && wtc_bf16 != nullptr) {   // tensor cores where covered (dgrad_tc.cu)
+        rc = convt_dgrad_tc_launch(dCat, stride, wtc_bf16, dAlow, N, H, W, Cl, Cu, st, &data_done);
+        if (rc) return rc;
+    }
+    if (!data_done) {
+        convt_bwd_data_kernel<<<ew_blocks(total, Cl), BW_THREADS, 0, st>>>(a);
+        count_launch();
+        rc = check_launch("convt_bwd_data");
+        if (rc) return rc;
+    }
     // bias gradient
     ConvtBwdArgs ab = a;
     ab.dBias = dBias;

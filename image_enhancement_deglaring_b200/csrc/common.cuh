@@ -182,6 +182,8 @@ int se_scale_launch(const double* act_sum, double plane, const float* w1, const 
                     float* scale, cudaStream_t st);
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
                             cudaStream_t st, bool* handled);
+int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
+                          cudaStream_t st, bool* handled);
 int convt_wgrad_tc_launch(int dtype, const float* dCat, int stride, const void* raw_low, const double* stats, const float* gamma,
                           const float* beta, float* dWt, int N, int H, int W, int Cl, int Cu, int groups, float eps,
                           cudaStream_t st, bool* handled);
@@ -199,7 +201,7 @@ int head_bwd_launch(int dtype, const void* raw, const double* stats, const float
                     float eps, cudaStream_t st);
 int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low, const double* stats,
                      const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias, float* coefbuf, int N,
-                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st);
+                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st, const void* wtc_bf16 = nullptr);
 int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, float lr,
                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t st);
 int tc_conv3x3_bytes(int cin, int cout, size_t* bytes);

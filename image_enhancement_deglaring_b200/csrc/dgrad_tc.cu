@@ -211,6 +211,155 @@ int launch_dgr(const DgradArgs& a, cudaStream_t st) {
     return check_launch("dgrad_tc");
 }
 
+
+// ---- ConvTranspose2d(k=2, s=2) data gradient (src/model.py:47-53 backward) ----------------------------------------------
+//   dLow[n, i, j, ci] = sum over (a, b, co) of  dUp[n, 2i+a, 2j+b, co] * Wt[ci][co][a][b]
+// GEMM with M = low pixels, K = (position, co) = 4 CU, N = ci.  A = the up half of the concat gradient gathered per position
+// into bf16 planes [pos * CU/8 + co8][low pixel][8]; B = the forward ConvTranspose packing ([ci/16][k-half][pos*CU + co][8],
+// bf16) read with ldmatrix.trans: rows (pos, co) = K, 8 ci per row = N.
+struct CtDgradArgs {
+    const float* dCat; int stride;   // [N, 2Hl, 2Wl, stride], up half = channels 0..CU
+    const void* wtc;                 // dg_pack_convt2x2_tc(..., DG_BF16)
+    float* out;                      // [N, Hl, Wl, CL]
+    int N, Hl, Wl;
+};
+
+template <int CL, int CU, int NB, int TH, int TW>
+__global__ void __launch_bounds__(DGR_THREADS) convt_dgrad_tc_kernel(const CtDgradArgs p) {
+    using BF = __nv_bfloat16;
+    constexpr int KP = 4 * CU / 8;                 // A planes: (pos, co8)
+    constexpr int KCH = 4 * CU / 16;               // K chunks
+    constexpr int NB8 = NB / 8, CTN = 4 * CU;
+    constexpr int SEGS = TW / 16, MTILES = TH * SEGS, MPW = MTILES / 8;
+    constexpr int PLANE = dgr_pad_plane(TH * TW, KP);
+    constexpr int A_BYTES = KP * PLANE * 16, W_BYTES = NB8 * CTN * 16;   // weights: [n8][k = pos*CU + co][8 ci]
+    static_assert(MTILES % 8 == 0 && MPW * NB8 * 4 <= 64 && CL % NB == 0 && (NB8 == 1 || NB8 % 2 == 0), "shape");
+    static_assert(DGR_THREADS % (CU / 8) == 0, "chunk ownership");
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* act = smem;
+    unsigned char* wsm = smem + A_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.y;
+    const int Hl = p.Hl, Wl = p.Wl, W = 2 * Wl;
+    const int tiles_x = (Wl + TW - 1) / TW;
+    const int y0 = (blockIdx.x / tiles_x) * TH, x0 = (blockIdx.x % tiles_x) * TW;
+    const int nb8_0 = blockIdx.z * NB8;
+    {   // packed weights of this CTA's ci blocks: n8 block j -> (chunk = n8g / 2, k-half = n8g & 1), CTN rows of 16 bytes
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wtc);
+        const uint32_t dst = smem_u32(wsm);
+        for (int i = tid; i < NB8 * CTN; i += DGR_THREADS) {
+            const int k = i % CTN, j8 = i / CTN;
+            const int n8g = nb8_0 + j8;
+            cp_async16(dst + (uint32_t)i * 16, src + ((size_t)((n8g >> 1) * 2 + (n8g & 1)) * CTN + k) * 16);
+        }
+        cp_async_commit();
+    }
+    {   // gradient planes
+        constexpr int CU8 = CU / 8;
+        const int c8 = tid % CU8;
+        const float* gsrc = p.dCat + (size_t)n * (2 * Hl) * W * p.stride + c8 * 8;
+#pragma unroll 4
+        for (int it = tid / CU8; it < 4 * TH * TW; it += DGR_THREADS / CU8) {
+            const int pos = it / (TH * TW), pix = it - pos * (TH * TW);
+            const int r = pix / TW, c = pix - r * TW;
+            const int gy = y0 + r, gx = x0 + c;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (gy < Hl && gx < Wl) {
+                const float* q = gsrc + ((size_t)(2 * gy + (pos >> 1)) * W + 2 * gx + (pos & 1)) * p.stride;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(q));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(q) + 1);
+                o = make_uint4(pack2<BF>(a.x, a.y), pack2<BF>(a.z, a.w), pack2<BF>(b.x, b.y), pack2<BF>(b.z, b.w));
+            }
+            *reinterpret_cast<uint4*>(act + ((size_t)(pos * CU8 + c8) * PLANE + pix) * 16) = o;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const uint32_t act_u = smem_u32(act), wsm_u = smem_u32(wsm);
+    float acc[MPW][NB8][4];
+    uint32_t a_pix[MPW];
+#pragma unroll
+    for (int m = 0; m < MPW; ++m) {
+        a_pix[m] = (uint32_t)(((warp + 8 * m) * 16 + (lane & 15)) * 16);
+#pragma unroll
+        for (int j = 0; j < NB8; ++j) acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f;
+    }
+#pragma unroll 2
+    for (int kc = 0; kc < KCH; ++kc) {
+        uint32_t bf[NB8][2];
+        const uint32_t row = (uint32_t)((kc * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
+        if constexpr (NB8 == 1) {
+            dgr_ldsm_x2_t(wsm_u + row, bf[0][0], bf[0][1]);
+        } else {
+#pragma unroll
+            for (int jp = 0; jp < NB8 / 2; ++jp)
+                dgr_ldsm_x4_t(wsm_u + (uint32_t)((2 * jp + (lane >> 4)) * CTN * 16) + row, bf[2 * jp][0], bf[2 * jp][1], bf[2 * jp + 1][0],
+                              bf[2 * jp + 1][1]);
+        }
+        const uint32_t a_off = (uint32_t)((2 * kc + (lane >> 4)) * PLANE * 16);
+#pragma unroll
+        for (int m = 0; m < MPW; ++m) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(act_u + a_pix[m] + a_off, a0, a1, a2, a3);
+#pragma unroll
+            for (int j = 0; j < NB8; ++j) mma16816<BF>(acc[m][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
+        }
+    }
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int m = 0; m < MPW; ++m) {
+        const int mt = warp + 8 * m;
+        const int gy = y0 + mt / SEGS;
+        if (gy >= Hl) continue;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int gx = x0 + (mt % SEGS) * 16 + g + 8 * hf;
+            if (gx >= Wl) continue;
+            float* o = p.out + ((size_t)(n * Hl + gy) * Wl + gx) * CL + nb8_0 * 8 + 2 * q;
+#pragma unroll
+            for (int j = 0; j < NB8; ++j)
+                *reinterpret_cast<float2*>(o + j * 8) = make_float2(acc[m][j][2 * hf], acc[m][j][2 * hf + 1]);
+        }
+    }
+}
+
+template <int CL, int CU, int NB, int TH, int TW>
+int launch_ctdgr(const CtDgradArgs& a, cudaStream_t st) {
+    constexpr int KP = 4 * CU / 8;
+    constexpr int SMEM = KP * dgr_pad_plane(TH * TW, KP) * 16 + (NB / 8) * 4 * CU * 16;
+    auto kern = convt_dgrad_tc_kernel<CL, CU, NB, TH, TW>;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) { set_error("convt_dgrad_tc: cudaFuncSetAttribute(%d B): %s", SMEM, cudaGetErrorString(e)); return 4; }
+        done = true;
+    }
+    dim3 grid(((a.Wl + TW - 1) / TW) * ((a.Hl + TH - 1) / TH), a.N, CL / NB);
+    kern<<<grid, DGR_THREADS, SMEM, st>>>(a);
+    count_launch();
+    return check_launch("convt_dgrad_tc");
+}
+
+}  // namespace
+
+// dLow [N,H/2,W/2,Cl] = ConvTranspose2d data gradient of the up half (channels 0..Cu of dCat [N,H,W,stride]);
+// wtc_bf16 = dg_pack_convt2x2_tc(packed Wt, Cl, Cu, DG_BF16)
+int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
+                          cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (wtc_bf16 == nullptr || N < 1 || N > 65535 || ((H | W) & 1) || (stride & 3)) return 0;
+    if ((reinterpret_cast<uintptr_t>(dCat) | reinterpret_cast<uintptr_t>(dLow) | reinterpret_cast<uintptr_t>(wtc_bf16)) & 15) return 0;
+    CtDgradArgs a{dCat, stride, wtc_bf16, dLow, N, H / 2, W / 2};
+    *handled = true;
+    if (Cl == 128 && Cu == 64) return launch_ctdgr<128, 64, 64, 4, 32>(a, st);   // upconv4
+    if (Cl == 64 && Cu == 32) return launch_ctdgr<64, 32, 64, 8, 32>(a, st);     // upconv3
+    if (Cl == 32 && Cu == 16) return launch_ctdgr<32, 16, 32, 8, 32>(a, st);     // upconv2
+    if (Cl == 16 && Cu == 8) return launch_ctdgr<16, 8, 16, 8, 32>(a, st);       // upconv1
+    *handled = false;
+    return 0;
+}
+
+namespace {
 }  // namespace
 
 // out[N,H,W,cn] = conv3x3(dR[N,H,W,ck], flipped / transposed W); wtc_bf16 = dg_pack_conv3x3_tc(W packed, cin = cn, cout = ck, DG_BF16)

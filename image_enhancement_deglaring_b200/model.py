@@ -130,7 +130,11 @@ class LightweightUNet(nn.Module):
             wtc = ops.pack_convt2x2_tc(w, pc.dtype) if self.path != 1 else None
             wtt = m.weight.detach().float().permute(2, 3, 1, 0).contiguous() if train else None   # [2,2,Co,Ci]
             pc.up_w_t[u] = None if wtt is None else wtt.data_ptr()
-            keep += [w, bt, wtc, wtt]
+            wbf = None
+            if train and self.path != 1 and pc.dtype != ops.DG_F32:
+                wbf = wtc if pc.dtype == ops.DG_BF16 else ops.pack_convt2x2_tc(w, ops.DG_BF16)
+            pc.up_w_tc_bf16[u] = None if wbf is None else wbf.data_ptr()
+            keep += [w, bt, wtc, wtt, wbf]
             pc.up_w_tc[u] = None if wtc is None else wtc.data_ptr()
             pc.up_w[u] = w.data_ptr()
             pc.up_b[u] = bt.data_ptr()

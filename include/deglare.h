@@ -169,6 +169,8 @@ typedef struct {
     const float* conv_w_flip[DG_MAX_BLOCKS][2]; /* backward only: [3][3][Cout][Cin] with taps flipped
                                                (w.flip(2,3).permute(2,3,0,1)): dgrad is a forward conv */
     const float* up_w_t[4];                 /* backward only: ConvTranspose weights as [2][2][Cout][Cin]   */
+    const void* up_w_tc_bf16[4];            /* backward only, optional: dg_pack_convt2x2_tc(..., DG_BF16) for the tensor-core
+                                               ConvTranspose data gradient                                    */
     const void* conv_w_tc_bf16[DG_MAX_BLOCKS][2]; /* backward only, optional: dg_pack_conv3x3_tc(..., DG_BF16) of the forward
                                                weights; the tensor-core dgrad reads it transposed (NULL = CUDA-core dgrad) */
     const float* head_w;                    /* output_conv.weight [out][f0]                */
