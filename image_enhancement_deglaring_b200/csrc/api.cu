@@ -386,6 +386,10 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
             }
             if (!wg_done) fwd_conv_args(p, pl, fw, x, N, i, &a);  // restore the fused description for the generic kernel
         }
+        if (i == 0 && (p->path & 3) != 1 && p->in_channels == 1) {   // first conv: dedicated streaming kernel (backward.cu)
+            rc = first_wgrad_launch(x, G(0), grads + gl.conv_w[0][0], N, Hi, Wi, C, st, &wg_done);
+            if (rc) return rc;
+        }
         if (!wg_done) {
             rc = conv3x3_wgrad_launch(a, G(i), grads + gl.conv_w[b][j], /*tap*/ 1, /*ci*/ 9, /*co*/ 9 * bp.cin_tot[i], st);
             if (rc) return rc;
