@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(WgGeo<T, CI, CO, MODE, TH, TW, CIB, NTW>::THRE
             else base = reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * CS * 2;
             base += cc8 * 16;
             unsigned char* dst = act + (size_t)c8 * G::APLANE * 16;
+            // (explicitly batching 4 loads per thread here and in the dR loop was measured: the persistent accumulators stay
+            // live across the staging, registers went to 128-168 (or 64-360 B of spills under a launch bound) and the wgrad
+            // total rose from 2.57 to 2.76 ms.  The cure for the long-scoreboard stalls ncu shows on the narrow layers
+            // (profiles/r01_ncu_wgrad.txt) is a cp.async double buffer of the RAW tiles, not more registers.)
 #pragma unroll 4
             for (int pix = tid / G::NC8; pix < NPIX; pix += WG_THREADS / G::NC8) {
                 const int r = pix / G::PW, c = pix - r * G::PW;
