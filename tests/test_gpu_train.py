@@ -113,12 +113,14 @@ def test_backward_against_autograd_oracle_other_shape(best_sd):
         assert err <= 2e-5 + 2e-4 * float(np.abs(ref).max()), (k, err)
 
 
+@pytest.mark.parametrize("storage,tensor_tol,global_tol", [("fp16", 2e-2, 5e-3), ("bf16", 8e-2, 2e-2)])
 @pytest.mark.parametrize("shape", [(2, 1, 64, 64), (2, 1, 128, 160)])
-def test_training_16bit_storage_tensor_core_backward_is_close(best_sd, shape):
-    """fp16 storage of the saved activations, tensor-core forward / wgrad / ConvTranspose wgrad (bf16 operands, fp32
-    accumulate): every parameter gradient within 2 % (measured <= 0.7 %) and the whole gradient within 0.5 % (measured
-    0.18 %) of the fp32 oracle step -- the same size as the CUDA-core backward on the same storage (0.07-0.11 %)."""
-    net = _net(best_sd, storage="fp16")
+def test_training_16bit_storage_tensor_core_backward_is_close(best_sd, shape, storage, tensor_tol, global_tol):
+    """16-bit storage of the saved activations, tensor-core forward / dgrad / wgrad / ConvTranspose gradients (bf16 operands,
+    fp32 accumulate).  fp16 storage: every parameter gradient within 2 % (measured <= 1.4 %, the worst being the cancelling sum
+    upconv1.bias) and the whole gradient within 0.5 % (measured 0.26 %) of the fp32 oracle step -- the CUDA-core backward on the
+    same storage sits at 0.07-0.11 %.  bf16 storage (reported, not the parity tier): <= 4.4 % per tensor, 1.1 % overall."""
+    net = _net(best_sd, storage=storage)
     x, t = _rand(shape, 0), _rand(shape, 1)
     r = tpo.train_step(best_sd, x, t, max_norm=0.0)
     torch.nn.L1Loss()(net(x.cuda()), t.cuda()).backward()
@@ -126,7 +128,7 @@ def test_training_16bit_storage_tensor_core_backward_is_close(best_sd, shape):
     for k, p in net.named_parameters():
         ref = r["grads"][k]
         g = p.grad.cpu()
-        assert float((g - ref).norm()) <= 2e-2 * float(ref.norm()) + 1e-12, k
+        assert float((g - ref).norm()) <= tensor_tol * float(ref.norm()) + 1e-12, k
         num += float(((g - ref) ** 2).sum())
         den += float((ref ** 2).sum())
-    assert (num / den) ** 0.5 <= 5e-3
+    assert (num / den) ** 0.5 <= global_tol
