@@ -65,6 +65,8 @@ SYMBOLS = {
     "dg_conv3x3_wgrad": (C.c_int, [C.POINTER(DgConv3x3Args), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p]),
     "dg_head1x1": (C.c_int, [C.POINTER(DgHeadArgs), C.c_void_p]),
+    "dg_image_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
+                                   C.c_void_p]),
     "dg_lw_workspace_bytes": (C.c_int, [C.POINTER(DgLwParams), C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_size_t)]),
     "dg_lw_forward": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

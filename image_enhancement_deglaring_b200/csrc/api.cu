@@ -534,6 +534,12 @@ int dg_conv3x3_wgrad(const dg_conv3x3_args* a, const float* dR, float* dW, int32
     return conv3x3_wgrad_launch(*a, dR, dW, s_tap, s_ci, s_co, st);
 }
 
+int dg_image_metrics(const float* output, const float* target, int32_t N, int32_t H, int32_t W, int32_t clip01, double data_range,
+                     double* acc, dg_stream_t stream) {
+    if (output == nullptr || target == nullptr || acc == nullptr) { set_error("metrics: null pointer"); return 2; }
+    return image_metrics_launch(output, target, N, H, W, clip01, data_range, acc, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int dg_head1x1(const dg_head_args* a, dg_stream_t stream) {
     if (a == nullptr) { set_error("head: null args"); return 2; }
     int rc = validate_src(a->src, "head");

@@ -182,6 +182,8 @@ int se_scale_launch(const double* act_sum, double plane, const float* w1, const 
                     float* scale, cudaStream_t st);
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
                             cudaStream_t st, bool* handled);
+int image_metrics_launch(const float* out, const float* tgt, int N, int H, int W, int clip01, double data_range, double* acc,
+                         cudaStream_t st);
 int first_wgrad_launch(const float* x, const float* dR, float* dW, int N, int H, int W, int CO, cudaStream_t st, bool* handled);
 int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
                           cudaStream_t st, bool* handled);

@@ -136,6 +136,15 @@ typedef struct {
 
 int dg_head1x1(const dg_head_args* args, dg_stream_t stream);
 
+/* On-device validation metrics for fp32 [N,1,H,W] tensors: what optimized_train.py:92-122 / evaluate.py:254-272
+ * get per image on the host from skimage's peak_signal_noise_ratio(target, output, data_range) and
+ * structural_similarity(target, output, data_range) with default arguments (7x7 uniform window, K1 .01, K2 .03, sample
+ * covariance, border cropped).  acc [N][2] doubles, zero on entry: acc[n][0] += sum of squared errors,
+ * acc[n][1] += sum of S over the (H-6)(W-6) full windows.  PSNR = 10 log10(R^2 H W / acc[n][0]), SSIM = acc[n][1] / ((H-6)(W-6)).
+ * clip01 != 0 clips the OUTPUT to [0, 1] first (evaluate.py:262). */
+int dg_image_metrics(const float* output, const float* target, int32_t N, int32_t H, int32_t W, int32_t clip01, double data_range,
+                     double* acc, dg_stream_t stream);
+
 /* Stand-alone nn.ConvTranspose2d(k=2, s=2) + bias (src/model.py:47-53) of the ACTIVATED low-resolution tensor described by
  * `src` (xform DG_X_CONVT2 with ct_w_tc / ct_b / ct_cout; GroupNorm + SiLU applied on load), on the tensor cores, 16-bit
  * storage only.  out: NHWC [N,H,W,ct_cout] (H, W = the up-sampled size).  The result is consumed by dg_conv3x3_fused as an

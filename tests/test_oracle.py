@@ -135,3 +135,18 @@ def test_l1_grad_restatement():
     t = np.array([[0.5, 0.5], [0.1, 0.4]])
     assert npo.l1_loss(o, t) == pytest.approx(0.3)
     assert np.array_equal(npo.l1_loss_grad(o, t), np.array([[-0.25, 0.0], [0.25, -0.25]]))
+
+
+# ---- validation metrics oracle (skimage is absent: the restatement is checked against a direct evaluation) ----
+def test_metrics_oracle_self_consistency():
+    from oracle import metrics_np as M
+    rs = np.random.RandomState(3)
+    a = rs.rand(24, 31).astype(np.float32)
+    b = np.clip(a + 0.1 * rs.standard_normal(a.shape), 0, 1).astype(np.float32)
+    assert abs(M.ssim(a, a) - 1.0) < 1e-6
+    assert abs(M.ssim(a, b) - M.ssim_bruteforce(a, b)) < 2e-5          # float32 filter outputs vs float64 windows
+    assert abs(M.ssim(a, b) - M.ssim(b, a)) < 1e-6                      # symmetric
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    assert abs(M.psnr(a, b) - 10 * np.log10(1.0 / mse)) < 1e-9
+    flat = np.full((16, 16), 0.5, np.float32)
+    assert abs(M.ssim(flat, flat * 0.5) - (2 * 0.5 * 0.25 + 1e-4) / (0.25 + 0.0625 + 1e-4)) < 1e-6   # luminance term only
