@@ -188,7 +188,7 @@ int first_wgrad_launch(const float* x, const float* dR, float* dW, int N, int H,
 int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
                           cudaStream_t st, bool* handled);
 int convt_wgrad_tc_launch(int dtype, const float* dCat, int stride, const void* raw_low, const double* stats, const float* gamma,
-                          const float* beta, float* dWt, int N, int H, int W, int Cl, int Cu, int groups, float eps,
+                          const float* beta, float* dWt, float* dBias, int N, int H, int W, int Cl, int Cu, int groups, float eps,
                           cudaStream_t st, bool* handled);
 int conv3x3_wgrad_tc_launch(const dg_conv3x3_args& a, const float* dR, float* dW, int s_tap, int s_ci, int s_co,
                             cudaStream_t st, bool* handled);

@@ -90,16 +90,32 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
         const int c8 = tid % G::KC8;
         const float* gsrc = p.dR + (size_t)n * H * W * CK + c8 * 8;
         unsigned char* dst = act + (size_t)c8 * G::PLANE * 16;
-        for (int pix = tid / G::KC8; pix < G::PH * G::PW; pix += DGR_THREADS / G::KC8) {
-            const int r = pix / G::PW, c = pix - r * G::PW;
-            const int gy = y0 + r - 1, gx = x0 + c - 1;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CK));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CK) + 1);
-                o = make_uint4(pack2<BF>(a.x, a.y), pack2<BF>(a.z, a.w), pack2<BF>(b.x, b.y), pack2<BF>(b.z, b.w));
+        // four items (eight 128-bit loads) in flight per thread: nothing else is live yet, registers are free here
+        constexpr int STEP = DGR_THREADS / G::KC8, NPIX = G::PH * G::PW, SB = 4;
+#pragma unroll 1
+        for (int pix0 = tid / G::KC8; pix0 < NPIX; pix0 += SB * STEP) {
+            float4 va[SB], vb[SB];
+            bool ok[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) {
+                const int pix = pix0 + k * STEP;
+                const int r = pix / G::PW, c = pix - r * G::PW;
+                const int gy = y0 + r - 1, gx = x0 + c - 1;
+                ok[k] = pix < NPIX && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+                if (ok[k]) {
+                    va[k] = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CK));
+                    vb[k] = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CK) + 1);
+                }
             }
-            *reinterpret_cast<uint4*>(dst + (size_t)pix * 16) = o;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) {
+                const int pix = pix0 + k * STEP;
+                if (pix >= NPIX) continue;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[k]) o = make_uint4(pack2<BF>(va[k].x, va[k].y), pack2<BF>(va[k].z, va[k].w), pack2<BF>(vb[k].x, vb[k].y),
+                                          pack2<BF>(vb[k].z, vb[k].w));
+                *reinterpret_cast<uint4*>(dst + (size_t)pix * 16) = o;
+            }
         }
     }
     cp_async_wait<0>();

@@ -342,6 +342,7 @@ struct CtWgArgs {
     const void* raw_low; const double* stats; const float* gamma; const float* beta; int groups;
     const float* dCat; int stride;   // [N, 2Hl, 2Wl, stride], up half = channels 0..CU
     float* dWt;                      // [CL][CU][2][2], accumulated atomically
+    float* dBias;                    // optional [CU]: sum of the up-half gradient over every pixel (ConvTranspose bias gradient)
     int N, Hl, Wl; float eps;
     int tiles_x, tiles_y;
 };
@@ -358,8 +359,11 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
     unsigned char* act = smem;
     unsigned char* dsm = smem + A_BYTES;
     float2* coef = reinterpret_cast<float2*>(smem + A_BYTES + D_BYTES);
+    float* bias_sm = reinterpret_cast<float*>(coef + CL);   // [CU]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pos0 = blockIdx.y * POSG;
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias gradient partials of this thread's 8 output channels
+    for (int c = tid; c < CU; c += WG_THREADS) bias_sm[c] = 0.f;
     const int Hl = p.Hl, Wl = p.Wl, H = 2 * Hl, W = 2 * Wl;
     const int tiles_per_img = p.tiles_x * p.tiles_y, ntiles = tiles_per_img * p.N;
     float acc[IPW][NTW][4];
@@ -417,6 +421,9 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
                     const float4 a = __ldg(reinterpret_cast<const float4*>(q));
                     const float4 b = __ldg(reinterpret_cast<const float4*>(q) + 1);
                     o = make_uint4(pack2<BF>(a.x, a.y), pack2<BF>(a.z, a.w), pack2<BF>(b.x, b.y), pack2<BF>(b.z, b.w));
+                    // every up-half gradient element passes through here exactly once over the whole grid
+                    bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w;
+                    bsum[4] += b.x; bsum[5] += b.y; bsum[6] += b.z; bsum[7] += b.w;
                 }
                 *reinterpret_cast<uint4*>(dsm + ((size_t)(ps * NTW + j8) * DPLANE + pix) * 16) = o;
             }
@@ -452,6 +459,13 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
             }
         }
     }
+    if (p.dBias != nullptr) {
+        const int j8 = tid % NTW;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&bias_sm[j8 * 8 + k], bsum[k]);
+        __syncthreads();
+        for (int c = tid; c < CU; c += WG_THREADS) atomicAdd(p.dBias + c, bias_sm[c]);
+    }
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int s = 0; s < IPW; ++s) {
@@ -475,7 +489,7 @@ template <typename T, int CL, int CU, int POSG>
 int launch_ctwg(CtWgArgs a, cudaStream_t st) {
     constexpr int TH = 8, TW = 32;
     constexpr int NC8 = CL / 8, NTW = CU / 8;
-    constexpr int SMEM = NC8 * wg_pad_plane(TH * TW, NC8) * 16 + POSG * NTW * wg_pad_plane(TH * TW, NTW) * 16 + CL * 8;
+    constexpr int SMEM = NC8 * wg_pad_plane(TH * TW, NC8) * 16 + POSG * NTW * wg_pad_plane(TH * TW, NTW) * 16 + CL * 8 + CU * 4;
     auto kern = convt_wgrad_tc_kernel<T, CL, CU, TH, TW, POSG>;
     static bool done = false;
     if (!done) {
@@ -509,15 +523,16 @@ int dispatch_ctwg(const CtWgArgs& a, int cl, int cu, cudaStream_t st, bool* hand
 
 }  // namespace
 
+// dBias [Cu] (optional) += sum of the up half over all pixels, folded into the gradient staging.
 // dWt [Cl][Cu][2][2] += correlation of the activated low-resolution producer with the up half (channels 0..Cu of a
 // [N,H,W,stride] fp32 tensor) of the concat gradient.  16-bit storage, LightweightUNet(features_start=8) channel pairs.
 int convt_wgrad_tc_launch(int dtype, const float* dCat, int stride, const void* raw_low, const double* stats, const float* gamma,
-                          const float* beta, float* dWt, int N, int H, int W, int Cl, int Cu, int groups, float eps,
+                          const float* beta, float* dWt, float* dBias, int N, int H, int W, int Cl, int Cu, int groups, float eps,
                           cudaStream_t st, bool* handled) {
     *handled = false;
     if (dtype != DG_F16 && dtype != DG_BF16) return 0;
     if ((reinterpret_cast<uintptr_t>(dCat) & 15) || (stride & 3) || (reinterpret_cast<uintptr_t>(raw_low) & 15) || ((H | W) & 1)) return 0;
-    CtWgArgs a{raw_low, stats, gamma, beta, groups, dCat, stride, dWt, N, H / 2, W / 2, eps, 0, 0};
+    CtWgArgs a{raw_low, stats, gamma, beta, groups, dCat, stride, dWt, dBias, N, H / 2, W / 2, eps, 0, 0};
     if (dtype == DG_F16) return dispatch_ctwg<__half>(a, Cl, Cu, st, handled);
     return dispatch_ctwg<__nv_bfloat16>(a, Cl, Cu, st, handled);
 }
