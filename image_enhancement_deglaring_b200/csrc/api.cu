@@ -327,11 +327,15 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
         return 4;
     }
     if (x == nullptr || grad_y == nullptr || grads == nullptr) { set_error("backward: null pointer"); return 2; }
+    // conv_w_flip / up_w_t feed the CUDA-core data-gradient kernels only: required where a tensor-core packing is absent
     for (int b = 0; b < 9; ++b)
         for (int j = 0; j < 2; ++j)
-            if ((2 * b + j) > 0 && p->conv_w_flip[b][j] == nullptr) { set_error("backward: flipped weights missing"); return 2; }
+            if ((2 * b + j) > 0 && p->conv_w_flip[b][j] == nullptr && p->conv_w_tc_bf16[b][j] == nullptr) {
+                set_error("backward: neither flipped weights nor a bf16 tensor-core packing for conv %d", 2 * b + j);
+                return 2;
+            }
     for (int u = 0; u < 4; ++u)
-        if (p->up_w_t[u] == nullptr) { set_error("backward: transposed ConvTranspose weights missing"); return 2; }
+        if (p->up_w_t[u] == nullptr && p->up_w_tc_bf16[u] == nullptr) { set_error("backward: transposed ConvTranspose weights missing"); return 2; }
     char* fw = static_cast<char*>(fwd_ws);
     char* bw = static_cast<char*>(bwd_ws);
     cudaError_t e = cudaMemsetAsync(bw, 0, bp.p_bytes, st);
@@ -417,6 +421,7 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
         d.src[0].groups = 1;
         d.src[0].xform = DG_X_SAME;
         if (!dg_done) {
+            if (d.weight == nullptr) { set_error("backward: conv %d needs the CUDA-core dgrad but conv_w_flip is NULL", i); return 2; }
             rc = conv3x3_generic_launch(d, st);
             if (rc) return rc;
         }

@@ -797,6 +797,7 @@ int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, 
         if (rc) return rc;
     }
     if (!data_done) {
+        if (wt_t == nullptr) { set_error("convT backward: the CUDA-core data gradient needs up_w_t"); return 2; }
         convt_bwd_data_kernel<<<ew_blocks(total, Cl), BW_THREADS, 0, st>>>(a);
         count_launch();
         rc = check_launch("convt_bwd_data");

@@ -110,12 +110,14 @@ class LightweightUNet(nn.Module):
                 g = blk[gi].weight.detach().float().contiguous()
                 bt = blk[gi].bias.detach().float().contiguous()
                 wtc = ops.pack_conv3x3_tc(w, pc.dtype) if self.path != 1 else None
-                # backward only: dgrad runs as a forward conv with the taps flipped and Cin/Cout swapped
-                wfl = blk[ci].weight.detach().float().flip(2, 3).permute(2, 3, 0, 1).contiguous() if train else None
+                # backward only, CUDA-core tier: dgrad runs as a forward conv with the taps flipped and Cin/Cout swapped
+                # (the tensor-core tier reads the bf16 packing below instead; it covers the features_start = 8 channel sets)
+                tc_bwd = train and self.path != 1 and pc.dtype != ops.DG_F32 and self.features_start == 8
+                wfl = blk[ci].weight.detach().float().flip(2, 3).permute(2, 3, 0, 1).contiguous() if (train and not tc_bwd) else None
                 pc.conv_w_flip[b][j] = None if wfl is None else wfl.data_ptr()
                 # tensor-core dgrad: bf16 packing of the forward weights (read transposed; bf16 because dR underflows fp16)
                 wbf = None
-                if train and self.path != 1 and pc.dtype != ops.DG_F32:
+                if tc_bwd and (b, j) != (0, 0):
                     wbf = wtc if pc.dtype == ops.DG_BF16 else ops.pack_conv3x3_tc(w, ops.DG_BF16)
                 pc.conv_w_tc_bf16[b][j] = None if wbf is None else wbf.data_ptr()
                 keep += [w, g, bt, wtc, wfl, wbf]
@@ -128,10 +130,11 @@ class LightweightUNet(nn.Module):
             w = ops.pack_convt2x2(m.weight)
             bt = m.bias.detach().float().contiguous()
             wtc = ops.pack_convt2x2_tc(w, pc.dtype) if self.path != 1 else None
-            wtt = m.weight.detach().float().permute(2, 3, 1, 0).contiguous() if train else None   # [2,2,Co,Ci]
+            tc_bwd = train and self.path != 1 and pc.dtype != ops.DG_F32 and self.features_start == 8
+            wtt = m.weight.detach().float().permute(2, 3, 1, 0).contiguous() if (train and not tc_bwd) else None   # [2,2,Co,Ci]
             pc.up_w_t[u] = None if wtt is None else wtt.data_ptr()
             wbf = None
-            if train and self.path != 1 and pc.dtype != ops.DG_F32:
+            if tc_bwd:
                 wbf = wtc if pc.dtype == ops.DG_BF16 else ops.pack_convt2x2_tc(w, ops.DG_BF16)
             pc.up_w_tc_bf16[u] = None if wbf is None else wbf.data_ptr()
             keep += [w, bt, wtc, wtt, wbf]
