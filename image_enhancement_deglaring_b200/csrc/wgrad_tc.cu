@@ -82,6 +82,9 @@ struct WgGeo {
     static constexpr int A_BYTES = NC8 * APLANE * 16, D_BYTES = NTW * DPLANE * 16;
     static constexpr int NCOEF = MODE == WG_CAT2 ? CI / 2 : CI;
     static constexpr int SMEM = A_BYTES + D_BYTES + NCOEF * 8;
+    // the narrow layers are staging-latency bound: make the register allocator leave room for 3 (288-thread) / 4 (256-thread)
+    // resident CTAs -- dec1.0 sat at 84 registers = 2 CTAs/SM and ran 2x slower than its 8-channel neighbours
+    static constexpr int MIN_CTAS = (IPW * NTW * 4 <= 16) ? (PAIR ? 4 : 3) : 2;
     static_assert(!PAIR || CIB == 8, "8 input channels: one block");
     static_assert(CI % CIB == 0 && (PAIR || CIB % 16 == 0) && CO % (8 * NTW) == 0 && TW % 16 == 0, "shape");
     static_assert(IPW * NTW * 4 <= 64, "accumulator budget");
@@ -90,7 +93,8 @@ struct WgGeo {
 };
 
 template <typename T, int CI, int CO, int MODE, int TH, int TW, int CIB, int NTW>
-__global__ void __launch_bounds__(WgGeo<T, CI, CO, MODE, TH, TW, CIB, NTW>::THREADS) wgrad_tc_kernel(const WgArgs p) {
+__global__ void __launch_bounds__(WgGeo<T, CI, CO, MODE, TH, TW, CIB, NTW>::THREADS, WgGeo<T, CI, CO, MODE, TH, TW, CIB, NTW>::MIN_CTAS)
+wgrad_tc_kernel(const WgArgs p) {
     using G = WgGeo<T, CI, CO, MODE, TH, TW, CIB, NTW>;
     constexpr int WG_THREADS = G::THREADS;
     using BF = __nv_bfloat16;
