@@ -192,6 +192,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = None
+    if world > 1:   # one process per GPU: keep each rank (and the pinned buffers it allocates) on its GPU's NUMA node
+        from image_enhancement_deglaring_b200.parallel import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -359,7 +363,7 @@ def main():
         }
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # rank 0 at N = 1 only (the other ranks would idle behind it)
         reps = 3
         rate, cores, times = cpu_reference_rate(args.ref_batch, reps, H, W)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -374,6 +378,7 @@ def main():
             "config": {"workload": f"best_model.pth LightweightUNet (486,409 params) batched inference, batch {B} x 1x{H}x{W} "
                                    f"per GPU, {args.storage} storage / fp32 accumulate (BASELINE.json configs[1])",
                        "batch_per_gpu": B, "global_batch": B * world, "sharding": "images over ranks, no collective",
+                       "cpu_affinity": (f"rank 0 bound to {len(numa_cpus)} CPUs local to its GPU (NVML)" if numa_cpus else "unbound"),
                        "l2": f"inputs+intermediates per step ({sum(algorithmic_bytes_per_image(H, W)) * B / 2**20:.0f} MiB) exceed the 126 MB L2; no flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 4, "d2h_bytes_per_step": B * H * W * 4,

@@ -20,6 +20,34 @@ def shard_range(n_items, rank, world):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs NVML reports as local to `device_index` (its NUMA node), so that the pinned host
+    buffers it allocates afterwards are first-touched next to that GPU's PCIe root.  One process per GPU on a two-socket box:
+    without this, half of the ranks stream their host buffers across the inter-socket link and the 8-GPU end-to-end rate with
+    fp32 I/O (2 x 67 MB per 64-image batch per GPU) collapsed to 2.9x of one GPU (measured; uint8 I/O, a quarter of the bytes,
+    scaled 7.9x).  Returns the CPU set, or None if NVML / affinity control is unavailable (never raises)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            props = torch.cuda.get_device_properties(device_index)
+            bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class FlatGradBucket:
     """One flat fp32 buffer aliasing every parameter's .grad, so the data-parallel exchange is a single all-reduce.
 
