@@ -96,11 +96,20 @@ __device__ __forceinline__ void gn_coef(const double* __restrict__ stats, const 
         s1 += stats[(size_t)(n * C + g0 + k) * 2];
         s2 += stats[(size_t)(n * C + g0 + k) * 2 + 1];
     }
+    // Every conv CTA runs this serial chain before it can stage its tile (the other warps wait at the barrier), so the two
+    // double divisions and the double rsqrt (~100 instructions) are replaced by float seeds + Newton steps in double:
+    // 1/cnt and rsqrt(var + eps) to ~1e-16 relative, i.e. the same floats a and b after rounding.
     const double cnt = plane * cpg;
-    const double mean = s1 / cnt;
-    double var = s2 / cnt - mean * mean;
+    double inv = (double)__frcp_rn((float)cnt);
+    inv = inv * (2.0 - cnt * inv);
+    inv = inv * (2.0 - cnt * inv);
+    const double mean = s1 * inv;
+    double var = fma(s2, inv, -mean * mean);
     if (var < 0.0) var = 0.0;
-    const double rstd = rsqrt(var + (double)eps);
+    const double x = var + (double)eps;
+    double rstd = (double)rsqrtf((float)x);
+    rstd = rstd * (1.5 - 0.5 * x * rstd * rstd);
+    rstd = rstd * (1.5 - 0.5 * x * rstd * rstd);
     a = (float)(rstd * (double)gamma[c]);
     b = (float)((double)beta[c] - mean * rstd * (double)gamma[c]);
 }
