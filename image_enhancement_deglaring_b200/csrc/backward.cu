@@ -32,12 +32,20 @@ __device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, i
         s1 += stats[(size_t)(n * C + g0 + k) * 2];
         s2 += stats[(size_t)(n * C + g0 + k) * 2 + 1];
     }
+    // float-seeded Newton steps in double instead of double division / rsqrt (see gn_coef in common.cuh)
     const double cnt = plane * cpg;
-    const double m = s1 / cnt;
-    double var = s2 / cnt - m * m;
+    double inv = (double)__frcp_rn((float)cnt);
+    inv = inv * (2.0 - cnt * inv);
+    inv = inv * (2.0 - cnt * inv);
+    const double m = s1 * inv;
+    double var = fma(s2, inv, -m * m);
     if (var < 0.0) var = 0.0;
+    const double x = var + (double)eps;
+    double r = (double)rsqrtf((float)x);
+    r = r * (1.5 - 0.5 * x * r * r);
+    r = r * (1.5 - 0.5 * x * r * r);
     mean = (float)m;
-    rstd = (float)rsqrt(var + (double)eps);
+    rstd = (float)r;
 }
 
 // ---- G = (dA_a + 0.25 * up2(dA_b)) * silu'(y);  P[n][c] += (sum G, sum G*xhat) -------------------------------------
