@@ -162,7 +162,11 @@ wgrad_tc_kernel(const WgArgs p) {
             // (explicitly batching 4 loads per thread here and in the dR loop was measured: the persistent accumulators stay
             // live across the staging, registers went to 128-168 (or 64-360 B of spills under a launch bound) and the wgrad
             // total rose from 2.57 to 2.76 ms.  The cure for the long-scoreboard stalls ncu shows on the narrow layers
-            // (profiles/r01_ncu_wgrad.txt) is a cp.async double buffer of the RAW tiles, not more registers.)
+            // (profiles/r01_ncu_wgrad.txt) is not more registers.  A cp.async version -- every 16-byte piece of both raw tiles in
+            // flight at once, the 16-bit input activated in place in its plane slot -- was ALSO measured and is no faster
+            // (2.37 vs 2.34 ms): these kernels execute ~5.5 warp-instructions per pixel, 2.5 of them in the K loop, where each
+            // of the five tap-pair warps re-loads the B fragment for every 16 pixels to feed ONE small MMA.  Next step: split K
+            // (rows) across warps and let every warp sweep all taps per B load, with a shared-memory reduction at the end.)
 #pragma unroll 4
             for (int pix = tid / G::NC8; pix < NPIX; pix += WG_THREADS / G::NC8) {
                 const int r = pix / G::PW, c = pix - r * G::PW;
