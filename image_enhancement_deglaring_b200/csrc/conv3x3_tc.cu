@@ -117,7 +117,10 @@ struct Geo {
 // ITERS batches of BATCH; all loads of a batch are issued before any math, the slot count is matched to the tile, the
 // (row, column) of a slot advances incrementally, and tiles whose halo lies inside the image skip every bounds test
 // (profiles r1b/r1c: addressing was ~1/3 of the instructions).  `src` points at image n; offsets are 32-bit.
-template <typename T, typename G, int C, bool POOL, int ACT, bool IDENT = false>
+// SYNC_FIRST: the GroupNorm coefficients `cfs` are still being written by other threads when this is called; the CTA barrier
+// that publishes them is taken here, AFTER the first batch of global loads has been issued, so the coefficient chain
+// (statistics load -> double math -> shared memory) and the first tile loads overlap instead of running back to back.
+template <typename T, typename G, int C, bool POOL, int ACT, bool IDENT = false, bool SYNC_FIRST = false>
 __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned char* __restrict__ src,
                                              const float2* __restrict__ cfs, int plane0, int y0, int x0, int H, int W) {
     constexpr int NC = C / 8;
@@ -135,17 +138,20 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
     const int p0 = threadIdx.x / NC;
     float2 cf[H2 ? 1 : 8];
     uint32_t ah[H2 ? 4 : 1], bh[H2 ? 4 : 1];
-    if constexpr (H2) {
+    auto read_coefs = [&]() {
+        if constexpr (H2) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 c0 = cfs[c8 * 8 + 2 * k], c1 = cfs[c8 * 8 + 2 * k + 1];
-            ah[k] = pack2<__half>(c0.x, c1.x);
-            bh[k] = pack2<__half>(c0.y, c1.y);
+            for (int k = 0; k < 4; ++k) {
+                const float2 c0 = cfs[c8 * 8 + 2 * k], c1 = cfs[c8 * 8 + 2 * k + 1];
+                ah[k] = pack2<__half>(c0.x, c1.x);
+                bh[k] = pack2<__half>(c0.y, c1.y);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cf[k] = cfs[c8 * 8 + k];
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cf[k] = cfs[c8 * 8 + k];
-    }
+    };
+    if constexpr (!SYNC_FIRST) read_coefs();
     unsigned char* dst = act + (size_t)(plane0 + c8) * G::PLANE * 16;
     const uint32_t rowb = (uint32_t)(POOL ? 2 * W : W) * C * 2;    // source row pitch in bytes
     const unsigned char* srcc = src + c8 * 16;
@@ -180,6 +186,12 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
                 r += DR;
                 c += DC;
                 if (c >= G::PW) { c -= G::PW; r += 1; }
+            }
+            if constexpr (SYNC_FIRST) {
+                if (it == 0) {
+                    __syncthreads();   // coefficients published (uniform: every thread runs the same ITERS)
+                    read_coefs();
+                }
             }
 #pragma unroll
             for (int b = 0; b < BATCH; ++b) {
@@ -298,20 +310,20 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
             coef[c] = make_float2(a, b);
         }
     }
-    __syncthreads();
+    if constexpr (G::MODE != M_SAME && G::MODE != M_POOL) __syncthreads();   // SAME / POOL: inside stage_planes (SYNC_FIRST)
 
     // ---- (2) stage the activated halo tile ------------------------------------------------------------
     if constexpr (G::MODE == M_SAME) {
-        stage_planes<T, G, G::CIN, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 2,
-                                                coef, 0, y0, x0, H, W);
+        stage_planes<T, G, G::CIN, false, ACT, false, true>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 2,
+                                                             coef, 0, y0, x0, H, W);
     } else if constexpr (G::MODE == M_CAT2) {
         stage_planes<T, G, G::COUT, false, ACT, true>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::COUT * 2,
                                                       coef, 0, y0, x0, H, W);
         stage_planes<T, G, G::COUT, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::COUT * 2,
                                                  coef, G::COUT / 8, y0, x0, H, W);
     } else if constexpr (G::MODE == M_POOL) {
-        stage_planes<T, G, G::CIN, true, ACT>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 8,
-                                               coef, 0, y0, x0, H, W);
+        stage_planes<T, G, G::CIN, true, ACT, false, true>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 8,
+                                                            coef, 0, y0, x0, H, W);
     } else {
         // skip -> planes [CU/8, 2CU/8)
         stage_planes<T, G, G::CU, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::CU * 2,
