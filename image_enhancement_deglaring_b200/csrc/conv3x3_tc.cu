@@ -151,7 +151,7 @@ __device__ __forceinline__ void stage_planes(unsigned char* act, const unsigned 
             for (int k = 0; k < 8; ++k) cf[k] = cfs[c8 * 8 + k];
         }
     };
-    if constexpr (!SYNC_FIRST) read_coefs();
+    if constexpr (!SYNC_FIRST && !IDENT) read_coefs();
     unsigned char* dst = act + (size_t)(plane0 + c8) * G::PLANE * 16;
     const uint32_t rowb = (uint32_t)(POOL ? 2 * W : W) * C * 2;    // source row pitch in bytes
     const unsigned char* srcc = src + c8 * 16;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
             coef[c] = make_float2(a, b);
         }
     }
-    if constexpr (G::MODE != M_SAME && G::MODE != M_POOL) __syncthreads();   // SAME / POOL: inside stage_planes (SYNC_FIRST)
+    // the barrier that publishes the coefficients is taken inside the first stage_planes call that needs them (SYNC_FIRST)
 
     // ---- (2) stage the activated halo tile ------------------------------------------------------------
     if constexpr (G::MODE == M_SAME) {
@@ -319,15 +319,15 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
     } else if constexpr (G::MODE == M_CAT2) {
         stage_planes<T, G, G::COUT, false, ACT, true>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::COUT * 2,
                                                       coef, 0, y0, x0, H, W);
-        stage_planes<T, G, G::COUT, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::COUT * 2,
-                                                 coef, G::COUT / 8, y0, x0, H, W);
+        stage_planes<T, G, G::COUT, false, ACT, false, true>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::COUT * 2,
+                                                              coef, G::COUT / 8, y0, x0, H, W);
     } else if constexpr (G::MODE == M_POOL) {
         stage_planes<T, G, G::CIN, true, ACT, false, true>(act, reinterpret_cast<const unsigned char*>(p.src0) + (size_t)n * H * W * G::CIN * 8,
                                                             coef, 0, y0, x0, H, W);
     } else {
         // skip -> planes [CU/8, 2CU/8)
-        stage_planes<T, G, G::CU, false, ACT>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::CU * 2,
-                                               coef + G::CL, G::CU / 8, y0, x0, H, W);
+        stage_planes<T, G, G::CU, false, ACT, false, true>(act, reinterpret_cast<const unsigned char*>(p.src1) + (size_t)n * H * W * G::CU * 2,
+                                                            coef + G::CL, G::CU / 8, y0, x0, H, W);
         // activated low-res tile -> low planes
         unsigned char* low = smem + G::OFF_LOW;
         const T* raw = reinterpret_cast<const T*>(p.src0);
