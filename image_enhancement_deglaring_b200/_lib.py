@@ -102,6 +102,7 @@ SYMBOLS = {
     "dg_last_error_string": (C.c_char_p, []),
     "dg_version": (C.c_int, []),
     "dg_set_pdl": (C.c_int, [C.c_int]),
+    "dg_set_batch_split": (C.c_int, [C.c_int]),
     "dg_launch_count": (C.c_uint64, []),
 }
 

@@ -262,6 +262,11 @@ int dg_pack_convt2x2_tc(const float* w, void* out, int32_t cin, int32_t cout, in
 /* ---- misc --------------------------------------------------------------------------- */
 const char* dg_last_error_string(void);
 int dg_version(void);
+/* dg_lw_forward / dg_lw_forward_u8 run the two halves of a batch of at least `min_batch` images (default 16) concurrently
+ * on two library-private streams forked from and joined to the caller's stream; 0 disables.  Returns the previous value.
+ * Results do not depend on it (images are independent). */
+int dg_set_batch_split(int min_batch);
+
 /* Programmatic dependent launch for the library's kernel chain (default on); returns the previous setting. */
 int dg_set_pdl(int enabled);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */

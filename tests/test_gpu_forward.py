@@ -265,3 +265,26 @@ def test_tiled_high_resolution_equals_per_tile_forward(best_sd):
         u = (img * 255).to(torch.uint8)
         full8 = infer_tiled(net.forward_u8, u, tile=512)
         assert full8.dtype == torch.uint8 and torch.equal(full8[:, :512, 1024:], net.forward_u8(split_tiles(u, 512)[0][2:3])[0])
+
+
+def test_two_stream_batch_split_is_bit_identical(best_sd):
+    """dg_lw_forward runs the halves of a large batch on two private streams (dg_set_batch_split): same bits as one stream,
+    for the float and the uint8 entry points, odd batch included."""
+    from image_enhancement_deglaring_b200 import _lib
+    lib = _lib.load()
+    net = _net(best_sd, storage="fp16")
+    x = _rand((5, 1, 64, 96), 41).cuda()
+    u = (x * 255).to(torch.uint8)
+    old = lib.dg_set_batch_split(0)
+    try:
+        with torch.no_grad():
+            y1, u1 = net(x).clone(), net.forward_u8(u).clone()
+        assert lib.dg_set_batch_split(2) == 0
+        with torch.no_grad():
+            y2, u2 = net(x).clone(), net.forward_u8(u).clone()
+            for _ in range(3):   # back-to-back calls reuse the fork / join events
+                y3 = net(x)
+        assert torch.equal(y1, y2) and torch.equal(u1, u2) and torch.equal(y1, y3)
+    finally:
+        lib.dg_set_batch_split(old)
+    assert old == 16
