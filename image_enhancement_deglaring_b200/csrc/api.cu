@@ -304,7 +304,7 @@ static void make_grad_layout(const dg_lw_params* p, const LwPlan& pl, GradLayout
 
 struct BwdPlan {
     size_t p_off[18], g_off[18], t_off[18], low_off[4], coef_off, p_bytes, total;
-    int cin_tot[18];
+    int cin_tot[18], maxc;
 };
 
 static void make_bwd_plan(const dg_lw_params* p, const LwPlan& pl, int N, BwdPlan* bp) {
@@ -328,43 +328,50 @@ static void make_bwd_plan(const dg_lw_params* p, const LwPlan& pl, int N, BwdPla
         off += align_up((size_t)N * (pl.conv_h[2 * lvl + 2]) * (pl.conv_w[2 * lvl + 2]) * pl.f[lvl + 1] * sizeof(float), 256);
     }
     bp->coef_off = off;
+    bp->maxc = maxc;
     off += align_up((size_t)N * maxc * 2 * sizeof(float), 256);
     bp->total = off;
 }
 
-static void fwd_conv_args(const dg_lw_params* p, const LwPlan& pl, char* ws, const float* x, int N, int i, dg_conv3x3_args* a) {
+// the forward conv i's argument block for images [n0, n0 + nn) (x = the WHOLE batch's input)
+static void fwd_conv_args(const dg_lw_params* p, const LwPlan& pl, char* ws, const float* x, int nn, int i, dg_conv3x3_args* a,
+                          int n0 = 0) {
     const int b = i / 2;
     memset(a, 0, sizeof(*a));
     a->dtype = p->dtype;
-    a->N = N; a->H = pl.conv_h[i]; a->W = pl.conv_w[i];
+    a->N = nn; a->H = pl.conv_h[i]; a->W = pl.conv_w[i];
     a->cout = pl.conv_c[i];
     a->weight = p->conv_w[b][i % 2];
     a->weight_tc = p->conv_w_tc[b][i % 2];
-    a->out = ws + pl.raw_off[i];
-    a->out_stats = reinterpret_cast<double*>(ws + pl.stats_off[i]);
+    a->out = ws + pl.raw_off[i] + (size_t)n0 * a->H * a->W * a->cout * dtype_size(p->dtype);
+    a->out_stats = reinterpret_cast<double*>(ws + pl.stats_off[i]) + (size_t)n0 * a->cout * 2;
     a->eps = 1e-5f;
     a->path = p->path;
     a->nsrc = 1;
     if (i == 0) {
-        a->src[0].raw = x;
+        a->src[0].raw = x + (size_t)n0 * p->in_channels * pl.conv_h[0] * pl.conv_w[0];
         a->src[0].channels = p->in_channels;
         a->src[0].groups = 1;
         a->src[0].xform = DG_X_IMAGE;
     } else if (i % 2 == 1) {
-        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_SAME);
+        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_SAME, n0);
     } else if (b < 5) {
-        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_POOL2);       // pool1..4, src/model.py:107-112
+        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_POOL2, n0);       // pool1..4, src/model.py:107-112
     } else {
         const int lvl = block_level(b), u = b - 5;
-        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_CONVT2);     // upconv4..1, src/model.py:115-127
+        a->src[0] = gn_src(p, pl, ws, i - 1, DG_X_CONVT2, n0);     // upconv4..1, src/model.py:115-127
         a->src[0].ct_w = p->up_w[u];
         a->src[0].ct_b = p->up_b[u];
         a->src[0].ct_w_tc = p->up_w_tc[u];
         a->src[0].ct_cout = pl.f[lvl];
-        a->src[1] = gn_src(p, pl, ws, 2 * lvl + 1, DG_X_SAME); // skip: torch.cat((up, skip), 1)
+        a->src[1] = gn_src(p, pl, ws, 2 * lvl + 1, DG_X_SAME, n0); // skip: torch.cat((up, skip), 1)
         a->nsrc = 2;
     }
 }
+
+static int lw_backward_range(const dg_lw_params* p, const struct LwPlan& pl, const struct BwdPlan& bp, const struct GradLayout& gl,
+                             const float* x, const float* grad_y, int n0, int N, int H, int W, char* fw, char* bw, float* grads,
+                             cudaStream_t st);
 
 static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_y, int N, int H, int W, void* fwd_ws,
                        size_t fwd_bytes, void* bwd_ws, size_t bwd_bytes, float* grads, cudaStream_t st) {
@@ -394,17 +401,43 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
     cudaError_t e = cudaMemsetAsync(bw, 0, bp.p_bytes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(grads, 0, gl.total * sizeof(float), st);
     if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 10; }
-    auto G = [&](int i) { return reinterpret_cast<float*>(bw + bp.g_off[i]); };
-    auto T = [&](int i) { return reinterpret_cast<float*>(bw + bp.t_off[i]); };
-    auto P = [&](int i) { return reinterpret_cast<double*>(bw + bp.p_off[i]); };
-    auto raw = [&](int i) { return static_cast<const void*>(fw + pl.raw_off[i]); };
-    auto stats = [&](int i) { return reinterpret_cast<const double*>(fw + pl.stats_off[i]); };
+    const int split = g_split.load();
+    if (split > 0 && N >= split && N >= 2) {   // two concurrent halves, as in lw_forward
+        if ((rc = fork_init())) return rc;
+        FwdFork& F = g_fork;
+        cudaEventRecord(F.fork, st);
+        const int half = N / 2;
+        for (int k = 0; k < 2; ++k) {
+            cudaStreamWaitEvent(F.s[k], F.fork, 0);
+            rc = lw_backward_range(p, pl, bp, gl, x, grad_y, k ? half : 0, k ? N - half : half, H, W, fw, bw, grads, F.s[k]);
+            cudaEventRecord(F.join[k], F.s[k]);
+            cudaStreamWaitEvent(st, F.join[k], 0);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    return lw_backward_range(p, pl, bp, gl, x, grad_y, 0, N, H, W, fw, bw, grads, st);
+}
+
+// Backward over images [n0, n0 + N) of a batch of N_total; every buffer was laid out for the whole batch (`N` below is the
+// sub-batch size).  Parameter gradients are accumulated atomically, so concurrent sub-batches add up.
+static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdPlan& bp, const GradLayout& gl, const float* x,
+                             const float* grad_y, int n0, int N, int H, int W, char* fw, char* bw, float* grads, cudaStream_t st) {
+    int rc = 0;
+    const size_t esz = dtype_size(p->dtype);
+    auto hwc = [&](int i, int c) { return (size_t)pl.conv_h[i] * pl.conv_w[i] * c; };
+    auto G = [&](int i) { return reinterpret_cast<float*>(bw + bp.g_off[i]) + (size_t)n0 * hwc(i, pl.conv_c[i]); };
+    auto T = [&](int i) { return reinterpret_cast<float*>(bw + bp.t_off[i]) + (size_t)n0 * hwc(i, bp.cin_tot[i]); };
+    auto P = [&](int i) { return reinterpret_cast<double*>(bw + bp.p_off[i]) + (size_t)n0 * pl.conv_c[i] * 2; };
+    auto raw = [&](int i) { return static_cast<const void*>(fw + pl.raw_off[i] + (size_t)n0 * hwc(i, pl.conv_c[i]) * esz); };
+    auto stats = [&](int i) { return reinterpret_cast<const double*>(fw + pl.stats_off[i]) + (size_t)n0 * pl.conv_c[i] * 2; };
     auto act_bwd = [&](int j, const float* da, int sa, int oa, const float* db, int sb, int ob) {
         return act_bwd_launch(p->dtype, raw(j), stats(j), p->gn_w[j / 2][j % 2], p->gn_b[j / 2][j % 2], da, sa, oa, db, sb, ob, G(j),
                               P(j), N, pl.conv_h[j], pl.conv_w[j], pl.conv_c[j], p->groups[j / 2], 1e-5f, st);
     };
     // head: src/model.py:131 backward
-    rc = head_bwd_launch(p->dtype, raw(17), stats(17), p->gn_w[8][1], p->gn_b[8][1], grad_y, p->head_w, G(17), P(17),
+    rc = head_bwd_launch(p->dtype, raw(17), stats(17), p->gn_w[8][1], p->gn_b[8][1],
+                         grad_y + (size_t)n0 * p->out_channels * H * W, p->head_w, G(17), P(17),
                          grads + gl.head_w, grads + gl.head_b, N, H, W, pl.conv_c[17], p->out_channels, p->groups[8], 1e-5f, st);
     if (rc) return rc;
     for (int i = 17; i >= 0; --i) {
@@ -415,7 +448,7 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
         if (rc) return rc;
         // dW_i: same sources as the forward conv, correlated with dR_i; written in the parameter's [Co][Ci][3][3] layout
         dg_conv3x3_args a;
-        fwd_conv_args(p, pl, fw, x, N, i, &a);
+        fwd_conv_args(p, pl, fw, x, N, i, &a, n0);
         bool wg_done = false;
         if (p->dtype != DG_F32 && (p->path & 3) != 1 && i > 0) {
             // tensor-core wgrad (wgrad_tc.cu); a decoder conv reads the MATERIALISED ConvTranspose output: the forward left it
@@ -423,7 +456,7 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
             bool ok = true;
             if (a.nsrc == 2) {
                 const int lvl = block_level(b), u = b - 5;
-                void* up = fw + pl.up_off[u];
+                void* up = fw + pl.up_off[u] + (size_t)n0 * Hi * Wi * pl.f[lvl] * esz;
                 const bool have_up = (u < 2 || (u == 2 && (p->path & 32)));
                 if (!have_up) {
                     rc = convt_tc_launch(a.src[0], p->dtype, N, Hi, Wi, up, 1e-5f, p->path, st, &ok);
@@ -441,10 +474,10 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
                 rc = conv3x3_wgrad_tc_launch(a, G(i), grads + gl.conv_w[b][j], 1, 9, 9 * bp.cin_tot[i], st, &wg_done);
                 if (rc) return rc;
             }
-            if (!wg_done) fwd_conv_args(p, pl, fw, x, N, i, &a);  // restore the fused description for the generic kernel
+            if (!wg_done) fwd_conv_args(p, pl, fw, x, N, i, &a, n0);  // restore the fused description for the generic kernel
         }
         if (i == 0 && (p->path & 3) != 1 && p->in_channels == 1) {   // first conv: dedicated streaming kernel (backward.cu)
-            rc = first_wgrad_launch(x, G(0), grads + gl.conv_w[0][0], N, Hi, Wi, C, st, &wg_done);
+            rc = first_wgrad_launch(x + (size_t)n0 * p->in_channels * H * W, G(0), grads + gl.conv_w[0][0], N, Hi, Wi, C, st, &wg_done);
             if (rc) return rc;
         }
         if (!wg_done) {
@@ -486,10 +519,10 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
             rc = act_bwd(i - 1, T(dconv), 2 * pl.f[lvl], pl.f[lvl], T(i), pl.f[lvl], 0);
         } else {
             const int lvl = block_level(b), u = b - 5;
-            float* dlow = reinterpret_cast<float*>(bw + bp.low_off[u]);
+            float* dlow = reinterpret_cast<float*>(bw + bp.low_off[u]) + (size_t)n0 * (Hi / 2) * (Wi / 2) * pl.f[lvl + 1];
             rc = convt_bwd_launch(p->dtype, T(i), 2 * pl.f[lvl], p->up_w[u], p->up_w_t[u], raw(i - 1), stats(i - 1), p->gn_w[b - 1][1],
                                   p->gn_b[b - 1][1], dlow, grads + gl.up_w[u], grads + gl.up_b[u],
-                                  reinterpret_cast<float*>(bw + bp.coef_off), N, Hi, Wi, pl.f[lvl + 1], pl.f[lvl],
+                                  reinterpret_cast<float*>(bw + bp.coef_off) + (size_t)n0 * bp.maxc * 2, N, Hi, Wi, pl.f[lvl + 1], pl.f[lvl],
                                   p->groups[b - 1], 1e-5f, st, (p->path & 3) != 1 ? p->up_w_tc_bf16[u] : nullptr);
             if (rc) return rc;
             rc = act_bwd(i - 1, dlow, pl.f[lvl + 1], 0, nullptr, 0, 0);

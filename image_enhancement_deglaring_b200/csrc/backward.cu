@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(BW_THREADS) gn_bwd_apply_kernel(const GnBwdArg
                 db += p.P[((size_t)i * C + c) * 2];
                 dg += p.P[((size_t)i * C + c) * 2 + 1];
             }
-            p.dgamma[c] = (float)dg;
-            p.dbeta[c] = (float)db;
+            atomicAdd(p.dgamma + c, (float)dg);   // accumulated: concurrent sub-batches (api.cu) each add their images' share
+            atomicAdd(p.dbeta + c, (float)db);
         }
     }
     __syncthreads();
@@ -275,8 +275,8 @@ __global__ void __launch_bounds__(BW_THREADS) gn_bwd_apply_vec_kernel(const GnBw
                 db += p.P[((size_t)i * C + c) * 2];
                 dg += p.P[((size_t)i * C + c) * 2 + 1];
             }
-            p.dgamma[c] = (float)dg;
-            p.dbeta[c] = (float)db;
+            atomicAdd(p.dgamma + c, (float)dg);   // accumulated: concurrent sub-batches (api.cu) each add their images' share
+            atomicAdd(p.dbeta + c, (float)db);
         }
     }
     __syncthreads();

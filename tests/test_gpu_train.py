@@ -132,3 +132,25 @@ def test_training_16bit_storage_tensor_core_backward_is_close(best_sd, shape, st
         num += float(((g - ref) ** 2).sum())
         den += float((ref ** 2).sum())
     assert (num / den) ** 0.5 <= global_tol
+
+
+def test_backward_two_stream_split_matches_single_stream(best_sd):
+    """dg_lw_backward runs the two halves of the batch on two private streams (dg_set_batch_split); parameter gradients are
+    accumulated atomically from both: same gradients as one stream up to fp32 summation order."""
+    from image_enhancement_deglaring_b200 import _lib
+    lib = _lib.load()
+    x, t = _rand((5, 1, 64, 64), 3), _rand((5, 1, 64, 64), 4)
+    grads = []
+    old = lib.dg_set_batch_split(0)
+    try:
+        for split in (0, 2):
+            lib.dg_set_batch_split(split)
+            for storage in ("fp32", "fp16"):
+                net = _net(best_sd, storage=storage)
+                torch.nn.L1Loss()(net(x.cuda()), t.cuda()).backward()
+                grads.append({k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()})
+    finally:
+        lib.dg_set_batch_split(old)
+    for a, b in ((grads[0], grads[2]), (grads[1], grads[3])):
+        for k in a:
+            assert float((a[k] - b[k]).norm()) <= 1e-5 * float(a[k].norm()) + 1e-12, k
