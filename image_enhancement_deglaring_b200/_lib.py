@@ -124,6 +124,8 @@ def load():
             fn.argtypes = args
         if os.environ.get("DG_PDL") == "0":   # A/B switch for programmatic dependent launch
             lib.dg_set_pdl(0)
+        if os.environ.get("DG_BATCH_SPLIT") is not None:   # A/B switch / threshold for the two-stream batch split
+            lib.dg_set_batch_split(int(os.environ["DG_BATCH_SPLIT"]))
         _lib = lib
     return _lib
 

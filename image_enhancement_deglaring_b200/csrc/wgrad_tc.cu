@@ -165,8 +165,9 @@ wgrad_tc_kernel(const WgArgs p) {
             // (profiles/r01_ncu_wgrad.txt) is not more registers.  A cp.async version -- every 16-byte piece of both raw tiles in
             // flight at once, the 16-bit input activated in place in its plane slot -- was ALSO measured and is no faster
             // (2.37 vs 2.34 ms): these kernels execute ~5.5 warp-instructions per pixel, 2.5 of them in the K loop, where each
-            // of the five tap-pair warps re-loads the B fragment for every 16 pixels to feed ONE small MMA.  Next step: split K
-            // (rows) across warps and let every warp sweep all taps per B load, with a shared-memory reduction at the end.)
+            // of the five tap-pair warps re-loads the B fragment for every 16 pixels to feed ONE small MMA.  Splitting K (rows)
+            // across warps so that every warp sweeps all taps per B load (shared-memory reduction at the end) was measured
+            // too: 2.42 vs 2.34 ms -- more accumulators per warp, spills under the launch bound.  Left as is.)
 #pragma unroll 4
             for (int pix = tid / G::NC8; pix < NPIX; pix += WG_THREADS / G::NC8) {
                 const int r = pix / G::PW, c = pix - r * G::PW;
