@@ -220,10 +220,13 @@ struct FwdFork {
     cudaStream_t s[2];
     cudaEvent_t fork, join[2];
 };
-static FwdFork g_fork;
+// slot 0: calls on the caller's stream (dg_lw_forward / dg_lw_backward); slots 1..4: the chunks in flight of the host pipeline,
+// which must not share fork streams (that would serialise the chunks again)
+static FwdFork g_forks[5];
 static std::atomic<int> g_split{16};   // minimum batch for the two-stream split; 0 disables (dg_set_batch_split)
 
-static int fork_init() {
+static int fork_init(int slot = 0) {
+    FwdFork& g_fork = g_forks[slot];
     int dev = 0;
     cudaGetDevice(&dev);
     if (g_fork.ready && g_fork.device == dev) return 0;
@@ -239,7 +242,7 @@ static int fork_init() {
 
 static int lw_forward(const dg_lw_params* p, const void* x, void* y, int N, int H, int W, void* workspace,
                       size_t ws_bytes, const float* target, double* l1_sum, cudaStream_t stream,
-                      cudaEvent_t* evs = nullptr, int io = 0) {
+                      cudaEvent_t* evs = nullptr, int io = 0, int fork_slot = 0) {
     LwPlan pl;
     int rc = make_plan(p, N, H, W, &pl);
     if (rc) return rc;
@@ -253,8 +256,8 @@ static int lw_forward(const dg_lw_params* p, const void* x, void* y, int N, int 
     if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 10; }
     const int split = g_split.load();
     if (evs == nullptr && split > 0 && N >= split && N >= 2) {
-        if ((rc = fork_init())) return rc;
-        FwdFork& F = g_fork;
+        if ((rc = fork_init(fork_slot))) return rc;
+        FwdFork& F = g_forks[fork_slot];
         cudaEventRecord(F.fork, stream);
         const int half = N / 2;
         for (int k = 0; k < 2; ++k) {
@@ -404,7 +407,7 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
     const int split = g_split.load();
     if (split > 0 && N >= split && N >= 2) {   // two concurrent halves, as in lw_forward
         if ((rc = fork_init())) return rc;
-        FwdFork& F = g_fork;
+        FwdFork& F = g_forks[0];
         cudaEventRecord(F.fork, st);
         const int half = N / 2;
         for (int k = 0; k < 2; ++k) {
@@ -819,7 +822,7 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
         cudaEventRecord(P.in_done[b], P.s_in);
         cudaStreamWaitEvent(P.s_cmp[b], P.in_done[b], 0);
         if (i >= NS) cudaStreamWaitEvent(P.s_cmp[b], P.out_done[b], 0);  // dy[b] drained by chunk i-NS
-        rc = dg::lw_forward(p, dx[b], dy[b], nn, H, W, ws[b], pl.total_bytes, nullptr, nullptr, P.s_cmp[b], nullptr, io);
+        rc = dg::lw_forward(p, dx[b], dy[b], nn, H, W, ws[b], pl.total_bytes, nullptr, nullptr, P.s_cmp[b], nullptr, io, 1 + b);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         cudaEventRecord(P.cmp_done[b], P.s_cmp[b]);
         cudaStreamWaitEvent(P.s_out, P.cmp_done[b], 0);
