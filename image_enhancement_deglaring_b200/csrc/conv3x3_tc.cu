@@ -400,6 +400,9 @@ __global__ void __launch_bounds__(G::THREADS, G::MIN_CTAS) conv3x3_tc_kernel(con
                     }
                 }
                 // scatter (+bias) into the up planes [0, CU/8); outside the image the concat is zero-padded.
+                // (Measured and rejected: re-mapping the m-tiles so that the interior TH/2 x TW/2 low pixels form mask-free
+                // m-tiles and the border ring is handled separately -- .319 -> .330 ms on up1+dec1.0: the ring's strided
+                // ldmatrix rows and the index arithmetic cost more than the mask tests save.)
                 // Geometry of the two accumulator rows is n-tile independent: low pixel (li, lj) feeds the 2x2 block at
                 // tile (2li-1+a, 2lj-1+b); bit (2a+b) of `okm` = inside the staged tile, bit 4+(2a+b) = inside the image.
                 uint32_t boff[2], okm[2];
