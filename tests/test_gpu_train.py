@@ -154,3 +154,28 @@ def test_backward_two_stream_split_matches_single_stream(best_sd):
     for a, b in ((grads[0], grads[2]), (grads[1], grads[3])):
         for k in a:
             assert float((a[k] - b[k]).norm()) <= 1e-5 * float(a[k].norm()) + 1e-12, k
+
+
+@pytest.mark.parametrize("storage", ["fp32", "fp16"])
+def test_backward_properties_at_full_resolution(best_sd, storage):
+    """Size-independent properties of the backward at BASELINE's 512x512 (the oracle step is too slow there):
+    (1) linearity in the loss scale -- x4 is exact in bf16 / fp32, so gradients scale by 4 up to fp32 summation order;
+    (2) batch additivity -- GroupNorm is per sample, so the gradient of the mean loss over a batch is the mean of the
+        single-sample gradients (this also exercises the two-stream split and the atomic accumulation: batch 4 >= ... is not
+        split, batch 16 would be; see test_backward_two_stream_split_matches_single_stream)."""
+    net = _net(best_sd, storage=storage)
+    x, t = _rand((4, 1, 512, 512), 5).cuda(), _rand((4, 1, 512, 512), 6).cuda()
+    crit = torch.nn.L1Loss()
+
+    def grads(xb, tb, scale=1.0):
+        net.zero_grad(set_to_none=True)
+        (crit(net(xb), tb) * scale).backward()
+        return {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+
+    g1, g4 = grads(x, t), grads(x, t, 4.0)
+    for k in g1:
+        assert float((g4[k] - 4.0 * g1[k]).norm()) <= 2e-5 * float(g4[k].norm()) + 1e-12, f"linearity {k}"
+    per = [grads(x[i:i + 1], t[i:i + 1]) for i in range(4)]
+    for k in g1:
+        mean = sum(p[k] for p in per) / 4.0
+        assert float((g1[k] - mean).norm()) <= 2e-5 * float(g1[k].norm()) + 1e-12, f"additivity {k}"
