@@ -288,3 +288,21 @@ def test_two_stream_batch_split_is_bit_identical(best_sd):
     finally:
         lib.dg_set_batch_split(old)
     assert old == 16
+
+
+def test_4096_square_image_as_64_tiles(best_sd):
+    """BASELINE.json configs[2] at its full size: a 4096x4096 grayscale image = 64 tiles of 512x512 = one batch-64 forward
+    (run as four batches of 16 here).  Every checked output tile equals the module applied to that tile alone, the marked tile included."""
+    from image_enhancement_deglaring_b200.tiling import infer_tiled
+    net = _net(best_sd, storage="fp16")
+    img = _rand((4096, 4096), 51)
+    img[3 * 512:4 * 512, 5 * 512:6 * 512] = 0.25          # tile (row 3, col 5) = tile index 29: constant input
+    img = img.cuda()
+    with torch.no_grad():
+        out = infer_tiled(net, img, tile=512, batch=16)
+        assert out.shape == (1, 4096, 4096)
+        for r, c in ((0, 0), (3, 5), (7, 7)):
+            alone = net(img[None, None, r * 512:(r + 1) * 512, c * 512:(c + 1) * 512])[0]
+            assert torch.equal(out[:, r * 512:(r + 1) * 512, c * 512:(c + 1) * 512], alone), (r, c)
+        # the marked (constant-input) tile is not confused with its random neighbours
+        assert not torch.equal(out[:, 3 * 512:4 * 512, 5 * 512:6 * 512], out[:, 3 * 512:4 * 512, 4 * 512:5 * 512])
