@@ -9,8 +9,10 @@ A step = one forward pass of the 486,409-parameter best_model UNet over one batc
 1x512x512 grayscale images per GPU (BASELINE.json configs[1]); batches shard over GPUs with no
 collective (weak scaling).  `value` is device-resident throughput (CUDA events, max over ranks);
 `e2e` goes through the ORT-shaped `InferenceSession.run_pinned` -> `dg_lw_infer_host` C-ABI call with
-pinned HOST buffers, H2D + D2H inside the timed region.  `roofline` is for the dominant kernel,
-timed live with CUDA events by `dg_lw_profile`.  `cpu_baseline` / `--impl reference` time the CPU
+pinned HOST buffers, H2D + D2H inside the timed region (`e2e_u8`: the uint8-in / uint8-out twin).  `train_step` is one
+BASELINE.json configs[3] training step (batch 32 per GPU) in the same storage tier.  `roofline` is for the dominant kernel,
+timed live with CUDA events by `dg_lw_profile` (whole batch on one stream; the timed steps themselves run the batch as two
+concurrent halves).  `cpu_baseline` / `--impl reference` time the CPU
 oracle port of the reference's PyTorch-CPU path (oracle/torch_unet.py -- the reference itself cannot
 travel to the GPU box) on all host cores.
 """
