@@ -490,9 +490,20 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
         if (i == 0) break;
         // dA_in = conv3x3(dR_i, flipped weights): tensor cores where covered (dgrad_tc.cu) ...
         bool dg_done = false;
+        bool act_fused = false;
         if (p->dtype != DG_F32 && (p->path & 3) != 1 && p->conv_w_tc_bf16[b][j] != nullptr) {
-            rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], T(i), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done);
-            if (rc) return rc;
+            if (j == 1) {
+                // the second conv of a block: its input is the activated output of the first and nothing else consumes that, so
+                // the data gradient goes straight through the producer's SiLU' / statistics sums into G(i-1), P(i-1)
+                DgradAct act{raw(i - 1), stats(i - 1), p->gn_w[b][0], p->gn_b[b][0], P(i - 1), p->groups[b], p->dtype, 1e-5f};
+                rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], G(i - 1), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done, &act);
+                if (rc) return rc;
+                act_fused = dg_done;
+            }
+            if (!dg_done) {
+                rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], T(i), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done);
+                if (rc) return rc;
+            }
         }
         // ... else the forward generic kernel on an identity fp32 source
         dg_conv3x3_args d;
@@ -515,7 +526,7 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
             if (rc) return rc;
         }
         if (j == 1) {
-            rc = act_bwd(i - 1, T(i), C, 0, nullptr, 0, 0);
+            if (!act_fused) rc = act_bwd(i - 1, T(i), C, 0, nullptr, 0, 0);
         } else if (b < 5) {
             // producer = skip tensor of level b-1: gradient from the decoder's concat (skip half) + this pooled path
             const int lvl = b - 1, dconv = 2 * (8 - lvl);

@@ -189,8 +189,13 @@ int convt_tc_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, 
                     bool* handled);
 int se_scale_launch(const double* act_sum, double plane, const float* w1, const float* w2, int N, int C, int hidden,
                     float* scale, cudaStream_t st);
+// activation backward of the producer conv fused into the data-gradient epilogue (dgrad_tc.cu)
+struct DgradAct {
+    const void* raw; const double* stats; const float* gamma; const float* beta; double* P;
+    int groups, dtype; float eps;
+};
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
-                            cudaStream_t st, bool* handled);
+                            cudaStream_t st, bool* handled, const DgradAct* act = nullptr);
 int image_metrics_launch(const float* out, const float* tgt, int N, int H, int W, int clip01, double data_range, double* acc,
                          cudaStream_t st);
 int first_wgrad_launch(const float* x, const float* dR, float* dW, int N, int H, int W, int CO, cudaStream_t st, bool* handled);

@@ -28,7 +28,21 @@ struct DgradArgs {
     const void* wtc;   // forward packing of W [CK = Cout_fwd][CN = Cin_fwd][3][3] in bf16 (dg_pack_conv3x3_tc)
     float* out;        // [N,H,W,CN]
     int N, H, W;
+    // optional fused activation backward (the conv's only input is the activated output of ONE producer conv, src/model.py:93-98):
+    // out = G = dA * silu'(GroupNorm(raw_prev)) instead of dA, and P[n][c] += (sum G, sum G * xhat) -- what act_bwd_vec would
+    // compute from a materialised dA (backward.cu), without writing and re-reading it
+    const void* raw_prev;      // [N,H,W,CN] storage dtype, NULL = plain data gradient
+    const double* stats_prev;  // [N,CN,2]
+    const float* gamma_prev; const float* beta_prev;
+    double* P;                 // [N,CN,2], accumulated
+    int groups_prev, dtype_prev;
+    float eps;
 };
+
+__device__ __forceinline__ float dgr_silu_grad(float y) {
+    const float s = 1.f / (1.f + __expf(-y));
+    return s * (1.f + y * (1.f - s));
+}
 
 __device__ __forceinline__ void dgr_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -62,6 +76,8 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* act = smem;
     unsigned char* wsm = smem + G::A_BYTES;
+    __shared__ float4 pcoef[NB];          // fused activation backward: (mean, rstd, gamma, beta) of this CTA's channels
+    __shared__ float pslot[8][NB][2];     // per-warp (sum G, sum G*xhat)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.y;
     const int tiles_x = (p.W + TW - 1) / TW;
@@ -84,6 +100,27 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
             cp_async16(dst + (uint32_t)i * 16, src + ((size_t)(chunk * 2 + khalf) * CK + co) * 16);
         }
         cp_async_commit();
+    }
+    if (p.raw_prev != nullptr && tid < NB) {   // published by the barrier before the main loop
+        const int c = blockIdx.z * NB + tid;
+        const int cpg = CN / p.groups_prev, g0 = (c / cpg) * cpg;
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < cpg; ++k) {
+            s1 += p.stats_prev[(size_t)(n * CN + g0 + k) * 2];
+            s2 += p.stats_prev[(size_t)(n * CN + g0 + k) * 2 + 1];
+        }
+        const double cnt = (double)p.H * p.W * cpg;
+        double inv = (double)__frcp_rn((float)cnt);
+        inv = inv * (2.0 - cnt * inv);
+        inv = inv * (2.0 - cnt * inv);
+        const double mean = s1 * inv;
+        double var = fma(s2, inv, -mean * mean);
+        if (var < 0.0) var = 0.0;
+        const double xv = var + (double)p.eps;
+        double r = (double)rsqrtf((float)xv);
+        r = r * (1.5 - 0.5 * xv * r * r);
+        r = r * (1.5 - 0.5 * xv * r * r);
+        pcoef[tid] = make_float4((float)mean, (float)r, p.gamma_prev[c], p.beta_prev[c]);
     }
     // ---- haloed dR tile -> bf16 channel planes, zero outside the image -----------------------------------------------
     {
@@ -194,6 +231,63 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
     }
     // ---- epilogue: fp32 NHWC ------------------------------------------------------------------------------------------
     const int g = lane >> 2, q = lane & 3;
+    if (p.raw_prev != nullptr) {
+        float p1[G::NB8][2], p2[G::NB8][2];
+#pragma unroll
+        for (int j = 0; j < G::NB8; ++j) p1[j][0] = p1[j][1] = p2[j][0] = p2[j][1] = 0.f;
+#pragma unroll
+        for (int m = 0; m < G::MPW; ++m) {
+            const int mt = warp + 8 * m;
+            const int gy = y0 + mt / G::SEGS;
+            if (gy >= H) continue;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int gx = x0 + (mt % G::SEGS) * 16 + g + 8 * hf;
+                if (gx >= W) continue;
+                const size_t e = ((size_t)(n * H + gy) * W + gx) * CN + nb8_0 * 8 + 2 * q;
+                float* o = p.out + e;
+#pragma unroll
+                for (int j = 0; j < G::NB8; ++j) {
+                    float r0, r1;
+                    if (p.dtype_prev == DG_F16) {
+                        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(p.raw_prev) + e + j * 8));
+                        r0 = v.x; r1 = v.y;
+                    } else {
+                        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(p.raw_prev) + e + j * 8));
+                        r0 = v.x; r1 = v.y;
+                    }
+                    const float4 c0 = pcoef[j * 8 + 2 * q], c1 = pcoef[j * 8 + 2 * q + 1];
+                    const float xh0 = (r0 - c0.x) * c0.y, xh1 = (r1 - c1.x) * c1.y;
+                    const float g0 = acc[m][j][2 * hf] * dgr_silu_grad(xh0 * c0.z + c0.w);
+                    const float g1 = acc[m][j][2 * hf + 1] * dgr_silu_grad(xh1 * c1.z + c1.w);
+                    *reinterpret_cast<float2*>(o + j * 8) = make_float2(g0, g1);
+                    p1[j][0] += g0; p1[j][1] += g1;
+                    p2[j][0] = fmaf(g0, xh0, p2[j][0]); p2[j][1] = fmaf(g1, xh1, p2[j][1]);
+                }
+            }
+        }
+        // lanes with equal q hold the same channels: reduce over g, then over the 8 warps in a fixed order
+#pragma unroll
+        for (int j = 0; j < G::NB8; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float a = p1[j][k], b = p2[j][k];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                if (lane < 4) { pslot[warp][j * 8 + 2 * lane + k][0] = a; pslot[warp][j * 8 + 2 * lane + k][1] = b; }
+            }
+        __syncthreads();
+        for (int i = tid; i < 2 * NB; i += DGR_THREADS) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += (double)pslot[w][i >> 1][i & 1];
+            atomicAdd(p.P + ((size_t)n * CN + blockIdx.z * NB + (i >> 1)) * 2 + (i & 1), t);
+        }
+        return;
+    }
 #pragma unroll
     for (int m = 0; m < G::MPW; ++m) {
         const int mt = warp + 8 * m;
@@ -379,12 +473,20 @@ namespace {
 }  // namespace
 
 // out[N,H,W,cn] = conv3x3(dR[N,H,W,ck], flipped / transposed W); wtc_bf16 = dg_pack_conv3x3_tc(W packed, cin = cn, cout = ck, DG_BF16)
+// `act` (optional): fuse the producer's activation backward into the epilogue -- see DgradArgs
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
-                            cudaStream_t st, bool* handled) {
+                            cudaStream_t st, bool* handled, const DgradAct* act) {
     *handled = false;
     if (wtc_bf16 == nullptr || N < 1 || N > 65535) return 0;
     if ((reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(wtc_bf16)) & 15) return 0;
-    DgradArgs a{dR, wtc_bf16, out, N, H, W};
+    DgradArgs a{dR, wtc_bf16, out, N, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, 1, DG_F16, 1e-5f};
+    if (act != nullptr) {
+        if ((act->dtype != DG_F16 && act->dtype != DG_BF16) || (reinterpret_cast<uintptr_t>(act->raw) & 3) || act->groups < 1 ||
+            cn % act->groups != 0)
+            return 0;
+        a.raw_prev = act->raw; a.stats_prev = act->stats; a.gamma_prev = act->gamma; a.beta_prev = act->beta; a.P = act->P;
+        a.groups_prev = act->groups; a.dtype_prev = act->dtype; a.eps = act->eps;
+    }
     *handled = true;
 #define DG_DGR(CK_, CN_, NB_, TH_, TW_) if (ck == CK_ && cn == CN_) return launch_dgr<CK_, CN_, NB_, TH_, TW_>(a, st);
     DG_DGR(8, 8, 8, 16, 32)        // enc1.3, dec1.3
