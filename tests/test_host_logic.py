@@ -182,3 +182,20 @@ def test_tiled_inference_sharded_world2(tmp_path):
         img = torch.arange(h * w, dtype=torch.float32).reshape(h, w) / 7.0
         want = infer_tiled(_fake_forward, img, tile=4)
         assert torch.equal(r0[name], want) and torch.equal(r1[name], want), name
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores) prints ONE JSON line carrying the contract's
+    keys; it needs no GPU, so the line is checked here on a tiny workload."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-batch", "1", "--hw", "64"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "unet_deglare_512x512_images_per_sec" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
