@@ -84,6 +84,16 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+    # outside tests/ and oracle/ itself, only bench.py (cpu_baseline / --impl reference) and __graft_entry__.smoke() may use it
+    allowed = {"bench.py", "__graft_entry__.py"}
+    for d, _, files in os.walk(ROOT):
+        rel = os.path.relpath(d, ROOT)
+        if rel.split(os.sep)[0] in ("tests", "oracle", ".git", "gpurun_out", "baseline") or "__pycache__" in rel:
+            continue
+        for fn in files:
+            if fn.endswith(".py") and os.path.join(rel, fn).lstrip("./") not in allowed:
+                src = open(os.path.join(d, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), os.path.join(rel, fn)
 
 
 def test_shard_range_partitions_exactly():

@@ -3,8 +3,8 @@
 
     python tools/bench_train.py [--batch 32] [--steps 5] [--storage fp32]
     torchrun --nproc-per-node N tools/bench_train.py ...     (data parallel: one flat-gradient all-reduce per step)
-Prints one JSON line: images/s over all ranks, ms/step (CUDA events, max over ranks), and the CPU oracle's step time on a
-bounded sample for scale.
+Prints one JSON line: images/s over all ranks and ms/step (CUDA events, max over ranks).  (The CPU oracle's step is timed by the
+tests, not here: only tests/, smoke() and bench.py's cpu_baseline leg may touch oracle/.)
 """
 import argparse
 import json
@@ -26,7 +26,7 @@ ap.add_argument("--hw", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--storage", default="fp32")
-ap.add_argument("--cpu-batch", type=int, default=2)
+ap.add_argument("--cpu-batch", type=int, default=0, help="ignored (kept for old command lines)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -66,16 +66,7 @@ if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 ms = float(ms) / a.steps
 if rank == 0:
-    from oracle import torch_unet as tpo
-    torch.set_num_threads(os.cpu_count())
-    xc = torch.rand(a.cpu_batch, 1, a.hw, a.hw, generator=torch.Generator().manual_seed(0))
-    tc = torch.rand(a.cpu_batch, 1, a.hw, a.hw, generator=torch.Generator().manual_seed(1))
-    t0 = time.perf_counter()
-    tpo.train_step(sd, xc, tc)
-    cpu_s = time.perf_counter() - t0
     print(json.dumps({"metric": "unet_deglare_train_images_per_sec", "value": world * a.batch / (ms * 1e-3), "unit": "images/s",
-                      "n_gpus": world, "ms_per_step": ms, "batch_per_gpu": a.batch, "storage": a.storage, "loss": float(loss.detach()),
-                      "cpu_oracle": {"images_per_s": a.cpu_batch / cpu_s, "cores": os.cpu_count(),
-                                     "sample": f"one fp32 step of batch {a.cpu_batch}"}}))
+                      "n_gpus": world, "ms_per_step": ms, "batch_per_gpu": a.batch, "storage": a.storage, "loss": float(loss.detach())}))
 if world > 1:
     dist.destroy_process_group()
