@@ -380,6 +380,8 @@ def main():
             "config": {"workload": f"best_model.pth LightweightUNet (486,409 params) batched inference, batch {B} x 1x{H}x{W} "
                                    f"per GPU, {args.storage} storage / fp32 accumulate (BASELINE.json configs[1])",
                        "batch_per_gpu": B, "global_batch": B * world, "sharding": "images over ranks, no collective",
+                       "streams": "dg_lw_forward runs the two halves of the batch concurrently on two library-private streams "
+                                  "(default for >= 16 images; DG_BATCH_SPLIT=0 disables); roofline.per_kernel is timed on one stream",
                        "cpu_affinity": (f"rank 0 bound to {len(numa_cpus)} CPUs local to its GPU (NVML)" if numa_cpus else "unbound"),
                        "l2": f"inputs+intermediates per step ({sum(algorithmic_bytes_per_image(H, W)) * B / 2**20:.0f} MiB) exceed the 126 MB L2; no flush"},
             "clocks": clocks,
