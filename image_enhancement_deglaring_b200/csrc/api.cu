@@ -534,11 +534,23 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
         } else {
             const int lvl = block_level(b), u = b - 5;
             float* dlow = reinterpret_cast<float*>(bw + bp.low_off[u]) + (size_t)n0 * (Hi / 2) * (Wi / 2) * pl.f[lvl + 1];
+            // the low-resolution producer feeds nothing but this ConvTranspose: with the tensor-core data gradient its activation
+            // backward is fused into that kernel's epilogue, which then writes G(i-1) / P(i-1) directly
+            const bool try_fuse = p->dtype != DG_F32 && (p->path & 3) != 1 && p->up_w_tc_bf16[u] != nullptr;
+            DgradAct lact{raw(i - 1), stats(i - 1), p->gn_w[b - 1][1], p->gn_b[b - 1][1], P(i - 1), p->groups[b - 1], p->dtype, 1e-5f};
+            bool low_fused = false;
             rc = convt_bwd_launch(p->dtype, T(i), 2 * pl.f[lvl], p->up_w[u], p->up_w_t[u], raw(i - 1), stats(i - 1), p->gn_w[b - 1][1],
-                                  p->gn_b[b - 1][1], dlow, grads + gl.up_w[u], grads + gl.up_b[u],
+                                  p->gn_b[b - 1][1], try_fuse ? G(i - 1) : dlow, grads + gl.up_w[u], grads + gl.up_b[u],
                                   reinterpret_cast<float*>(bw + bp.coef_off) + (size_t)n0 * bp.maxc * 2, N, Hi, Wi, pl.f[lvl + 1], pl.f[lvl],
-                                  p->groups[b - 1], 1e-5f, st, (p->path & 3) != 1 ? p->up_w_tc_bf16[u] : nullptr);
+                                  p->groups[b - 1], 1e-5f, st, (p->path & 3) != 1 ? p->up_w_tc_bf16[u] : nullptr,
+                                  try_fuse ? &lact : nullptr, try_fuse ? &low_fused : nullptr);
             if (rc) return rc;
+            if (low_fused) continue;   // G(i-1), P(i-1) are done
+            if (try_fuse) {            // the kernel declined: G(i-1) holds the plain gradient; act_bwd works in place on it
+                rc = act_bwd(i - 1, G(i - 1), pl.f[lvl + 1], 0, nullptr, 0, 0);
+                if (rc) return rc;
+                continue;
+            }
             rc = act_bwd(i - 1, dlow, pl.f[lvl + 1], 0, nullptr, 0, 0);
         }
         if (rc) return rc;

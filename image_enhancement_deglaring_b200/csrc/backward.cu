@@ -792,7 +792,8 @@ int head_bwd_launch(int dtype, const void* raw, const double* stats, const float
 int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low,
                      const double* stats, const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias,
                      float* coefbuf, int N, int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st,
-                     const void* wtc_bf16) {
+                     const void* wtc_bf16, const DgradAct* act, bool* act_fused) {
+    if (act_fused) *act_fused = false;
     if (Cu % 4 || (stride % 4) || (reinterpret_cast<uintptr_t>(dCat) & 15)) { set_error("convT backward: unaligned gradient"); return 3; }
     ConvtBwdArgs a{dCat, stride, wt, wt_t, raw_low, stats, gamma, beta, dAlow, dWt, nullptr, coefbuf, N, H, W, Cl, Cu, groups, eps};
     gn_mean_rstd_kernel<<<N, 128, 0, st>>>(stats, coefbuf, Cl, groups, (double)(H / 2) * (W / 2), eps);
@@ -801,8 +802,15 @@ int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, 
     int rc = 0;
     bool data_done = false;
     if (dtype != DG_F32 && wtc_bf16 != nullptr) {   // tensor cores where covered (dgrad_tc.cu)
-        rc = convt_dgrad_tc_launch(dCat, stride, wtc_bf16, dAlow, N, H, W, Cl, Cu, st, &data_done);
-        if (rc) return rc;
+        if (act != nullptr && act_fused != nullptr) {   // dAlow is then G of the low-resolution producer, never the plain gradient
+            rc = convt_dgrad_tc_launch(dCat, stride, wtc_bf16, dAlow, N, H, W, Cl, Cu, st, &data_done, act);
+            if (rc) return rc;
+            *act_fused = data_done;
+        }
+        if (!data_done) {
+            rc = convt_dgrad_tc_launch(dCat, stride, wtc_bf16, dAlow, N, H, W, Cl, Cu, st, &data_done);
+            if (rc) return rc;
+        }
     }
     if (!data_done) {
         if (wt_t == nullptr) { set_error("convT backward: the CUDA-core data gradient needs up_w_t"); return 2; }

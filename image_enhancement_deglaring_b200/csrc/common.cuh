@@ -196,11 +196,12 @@ struct DgradAct {
 };
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
                             cudaStream_t st, bool* handled, const DgradAct* act = nullptr);
+int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
+                          cudaStream_t st, bool* handled, const DgradAct* act = nullptr);
 int image_metrics_launch(const float* out, const float* tgt, int N, int H, int W, int clip01, double data_range, double* acc,
                          cudaStream_t st);
 int first_wgrad_launch(const float* x, const float* dR, float* dW, int N, int H, int W, int CO, cudaStream_t st, bool* handled);
-int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
-                          cudaStream_t st, bool* handled);
+
 int convt_wgrad_tc_launch(int dtype, const float* dCat, int stride, const void* raw_low, const double* stats, const float* gamma,
                           const float* beta, float* dWt, float* dBias, int N, int H, int W, int Cl, int Cu, int groups, float eps,
                           cudaStream_t st, bool* handled);
@@ -218,7 +219,7 @@ int head_bwd_launch(int dtype, const void* raw, const double* stats, const float
                     float eps, cudaStream_t st);
 int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low, const double* stats,
                      const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias, float* coefbuf, int N,
-                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st, const void* wtc_bf16 = nullptr);
+                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st, const void* wtc_bf16 = nullptr, const DgradAct* act = nullptr, bool* act_fused = nullptr);
 int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, float lr,
                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t st);
 int tc_conv3x3_bytes(int cin, int cout, size_t* bytes);

@@ -44,6 +44,99 @@ __device__ __forceinline__ float dgr_silu_grad(float y) {
     return s * (1.f + y * (1.f - s));
 }
 
+// the producer description shared by the two data-gradient kernels
+struct ActFuse {
+    const void* raw; const double* stats; const float* gamma; const float* beta; double* P;
+    int groups, dtype; float eps;
+};
+
+// (mean, rstd, gamma, beta) of channel ch0 + threadIdx.x of image n (threads < NB); published by the caller's next barrier
+template <int CN>
+__device__ __forceinline__ void act_fuse_coef(const ActFuse& f, int n, int ch0, double plane, float4* pcoef) {
+    const int c = ch0 + threadIdx.x;
+    const int cpg = CN / f.groups, g0 = (c / cpg) * cpg;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+        s1 += f.stats[(size_t)(n * CN + g0 + k) * 2];
+        s2 += f.stats[(size_t)(n * CN + g0 + k) * 2 + 1];
+    }
+    const double cnt = plane * cpg;
+    double inv = (double)__frcp_rn((float)cnt);
+    inv = inv * (2.0 - cnt * inv);
+    inv = inv * (2.0 - cnt * inv);
+    const double mean = s1 * inv;
+    double var = fma(s2, inv, -mean * mean);
+    if (var < 0.0) var = 0.0;
+    const double xv = var + (double)f.eps;
+    double r = (double)rsqrtf((float)xv);
+    r = r * (1.5 - 0.5 * xv * r * r);
+    r = r * (1.5 - 0.5 * xv * r * r);
+    pcoef[threadIdx.x] = make_float4((float)mean, (float)r, f.gamma[c], f.beta[c]);
+}
+
+// Epilogue of both kernels when the activation backward is fused: out = G = acc * silu'(GroupNorm(raw)), P += (sum G, sum G*xhat).
+// acc[m][j][.] is the mma accumulator of m-tile (warp + 8 m) = 16 pixels of row mt / SEGS, n-tile j of this CTA's NB channels.
+template <int CN, int NB, int MPW, int SEGS>
+__device__ __forceinline__ void act_fuse_epilogue(const ActFuse& f, float* out, float (&acc)[MPW][NB / 8][4], const float4* pcoef,
+                                                  float (*pslot)[NB][2], int n, int H, int W, int y0, int x0, int ch0) {
+    constexpr int NB8 = NB / 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    float p1[NB8][2], p2[NB8][2];
+#pragma unroll
+    for (int j = 0; j < NB8; ++j) p1[j][0] = p1[j][1] = p2[j][0] = p2[j][1] = 0.f;
+#pragma unroll
+    for (int m = 0; m < MPW; ++m) {
+        const int mt = warp + 8 * m;
+        const int gy = y0 + mt / SEGS;
+        if (gy >= H) continue;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int gx = x0 + (mt % SEGS) * 16 + g + 8 * hf;
+            if (gx >= W) continue;
+            const size_t e = ((size_t)(n * H + gy) * W + gx) * CN + ch0 + 2 * q;
+            float* o = out + e;
+#pragma unroll
+            for (int j = 0; j < NB8; ++j) {
+                float r0, r1;
+                if (f.dtype == DG_F16) {
+                    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(f.raw) + e + j * 8));
+                    r0 = v.x; r1 = v.y;
+                } else {
+                    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(f.raw) + e + j * 8));
+                    r0 = v.x; r1 = v.y;
+                }
+                const float4 c0 = pcoef[j * 8 + 2 * q], c1 = pcoef[j * 8 + 2 * q + 1];
+                const float xh0 = (r0 - c0.x) * c0.y, xh1 = (r1 - c1.x) * c1.y;
+                const float g0 = acc[m][j][2 * hf] * dgr_silu_grad(xh0 * c0.z + c0.w);
+                const float g1 = acc[m][j][2 * hf + 1] * dgr_silu_grad(xh1 * c1.z + c1.w);
+                *reinterpret_cast<float2*>(o + j * 8) = make_float2(g0, g1);
+                p1[j][0] += g0; p1[j][1] += g1;
+                p2[j][0] = fmaf(g0, xh0, p2[j][0]); p2[j][1] = fmaf(g1, xh1, p2[j][1]);
+            }
+        }
+    }
+    // lanes with equal q hold the same channels: reduce over g, then over the 8 warps in a fixed order
+#pragma unroll
+    for (int j = 0; j < NB8; ++j)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            float a = p1[j][k], b = p2[j][k];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane < 4) { pslot[warp][j * 8 + 2 * lane + k][0] = a; pslot[warp][j * 8 + 2 * lane + k][1] = b; }
+        }
+    __syncthreads();
+    for (int i = tid; i < 2 * NB; i += DGR_THREADS) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += (double)pslot[w][i >> 1][i & 1];
+        atomicAdd(f.P + ((size_t)n * CN + ch0 + (i >> 1)) * 2 + (i & 1), t);
+    }
+}
+
 __device__ __forceinline__ void dgr_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -101,27 +194,8 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
         }
         cp_async_commit();
     }
-    if (p.raw_prev != nullptr && tid < NB) {   // published by the barrier before the main loop
-        const int c = blockIdx.z * NB + tid;
-        const int cpg = CN / p.groups_prev, g0 = (c / cpg) * cpg;
-        double s1 = 0.0, s2 = 0.0;
-        for (int k = 0; k < cpg; ++k) {
-            s1 += p.stats_prev[(size_t)(n * CN + g0 + k) * 2];
-            s2 += p.stats_prev[(size_t)(n * CN + g0 + k) * 2 + 1];
-        }
-        const double cnt = (double)p.H * p.W * cpg;
-        double inv = (double)__frcp_rn((float)cnt);
-        inv = inv * (2.0 - cnt * inv);
-        inv = inv * (2.0 - cnt * inv);
-        const double mean = s1 * inv;
-        double var = fma(s2, inv, -mean * mean);
-        if (var < 0.0) var = 0.0;
-        const double xv = var + (double)p.eps;
-        double r = (double)rsqrtf((float)xv);
-        r = r * (1.5 - 0.5 * xv * r * r);
-        r = r * (1.5 - 0.5 * xv * r * r);
-        pcoef[tid] = make_float4((float)mean, (float)r, p.gamma_prev[c], p.beta_prev[c]);
-    }
+    const ActFuse fuse{p.raw_prev, p.stats_prev, p.gamma_prev, p.beta_prev, p.P, p.groups_prev, p.dtype_prev, p.eps};
+    if (p.raw_prev != nullptr && tid < NB) act_fuse_coef<CN>(fuse, n, blockIdx.z * NB, (double)p.H * p.W, pcoef);   // published by the barrier below
     // ---- haloed dR tile -> bf16 channel planes, zero outside the image -----------------------------------------------
     {
         const int c8 = tid % G::KC8;
@@ -232,60 +306,7 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
     // ---- epilogue: fp32 NHWC ------------------------------------------------------------------------------------------
     const int g = lane >> 2, q = lane & 3;
     if (p.raw_prev != nullptr) {
-        float p1[G::NB8][2], p2[G::NB8][2];
-#pragma unroll
-        for (int j = 0; j < G::NB8; ++j) p1[j][0] = p1[j][1] = p2[j][0] = p2[j][1] = 0.f;
-#pragma unroll
-        for (int m = 0; m < G::MPW; ++m) {
-            const int mt = warp + 8 * m;
-            const int gy = y0 + mt / G::SEGS;
-            if (gy >= H) continue;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int gx = x0 + (mt % G::SEGS) * 16 + g + 8 * hf;
-                if (gx >= W) continue;
-                const size_t e = ((size_t)(n * H + gy) * W + gx) * CN + nb8_0 * 8 + 2 * q;
-                float* o = p.out + e;
-#pragma unroll
-                for (int j = 0; j < G::NB8; ++j) {
-                    float r0, r1;
-                    if (p.dtype_prev == DG_F16) {
-                        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(p.raw_prev) + e + j * 8));
-                        r0 = v.x; r1 = v.y;
-                    } else {
-                        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(p.raw_prev) + e + j * 8));
-                        r0 = v.x; r1 = v.y;
-                    }
-                    const float4 c0 = pcoef[j * 8 + 2 * q], c1 = pcoef[j * 8 + 2 * q + 1];
-                    const float xh0 = (r0 - c0.x) * c0.y, xh1 = (r1 - c1.x) * c1.y;
-                    const float g0 = acc[m][j][2 * hf] * dgr_silu_grad(xh0 * c0.z + c0.w);
-                    const float g1 = acc[m][j][2 * hf + 1] * dgr_silu_grad(xh1 * c1.z + c1.w);
-                    *reinterpret_cast<float2*>(o + j * 8) = make_float2(g0, g1);
-                    p1[j][0] += g0; p1[j][1] += g1;
-                    p2[j][0] = fmaf(g0, xh0, p2[j][0]); p2[j][1] = fmaf(g1, xh1, p2[j][1]);
-                }
-            }
-        }
-        // lanes with equal q hold the same channels: reduce over g, then over the 8 warps in a fixed order
-#pragma unroll
-        for (int j = 0; j < G::NB8; ++j)
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                float a = p1[j][k], b = p2[j][k];
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    a += __shfl_xor_sync(0xffffffffu, a, o);
-                    b += __shfl_xor_sync(0xffffffffu, b, o);
-                }
-                if (lane < 4) { pslot[warp][j * 8 + 2 * lane + k][0] = a; pslot[warp][j * 8 + 2 * lane + k][1] = b; }
-            }
-        __syncthreads();
-        for (int i = tid; i < 2 * NB; i += DGR_THREADS) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) t += (double)pslot[w][i >> 1][i & 1];
-            atomicAdd(p.P + ((size_t)n * CN + blockIdx.z * NB + (i >> 1)) * 2 + (i & 1), t);
-        }
+        act_fuse_epilogue<CN, NB, G::MPW, G::SEGS>(fuse, p.out, acc, pcoef, pslot, n, H, W, y0, x0, blockIdx.z * NB);
         return;
     }
 #pragma unroll
@@ -332,6 +353,7 @@ struct CtDgradArgs {
     const void* wtc;                 // dg_pack_convt2x2_tc(..., DG_BF16)
     float* out;                      // [N, Hl, Wl, CL]
     int N, Hl, Wl;
+    ActFuse act;                     // act.raw != NULL: fused activation backward of the low-resolution producer (out = G, act.P += sums)
 };
 
 template <int CL, int CU, int NB, int TH, int TW>
@@ -354,6 +376,9 @@ __global__ void __launch_bounds__(DGR_THREADS) convt_dgrad_tc_kernel(const CtDgr
     const int tiles_x = (Wl + TW - 1) / TW;
     const int y0 = (blockIdx.x / tiles_x) * TH, x0 = (blockIdx.x % tiles_x) * TW;
     const int nb8_0 = blockIdx.z * NB8;
+    __shared__ float4 pcoef[NB];
+    __shared__ float pslot[8][NB][2];
+    if (p.act.raw != nullptr && tid < NB) act_fuse_coef<CL>(p.act, n, blockIdx.z * NB, (double)Hl * Wl, pcoef);   // published by the barrier below
     {   // packed weights of this CTA's ci blocks: n8 block j -> (chunk = n8g / 2, k-half = n8g & 1), CTN rows of 16 bytes
         const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wtc);
         const uint32_t dst = smem_u32(wsm);
@@ -415,6 +440,10 @@ __global__ void __launch_bounds__(DGR_THREADS) convt_dgrad_tc_kernel(const CtDgr
             for (int j = 0; j < NB8; ++j) mma16816<BF>(acc[m][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
         }
     }
+    if (p.act.raw != nullptr) {
+        act_fuse_epilogue<CL, NB, MPW, SEGS>(p.act, p.out, acc, pcoef, pslot, n, Hl, Wl, y0, x0, blockIdx.z * NB);
+        return;
+    }
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int m = 0; m < MPW; ++m) {
@@ -455,11 +484,17 @@ int launch_ctdgr(const CtDgradArgs& a, cudaStream_t st) {
 // dLow [N,H/2,W/2,Cl] = ConvTranspose2d data gradient of the up half (channels 0..Cu of dCat [N,H,W,stride]);
 // wtc_bf16 = dg_pack_convt2x2_tc(packed Wt, Cl, Cu, DG_BF16)
 int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
-                          cudaStream_t st, bool* handled) {
+                          cudaStream_t st, bool* handled, const DgradAct* act) {
     *handled = false;
     if (wtc_bf16 == nullptr || N < 1 || N > 65535 || ((H | W) & 1) || (stride & 3)) return 0;
     if ((reinterpret_cast<uintptr_t>(dCat) | reinterpret_cast<uintptr_t>(dLow) | reinterpret_cast<uintptr_t>(wtc_bf16)) & 15) return 0;
-    CtDgradArgs a{dCat, stride, wtc_bf16, dLow, N, H / 2, W / 2};
+    CtDgradArgs a{dCat, stride, wtc_bf16, dLow, N, H / 2, W / 2, ActFuse{nullptr, nullptr, nullptr, nullptr, nullptr, 1, DG_F16, 1e-5f}};
+    if (act != nullptr) {
+        if ((act->dtype != DG_F16 && act->dtype != DG_BF16) || (reinterpret_cast<uintptr_t>(act->raw) & 3) || act->groups < 1 ||
+            Cl % act->groups != 0)
+            return 0;
+        a.act = ActFuse{act->raw, act->stats, act->gamma, act->beta, act->P, act->groups, act->dtype, act->eps};
+    }
     *handled = true;
     if (Cl == 128 && Cu == 64) return launch_ctdgr<128, 64, 64, 4, 32>(a, st);   // upconv4
     if (Cl == 64 && Cu == 32) return launch_ctdgr<64, 32, 64, 8, 32>(a, st);     // upconv3
