@@ -306,7 +306,7 @@ static void make_grad_layout(const dg_lw_params* p, const LwPlan& pl, GradLayout
 }
 
 struct BwdPlan {
-    size_t p_off[18], g_off[18], t_off[18], low_off[4], coef_off, p_bytes, total;
+    size_t p_off[18], g_off[18], t_off[18], gb_off[18], low_off[4], coef_off, p_bytes, total;   // gb: dR as bf16 (16-bit tiers)
     int cin_tot[18], maxc;
 };
 
@@ -329,6 +329,10 @@ static void make_bwd_plan(const dg_lw_params* p, const LwPlan& pl, int N, BwdPla
         const int lvl = 3 - u;  // upconv4 produces level 3 from level 4
         bp->low_off[u] = off;
         off += align_up((size_t)N * (pl.conv_h[2 * lvl + 2]) * (pl.conv_w[2 * lvl + 2]) * pl.f[lvl + 1] * sizeof(float), 256);
+    }
+    for (int i = 0; i < 18; ++i) {
+        bp->gb_off[i] = off;
+        if (i > 0 && p->dtype != DG_F32) off += align_up((size_t)N * pl.conv_h[i] * pl.conv_w[i] * pl.conv_c[i] * 2, 256);
     }
     bp->coef_off = off;
     bp->maxc = maxc;
@@ -445,13 +449,31 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
     if (rc) return rc;
     for (int i = 17; i >= 0; --i) {
         const int b = i / 2, j = i % 2, C = pl.conv_c[i], Hi = pl.conv_h[i], Wi = pl.conv_w[i];
-        // G_i -> dR_i in place, dgamma / dbeta
-        rc = gn_bwd_apply_launch(p->dtype, raw(i), stats(i), p->gn_w[b][j], P(i), G(i), grads + gl.gn_w[b][j], grads + gl.gn_b[b][j],
-                                 N, Hi, Wi, C, p->groups[b], 1e-5f, st);
-        if (rc) return rc;
         // dW_i: same sources as the forward conv, correlated with dR_i; written in the parameter's [Co][Ci][3][3] layout
         dg_conv3x3_args a;
         fwd_conv_args(p, pl, fw, x, N, i, &a, n0);
+        // G_i -> dR_i, dgamma / dbeta.  Where BOTH consumers of dR_i are tensor-core kernels (they round it to bf16 anyway) it is
+        // written once as bf16 instead of fp32 in place: they read half the bytes and copy the tile instead of converting it.
+        void* dRb = nullptr;
+        if (i > 0 && p->dtype != DG_F32 && (p->path & 3) != 1 && p->conv_w_tc_bf16[b][j] != nullptr) {
+            dg_conv3x3_args probe = a;
+            if (probe.nsrc == 2) {   // the wgrad kernel sees a decoder conv with its ConvTranspose source materialised
+                memset(&probe.src[0], 0, sizeof(dg_src));
+                probe.src[0].raw = fw + pl.up_off[b - 5];
+                probe.src[0].channels = pl.f[block_level(b)];
+                probe.src[0].groups = 1;
+                probe.src[0].xform = DG_X_SAME;
+            }
+            bool wg_ok = false, dgr_ok = false;
+            conv3x3_wgrad_tc_launch(probe, G(i), grads + gl.conv_w[b][j], 1, 9, 9 * bp.cin_tot[i], st, &wg_ok, nullptr, /*dry*/ true);
+            conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], G(i), N, Hi, Wi, C, bp.cin_tot[i], st, &dgr_ok, nullptr, nullptr, true);
+            if (wg_ok && dgr_ok) dRb = bw + bp.gb_off[i] + (size_t)n0 * hwc(i, C) * 2;
+        }
+        bool dr_bf16 = false;
+        rc = gn_bwd_apply_launch(p->dtype, raw(i), stats(i), p->gn_w[b][j], P(i), G(i), grads + gl.gn_w[b][j], grads + gl.gn_b[b][j],
+                                 N, Hi, Wi, C, p->groups[b], 1e-5f, st, dRb, &dr_bf16);
+        if (rc) return rc;
+        const void* dRb_in = dr_bf16 ? dRb : nullptr;   // when set, G(i) still holds G, NOT dR: only the bf16 copy is valid
         bool wg_done = false;
         if (p->dtype != DG_F32 && (p->path & 3) != 1 && i > 0) {
             // tensor-core wgrad (wgrad_tc.cu); a decoder conv reads the MATERIALISED ConvTranspose output: the forward left it
@@ -474,7 +496,7 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
                 }
             }
             if (ok) {
-                rc = conv3x3_wgrad_tc_launch(a, G(i), grads + gl.conv_w[b][j], 1, 9, 9 * bp.cin_tot[i], st, &wg_done);
+                rc = conv3x3_wgrad_tc_launch(a, G(i), grads + gl.conv_w[b][j], 1, 9, 9 * bp.cin_tot[i], st, &wg_done, dRb_in);
                 if (rc) return rc;
             }
             if (!wg_done) fwd_conv_args(p, pl, fw, x, N, i, &a, n0);  // restore the fused description for the generic kernel
@@ -483,6 +505,7 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
             rc = first_wgrad_launch(x + (size_t)n0 * p->in_channels * H * W, G(0), grads + gl.conv_w[0][0], N, Hi, Wi, C, st, &wg_done);
             if (rc) return rc;
         }
+        if (!wg_done && dRb_in != nullptr) { set_error("backward: conv %d wgrad probe / launch mismatch", i); return 11; }
         if (!wg_done) {
             rc = conv3x3_wgrad_launch(a, G(i), grads + gl.conv_w[b][j], /*tap*/ 1, /*ci*/ 9, /*co*/ 9 * bp.cin_tot[i], st);
             if (rc) return rc;
@@ -496,12 +519,12 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
                 // the second conv of a block: its input is the activated output of the first and nothing else consumes that, so
                 // the data gradient goes straight through the producer's SiLU' / statistics sums into G(i-1), P(i-1)
                 DgradAct act{raw(i - 1), stats(i - 1), p->gn_w[b][0], p->gn_b[b][0], P(i - 1), p->groups[b], p->dtype, 1e-5f};
-                rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], G(i - 1), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done, &act);
+                rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], G(i - 1), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done, &act, dRb_in);
                 if (rc) return rc;
                 act_fused = dg_done;
             }
             if (!dg_done) {
-                rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], T(i), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done);
+                rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], T(i), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done, nullptr, dRb_in);
                 if (rc) return rc;
             }
         }
@@ -520,6 +543,7 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
         d.src[0].channels = C;
         d.src[0].groups = 1;
         d.src[0].xform = DG_X_SAME;
+        if (!dg_done && dRb_in != nullptr) { set_error("backward: conv %d dgrad probe / launch mismatch", i); return 11; }
         if (!dg_done) {
             if (d.weight == nullptr) { set_error("backward: conv %d needs the CUDA-core dgrad but conv_w_flip is NULL", i); return 2; }
             rc = conv3x3_generic_launch(d, st);

@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(BW_THREADS) act_bwd_kernel(const ActBwdArgs p)
 // ---- dR = rstd*(gamma*G - m1 - xhat*m2) in place; block (0,0) also reduces dgamma/dbeta over the batch -----------------
 struct GnBwdArgs {
     const void* raw; const double* stats; const float* gamma; const double* P;
-    float* G;  // in: G, out: dR
+    float* G;  // in: G, out: dR (unless dRb)
+    void* dRb; // vector kernel only: write dR as bf16 [N,H,W,C] HERE instead of fp32 in place -- the tensor-core wgrad / dgrad round
+               // it to bf16 anyway, so they read half the bytes and copy instead of converting (bit-identical results)
     float* dgamma; float* dbeta;
     int N, H, W, C, groups; float eps;
 };
@@ -304,7 +306,13 @@ __global__ void __launch_bounds__(BW_THREADS) gn_bwd_apply_vec_kernel(const GnBw
             const float xh = (rr[k] - cm[k]) * cr[k];
             o[k] = cr[k] * (cg[k] * gg[k] - c1[k] - xh * c2[k]);
         }
-        *reinterpret_cast<float4*>(G + (size_t)pix * C) = make_float4(o[0], o[1], o[2], o[3]);
+        if (p.dRb != nullptr) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.dRb) + ((size_t)n * HW + pix) * C + 4 * c4) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        } else {
+            *reinterpret_cast<float4*>(G + (size_t)pix * C) = make_float4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -750,10 +758,18 @@ int first_wgrad_launch(const float* x, const float* dR, float* dW, int N, int H,
     return check_launch("first_wgrad");
 }
 
+// dRb (optional): ask for the bf16 copy instead of the in-place fp32 result; *wrote_bf16 reports whether that happened (only the
+// vector kernel can: otherwise dR is in G as always)
 int gn_bwd_apply_launch(int dtype, const void* raw, const double* stats, const float* gamma, const double* P, float* G,
-                        float* dgamma, float* dbeta, int N, int H, int W, int C, int groups, float eps, cudaStream_t st) {
-    GnBwdArgs a{raw, stats, gamma, P, G, dgamma, dbeta, N, H, W, C, groups, eps};
+                        float* dgamma, float* dbeta, int N, int H, int W, int C, int groups, float eps, cudaStream_t st,
+                        void* dRb, bool* wrote_bf16) {
+    if (wrote_bf16) *wrote_bf16 = false;
+    GnBwdArgs a{raw, stats, gamma, P, G, nullptr, dgamma, dbeta, N, H, W, C, groups, eps};
     if (ew_vec_ok(dtype, C, H, W) && aligned16(G) && aligned_raw(dtype, raw)) {
+        if (dRb != nullptr && wrote_bf16 != nullptr && (reinterpret_cast<uintptr_t>(dRb) & 15) == 0) {
+            a.dRb = dRb;
+            *wrote_bf16 = true;
+        }
         dim3 vgrid(ew_vec_blocks((size_t)H * W * (C / 4)), N);
         DG_BY_DTYPE(dtype, (gn_bwd_apply_vec_kernel<T><<<vgrid, BW_THREADS, (size_t)C * 5 * sizeof(float), st>>>(a)));
         count_launch();

@@ -195,7 +195,8 @@ struct DgradAct {
     int groups, dtype; float eps;
 };
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
-                            cudaStream_t st, bool* handled, const DgradAct* act = nullptr);
+                            cudaStream_t st, bool* handled, const DgradAct* act = nullptr, const void* dR_bf16 = nullptr,
+                            bool dry = false);
 int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
                           cudaStream_t st, bool* handled, const DgradAct* act = nullptr);
 int image_metrics_launch(const float* out, const float* tgt, int N, int H, int W, int clip01, double data_range, double* acc,
@@ -206,14 +207,14 @@ int convt_wgrad_tc_launch(int dtype, const float* dCat, int stride, const void* 
                           const float* beta, float* dWt, float* dBias, int N, int H, int W, int Cl, int Cu, int groups, float eps,
                           cudaStream_t st, bool* handled);
 int conv3x3_wgrad_tc_launch(const dg_conv3x3_args& a, const float* dR, float* dW, int s_tap, int s_ci, int s_co,
-                            cudaStream_t st, bool* handled);
+                            cudaStream_t st, bool* handled, const void* dR_bf16 = nullptr, bool dry = false);
 int conv3x3_wgrad_launch(const dg_conv3x3_args& a, const float* dR, float* dW, int s_tap, int s_ci, int s_co,
                          cudaStream_t stream);
 int act_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dA_a,
                    int stride_a, int off_a, const float* dA_b, int stride_b, int off_b, float* G, double* P, int N, int H,
                    int W, int C, int groups, float eps, cudaStream_t st);
 int gn_bwd_apply_launch(int dtype, const void* raw, const double* stats, const float* gamma, const double* P, float* G,
-                        float* dgamma, float* dbeta, int N, int H, int W, int C, int groups, float eps, cudaStream_t st);
+                        float* dgamma, float* dbeta, int N, int H, int W, int C, int groups, float eps, cudaStream_t st, void* dRb = nullptr, bool* wrote_bf16 = nullptr);
 int head_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dOut,
                     const float* w, float* G, double* P, float* dW, float* dB, int N, int H, int W, int C, int OC, int groups,
                     float eps, cudaStream_t st);

@@ -28,6 +28,8 @@ struct DgradArgs {
     const void* wtc;   // forward packing of W [CK = Cout_fwd][CN = Cin_fwd][3][3] in bf16 (dg_pack_conv3x3_tc)
     float* out;        // [N,H,W,CN]
     int N, H, W;
+    const void* dRb;   // optional: dR as bf16 [N,H,W,CK] (see gn_bwd_apply): the tile is copied, not converted
+    int dry;           // probe only
     // optional fused activation backward (the conv's only input is the activated output of ONE producer conv, src/model.py:93-98):
     // out = G = dA * silu'(GroupNorm(raw_prev)) instead of dA, and P[n][c] += (sum G, sum G * xhat) -- what act_bwd_vec would
     // compute from a materialised dA (backward.cu), without writing and re-reading it
@@ -203,6 +205,27 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
         unsigned char* dst = act + (size_t)c8 * G::PLANE * 16;
         // four items (eight 128-bit loads) in flight per thread: nothing else is live yet, registers are free here
         constexpr int STEP = DGR_THREADS / G::KC8, NPIX = G::PH * G::PW, SB = 4;
+        if (p.dRb != nullptr) {
+            const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(p.dRb) + ((size_t)n * H * W * CK + c8 * 8) * 2;
+#pragma unroll 1
+            for (int pix0 = tid / G::KC8; pix0 < NPIX; pix0 += SB * STEP) {
+                uint4 q[SB];
+#pragma unroll
+                for (int k = 0; k < SB; ++k) {
+                    const int pix = pix0 + k * STEP;
+                    const int r = pix / G::PW, c = pix - r * G::PW;
+                    const int gy = y0 + r - 1, gx = x0 + c - 1;
+                    q[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (pix < NPIX && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
+                        q[k] = __ldg(reinterpret_cast<const uint4*>(bsrc + ((size_t)gy * W + gx) * CK * 2));
+                }
+#pragma unroll
+                for (int k = 0; k < SB; ++k) {
+                    const int pix = pix0 + k * STEP;
+                    if (pix < NPIX) *reinterpret_cast<uint4*>(dst + (size_t)pix * 16) = q[k];
+                }
+            }
+        } else {
 #pragma unroll 1
         for (int pix0 = tid / G::KC8; pix0 < NPIX; pix0 += SB * STEP) {
             float4 va[SB], vb[SB];
@@ -227,6 +250,7 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
                                           pack2<BF>(vb[k].z, vb[k].w));
                 *reinterpret_cast<uint4*>(dst + (size_t)pix * 16) = o;
             }
+        }
         }
     }
     cp_async_wait<0>();
@@ -336,6 +360,7 @@ int launch_dgr(const DgradArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("dgrad_tc: cudaFuncSetAttribute(%d B): %s", G::SMEM, cudaGetErrorString(e)); return 4; }
         done = true;
     }
+    if (a.dry) return 0;
     dim3 grid(((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH), a.N, CN / NB);
     kern<<<grid, DGR_THREADS, G::SMEM, st>>>(a);
     count_launch();
@@ -510,11 +535,12 @@ namespace {
 // out[N,H,W,cn] = conv3x3(dR[N,H,W,ck], flipped / transposed W); wtc_bf16 = dg_pack_conv3x3_tc(W packed, cin = cn, cout = ck, DG_BF16)
 // `act` (optional): fuse the producer's activation backward into the epilogue -- see DgradArgs
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
-                            cudaStream_t st, bool* handled, const DgradAct* act) {
+                            cudaStream_t st, bool* handled, const DgradAct* act, const void* dR_bf16, bool dry) {
     *handled = false;
     if (wtc_bf16 == nullptr || N < 1 || N > 65535) return 0;
     if ((reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(wtc_bf16)) & 15) return 0;
-    DgradArgs a{dR, wtc_bf16, out, N, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, 1, DG_F16, 1e-5f};
+    if (dR_bf16 != nullptr && (reinterpret_cast<uintptr_t>(dR_bf16) & 15)) return 0;
+    DgradArgs a{dR, wtc_bf16, out, N, H, W, dR_bf16, dry ? 1 : 0, nullptr, nullptr, nullptr, nullptr, nullptr, 1, DG_F16, 1e-5f};
     if (act != nullptr) {
         if ((act->dtype != DG_F16 && act->dtype != DG_BF16) || (reinterpret_cast<uintptr_t>(act->raw) & 3) || act->groups < 1 ||
             cn % act->groups != 0)

@@ -34,6 +34,8 @@ struct WgArgs {
     const void* src0; const double* st0; const float* g0; const float* b0; int groups0;   // SAME/POOL source, or `up` (CAT2)
     const void* src1; const double* st1; const float* g1; const float* b1; int groups1;   // CAT2: skip
     const float* dR; float* dW;
+    const void* dRb;   // optional: dR already rounded to bf16 [N,H,W,CO] (gn_bwd_apply's second output form): copied, not converted
+    int dry;           // probe only: report whether a kernel exists for this configuration, launch nothing
     int N, H, W;
     int s_tap, s_ci, s_co;
     float eps;
@@ -207,13 +209,16 @@ wgrad_tc_kernel(const WgArgs p) {
         {
             const int j8 = tid % NTW;
             const float* gsrc = p.dR + (size_t)n * H * W * CO + co0 + j8 * 8;
+            const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(p.dRb) + ((size_t)n * H * W * CO + co0 + j8 * 8) * 2;
             unsigned char* dst = dsm + (size_t)j8 * G::DPLANE * 16;
 #pragma unroll 4
             for (int pix = tid / NTW; pix < TH * TW; pix += WG_THREADS / NTW) {
                 const int r = pix / TW, c = pix - r * TW;
                 const int gy = y0 + r, gx = x0 + c;
                 uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (gy < H && gx < W) {
+                if (p.dRb != nullptr) {
+                    if (gy < H && gx < W) o = __ldg(reinterpret_cast<const uint4*>(bsrc + ((size_t)gy * W + gx) * CO * 2));
+                } else if (gy < H && gx < W) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CO));
                     const float4 b = __ldg(reinterpret_cast<const float4*>(gsrc + ((size_t)gy * W + gx) * CO) + 1);
                     o = make_uint4(pack2<BF>(a.x, a.y), pack2<BF>(a.z, a.w), pack2<BF>(b.x, b.y), pack2<BF>(b.z, b.w));
@@ -300,6 +305,7 @@ int launch_wg(WgArgs a, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute(%d B): %s", G::SMEM, cudaGetErrorString(e)); return 4; }
         done = true;
     }
+    if (a.dry) return 0;
     a.tiles_x = (a.W + TW - 1) / TW;
     a.tiles_y = (a.H + TH - 1) / TH;
     const int ntiles = a.tiles_x * a.tiles_y * a.N;
@@ -553,7 +559,7 @@ namespace {
 // identity 16-bit NHWC `up` (stats == NULL, silu == 0), src[1] = the skip.  dW element (tap, ci, co) lives at
 // dW[tap*s_tap + ci*s_ci + co*s_co] and is accumulated atomically (zero it first).
 int conv3x3_wgrad_tc_launch(const dg_conv3x3_args& a, const float* dR, float* dW, int s_tap, int s_ci, int s_co,
-                            cudaStream_t st, bool* handled) {
+                            cudaStream_t st, bool* handled, const void* dR_bf16, bool dry) {
     *handled = false;
     if (a.dtype != DG_F16 && a.dtype != DG_BF16) return 0;
     if (a.N < 1 || (reinterpret_cast<uintptr_t>(dR) & 15)) return 0;
@@ -582,7 +588,8 @@ int conv3x3_wgrad_tc_launch(const dg_conv3x3_args& a, const float* dR, float* dW
     } else {
         return 0;
     }
-    w.dR = dR; w.dW = dW; w.N = a.N; w.H = a.H; w.W = a.W;
+    if (dR_bf16 != nullptr && (reinterpret_cast<uintptr_t>(dR_bf16) & 15)) return 0;
+    w.dR = dR; w.dW = dW; w.dRb = dR_bf16; w.dry = dry ? 1 : 0; w.N = a.N; w.H = a.H; w.W = a.W;
     w.s_tap = s_tap; w.s_ci = s_ci; w.s_co = s_co; w.eps = a.eps;
     if (a.dtype == DG_F16) return dispatch_wg<__half>(w, ci, a.cout, mode, st, handled);
     return dispatch_wg<__nv_bfloat16>(w, ci, a.cout, mode, st, handled);
