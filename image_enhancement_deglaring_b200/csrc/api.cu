@@ -432,6 +432,7 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
                              const float* grad_y, int n0, int N, int H, int W, char* fw, char* bw, float* grads, cudaStream_t st) {
     int rc = 0;
     const size_t esz = dtype_size(p->dtype);
+    bool t_split[18] = {};   // decoder conv i: T(i) holds the two halves of the concat gradient as two compact tensors
     auto hwc = [&](int i, int c) { return (size_t)pl.conv_h[i] * pl.conv_w[i] * c; };
     auto G = [&](int i) { return reinterpret_cast<float*>(bw + bp.g_off[i]) + (size_t)n0 * hwc(i, pl.conv_c[i]); };
     auto T = [&](int i) { return reinterpret_cast<float*>(bw + bp.t_off[i]) + (size_t)n0 * hwc(i, bp.cin_tot[i]); };
@@ -523,6 +524,14 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
                 if (rc) return rc;
                 act_fused = dg_done;
             }
+            if (!dg_done && j == 0 && b >= 5) {
+                // decoder conv: its input gradient is a concat gradient whose halves go to different consumers -- written as two
+                // compact tensors (up half at T(i), skip half right behind it) instead of one interleaved [.., 2C]
+                rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], T(i), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done, nullptr, dRb_in,
+                                             false, T(i) + (size_t)N * hwc(i, C));
+                if (rc) return rc;
+                t_split[i] = dg_done;
+            }
             if (!dg_done) {
                 rc = conv3x3_dgrad_tc_launch(G(i), p->conv_w_tc_bf16[b][j], T(i), N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done, nullptr, dRb_in);
                 if (rc) return rc;
@@ -554,7 +563,8 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
         } else if (b < 5) {
             // producer = skip tensor of level b-1: gradient from the decoder's concat (skip half) + this pooled path
             const int lvl = b - 1, dconv = 2 * (8 - lvl);
-            rc = act_bwd(i - 1, T(dconv), 2 * pl.f[lvl], pl.f[lvl], T(i), pl.f[lvl], 0);
+            if (t_split[dconv]) rc = act_bwd(i - 1, T(dconv) + (size_t)N * hwc(dconv, pl.f[lvl]), pl.f[lvl], 0, T(i), pl.f[lvl], 0);
+            else rc = act_bwd(i - 1, T(dconv), 2 * pl.f[lvl], pl.f[lvl], T(i), pl.f[lvl], 0);
         } else {
             const int lvl = block_level(b), u = b - 5;
             float* dlow = reinterpret_cast<float*>(bw + bp.low_off[u]) + (size_t)n0 * (Hi / 2) * (Wi / 2) * pl.f[lvl + 1];
@@ -563,7 +573,7 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
             const bool try_fuse = p->dtype != DG_F32 && (p->path & 3) != 1 && p->up_w_tc_bf16[u] != nullptr;
             DgradAct lact{raw(i - 1), stats(i - 1), p->gn_w[b - 1][1], p->gn_b[b - 1][1], P(i - 1), p->groups[b - 1], p->dtype, 1e-5f};
             bool low_fused = false;
-            rc = convt_bwd_launch(p->dtype, T(i), 2 * pl.f[lvl], p->up_w[u], p->up_w_t[u], raw(i - 1), stats(i - 1), p->gn_w[b - 1][1],
+            rc = convt_bwd_launch(p->dtype, T(i), t_split[i] ? pl.f[lvl] : 2 * pl.f[lvl], p->up_w[u], p->up_w_t[u], raw(i - 1), stats(i - 1), p->gn_w[b - 1][1],
                                   p->gn_b[b - 1][1], try_fuse ? G(i - 1) : dlow, grads + gl.up_w[u], grads + gl.up_b[u],
                                   reinterpret_cast<float*>(bw + bp.coef_off) + (size_t)n0 * bp.maxc * 2, N, Hi, Wi, pl.f[lvl + 1], pl.f[lvl],
                                   p->groups[b - 1], 1e-5f, st, (p->path & 3) != 1 ? p->up_w_tc_bf16[u] : nullptr,

@@ -196,7 +196,7 @@ struct DgradAct {
 };
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
                             cudaStream_t st, bool* handled, const DgradAct* act = nullptr, const void* dR_bf16 = nullptr,
-                            bool dry = false);
+                            bool dry = false, float* out2 = nullptr);
 int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
                           cudaStream_t st, bool* handled, const DgradAct* act = nullptr);
 int image_metrics_launch(const float* out, const float* tgt, int N, int H, int W, int clip01, double data_range, double* acc,

@@ -30,6 +30,9 @@ struct DgradArgs {
     int N, H, W;
     const void* dRb;   // optional: dR as bf16 [N,H,W,CK] (see gn_bwd_apply): the tile is copied, not converted
     int dry;           // probe only
+    float* out2;       // optional (plain epilogue): channels [CN/2, CN) go HERE as a compact [N,H,W,CN/2] tensor and channels
+                       // [0, CN/2) to `out`, also compact -- the two halves of a concat gradient have different consumers
+                       // (ConvTranspose backward / skip activation backward), which otherwise read every other 32 bytes
     // optional fused activation backward (the conv's only input is the activated output of ONE producer conv, src/model.py:93-98):
     // out = G = dA * silu'(GroupNorm(raw_prev)) instead of dA, and P[n][c] += (sum G, sum G * xhat) -- what act_bwd_vec would
     // compute from a materialised dA (backward.cu), without writing and re-reading it
@@ -342,6 +345,17 @@ __global__ void __launch_bounds__(DGR_THREADS) dgrad_tc_kernel(const DgradArgs p
         for (int hf = 0; hf < 2; ++hf) {
             const int gx = x0 + (mt % G::SEGS) * 16 + g + 8 * hf;
             if (gx >= W) continue;
+            if (p.out2 != nullptr) {
+                constexpr int HC = CN / 2;
+                const size_t pix = (size_t)(n * H + gy) * W + gx;
+#pragma unroll
+                for (int j = 0; j < G::NB8; ++j) {
+                    const int ch = nb8_0 * 8 + j * 8 + 2 * q;
+                    float* o = ch < HC ? p.out + pix * HC + ch : p.out2 + pix * HC + (ch - HC);
+                    *reinterpret_cast<float2*>(o) = make_float2(acc[m][j][2 * hf], acc[m][j][2 * hf + 1]);
+                }
+                continue;
+            }
             float* o = p.out + ((size_t)(n * H + gy) * W + gx) * CN + nb8_0 * 8 + 2 * q;
 #pragma unroll
             for (int j = 0; j < G::NB8; ++j)
@@ -535,12 +549,13 @@ namespace {
 // out[N,H,W,cn] = conv3x3(dR[N,H,W,ck], flipped / transposed W); wtc_bf16 = dg_pack_conv3x3_tc(W packed, cin = cn, cout = ck, DG_BF16)
 // `act` (optional): fuse the producer's activation backward into the epilogue -- see DgradArgs
 int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, int N, int H, int W, int ck, int cn,
-                            cudaStream_t st, bool* handled, const DgradAct* act, const void* dR_bf16, bool dry) {
+                            cudaStream_t st, bool* handled, const DgradAct* act, const void* dR_bf16, bool dry, float* out2) {
     *handled = false;
     if (wtc_bf16 == nullptr || N < 1 || N > 65535) return 0;
     if ((reinterpret_cast<uintptr_t>(dR) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(wtc_bf16)) & 15) return 0;
     if (dR_bf16 != nullptr && (reinterpret_cast<uintptr_t>(dR_bf16) & 15)) return 0;
-    DgradArgs a{dR, wtc_bf16, out, N, H, W, dR_bf16, dry ? 1 : 0, nullptr, nullptr, nullptr, nullptr, nullptr, 1, DG_F16, 1e-5f};
+    if (out2 != nullptr && ((reinterpret_cast<uintptr_t>(out2) & 15) || (cn & 15) || act != nullptr)) return 0;
+    DgradArgs a{dR, wtc_bf16, out, N, H, W, dR_bf16, dry ? 1 : 0, out2, nullptr, nullptr, nullptr, nullptr, nullptr, 1, DG_F16, 1e-5f};
     if (act != nullptr) {
         if ((act->dtype != DG_F16 && act->dtype != DG_BF16) || (reinterpret_cast<uintptr_t>(act->raw) & 3) || act->groups < 1 ||
             cn % act->groups != 0)
