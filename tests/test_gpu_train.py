@@ -152,8 +152,9 @@ def test_backward_two_stream_split_matches_single_stream(best_sd):
     finally:
         lib.dg_set_batch_split(old)
     for a, b in ((grads[0], grads[2]), (grads[1], grads[3])):
-        for k in a:
-            assert float((a[k] - b[k]).norm()) <= 1e-5 * float(a[k].norm()) + 1e-12, k
+        total = float(torch.sqrt(sum((v.double() ** 2).sum() for v in a.values())))
+        for k in a:   # fp32 atomics: order noise, larger for the cancelling bias sums (see the properties test below)
+            assert float((a[k] - b[k]).norm()) <= 1e-5 * float(a[k].norm()) + 5e-7 * total, k
 
 
 @pytest.mark.parametrize("storage", ["fp32", "fp16"])
@@ -172,10 +173,14 @@ def test_backward_properties_at_full_resolution(best_sd, storage):
         (crit(net(xb), tb) * scale).backward()
         return {k: p.grad.detach().clone() for k, p in net.named_parameters()}
 
+    # Parameter gradients are accumulated with fp32 atomics whose order differs from run to run; measured over 8 runs
+    # (tests/diag_grad_noise.py): <= 5e-6 of the tensor norm for the weights, 1.1e-5 for upconv1.bias -- a heavily cancelling sum
+    # whose norm is 6e-5 of the whole gradient's -- hence a per-tensor bound plus 5e-7 of the whole gradient's norm.
     g1, g4 = grads(x, t), grads(x, t, 4.0)
+    total1 = float(torch.sqrt(sum((v.double() ** 2).sum() for v in g1.values())))
     for k in g1:
-        assert float((g4[k] - 4.0 * g1[k]).norm()) <= 2e-5 * float(g4[k].norm()) + 1e-12, f"linearity {k}"
+        assert float((g4[k] - 4.0 * g1[k]).norm()) <= 2e-5 * float(g4[k].norm()) + 5e-7 * 4.0 * total1, f"linearity {k}"
     per = [grads(x[i:i + 1], t[i:i + 1]) for i in range(4)]
     for k in g1:
         mean = sum(p[k] for p in per) / 4.0
-        assert float((g1[k] - mean).norm()) <= 2e-5 * float(g1[k].norm()) + 1e-12, f"additivity {k}"
+        assert float((g1[k] - mean).norm()) <= 2e-5 * float(g1[k].norm()) + 5e-7 * total1, f"additivity {k}"
