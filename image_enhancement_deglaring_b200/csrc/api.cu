@@ -661,7 +661,10 @@ int dg_conv3x3_fused(const dg_conv3x3_args* a, dg_stream_t stream) {
         int rc = conv_first_tc_launch(*a, st, &handled);
         if (rc) return rc;
         if (handled) return 0;
-        rc = conv3x3_umma_launch(*a, st, &handled);   // tcgen05 + TMEM for the deep layers it covers
+        rc = conv3x3_t5_launch(*a, st, &handled);     // warp-specialised tcgen05 + TMEM kernel: every C_out >= 32 layer
+        if (rc) return rc;
+        if (handled) return 0;
+        rc = conv3x3_umma_launch(*a, st, &handled);   // round-1 tcgen05 kernel (opt-in, path bit 6)
         if (rc) return rc;
         if (handled) return 0;
         rc = conv3x3_tc_launch(*a, st, &handled);

@@ -1,0 +1,796 @@
+// Warp-specialised tcgen05 implicit-GEMM 3x3 conv (sm_100a) for every layer with C_out >= 32: the deep levels of the shipped
+// LightweightUNet(features_start=8) and ALL of the wide variant (features_start=64, BASELINE.json configs[4]).  Same fusion
+// contract as conv3x3_tc.cu -- GroupNorm apply + SiLU [+ AvgPool2d | identity `up` half of torch.cat] on load, raw NHWC
+// output + GroupNorm statistics of the stored values in the epilogue (src/model.py:92-99, :35-41, :116-128).
+//
+// Roles of one persistent CTA (one per SM, 14 warps), coupled only by mbarriers -- there is no CTA-wide barrier in the loop:
+//   warps 0-7   stagers: raw NHWC -> GroupNorm affine + SiLU (+ 2x2 mean | plain copy of `up`) -> 16-bit channel planes;
+//   warps 8-11  epilogue: tcgen05.ld -> round to the storage type -> 128-bit NHWC stores; the GroupNorm statistics are
+//               column sums of the stored tile, taken through a padded per-warp shared-memory transpose;
+//   warp 12     weight producer: one thread streams [tap][KC ci][NB co] weight tiles into a shared-memory ring with
+//               cp.async.bulk (TMA bulk copy, completes on the ring's `full` mbarrier);
+//   warp 13     MMA issuer: one thread issues tcgen05.mma (M = 128 pixels, N = NB <= 128 output channels, K = 16) with the
+//               accumulators in tensor memory, and releases ring slots / publishes accumulators with tcgen05.commit.
+// While the tensor core runs work item i, the stagers already build the A operand of item i+1 and the epilogue drains
+// item i-1 from the other TMEM stage.
+//
+// Implicit GEMM without im2col, "q-stream" tiling: the zero-padded image is the 1-D pixel stream q' = r'*(W+2) + c'
+// (r', c' = haloed coordinates).  Output pixel q = y*(W+2) + x reads input q + ky*(W+2) + kx for tap (ky, kx), so with the
+// activated stream in shared memory as 16-bit channel planes [KC/8][pixels][8 ch] (8 consecutive pixels of a plane = one
+// 128-byte core matrix of the no-swizzle K-major UMMA layout: LBO = plane stride, SBO = 128 B) EVERY tap, horizontal ones
+// included, is a pure start-address offset of the A descriptor.  An M-tile is any 128 consecutive q; the two halo columns
+// per row produce accumulator rows that are simply not stored (2/(W+2) of the MMA work).  One staged copy of the tile
+// serves all 9 taps -- the round-1 UMMA kernel needed three kx-shifted copies.  A work item is `mt` consecutive M-tiles
+// of one image times one block of NB output channels; K is walked in chunks of KC input channels (A ring) x 9 taps (B ring).
+#include <cstdio>
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace dg {
+
+namespace {
+
+enum { T5_SAME = 0, T5_POOL = 1, T5_CAT2 = 3 };
+constexpr int T5_STAGE_WARPS = 8;
+constexpr int T5_STAGE_THREADS = 32 * T5_STAGE_WARPS;
+// Warp roles by warp id.  The warp scheduler prefers the HIGHEST warp id among eligible warps (B300_MICROARCH.md, "arbiter
+// priority: hi-wid-first"), so the two single-thread control warps sit on top -- measured with the MMA issuer as warp 1 below
+// eight FFMA/MUFU-saturated stager warps: ~250 clk per issued MMA against the 56 clk the tensor core needs (tools/umma_rate.cu).
+constexpr int T5_EPI_WARP0 = T5_STAGE_WARPS;        // warps 0-7 stagers, 8-11 epilogue (warp % 4 = TMEM lane quarter)
+constexpr int T5_TMA_WARP = T5_EPI_WARP0 + 4;       // 12: weight producer
+constexpr int T5_MMA_WARP = T5_TMA_WARP + 1;        // 13, 14: MMA issuers (M-tiles interleaved between them); 13 owns the TMEM allocation
+constexpr int T5_MMA_WARPS = 2;
+constexpr int T5_THREADS = 32 * (T5_MMA_WARP + T5_MMA_WARPS);  // 480
+constexpr int T5_SCR_PITCH = 80;                                      // bytes per pixel row of the statistics transpose (64 + 16)
+constexpr int T5_MAX_RING = 8;
+
+struct T5Args {
+    const void* src0; const double* st0; const float* g0; const float* b0; const float* cf0; int groups0;
+    const void* src1; const double* st1; const float* g1; const float* b1; const float* cf1; int groups1;
+    const void* wgt; void* out; double* out_stats;
+    int N, H, W; float eps;
+    int cin, cout;
+    int pitch;        // W + 2
+    int mt;           // M-tiles (128 stream pixels each) per work item
+    int mtiles_img;   // M-tiles per image
+    int bands_img;    // work items per image and n-block
+    int kc, nchunk;   // input channels per A chunk, chunks
+    int nb, nnb;      // output channels per block, blocks
+    int plane_px;     // pixels per channel plane (padded for conflict-free staging stores)
+    int na, nbs, ts;  // ring depths: A chunks, weight tiles, TMEM accumulator stages
+    int a_stage_bytes, b_stage_bytes;
+    int tmem_cols;
+    int off_b, off_coef, off_scr, off_bar;
+    int ncoef;
+    int items;
+    int dbg;
+    long long* trace;   // DG_T5_TRACE=1: per-role clock64 timestamps of CTA 0 (debug aid, see t5_trace_dump)
+};
+
+__device__ __forceinline__ uint64_t t5_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+// Bounded wait: a protocol error must abort the launch, not hang the GPU.  try_wait suspends the thread in hardware (up to the
+// hint) and is woken by the completing arrive, so waiting warps do not take issue slots from the working ones; the clock is
+// only looked at every 64 wake-ups.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    for (uint32_t spin = 1;; ++spin) {
+        if (mbar_try(bar, parity)) return;
+        if ((spin & 63u) == 0 && clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void stager_bar() { asm volatile("bar.sync 1, %0;" ::"n"(T5_STAGE_THREADS) : "memory"); }
+
+// trace slots: [role 0..3][event index], 512 events per role
+#define T5_TRACE(role, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role) * 512 + (idx)] = clock64(); } while (0)
+
+// All MMAs one issuer warp owes to one tap: `count` M-tiles (every T5_MMA_WARPS-th of the work item) x KS K-steps, from ONE asm
+// block whose loop runs warp-uniformly; the elected lane's guard predicate issues.  (C++ loops around a per-MMA asm compiled to
+// ~70 SASS instructions of R2UR / predicate shuffling per M-tile = ~300 clk against the 56 clk an N = 32 MMA needs.)
+template <int KS>
+__device__ __forceinline__ void t5_issue_tap(uint32_t dc, uint64_t da, uint64_t db, uint32_t idesc, uint64_t dA, uint64_t dB,
+                                             uint32_t accumulate, int count, uint32_t dc_step) {
+    if constexpr (KS == 1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pel, pacc, ploop;\n\t.reg .b64 da;\n\t.reg .b32 dc, m;\n\t"
+            "elect.sync _|pel, 0xffffffff;\n\t"
+            "setp.ne.b32 pacc, %6, 0;\n\t"
+            "mov.b64 da, %1;\n\tmov.b32 dc, %0;\n\tmov.b32 m, %7;\n"
+            "T5_L1:\n\t"
+            "@pel tcgen05.mma.cta_group::1.kind::f16 [dc], da, %2, %3, pacc;\n\t"
+            "add.u64 da, da, %9;\n\tadd.u32 dc, dc, %8;\n\tsub.u32 m, m, 1;\n\t"
+            "setp.ne.b32 ploop, m, 0;\n\t@ploop bra.uni T5_L1;\n\t"
+            "}"
+            ::"r"(dc), "l"(da), "l"(db), "r"(idesc), "l"(dA), "l"(dB), "r"(accumulate), "r"(count), "r"(dc_step),
+              "l"((uint64_t)(128 * T5_MMA_WARPS)));
+    } else if constexpr (KS == 2) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pel, pacc, ptrue, ploop;\n\t.reg .b64 da, a1, b1;\n\t.reg .b32 dc, m;\n\t"
+            "elect.sync _|pel, 0xffffffff;\n\t"
+            "setp.ne.b32 pacc, %6, 0;\n\tsetp.eq.b32 ptrue, 0, 0;\n\t"
+            "add.u64 b1, %2, %5;\n\t"
+            "mov.b64 da, %1;\n\tmov.b32 dc, %0;\n\tmov.b32 m, %7;\n"
+            "T5_L2:\n\t"
+            "add.u64 a1, da, %4;\n\t"
+            "@pel tcgen05.mma.cta_group::1.kind::f16 [dc], da, %2, %3, pacc;\n\t"
+            "@pel tcgen05.mma.cta_group::1.kind::f16 [dc], a1, b1, %3, ptrue;\n\t"
+            "add.u64 da, da, %9;\n\tadd.u32 dc, dc, %8;\n\tsub.u32 m, m, 1;\n\t"
+            "setp.ne.b32 ploop, m, 0;\n\t@ploop bra.uni T5_L2;\n\t"
+            "}"
+            ::"r"(dc), "l"(da), "l"(db), "r"(idesc), "l"(dA), "l"(dB), "r"(accumulate), "r"(count), "r"(dc_step),
+              "l"((uint64_t)(128 * T5_MMA_WARPS)));
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pel, pacc, ptrue, ploop;\n\t.reg .b64 da, a1, a2, a3, b1, b2, b3;\n\t.reg .b32 dc, m;\n\t"
+            "elect.sync _|pel, 0xffffffff;\n\t"
+            "setp.ne.b32 pacc, %6, 0;\n\tsetp.eq.b32 ptrue, 0, 0;\n\t"
+            "add.u64 b1, %2, %5;\n\tadd.u64 b2, b1, %5;\n\tadd.u64 b3, b2, %5;\n\t"
+            "mov.b64 da, %1;\n\tmov.b32 dc, %0;\n\tmov.b32 m, %7;\n"
+            "T5_L4:\n\t"
+            "add.u64 a1, da, %4;\n\tadd.u64 a2, a1, %4;\n\tadd.u64 a3, a2, %4;\n\t"
+            "@pel tcgen05.mma.cta_group::1.kind::f16 [dc], da, %2, %3, pacc;\n\t"
+            "@pel tcgen05.mma.cta_group::1.kind::f16 [dc], a1, b1, %3, ptrue;\n\t"
+            "@pel tcgen05.mma.cta_group::1.kind::f16 [dc], a2, b2, %3, ptrue;\n\t"
+            "@pel tcgen05.mma.cta_group::1.kind::f16 [dc], a3, b3, %3, ptrue;\n\t"
+            "add.u64 da, da, %9;\n\tadd.u32 dc, dc, %8;\n\tsub.u32 m, m, 1;\n\t"
+            "setp.ne.b32 ploop, m, 0;\n\t@ploop bra.uni T5_L4;\n\t"
+            "}"
+            ::"r"(dc), "l"(da), "l"(db), "r"(idesc), "l"(dA), "l"(dB), "r"(accumulate), "r"(count), "r"(dc_step),
+              "l"((uint64_t)(128 * T5_MMA_WARPS)));
+    }
+}
+
+struct T5Item { int n, m0, mt_cur, nbk; };
+__device__ __forceinline__ T5Item t5_item(const T5Args& p, int item) {
+    T5Item it;
+    it.nbk = item % p.nnb;
+    const int rest = item / p.nnb;
+    it.n = rest / p.bands_img;
+    const int band = rest - it.n * p.bands_img;
+    it.m0 = band * p.mt;
+    const int left = p.mtiles_img - it.m0;
+    it.mt_cur = left < p.mt ? left : p.mt;
+    return it;
+}
+
+template <typename T, int MODE, int ACT>
+__global__ void __launch_bounds__(T5_THREADS, 1) conv3x3_t5_kernel(const __grid_constant__ T5Args p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int FACT = ACT == ACT_HALF2 ? ACT_TANH : ACT;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    // barrier table: a_full[R] a_empty[R] b_full[R] b_empty[R] t_full[2] t_empty[2], R = T5_MAX_RING
+    const uint32_t bar0 = smem_u32(bars);
+    auto A_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (T5_MAX_RING + s); };
+    auto B_FULL = [&](int s) { return bar0 + 8u * (2 * T5_MAX_RING + s); };
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (3 * T5_MAX_RING + s); };
+    auto T_FULL = [&](int s) { return bar0 + 8u * (4 * T5_MAX_RING + s); };
+    auto T_EMPTY = [&](int s) { return bar0 + 8u * (4 * T5_MAX_RING + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (4 * T5_MAX_RING + 4));
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int s = 0; s < T5_MAX_RING; ++s) {
+            mbar_init(A_FULL(s), T5_STAGE_THREADS);
+            mbar_init(A_EMPTY(s), T5_MMA_WARPS);
+            mbar_init(B_FULL(s), 1);
+            mbar_init(B_EMPTY(s), T5_MMA_WARPS);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(T_FULL(s), T5_MMA_WARPS);
+            mbar_init(T_EMPTY(s), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == T5_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = *tmem_slot;
+
+    // contiguous range of work items of this CTA (few image changes -> few statistics flushes / coefficient rebuilds)
+    const int it0 = (int)((long long)p.items * blockIdx.x / gridDim.x);
+    const int it1 = (int)((long long)p.items * (blockIdx.x + 1) / gridDim.x);
+    const int ksteps = p.kc >> 4;
+    const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
+    const uint32_t a_base = smem_u32(smem);
+    const uint32_t b_base = smem_u32(smem + p.off_b);
+
+    if (warp == T5_TMA_WARP) {
+        // ================= weight producer (TMA bulk copies) =================
+        if (lane == 0) {
+            int sb = 0; uint32_t pb = 0;
+            const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.wgt);
+            const int kst_tot = p.cin >> 4;
+            for (int item = it0; item < it1; ++item) {
+                const int nbk = item % p.nnb;
+                for (int ch = 0; ch < p.nchunk; ++ch)
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(B_EMPTY(sb), pb ^ 1u);
+                        if (ch == 0 && (tap == 0 || tap == 8)) T5_TRACE(3, 2 * (item - it0) + (tap ? 1 : 0));
+                        mbar_expect_tx(B_FULL(sb), (uint32_t)p.b_stage_bytes);
+                        const uint32_t dst = b_base + (uint32_t)sb * p.b_stage_bytes;
+                        const size_t ck = (size_t)tap * kst_tot + (size_t)ch * ksteps;   // first 16-channel weight chunk
+                        if (p.nnb == 1) {
+                            bulk_g2s(dst, wg + ck * p.cout * 32, (uint32_t)p.b_stage_bytes, B_FULL(sb));
+                        } else {
+                            for (int j = 0; j < 2 * ksteps; ++j)   // (k-step, k-half) slices of NB output channels
+                                bulk_g2s(dst + (uint32_t)j * p.nb * 16, wg + (ck * 2 + j) * p.cout * 16 + (size_t)nbk * p.nb * 16,
+                                         (uint32_t)p.nb * 16, B_FULL(sb));
+                        }
+                        if (++sb == p.nbs) { sb = 0; pb ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp >= T5_MMA_WARP) {
+        // ================= MMA issuers =================
+        // The WHOLE warp walks the loop nest (uniform control flow, so every descriptor lives in uniform registers and an MMA
+        // costs ~6 issue slots); one elected lane issues.  Measured with a single-lane loop: ~35 SASS instructions per MMA incl.
+        // a R2UR waterfall = 150-190 clk per MMA against the 56-64 clk the tensor core needs (tools/umma_rate.cu).
+        {
+            const uint32_t idesc = (1u << 4) | ((std::is_same<T, __half>::value ? 0u : 1u) << 7) |
+                                   ((std::is_same<T, __half>::value ? 0u : 1u) << 10) | ((uint32_t)(p.nb >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+            const uint64_t dA = 2u * (uint32_t)p.plane_px, dB = 2u * (uint32_t)p.nb;   // descriptor advance per K step (16-byte units)
+            const int mw = warp - T5_MMA_WARP;   // this warp issues M-tiles mw, mw + T5_MMA_WARPS, ...
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int k = 0;
+            for (int item = it0; item < it1; ++item, ++k) {
+                const T5Item it = t5_item(p, item);
+                const int tsg = p.ts == 2 ? (k & 1) : 0;
+                const uint32_t tph = p.ts == 2 ? ((k >> 1) & 1) : (k & 1);
+                mbar_wait(T_EMPTY(tsg), tph ^ 1u);
+                tc_fence_after();
+                if (lane == 0 && mw == 0) T5_TRACE(0, 4 * k);
+                const int cnt = it.mt_cur > mw ? (it.mt_cur - mw + T5_MMA_WARPS - 1) / T5_MMA_WARPS : 0;
+                const uint32_t dcol = taddr + (uint32_t)(tsg * p.mt * p.nb);
+                for (int ch = 0; ch < p.nchunk; ++ch) {
+                    mbar_wait(A_FULL(sa), pa);
+                    tc_fence_after();
+                    if (ch == 0 && lane == 0 && mw == 0) T5_TRACE(0, 4 * k + 1);
+                    const uint64_t da_chunk = t5_desc(a_base + (uint32_t)sa * p.a_stage_bytes, plane_bytes, 128);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(B_FULL(sb), pb);
+                        tc_fence_after();
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const uint64_t da = da_chunk + (uint32_t)(ky * p.pitch + kx);
+                        const uint64_t db = t5_desc(b_base + (uint32_t)sb * p.b_stage_bytes, (uint32_t)p.nb * 16u, 128);
+                        if (cnt > 0) {
+                            const uint32_t acc = (ch | tap) ? 1u : 0u;
+                            const uint32_t dc0 = dcol + (uint32_t)(mw * p.nb);
+                            const uint64_t da0 = da + (uint32_t)(mw * 128);
+                            if (ksteps == 4) t5_issue_tap<4>(dc0, da0, db, idesc, dA, dB, acc, cnt, (uint32_t)(T5_MMA_WARPS * p.nb));
+                            else if (ksteps == 2) t5_issue_tap<2>(dc0, da0, db, idesc, dA, dB, acc, cnt, (uint32_t)(T5_MMA_WARPS * p.nb));
+                            else t5_issue_tap<1>(dc0, da0, db, idesc, dA, dB, acc, cnt, (uint32_t)(T5_MMA_WARPS * p.nb));
+                        }
+                        __syncwarp();
+                        if (elect_one()) umma_commit(B_EMPTY(sb));
+                        if (++sb == p.nbs) { sb = 0; pb ^= 1u; }
+                    }
+                    if (elect_one()) umma_commit(A_EMPTY(sa));
+                    if (++sa == p.na) { sa = 0; pa ^= 1u; }
+                }
+                if (elect_one()) umma_commit(T_FULL(tsg));
+                if (lane == 0 && mw == 0) T5_TRACE(0, 4 * k + 2);
+            }
+        }
+    } else if (warp >= T5_EPI_WARP0 && warp < T5_TMA_WARP) {
+        // ================= epilogue: TMEM -> HBM + GroupNorm statistics =================
+        pdl_wait();   // the output buffer / statistics may still be read by the kernels before the producer of our inputs
+        const int wq = warp & 3;   // TMEM lane quarter this warp may access
+        unsigned char* scr = smem + p.off_scr + (warp - T5_EPI_WARP0) * (32 * T5_SCR_PITCH);
+        const int half = lane >> 4, pr = lane & 15;
+        float s1[4][2], s2[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s1[c][0] = s1[c][1] = s2[c][0] = s2[c][1] = 0.f;
+        int stats_n = -1, stats_nbk = 0;
+        const int ncc = p.nb >> 5;
+        auto flush = [&]() {
+            if (stats_n < 0 || p.out_stats == nullptr) return;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < ncc) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float a = s1[c][e] + __shfl_xor_sync(0xffffffffu, s1[c][e], 16);
+                        const float b = s2[c][e] + __shfl_xor_sync(0xffffffffu, s2[c][e], 16);
+                        if (half == 0) {
+                            double* d = p.out_stats + ((size_t)stats_n * p.cout + stats_nbk * p.nb + c * 32 + 2 * pr + e) * 2;
+                            atomicAdd(d, (double)a);
+                            atomicAdd(d + 1, (double)b);
+                        }
+                    }
+                }
+                s1[c][0] = s1[c][1] = s2[c][0] = s2[c][1] = 0.f;
+            }
+        };
+        int k = 0;
+        for (int item = it0; item < it1; ++item, ++k) {
+            const T5Item it = t5_item(p, item);
+            if (it.n != stats_n || it.nbk != stats_nbk) {
+                flush();
+                stats_n = it.n;
+                stats_nbk = it.nbk;
+            }
+            const int tsg = p.ts == 2 ? (k & 1) : 0;
+            const uint32_t tph = p.ts == 2 ? ((k >> 1) & 1) : (k & 1);
+            mbar_wait(T_FULL(tsg), tph);
+            tc_fence_after();
+            if (warp == T5_EPI_WARP0 && lane == 0) T5_TRACE(1, 2 * k);
+            for (int m = 0; m < it.mt_cur; ++m) {
+                const int q = (it.m0 + m) * 128 + wq * 32 + lane;
+                const int y = q / p.pitch, x = q - y * p.pitch;
+                const bool valid = x < p.W && y < p.H;
+                T* o = reinterpret_cast<T*>(p.out) + ((size_t)(it.n * p.H + y) * p.W + x) * p.cout + it.nbk * p.nb;
+                const uint32_t trow = taddr + ((uint32_t)(wq * 32) << 16) + (uint32_t)((tsg * p.mt + m) * p.nb);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < ncc) {
+                        uint32_t r[32];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                            : "r"(trow + (uint32_t)(c * 32)));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            pk[j] = valid ? pack2<T>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])) : 0u;
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(o + c * 32 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                        // statistics of the STORED values: transpose through shared memory, lane = (pixel half, channel pair)
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(scr + lane * T5_SCR_PITCH + j * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        __syncwarp();
+                        float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int row = half * 16 + ((i + 4 * half) & 15);   // the two halves hit disjoint banks
+                            const float2 v = unpack2<T>(*reinterpret_cast<const uint32_t*>(scr + row * T5_SCR_PITCH + pr * 4));
+                            a0 += v.x; q0 = fmaf(v.x, v.x, q0);
+                            a1 += v.y; q1 = fmaf(v.y, v.y, q1);
+                        }
+                        s1[c][0] += a0; s2[c][0] += q0;
+                        s1[c][1] += a1; s2[c][1] += q1;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(T_EMPTY(tsg));
+            if (warp == T5_EPI_WARP0 && lane == 0) T5_TRACE(1, 2 * k + 1);
+        }
+        flush();
+    } else {
+        // ================= stagers: raw -> activated channel planes =================
+        // A thread owns the same (pixel, 8-channel chunk) slots in every job (job = one A-ring stage = one K chunk of one work
+        // item).  SAME / CAT2: the raw 16-byte chunks go global -> shared with cp.async straight into their final position in the
+        // channel planes (zero-filled outside the image), one whole job ahead of the arithmetic, so HBM latency is paid by the
+        // copy engine and not by a register-staged load -> use chain; the GroupNorm affine + SiLU then runs IN PLACE on the
+        // thread's own chunks (no cross-thread hand-over until the stage's `full` barrier).  POOL: the 2x2 mean shrinks the data
+        // four-fold, so it keeps register staging (8 loads in flight per thread).
+        pdl_wait();   // the producer's activations / statistics are complete from here on
+        const int ts_ = tid;
+        const int nc8 = p.kc >> 3;
+        const int l2 = nc8 == 8 ? 3 : (nc8 == 4 ? 2 : 1);
+        const int c8 = ts_ & (nc8 - 1), p0 = ts_ >> l2, pstr = T5_STAGE_THREADS >> l2;
+        const int DR = pstr / p.pitch, DC = pstr - DR * p.pitch;
+        float2* coef = reinterpret_cast<float2*>(smem + p.off_coef);
+        const int H = p.H, W = p.W;
+        const int Hs = MODE == T5_POOL ? 2 * H : H, Ws = MODE == T5_POOL ? 2 * W : W;
+        const int Cs = MODE == T5_CAT2 ? p.cout : p.cin;           // channels of one source tensor
+        const uint32_t rowb = (uint32_t)Ws * Cs * 2;
+        const int njobs = (it1 - it0) * p.nchunk;
+
+        struct Job { int n, apix, r0, c0, cs; bool ident; const unsigned char* src; };
+        auto job_of = [&](int j) {
+            Job jb;
+            const int item = it0 + j / p.nchunk, ch = j - (j / p.nchunk) * p.nchunk;
+            const T5Item it = t5_item(p, item);
+            jb.n = it.n;
+            jb.apix = 128 * it.mt_cur + 2 * p.pitch + 2;
+            const int q0 = it.m0 * 128 + p0;
+            jb.r0 = q0 / p.pitch;
+            jb.c0 = q0 - jb.r0 * p.pitch;
+            const int cg = ch * p.kc + c8 * 8;                         // first of this thread's 8 input channels
+            jb.ident = MODE == T5_CAT2 && cg < p.cout;                // `up` half of the concat: plain copy
+            jb.cs = (MODE == T5_CAT2 && !jb.ident) ? cg - p.cout : cg;
+            jb.src = reinterpret_cast<const unsigned char*>((MODE == T5_CAT2 && !jb.ident) ? p.src1 : p.src0) +
+                     (size_t)it.n * Hs * Ws * Cs * 2 + (size_t)jb.cs * 2;
+            return jb;
+        };
+        auto stage_ptr = [&](int sa) { return smem + (size_t)sa * p.a_stage_bytes + (size_t)c8 * plane_bytes; };
+        // pass 1 (SAME / CAT2): one cp.async per slot into the planes
+        auto issue_loads = [&](const Job& jb, int sa) {
+            const uint32_t dst = smem_u32(stage_ptr(sa));
+            int r = jb.r0, c = jb.c0;
+#pragma unroll 4
+            for (int s = p0; s < jb.apix; s += pstr) {
+                const int gy = r - 1, gx = c - 1;
+                const bool ok = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+                const unsigned char* g = jb.src + (ok ? ((size_t)gy * rowb + (size_t)gx * (Cs * 2)) : 0);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)s * 16u), "l"(g), "r"(ok ? 16u : 0u) : "memory");
+                r += DR; c += DC;
+                if (c >= p.pitch) { c -= p.pitch; r += 1; }
+            }
+            cp_async_commit();
+        };
+        // pass 2 (SAME / CAT2): in-place GroupNorm affine + SiLU of the thread's own chunks; pixels outside the image stay zero
+        auto transform = [&](const Job& jb, int sa) {
+            if (jb.ident) return;
+            float2 cf[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cf[e] = coef[jb.cs + e];
+            unsigned char* dst = stage_ptr(sa);
+            int r = jb.r0, c = jb.c0;
+            int s = p0;
+#pragma unroll 1
+            while (s < jb.apix) {
+                uint4 qv[4];
+                int ss[4];
+                bool ok[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    ss[b] = s;
+                    ok[b] = s < jb.apix && (unsigned)(r - 1) < (unsigned)H && (unsigned)(c - 1) < (unsigned)W;
+                    if (ok[b]) qv[b] = *reinterpret_cast<const uint4*>(dst + (size_t)s * 16);
+                    s += pstr; r += DR; c += DC;
+                    if (c >= p.pitch) { c -= p.pitch; r += 1; }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (ok[b]) {
+                        float yv[8];
+                        act8<T, FACT>(qv[b], cf, yv);
+                        *reinterpret_cast<uint4*>(dst + (size_t)ss[b] * 16) = pack8<T>(yv);
+                    }
+                }
+            }
+        };
+        // POOL: register-staged 2x2 mean of the activated source
+        auto stage_pool = [&](const Job& jb, int sa) {
+            float2 cf[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cf[e] = coef[jb.cs + e];
+            unsigned char* dst = stage_ptr(sa);
+            int s = p0, r = jb.r0, c = jb.c0;
+            constexpr int B = 2;
+#pragma unroll 1
+            while (s < jb.apix) {
+                uint4 qv[B][4];
+                int ss[B];
+                bool ok[B];
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const int gy = r - 1, gx = c - 1;
+                    ss[b] = s;
+                    ok[b] = s < jb.apix && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+                    if (ok[b]) {
+                        const unsigned char* base = jb.src + ((size_t)(2 * gy) * rowb + (size_t)(2 * gx) * (Cs * 2));
+                        qv[b][0] = __ldg(reinterpret_cast<const uint4*>(base));
+                        qv[b][1] = __ldg(reinterpret_cast<const uint4*>(base + Cs * 2));
+                        qv[b][2] = __ldg(reinterpret_cast<const uint4*>(base + rowb));
+                        qv[b][3] = __ldg(reinterpret_cast<const uint4*>(base + rowb + Cs * 2));
+                    }
+                    s += pstr; r += DR; c += DC;
+                    if (c >= p.pitch) { c -= p.pitch; r += 1; }
+                }
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    if (ss[b] >= jb.apix) continue;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok[b]) {
+                        float yv[8], t[8];
+                        act8<T, FACT>(qv[b][0], cf, yv);
+#pragma unroll
+                        for (int j = 1; j < 4; ++j) {
+                            act8<T, FACT>(qv[b][j], cf, t);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) yv[e] += t[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) yv[e] *= 0.25f;
+                        o = pack8<T>(yv);
+                    }
+                    *reinterpret_cast<uint4*>(dst + (size_t)ss[b] * 16) = o;
+                }
+            }
+        };
+        auto ensure_coefs = [&](int n, int& coef_n) {
+            if (n == coef_n) return;
+            stager_bar();   // every stager is done with the previous image's coefficients
+            const double plane = (double)Hs * Ws;
+            for (int c = ts_; c < p.ncoef; c += T5_STAGE_THREADS) {
+                float a, b;
+                if (MODE == T5_CAT2) {
+                    if (p.cf1) { a = __ldg(p.cf1 + (size_t)(n * p.ncoef + c) * 2); b = __ldg(p.cf1 + (size_t)(n * p.ncoef + c) * 2 + 1); }
+                    else gn_coef(p.st1, p.g1, p.b1, n, p.ncoef, p.groups1, c, plane, p.eps, a, b);
+                } else {
+                    if (p.cf0) { a = __ldg(p.cf0 + (size_t)(n * p.ncoef + c) * 2); b = __ldg(p.cf0 + (size_t)(n * p.ncoef + c) * 2 + 1); }
+                    else gn_coef(p.st0, p.g0, p.b0, n, p.ncoef, p.groups0, c, plane, p.eps, a, b);
+                }
+                if constexpr (FACT != ACT_EXACT) { a *= 0.5f; b *= 0.5f; }
+                coef[c] = make_float2(a, b);
+            }
+            coef_n = n;
+            stager_bar();
+        };
+
+        int coef_n = -1;
+        if constexpr (MODE == T5_POOL) {
+            int sa = 0; uint32_t pa = 0;
+            for (int j = 0; j < njobs; ++j) {
+                const Job jb = job_of(j);
+                ensure_coefs(jb.n, coef_n);
+                mbar_wait(A_EMPTY(sa), pa ^ 1u);
+                stage_pool(jb, sa);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA reads
+                mbar_arrive(A_FULL(sa));
+                if (++sa == p.na) { sa = 0; pa ^= 1u; }
+            }
+        } else {
+            // software pipeline over jobs.  With >= 3 ring stages the loads of job j+1 are issued before job j is transformed
+            // (they need the stage the MMAs of job j-2 have long released); with 2 stages they are issued right after job j is
+            // handed over (the stage of job j-1, still being read by its MMAs, frees up while job j is transformed).
+            const bool ahead = p.na >= 3;
+            int sa = 0, sl = 0; uint32_t pl = 0;   // sa: stage being transformed; (sl, pl): stage / phase the next loads go to
+            Job cur = job_of(0), nxt = cur;
+            auto prefetch = [&](const Job& jb) {
+                mbar_wait(A_EMPTY(sl), pl ^ 1u);
+                issue_loads(jb, sl);
+                if (++sl == p.na) { sl = 0; pl ^= 1u; }
+            };
+            prefetch(cur);
+            for (int j = 0; j < njobs; ++j) {
+                const bool more = j + 1 < njobs;
+                if (tid == 0) T5_TRACE(2, 4 * j);
+                if (more) nxt = job_of(j + 1);
+                if (more && ahead) {
+                    prefetch(nxt);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                if (tid == 0) T5_TRACE(2, 4 * j + 1);
+                ensure_coefs(cur.n, coef_n);
+                transform(cur, sa);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA reads
+                mbar_arrive(A_FULL(sa));
+                if (tid == 0) T5_TRACE(2, 4 * j + 2);
+                if (++sa == p.na) { sa = 0; }
+                if (more && !ahead) prefetch(nxt);
+                if (tid == 0) T5_TRACE(2, 4 * j + 3);
+                cur = nxt;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == T5_MMA_WARP) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(p.tmem_cols));
+    }
+}
+
+int t5_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+// Geometry / shared-memory plan.  Returns false when the configuration does not fit (caller falls back to mma.sync).
+bool t5_plan(T5Args& t, int mode) {
+    const int cin = t.cin, cout = t.cout;
+    if (cin < 16 || cin % 16 || cout < 32 || cout % 32) return false;
+    t.nb = cout <= 128 ? cout : 128;
+    if (cout % t.nb || (t.nb != 32 && t.nb != 64 && t.nb != 128 && t.nb != 96)) return false;
+    if (t.nb == 96) return false;   // keep N a power of two (TMEM stage arithmetic)
+    t.nnb = cout / t.nb;
+    const int csrc = mode == T5_CAT2 ? cout : cin;           // channels of one source tensor
+    t.kc = csrc >= 64 ? 64 : csrc;
+    if (t.kc != 16 && t.kc != 32 && t.kc != 64) return false;
+    if (csrc % t.kc || cin % t.kc) return false;
+    t.nchunk = cin / t.kc;
+    t.ncoef = csrc;
+    t.pitch = t.W + 2;
+    const long long stream_px = (long long)(t.H - 1) * t.pitch + t.W;
+    t.mtiles_img = (int)((stream_px + 127) / 128);
+    const int ksteps_total = 9 * (cin / 16);
+    // accumulators: double-buffered in TMEM unless K is so long that the epilogue is negligible and M reuse of the streamed
+    // weights matters more (wide variant)
+    t.ts = ksteps_total >= 576 ? 1 : 2;
+    int mt_max = 512 / (t.ts * t.nb);
+    for (;; ) {
+        if (mt_max < 1) return false;
+        const int bands = (t.mtiles_img + mt_max - 1) / mt_max;
+        t.mt = (t.mtiles_img + bands - 1) / bands;
+        t.bands_img = (t.mtiles_img + t.mt - 1) / t.mt;
+        const int apix = 128 * t.mt + 2 * t.pitch + 2;
+        const int nc8 = t.kc / 8;
+        const int want = nc8 >= 8 ? 1 : 8 / nc8;
+        int px = apix;
+        while (px % 8 != want) ++px;
+        t.plane_px = px;
+        t.a_stage_bytes = nc8 * px * 16;
+        t.b_stage_bytes = (t.kc / 16) * t.nb * 32;
+        const int fixed = t.ncoef * 8 + 4 * 32 * T5_SCR_PITCH + 8 * (4 * T5_MAX_RING + 4) + 16 + 1024;
+        // ring depths: at least 2 A chunks and 3 weight tiles, more while shared memory lasts
+        int budget = 227 * 1024 - fixed;
+        t.na = 2; t.nbs = 3;
+        if (t.na * t.a_stage_bytes + t.nbs * t.b_stage_bytes > budget) {
+            if (mt_max > 1) { mt_max /= 2; continue; }
+            return false;
+        }
+        budget -= t.na * t.a_stage_bytes + t.nbs * t.b_stage_bytes;
+        while (t.nbs < T5_MAX_RING && t.nbs < 6 && budget >= t.b_stage_bytes) { ++t.nbs; budget -= t.b_stage_bytes; }
+        if (t.nchunk > 2 && budget >= t.a_stage_bytes && t.na < T5_MAX_RING) { ++t.na; budget -= t.a_stage_bytes; }
+        break;
+    }
+    int cols = t.ts * t.mt * t.nb, pw = 32;
+    while (pw < cols) pw <<= 1;
+    if (pw > 512) return false;
+    t.tmem_cols = pw;
+    t.off_b = (t.na * t.a_stage_bytes + 127) / 128 * 128;
+    t.off_coef = t.off_b + t.nbs * t.b_stage_bytes;
+    t.off_scr = (t.off_coef + t.ncoef * 8 + 15) / 16 * 16;
+    t.off_bar = t.off_scr + 4 * 32 * T5_SCR_PITCH;
+    const long long items = (long long)t.N * t.bands_img * t.nnb;
+    if (items > 0x7fffffffLL) return false;
+    t.items = (int)items;
+    return true;
+}
+
+int t5_smem_bytes(const T5Args& t) { return t.off_bar + 8 * (4 * T5_MAX_RING + 4) + 16; }
+
+void t5_trace_dump(const T5Args& t, long long* dev, cudaStream_t st) {
+    cudaStreamSynchronize(st);
+    static long long h[4 * 512];
+    cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
+    const int items = (int)(((long long)t.items + 0) / (t.items < t5_sm_count() ? t.items : t5_sm_count()));
+    long long t0 = h[0];
+    for (int i = 0; i < 4 * 512; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+    fprintf(stderr, "[t5 trace] cin %d cout %d HxW %dx%d N %d: mt %d nb %d kc %d na %d nbs %d ts %d items %d (~%d per CTA)\n", t.cin, t.cout, t.H, t.W,
+            t.N, t.mt, t.nb, t.kc, t.na, t.nbs, t.ts, t.items, items);
+    for (int k = 0; k < items + 1 && k < 12; ++k)
+        fprintf(stderr, "  item %2d  mma: tmem_free %7lld a_full %7lld done_issue %7lld | epi: t_full %7lld done %7lld | stage: start %7lld loaded %7lld arrived %7lld next %7lld | tma: tap0 %7lld tap8 %7lld\n",
+                k, h[4 * k] - t0, h[4 * k + 1] - t0, h[4 * k + 2] - t0, h[512 + 2 * k] - t0, h[512 + 2 * k + 1] - t0, h[1024 + 4 * k] - t0,
+                h[1024 + 4 * k + 1] - t0, h[1024 + 4 * k + 2] - t0, h[1024 + 4 * k + 3] - t0, h[1536 + 2 * k] - t0, h[1536 + 2 * k + 1] - t0);
+}
+
+template <typename T, int MODE, int ACT>
+int launch_t5(const T5Args& t, cudaStream_t st) {
+    auto kern = conv3x3_t5_kernel<T, MODE, ACT>;
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("conv3x3 t5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 4; }
+        done = true;
+    }
+    const int sms = t5_sm_count();
+    const int grid = t.items < sms ? t.items : sms;
+    static long long* trace_buf = nullptr;
+    static const bool tracing = getenv("DG_T5_TRACE") != nullptr;
+    T5Args tt = t;
+    if (tracing) {
+        if (trace_buf == nullptr) cudaMalloc(&trace_buf, 4 * 512 * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 4 * 512 * sizeof(long long), st);
+        tt.trace = trace_buf;
+    }
+    cudaError_t le = launch_kernel(kern, dim3(grid), dim3(T5_THREADS), (size_t)t5_smem_bytes(t), st, tt);
+    if (le != cudaSuccess) { set_error("conv3x3 t5 launch: %s", cudaGetErrorString(le)); return 10; }
+    count_launch();
+    if (tracing) t5_trace_dump(tt, trace_buf, st);
+    return check_launch("conv3x3_t5");
+}
+
+template <typename T, int ACT>
+int dispatch_t5(const T5Args& t, int mode, cudaStream_t st) {
+    if (mode == T5_SAME) return launch_t5<T, T5_SAME, ACT>(t, st);
+    if (mode == T5_POOL) return launch_t5<T, T5_POOL, ACT>(t, st);
+    return launch_t5<T, T5_CAT2, ACT>(t, st);
+}
+}  // namespace
+
+// path bit 7 (128): do not use this kernel; bit 8 (256): the caller insists on it (tests) -- unsupported is then an error.
+int conv3x3_t5_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    const bool forced = (a.path & 256) != 0;
+    auto decline = [&](const char* why) {
+        if (forced) { set_error("conv3x3 t5: %s", why); return 3; }
+        return 0;
+    };
+    if (a.path & 128) return 0;
+    if (a.dtype != DG_F16 && a.dtype != DG_BF16) return decline("needs 16-bit storage");
+    if (a.weight_tc == nullptr || a.act_sum != nullptr) return decline("needs the tensor-core weight packing and no act_sum");
+    const dg_src& s0 = a.src[0];
+    T5Args t;
+    memset(&t, 0, sizeof(t));
+    int mode;
+    if (a.nsrc == 1 && (s0.xform == DG_X_SAME || s0.xform == DG_X_POOL2)) {
+        if (s0.stats == nullptr || !s0.silu || s0.scale != nullptr) return decline("source must be GroupNorm + SiLU");
+        mode = s0.xform == DG_X_SAME ? T5_SAME : T5_POOL;
+        t.cin = s0.channels;
+    } else if (a.nsrc == 2 && s0.xform == DG_X_SAME && a.src[1].xform == DG_X_SAME && s0.stats == nullptr && !s0.silu &&
+               s0.scale == nullptr) {
+        const dg_src& s1 = a.src[1];
+        if (s1.stats == nullptr || !s1.silu || s1.scale || s0.channels != a.cout || s1.channels != a.cout)
+            return decline("concat must be (identity up C, GroupNorm+SiLU skip C) -> C");
+        mode = T5_CAT2;
+        t.cin = 2 * a.cout;
+        t.src1 = s1.raw; t.st1 = s1.stats; t.g1 = s1.gamma; t.b1 = s1.beta; t.cf1 = s1.coef; t.groups1 = s1.groups;
+    } else {
+        return decline("source combination not covered");
+    }
+    if ((reinterpret_cast<uintptr_t>(s0.raw) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.weight_tc) |
+         reinterpret_cast<uintptr_t>(t.src1)) & 15)
+        return decline("pointers must be 16-byte aligned");
+    t.src0 = s0.raw; t.st0 = s0.stats; t.g0 = s0.gamma; t.b0 = s0.beta; t.cf0 = s0.coef; t.groups0 = s0.groups;
+    t.wgt = a.weight_tc;
+    t.out = a.out; t.out_stats = a.out_stats;
+    t.N = a.N; t.H = a.H; t.W = a.W; t.eps = a.eps;
+    t.cout = a.cout;
+    if (!t5_plan(t, mode)) return decline("shape does not fit the tcgen05 plan");
+    { const char* e = getenv("DG_T5_DBG"); t.dbg = e ? atoi(e) : 0; }
+    *handled = true;
+    const int flavour = (a.path >> 2) & 3;
+    if (a.dtype == DG_F16)
+        return flavour == 1 ? dispatch_t5<__half, ACT_EXACT>(t, mode, stream) : dispatch_t5<__half, ACT_TANH>(t, mode, stream);
+    return flavour == 1 ? dispatch_t5<__nv_bfloat16, ACT_EXACT>(t, mode, stream) : dispatch_t5<__nv_bfloat16, ACT_TANH>(t, mode, stream);
+}
+
+}  // namespace dg

@@ -6,8 +6,13 @@ Reference call sequence (optimized_train.py:197-236, fp32 branch :220-233):
 `model(inputs)` lands in `lightweight_forward_train` when autograd is recording; gradients of every parameter come back
 through `torch.autograd.Function.backward`, i.e. they land in `param.grad` the normal way (wandb.watch hooks keep working).
 `FusedAdamW` is a `torch.optim.Optimizer` with AdamW's constructor that keeps parameters, gradients and both moments in flat
-buffers and runs clip + update as two kernels (dg_adamw_step); with torch.distributed initialised it first all-reduces the
-flat gradient (one bucket).
+buffers and runs clip + update as two kernels (dg_adamw_step).
+
+Data parallel (one process per GPU): the ONE collective of a training step -- the mean all-reduce of the
+flat 486,409-float gradient -- is issued at the END OF BACKWARD (`_LightweightUNetFn.backward`), i.e. between `loss.backward()`
+and everything the reference does next (optimized_train.py:210-219 / :226-233): `scaler.unscale_` + its inf check,
+`clip_grad_norm_`, `optimizer.step()` all see the already-averaged gradient, every rank takes the same skip / clip decision,
+and no rank can miss the collective.  `module.ddp_sync = False` turns it off (gradient accumulation over micro-batches).
 """
 import ctypes as C
 
@@ -51,12 +56,30 @@ class _LightweightUNetFn(torch.autograd.Function):
                                       ctx.ws.numel(), bws.data_ptr(), bws.numel(), flat.data_ptr(),
                                       torch.cuda.current_stream().cuda_stream))
         ctx.ws = None
+        sync_gradients(flat, getattr(module, "ddp_sync", True))
         grads, off = [], 0
         for p in params:
             n = p.numel()
             grads.append(flat[off:off + n].view_as(p) if p.requires_grad else None)
             off += n
         return (None, None, *grads)
+
+
+def sync_gradients(flat, enabled=True, group=None):
+    """Mean all-reduce of the flat gradient over the data-parallel ranks (no-op without an initialised process group).
+    NCCL averages inside the collective; backends without AVG (gloo) sum and scale."""
+    import torch.distributed as dist
+    if not enabled or not (dist.is_available() and dist.is_initialized()):
+        return flat
+    world = dist.get_world_size(group)
+    if world <= 1:
+        return flat
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
+    return flat
 
 
 def lightweight_forward_train(module, x):
@@ -69,11 +92,18 @@ class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW (optimized_train.py:440-446) with flat storage and a fused clip + update (dg_adamw_step).
 
     max_grad_norm > 0 folds `torch.nn.utils.clip_grad_norm_(params, max_grad_norm)` (optimized_train.py:215,230) into the
-    step; leave it 0 if the caller clips itself.  All parameters must be fp32 on one CUDA device."""
+    step; leave it 0 if the caller clips itself.  All parameters must be fp32 on one CUDA device, in ONE param group.
+
+    Checkpoints: `state_dict()` / `load_state_dict()` use torch.optim.AdamW's own layout (per-parameter `step`, `exp_avg`,
+    `exp_avg_sq`), so the `optimizer_state_dict` entry the reference writes into every checkpoint (optimized_train.py:69)
+    round-trips with a plain AdamW in either direction.  The data-parallel gradient exchange is NOT here: it happens at the
+    end of backward (see the module docstring), before any clipping or inf check."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0):
         params = [p for p in params]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm))
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdamW keeps one flat buffer: pass a single param group (per-group hyper-parameters are not supported)")
         ps = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
         if not ps or any(not p.is_cuda or p.dtype != torch.float32 for p in ps):
             raise RuntimeError("FusedAdamW needs fp32 CUDA parameters")
@@ -86,6 +116,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self._scratch = torch.zeros(1, dtype=torch.float64, device=dev)
         self._step = 0
+        self._step_t = torch.tensor(0.0)      # shared by every parameter's state entry (AdamW keeps `step` as a CPU float tensor)
         off = 0
         with torch.no_grad():
             for p in ps:
@@ -95,12 +126,59 @@ class FusedAdamW(torch.optim.Optimizer):
                 off += k
         self._attach_grads()
 
+    def add_param_group(self, param_group):
+        if getattr(self, "param_groups", None):
+            raise ValueError("FusedAdamW supports a single param group")
+        super().add_param_group(param_group)
+
     def _attach_grads(self):
         off = 0
         for p in self._ps:
             k = p.numel()
             p.grad = self.flat_g[off:off + k].view_as(p)
             off += k
+
+    def _publish_state(self):
+        """Expose the flat moments through `self.state` in torch.optim.AdamW's layout (views, no copies)."""
+        off = 0
+        for p in self._ps:
+            k = p.numel()
+            self.state[p] = {"step": self._step_t, "exp_avg": self.exp_avg[off:off + k].view_as(p),
+                             "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p)}
+            off += k
+
+    def state_dict(self):
+        if self._step > 0:
+            self._publish_state()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)   # validates the groups / sizes and fills self.state with (copied) tensors
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdamW supports a single param group")
+        steps = set()
+        off = 0
+        with torch.no_grad():
+            for p in self._ps:
+                k = p.numel()
+                st = self.state.get(p)
+                if st:
+                    self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(float(st["step"])))
+                else:
+                    self.exp_avg[off:off + k].zero_()
+                    self.exp_avg_sq[off:off + k].zero_()
+                    steps.add(0)
+                off += k
+        if len(steps) != 1:
+            raise ValueError(f"FusedAdamW needs one common step count, checkpoint has {sorted(steps)}")
+        self._step = steps.pop()
+        self._step_t = torch.tensor(float(self._step))
+        if self._step > 0:
+            self._publish_state()
+        else:
+            self.state.clear()
 
     def zero_grad(self, set_to_none=True):
         # the reference calls zero_grad(set_to_none=True) (optimized_train.py:201); keep the flat aliasing instead
@@ -126,20 +204,16 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         self._gather()
         g = self.param_groups[0]
-        scale = 1.0
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)   # the one collective of data-parallel training
-            scale = 1.0 / dist.get_world_size()
         self._step += 1
+        self._step_t.fill_(float(self._step))
         _lib.check(_lib.load().dg_adamw_step(
             self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
             self.flat_p.numel(), self._scratch.data_ptr(), float(g["max_grad_norm"]), float(g["lr"]), float(g["betas"][0]),
-            float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self._step, scale,
+            float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self._step, 1.0,
             torch.cuda.current_stream().cuda_stream))
         _lib.bump_generation()   # parameters changed behind autograd's back: invalidate packed-weight caches
         return loss
 
     def grad_norm(self):
-        """Total L2 norm of the (scaled) gradient seen by the last step (the value clip_grad_norm_ returns)."""
+        """Total L2 norm of the gradient seen by the last step (the value clip_grad_norm_ returns)."""
         return float(self._scratch.sqrt().item())

@@ -354,40 +354,95 @@ def test_tc_standalone_convt_then_cat2(dtype, c, H, W):
         1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("dtype", TC_DTYPES)
-@pytest.mark.parametrize("mode,cin,cout,H,W", [("same", 64, 64, 16, 64), ("same", 64, 64, 8, 32), ("same", 64, 64, 12, 40),
-                                                 ("pool", 32, 64, 16, 32), ("pool", 32, 64, 6, 10), ("cat2", 64, 32, 16, 64),
-                                                 ("cat2", 64, 32, 10, 36)])
-def test_umma_matches_hmma_and_generic(dtype, mode, cin, cout, H, W):
-    """tcgen05/TMEM kernel (path 2 | 64) vs the mma.sync kernel (path 2) vs the generic kernel on identical inputs."""
-    rs = _rs(17)
-    N = 3
+def _deep_case(rs, dtype, mode, cin, cout, N, H, W, groups=8):
     w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * (1.0 / np.sqrt(9 * cin))).astype(np.float32))
     wp = ops.pack_conv3x3(w.cuda())
     wtc = ops.pack_conv3x3_tc(wp, dtype)
     if mode == "cat2":
         up = torch.from_numpy((rs.standard_normal((N, cout, H, W)) * 1.5).astype(np.float32))
         skip = torch.from_numpy((rs.standard_normal((N, cout, H, W)) * 2 + 0.3).astype(np.float32))
-        qu, _ = _nhwc(up, dtype)
+        qu, seen_u = _nhwc(up, dtype)
         qs, seen = _nhwc(skip, dtype)
         g, b = _gn_params(rs, cout)
-        srcs = [ops.make_src(qu, cout, silu=False), ops.make_src(qs, cout, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=8)]
+        srcs = [ops.make_src(qu, cout, silu=False), ops.make_src(qs, cout, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=groups)]
+        act = torch.cat((seen_u, tpo.gn_silu(seen, groups, g, b)), 1)
     else:
         f = 2 if mode == "pool" else 1
         raw = torch.from_numpy((rs.standard_normal((N, cin, f * H, f * W)) * 3 + 1).astype(np.float32))
         q, seen = _nhwc(raw, dtype)
         g, b = _gn_params(rs, cin)
         srcs = [ops.make_src(q, cin, xform=ops.DG_X_POOL2 if mode == "pool" else ops.DG_X_SAME, stats=_stats(seen),
-                             gamma=g.cuda(), beta=b.cuda(), groups=8)]
-    o_gen, s_gen = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=1)
-    o_um, s_um = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2 | 64, weight_tc=wtc)
-    o_hm, s_hm = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2, weight_tc=wtc)
+                             gamma=g.cuda(), beta=b.cuda(), groups=groups)]
+        act = tpo.gn_silu(seen, groups, g, b)
+        if mode == "pool":
+            act = F.avg_pool2d(act, 2, 2)
+    ref = F.conv2d(act, w, None, 1, 1)
+    return srcs, wp, wtc, ref
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("mode,cin,cout,H,W", [("same", 64, 64, 16, 64), ("same", 64, 64, 8, 32), ("same", 64, 64, 12, 40),
+                                                 ("pool", 32, 64, 16, 32), ("pool", 32, 64, 6, 10), ("cat2", 64, 32, 16, 64),
+                                                 ("cat2", 64, 32, 10, 36)])
+def test_umma_matches_hmma_and_generic(dtype, mode, cin, cout, H, W):
+    """round-1 tcgen05/TMEM kernel (path 2 | 64, with the round-2 kernel disabled by bit 7) vs the mma.sync kernel (path 2 | 128)
+    vs the generic kernel on identical inputs."""
+    srcs, wp, wtc, _ = _deep_case(_rs(17), dtype, mode, cin, cout, 3, H, W)
+    o_gen, s_gen = ops.conv3x3_fused(srcs, wp, cout, 3, H, W, dtype, path=1)
+    o_um, s_um = ops.conv3x3_fused(srcs, wp, cout, 3, H, W, dtype, path=2 | 64 | 128, weight_tc=wtc)
+    o_hm, s_hm = ops.conv3x3_fused(srcs, wp, cout, 3, H, W, dtype, path=2 | 128, weight_tc=wtc)
     torch.cuda.synchronize()
     _tc_check(o_um, s_um, o_gen, s_gen, dtype, f"umma {mode} {cin}->{cout}")
     _tc_check(o_hm, s_hm, o_gen, s_gen, dtype, f"hmma {mode} {cin}->{cout}")
     # both tensor paths round the same fp16 operands: they agree far tighter than either does with the fp32-staged generic path
     scale = max(1.0, float(o_gen.float().abs().max()))
     assert float((o_um.float() - o_hm.float()).abs().max()) <= (2e-3 if dtype == ops.DG_F16 else 1.6e-2) * scale
+
+
+# every deep layer of LightweightUNet(features_start=8) at its real 512^2 geometry plus ragged / tiny shapes, then the channel
+# sets of the wide variant (features_start=64: n-blocks, streamed K chunks, single-buffered accumulators)
+T5_CASES = [("pool", 16, 32, 128, 128), ("same", 32, 32, 128, 128), ("cat2", 64, 32, 128, 128),
+            ("pool", 32, 64, 64, 64), ("same", 64, 64, 64, 64), ("cat2", 128, 64, 64, 64),
+            ("pool", 64, 128, 32, 32), ("same", 128, 128, 32, 32),
+            ("same", 32, 32, 16, 16), ("same", 64, 64, 12, 40), ("pool", 32, 64, 6, 10), ("cat2", 64, 32, 10, 36),
+            ("same", 128, 128, 2, 2), ("pool", 64, 128, 1, 1), ("same", 64, 64, 48, 80),
+            ("same", 256, 256, 16, 16), ("pool", 128, 256, 16, 32), ("cat2", 512, 256, 16, 16), ("same", 512, 512, 8, 8),
+            ("pool", 512, 1024, 4, 4), ("same", 1024, 1024, 4, 8), ("cat2", 1024, 512, 8, 8)]
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("mode,cin,cout,H,W", T5_CASES)
+def test_t5_warp_specialised_tcgen05_conv(dtype, mode, cin, cout, H, W):
+    """Round-2 tcgen05 kernel (path 2 | 256 = insist on it) vs the oracle's decomposition and vs the generic CUDA-core kernel."""
+    N = 3 if H * W <= 4096 else 2
+    srcs, wp, wtc, ref = _deep_case(_rs(18), dtype, mode, cin, cout, N, H, W)
+    o_t5, s_t5 = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=2 | 256, weight_tc=wtc)
+    torch.cuda.synchronize()
+    got = o_t5.float().cpu().permute(0, 3, 1, 2)
+    scale = max(1.0, float(ref.abs().max()))
+    err = float((got - ref).abs().max())
+    assert err <= (6e-3 if dtype == ops.DG_F16 else 4e-2) * scale, f"t5 {mode} {cin}->{cout} vs oracle: {err:.3e} (scale {scale:.2f})"
+    # the epilogue's statistics are those of the STORED values
+    want = torch.stack((got.double().sum(dim=(2, 3)), (got.double() ** 2).sum(dim=(2, 3))), dim=2)
+    serr = float((s_t5.cpu() - want).abs().max() / max(1.0, float(want.abs().max())))
+    assert serr <= 2e-5, f"t5 {mode} {cin}->{cout}: stats rel err {serr:.3e}"
+    if cin * cout <= 128 * 128:
+        o_gen, s_gen = ops.conv3x3_fused(srcs, wp, cout, N, H, W, dtype, path=1)
+        torch.cuda.synchronize()
+        _tc_check(o_t5, s_t5, o_gen, s_gen, dtype, f"t5 {mode} {cin}->{cout}")
+
+
+def test_t5_is_the_default_for_deep_layers_and_can_be_disabled():
+    srcs, wp, wtc, _ = _deep_case(_rs(19), ops.DG_F16, "same", 64, 64, 2, 16, 32)
+    o_def, _ = ops.conv3x3_fused(srcs, wp, 64, 2, 16, 32, ops.DG_F16, weight_tc=wtc)
+    o_t5, _ = ops.conv3x3_fused(srcs, wp, 64, 2, 16, 32, ops.DG_F16, path=2 | 256, weight_tc=wtc)
+    o_hm, _ = ops.conv3x3_fused(srcs, wp, 64, 2, 16, 32, ops.DG_F16, path=2 | 128, weight_tc=wtc)
+    torch.cuda.synchronize()
+    assert torch.equal(o_def, o_t5)
+    assert float((o_t5.float() - o_hm.float()).abs().max()) <= 2e-3 * max(1.0, float(o_hm.float().abs().max()))
+    src8 = _deep_case(_rs(19), ops.DG_F16, "same", 8, 8, 2, 16, 32)
+    with pytest.raises(RuntimeError, match="t5"):
+        ops.conv3x3_fused(src8[0], src8[1], 8, 2, 16, 32, ops.DG_F16, path=2 | 256, weight_tc=src8[2])
 
 
 def test_tc_path_refuses_unsupported():

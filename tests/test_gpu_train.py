@@ -184,3 +184,86 @@ def test_backward_properties_at_full_resolution(best_sd, storage):
     for k in g1:
         mean = sum(p[k] for p in per) / 4.0
         assert float((g1[k] - mean).norm()) <= 2e-5 * float(g1[k].norm()) + 5e-7 * total1, f"additivity {k}"
+
+
+def _reference_cuda_branch_step(net, opt, scaler, x, t):
+    """optimized_train.py:201-219 verbatim (the branch the reference takes on every CUDA device)."""
+    crit = torch.nn.L1Loss()
+    opt.zero_grad(set_to_none=True)                       # :201
+    with torch.amp.autocast("cuda"):                      # :205
+        outputs = net(x)                                  # :206
+        loss = crit(outputs, t)                           # :207
+    scaler.scale(loss).backward()                         # :210
+    scaler.unscale_(opt)                                  # :214
+    total = torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)   # :215
+    scaler.step(opt)                                      # :218
+    scaler.update()                                       # :219
+    return float(loss.detach()), float(total)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_reference_amp_gradscaler_branch_verbatim(best_sd, golden, fused):
+    """The reference's CUDA branch -- autocast + GradScaler.scale/unscale_/step/update + clip_grad_norm_ -- runs unchanged on the
+    drop-in module, with torch.optim.AdamW and with FusedAdamW, and lands on the reference's own fp32 step (the module keeps
+    its own precision under autocast; the loss scale cancels exactly because it is a power of two)."""
+    from image_enhancement_deglaring_b200.train import FusedAdamW
+    g = golden("lw_train.npz")
+    net = _net(best_sd, path=1)
+    if fused:
+        opt = FusedAdamW(net.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    else:
+        opt = torch.optim.AdamW(net.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    scaler = torch.amp.GradScaler("cuda")
+    x, t = _rand((2, 1, 64, 64), 0).cuda(), _rand((2, 1, 64, 64), 1).cuda()
+    loss, total = _reference_cuda_branch_step(net, opt, scaler, x, t)
+    assert abs(loss - float(g["loss"])) <= 1e-5
+    assert abs(total - float(g["total_norm"])) <= 1e-3
+    loose = n = 0
+    for k, p in net.named_parameters():
+        err = np.abs(p.detach().cpu().numpy() - g["new/" + k])
+        assert err.max() <= 2 * TRAIN_LR, k
+        loose += int((err > 2e-5).sum())
+        n += err.size
+    assert loose <= 1e-4 * n, (loose, n)
+
+
+def test_fused_adamw_checkpoint_roundtrip_with_torch_adamw(best_sd):
+    """optimized_train.py:63-73 saves optimizer.state_dict() in every checkpoint: FusedAdamW's is in torch.optim.AdamW's layout,
+    loads into a plain AdamW (and back), and the step after the reload is the step an uninterrupted run would have taken."""
+    from image_enhancement_deglaring_b200.train import FusedAdamW
+    x, t = _rand((2, 1, 64, 64), 0).cuda(), _rand((2, 1, 64, 64), 1).cuda()
+    crit = torch.nn.L1Loss()
+
+    def step(net, opt):
+        opt.zero_grad(set_to_none=True)
+        crit(net(x), t).backward()
+        opt.step()
+
+    a = _net(best_sd, path=1)
+    oa = FusedAdamW(a.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    for _ in range(2):
+        step(a, oa)
+    ck = {"model_state_dict": {k: v.detach().clone() for k, v in a.state_dict().items()}, "optimizer_state_dict": oa.state_dict()}
+    st = ck["optimizer_state_dict"]["state"]
+    assert len(st) == 64 and all(set(v) == {"step", "exp_avg", "exp_avg_sq"} and float(v["step"]) == 2.0 for v in st.values())
+    step(a, oa)                                             # the uninterrupted third step
+    # resume into torch.optim.AdamW ...
+    b = _net(ck["model_state_dict"], path=1)
+    ob = torch.optim.AdamW(b.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    ob.load_state_dict(ck["optimizer_state_dict"])
+    step(b, ob)
+    # ... and into a fresh FusedAdamW (from its own checkpoint and from the plain AdamW's)
+    c = _net(ck["model_state_dict"], path=1)
+    oc = FusedAdamW(c.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    oc.load_state_dict(ck["optimizer_state_dict"])
+    step(c, oc)
+    d = _net({k: v.detach().clone() for k, v in b.state_dict().items()}, path=1)
+    od = FusedAdamW(d.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    od.load_state_dict(ob.state_dict())
+    assert od._step == 3
+    for (k, pa), pb, pc in zip(a.named_parameters(), b.parameters(), c.parameters()):
+        assert float((pa - pb).abs().max()) <= 2e-6, k
+        assert float((pa - pc).abs().max()) <= 2e-6, k
+    with pytest.raises(ValueError, match="single param group"):
+        ps = list(_net(best_sd, path=1).parameters())
+        FusedAdamW([{"params": ps[:10]}, {"params": ps[10:], "lr": 1e-4}])
