@@ -103,6 +103,13 @@ static int make_plan(const dg_lw_params* p, int N, int H, int W, LwPlan* pl) {
     return 0;
 }
 
+// Decoder levels whose ConvTranspose output is materialised by a stand-alone tensor-core GEMM (16-bit tiers) and read by the
+// consuming conv as an identity source: every level with C_up >= 32 -- upconv4 / upconv3 of the shipped model, ALL levels of the
+// wide variant (features_start = 64) -- plus upconv2 with path bit 5.  The concat itself is never stored.
+static inline bool lw_up_materialised(const dg_lw_params* p, const LwPlan& pl, int u) {
+    return pl.f[3 - u] >= 32 || (u == 2 && (p->path & 32));
+}
+
 // n0: first image of the sub-batch the descriptor is for (every per-image tensor is contiguous over the batch)
 static dg_src gn_src(const dg_lw_params* p, const LwPlan& pl, char* ws, int conv_idx, int xform, int n0 = 0) {
     dg_src s;
@@ -171,7 +178,7 @@ static int lw_forward_range(const dg_lw_params* p, const LwPlan& pl, char* ws, c
             a.nsrc = 2;
             // deep levels (upconv4, upconv3; upconv2 with path bit 5): run the transposed conv as its own tensor-core GEMM and
             // feed its output as an identity source -- see convt_tc.cu for why this beats fusing there
-            const bool unfuse = p->dtype != DG_F32 && (p->path & 3) != 1 && (u < 2 || (u == 2 && (p->path & 32)));
+            const bool unfuse = p->dtype != DG_F32 && (p->path & 3) != 1 && lw_up_materialised(p, pl, u);
             if (unfuse) {
                 bool handled = false;
                 void* up = ws + pl.up_off[u] + (size_t)n0 * a.H * a.W * pl.f[lvl] * esz;
@@ -483,7 +490,7 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
             if (a.nsrc == 2) {
                 const int lvl = block_level(b), u = b - 5;
                 void* up = fw + pl.up_off[u] + (size_t)n0 * Hi * Wi * pl.f[lvl] * esz;
-                const bool have_up = (u < 2 || (u == 2 && (p->path & 32)));
+                const bool have_up = lw_up_materialised(p, pl, u);
                 if (!have_up) {
                     rc = convt_tc_launch(a.src[0], p->dtype, N, Hi, Wi, up, 1e-5f, p->path, st, &ok);
                     if (rc) return rc;

@@ -171,6 +171,14 @@ int convt_tc_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, 
                     bool* handled) {
     *handled = false;
     if (dtype != DG_F16 && dtype != DG_BF16) return 0;
+    // Channel sets the mma.sync kernel below does not cover (the wide variant's 1024 -> 512 ... 128 -> 64) go to the tcgen05 kernel;
+    // on the shipped model's upconv4 / upconv3 the mma.sync kernel measured faster (0.043 / 0.055 vs 0.059 / 0.067 ms at batch 64).
+    const bool hmma_covers = (s.channels == 128 && s.ct_cout == 64) || (s.channels == 64 && s.ct_cout == 32) ||
+                             (s.channels == 32 && s.ct_cout == 16) || (s.channels == 16 && s.ct_cout == 8);
+    if (!hmma_covers || (path & 256)) {
+        int rc = convt_t5_launch(s, dtype, N, H, W, out, eps, path, st, handled);
+        if (rc || *handled) return rc;
+    }
     if (s.xform != DG_X_CONVT2 || s.ct_w_tc == nullptr || s.ct_b == nullptr || s.stats == nullptr || !s.silu || s.scale) return 0;
     if ((H | W) & 1) return 0;
     if ((reinterpret_cast<uintptr_t>(s.raw) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(s.ct_w_tc)) & 15) return 0;

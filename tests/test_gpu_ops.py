@@ -432,6 +432,34 @@ def test_t5_warp_specialised_tcgen05_conv(dtype, mode, cin, cout, H, W):
         _tc_check(o_t5, s_t5, o_gen, s_gen, dtype, f"t5 {mode} {cin}->{cout}")
 
 
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("c,H,W", [(64, 16, 32), (32, 16, 32), (64, 2, 2), (32, 6, 10), (128, 32, 32), (256, 16, 16), (512, 8, 8),
+                                     (64, 128, 128)])
+def test_t5_convtranspose(dtype, c, H, W):
+    """ConvTranspose2d(2c -> c, k=2, s=2) + bias of the activated low-resolution tensor on the tcgen05 kernel (1-tap GEMM, N = 4c):
+    upconv4 / upconv3 of the shipped model and every up-convolution of the wide variant."""
+    rs = _rs(21)
+    N = 2
+    low = torch.from_numpy((rs.standard_normal((N, 2 * c, H // 2, W // 2)) * 2).astype(np.float32))
+    ql, seen_l = _nhwc(low, dtype)
+    g1, b1 = _gn_params(rs, 2 * c)
+    ctw = torch.from_numpy((rs.standard_normal((2 * c, c, 2, 2)) * (1.0 / np.sqrt(2 * c))).astype(np.float32))
+    ctb = torch.from_numpy((rs.standard_normal(c) * 0.2).astype(np.float32))
+    ctp = ops.pack_convt2x2(ctw.cuda())
+    s0 = ops.make_src(ql, 2 * c, xform=ops.DG_X_CONVT2, stats=_stats(seen_l), gamma=g1.cuda(), beta=b1.cuda(),
+                      groups=8, ct_w=ctp, ct_b=ctb.cuda(), ct_cout=c, ct_w_tc=ops.pack_convt2x2_tc(ctp, dtype))
+    up = ops.convt2x2_fused(s0, N, H, W, dtype, path=256)   # bit 8: insist on the tcgen05 kernel
+    torch.cuda.synchronize()
+    up_ref = F.conv_transpose2d(tpo.gn_silu(seen_l, 8, g1, b1), ctw, ctb, stride=2)
+    tol = (6e-3 if dtype == ops.DG_F16 else 4e-2) * max(1.0, float(up_ref.abs().max()))
+    err = float((up.float().cpu().permute(0, 3, 1, 2) - up_ref).abs().max())
+    assert err <= tol, f"convT {2 * c}->{c}: {err:.3e}"
+    if c <= 64:   # the mma.sync kernel (path bit 7) must agree
+        up_h = ops.convt2x2_fused(s0, N, H, W, dtype, path=128)
+        torch.cuda.synchronize()
+        assert float((up.float() - up_h.float()).abs().max()) <= 0.5 * tol
+
+
 def test_t5_is_the_default_for_deep_layers_and_can_be_disabled():
     srcs, wp, wtc, _ = _deep_case(_rs(19), ops.DG_F16, "same", 64, 64, 2, 16, 32)
     o_def, _ = ops.conv3x3_fused(srcs, wp, 64, 2, 16, 32, ops.DG_F16, weight_tc=wtc)
