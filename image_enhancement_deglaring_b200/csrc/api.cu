@@ -674,6 +674,9 @@ int dg_conv3x3_fused(const dg_conv3x3_args* a, dg_stream_t stream) {
         rc = conv3x3_umma_launch(*a, st, &handled);   // round-1 tcgen05 kernel (opt-in, path bit 6)
         if (rc) return rc;
         if (handled) return 0;
+        rc = conv3x3_ring_launch(*a, st, &handled);   // persistent TMA-fed kernel for the 8 -> 8 full-resolution layers
+        if (rc) return rc;
+        if (handled) return 0;
         rc = conv3x3_tc_launch(*a, st, &handled);
         if (rc) return rc;
         if (handled) return 0;

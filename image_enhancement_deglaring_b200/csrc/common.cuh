@@ -185,6 +185,7 @@ int conv3x3_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handl
 int conv_first_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int conv3x3_umma_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int conv3x3_t5_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
+int conv3x3_ring_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int convt_t5_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, float eps, int path, cudaStream_t st, bool* handled);
 int head_launch(const dg_head_args& a, cudaStream_t stream);
 int convt_tc_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, float eps, int path, cudaStream_t st,

@@ -335,9 +335,11 @@ __global__ void __launch_bounds__(T5_THREADS, 1) conv3x3_t5_kernel(const __grid_
         const int wq = warp & 3;   // TMEM lane quarter this warp may access
         unsigned char* scr = smem + p.off_scr + (warp - T5_EPI_WARP0) * (32 * T5_SCR_PITCH);
         const int half = lane >> 4, pr = lane & 15;
-        float s1[4][2], s2[4][2];
+        // fp32 partial sums cover 16 pixels of ONE M-tile (fixed order); everything above that is accumulated in double, so the
+        // statistics -- and with them the network output -- do not depend on how work items are spread over CTAs / batch sizes
+        double s1[4][2], s2[4][2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) s1[c][0] = s1[c][1] = s2[c][0] = s2[c][1] = 0.f;
+        for (int c = 0; c < 4; ++c) s1[c][0] = s1[c][1] = s2[c][0] = s2[c][1] = 0.0;
         int stats_n = -1, stats_nbk = 0;
         const int ncc = p.nb >> 5;
         auto flush = [&]() {
@@ -347,16 +349,16 @@ __global__ void __launch_bounds__(T5_THREADS, 1) conv3x3_t5_kernel(const __grid_
                 if (c < ncc) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const float a = s1[c][e] + __shfl_xor_sync(0xffffffffu, s1[c][e], 16);
-                        const float b = s2[c][e] + __shfl_xor_sync(0xffffffffu, s2[c][e], 16);
+                        const double a = s1[c][e] + __shfl_xor_sync(0xffffffffu, s1[c][e], 16);
+                        const double b = s2[c][e] + __shfl_xor_sync(0xffffffffu, s2[c][e], 16);
                         if (half == 0) {
                             double* d = p.out_stats + ((size_t)stats_n * p.cout + stats_nbk * p.nb + c * 32 + 2 * pr + e) * 2;
-                            atomicAdd(d, (double)a);
-                            atomicAdd(d + 1, (double)b);
+                            atomicAdd(d, a);
+                            atomicAdd(d + 1, b);
                         }
                     }
                 }
-                s1[c][0] = s1[c][1] = s2[c][0] = s2[c][1] = 0.f;
+                s1[c][0] = s1[c][1] = s2[c][0] = s2[c][1] = 0.0;
             }
         };
         int k = 0;
@@ -435,8 +437,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1) conv3x3_t5_kernel(const __grid_
                             a0 += v.x; q0 = fmaf(v.x, v.x, q0);
                             a1 += v.y; q1 = fmaf(v.y, v.y, q1);
                         }
-                        s1[c][0] += a0; s2[c][0] += q0;
-                        s1[c][1] += a1; s2[c][1] += q1;
+                        s1[c][0] += (double)a0; s2[c][0] += (double)q0;
+                        s1[c][1] += (double)a1; s2[c][1] += (double)q1;
                     }
                 }
             }

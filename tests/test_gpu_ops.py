@@ -473,6 +473,33 @@ def test_t5_is_the_default_for_deep_layers_and_can_be_disabled():
         ops.conv3x3_fused(src8[0], src8[1], 8, 2, 16, 32, ops.DG_F16, path=2 | 256, weight_tc=src8[2])
 
 
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("N,H,W", [(2, 64, 128), (3, 48, 80), (1, 16, 64), (2, 16, 16), (5, 128, 192), (1, 512, 512)])
+def test_ring_tma_kernel_matches_per_tile_kernel(dtype, N, H, W):
+    """Persistent TMA-fed 8 -> 8 kernel (default) vs the per-tile mma.sync kernel (path bit 9) vs the oracle: same fp16 operands,
+    same fp32 accumulation order inside an MMA -> they agree to a rounding of the stored value."""
+    rs = _rs(23)
+    raw = torch.from_numpy((rs.standard_normal((N, 8, H, W)) * 3 + 1).astype(np.float32))
+    q, seen = _nhwc(raw, dtype)
+    g, b = _gn_params(rs, 8)
+    w = torch.from_numpy((rs.standard_normal((8, 8, 3, 3)) * (1.0 / np.sqrt(72))).astype(np.float32))
+    wp = ops.pack_conv3x3(w.cuda())
+    wtc = ops.pack_conv3x3_tc(wp, dtype)
+    src = ops.make_src(q, 8, stats=_stats(seen), gamma=g.cuda(), beta=b.cuda(), groups=8)
+    o_ring, s_ring = ops.conv3x3_fused([src], wp, 8, N, H, W, dtype, path=2, weight_tc=wtc)
+    o_tile, s_tile = ops.conv3x3_fused([src], wp, 8, N, H, W, dtype, path=2 | 512, weight_tc=wtc)
+    torch.cuda.synchronize()
+    scale = max(1.0, float(o_tile.float().abs().max()))
+    assert float((o_ring.float() - o_tile.float()).abs().max()) <= (1e-3 if dtype == ops.DG_F16 else 8e-3) * scale
+    assert float((s_ring - s_tile).abs().max() / max(1.0, float(s_tile.abs().max()))) <= 1e-5
+    ref = F.conv2d(tpo.gn_silu(seen, 8, g, b), w, None, 1, 1)
+    err = float((o_ring.float().cpu().permute(0, 3, 1, 2) - ref).abs().max())
+    assert err <= (6e-3 if dtype == ops.DG_F16 else 4e-2) * max(1.0, float(ref.abs().max())), f"ring vs oracle {err:.3e}"
+    got = o_ring.float().cpu().permute(0, 3, 1, 2).double()
+    want = torch.stack((got.sum(dim=(2, 3)), (got ** 2).sum(dim=(2, 3))), dim=2)
+    assert float((s_ring.cpu() - want).abs().max() / max(1.0, float(want.abs().max()))) <= 6e-4
+
+
 def test_tc_path_refuses_unsupported():
     w = torch.zeros(3, 3, 24, 24, device="cuda")
     raw = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.float16)
