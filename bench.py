@@ -10,11 +10,12 @@ A step = one forward pass of the 486,409-parameter best_model UNet over one batc
 collective (weak scaling).  `value` is device-resident throughput (CUDA events, max over ranks);
 `e2e` goes through the ORT-shaped `InferenceSession.run_pinned` -> `dg_lw_infer_host` C-ABI call with
 pinned HOST buffers, H2D + D2H inside the timed region (`e2e_u8`: the uint8-in / uint8-out twin).  `train_step` is one
-BASELINE.json configs[3] training step (batch 32 per GPU) in the same storage tier.  `roofline` is for the dominant kernel,
+BASELINE.json configs[3] training step (batch 32 per GPU) in the same storage tier; `latency_n1` is configs[0] (fp32, batch 1) and
+`wide` configs[4] (features_start=64 on the tcgen05 kernel), both rank 0 only.  `roofline` is for the dominant kernel,
 timed live with CUDA events by `dg_lw_profile` (whole batch on one stream; the timed steps themselves run the batch as two
-concurrent halves).  `cpu_baseline` / `--impl reference` time the CPU
-oracle port of the reference's PyTorch-CPU path (oracle/torch_unet.py -- the reference itself cannot
-travel to the GPU box) on all host cores.
+concurrent halves).  `cpu_baseline` / `--impl reference` time the reference's
+PyTorch-CPU path on all host cores: the unmodified reference module when oracle/_ref exists (oracle/build_ref.py puts it there in
+the build container; it travels to the GPU box with the snapshot), else the pinned oracle port oracle/torch_unet.py.
 """
 import argparse
 import ctypes as C
@@ -52,6 +53,18 @@ def algorithmic_bytes_per_image(H, W, fs=8, esize=2):
         out.append(2 * px[l] * f[l] * esize)                                        # dec.3
     out.append(px[0] * f[0] * esize + px[0] * 4)                                    # head
     return out
+
+
+def training_algorithmic_bytes_per_image(H, W, fs=8, esize=2):
+    """Minimal-traffic model of one training step: the forward bytes, plus in backward, for every raw conv
+    output X (18 tensors, E elements each): X re-read twice (by its own GroupNorm/SiLU backward and as the recomputed input of
+    its consumer's weight gradient), its gradient written once and read twice (data- and weight-gradient of the producing conv),
+    all in the 16-bit storage type -> 5 * esize bytes per element; plus target and output (fp32) read once by the loss."""
+    fwd = sum(algorithmic_bytes_per_image(H, W, fs, esize))
+    f = [fs << i for i in range(5)]
+    px = [(H >> i) * (W >> i) for i in range(5)]
+    elems = 2 * sum(px[l] * f[l] for l in range(5)) + 2 * sum(px[l] * f[l] for l in range(4))   # enc + bottleneck, dec
+    return fwd + 5 * esize * elems + 2 * px[0] * 4
 
 
 class ClockSampler:
@@ -106,26 +119,56 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(batch, reps, H, W):
-    """Oracle port of the reference's PyTorch-CPU path on all host cores; returns (images/s, cores)."""
+ORT_NOTE = "onnxruntime unavailable \u2014 not installed, no network"
+
+
+def onnxruntime_status():
+    """BASELINE.md asks for the reference's ONNX-Runtime-CPU path beside the PyTorch-CPU one; say so when it cannot be timed."""
+    try:
+        import onnxruntime  # noqa: F401
+        return "onnxruntime importable but the reference's best_model.onnx does not travel to the GPU box: not timed"
+    except Exception:
+        return ORT_NOTE
+
+
+def cpu_forward_fn():
+    """The reference's PyTorch-CPU forward: the UNMODIFIED reference module from oracle/_ref (placed there by oracle/build_ref.py
+    in the build container; kind "reference") when present, else the pinned oracle port (kind "port")."""
     import torch
+    sd = torch.load(os.path.join(ROOT, "weights", "best_model.pth"))
+    try:
+        from oracle import build_ref
+        mod = build_ref.load("model")
+    except Exception:
+        mod = None
+    if mod is not None:
+        net = mod.LightweightUNet()
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        return (lambda x: net(x)), "reference"
     from oracle import torch_unet as tpo
+    return (lambda x: tpo.lightweight_forward(x, sd)), "port"
+
+
+def cpu_reference_rate(batch, reps, H, W):
+    """The reference's PyTorch-CPU path on all host cores; returns (images/s, cores, times, kind)."""
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = torch.load(os.path.join(ROOT, "weights", "best_model.pth"))
+    fwd, kind = cpu_forward_fn()
     x = torch.rand(batch, 1, H, W, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
-        tpo.lightweight_forward(x[:1], sd)
+        fwd(x[:1])
         times = []
         t_all = time.perf_counter()
         # bounded sample: at least `reps` forwards and ~10 s of CPU work, at most 30 s
         while len(times) < reps or (time.perf_counter() - t_all < 10.0 and time.perf_counter() - t_all < 30.0):
             t = time.perf_counter()
-            tpo.lightweight_forward(x, sd)
+            fwd(x)
             times.append(time.perf_counter() - t)
             if time.perf_counter() - t_all > 30.0:
                 break
-    return batch / statistics.median(times), cores, times
+    return batch / statistics.median(times), cores, times, kind
 
 
 def run_reference(args, rank, world):
@@ -134,27 +177,30 @@ def run_reference(args, rank, world):
     batch = args.ref_batch
     t0 = time.perf_counter()
     import torch
-    from oracle import torch_unet as tpo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = torch.load(os.path.join(ROOT, "weights", "best_model.pth"))
+    fwd, kind = cpu_forward_fn()
     x = torch.rand(batch, 1, args.hw, args.hw, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
         for _ in range(args.warmup):
-            tpo.lightweight_forward(x, sd)
+            fwd(x)
         t = time.perf_counter()
         for _ in range(args.steps):
-            tpo.lightweight_forward(x, sd)
+            fwd(x)
         dt = time.perf_counter() - t
     rate = batch * args.steps / dt
-    sample = f"{args.steps} steps x {batch} images of 1x{args.hw}x{args.hw}, fp32, torch CPU {cores} threads"
+    sample = (f"{args.steps} steps x {batch} images of 1x{args.hw}x{args.hw}, fp32, torch CPU {cores} threads; a bounded sample of the "
+              f"configs[1] workload (the GPU arm runs batch {args.batch} x 1x{args.hw}x{args.hw} in 16-bit storage: per-image CPU cost is flat in "
+              "the batch size, measured 8 vs 1)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": f"best_model.pth LightweightUNet inference, bounded sample of batch {batch} x 1x{args.hw}x{args.hw} "
-                               "(configs[1] shape), reference PyTorch-CPU path via oracle port", "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                               "(configs[1] shape), reference PyTorch-CPU path ("
+                               + ("the unmodified reference module, oracle/_ref" if kind == "reference" else "pinned oracle port") + ")",
+                   "batch": batch, "l2": "n/a (CPU)", "onnxruntime_cpu": onnxruntime_status()},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }))
@@ -173,6 +219,7 @@ def main():
     ap.add_argument("--path", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[3] training-step measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[0] latency and configs[4] wide-variant side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -311,11 +358,88 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1) / tsteps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tbytes = training_algorithmic_bytes_per_image(H, W, 8, 4 if args.storage == "fp32" else 2) * tb
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                tpk = float(json.load(f).get("hbm_gbs", 6650.0))
+        except (OSError, ValueError):
+            tpk = 6650.0
         train_step = {"value": world * tb / (float(t.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t.item()), "batch_per_gpu": tb,
+                      "roofline": {"bound": "hbm", "scope": "whole step (per GPU)", "algorithmic_bytes_per_step": tbytes,
+                                   "achieved": tbytes / (float(t.item()) * 1e-3) / 1e9, "peak": tpk, "unit": "GB/s",
+                                   "frac": tbytes / (float(t.item()) * 1e-3) / 1e9 / tpk},
                       "steps": tsteps, "loss": float(tloss.detach()),
                       "what": "forward + L1 + backward + clip_grad_norm 1.0 + AdamW (FusedAdamW), tensor-core forward / dgrad / wgrad "
                               "for 16-bit storage, CUDA events, max over ranks"}
         del tnet, opt, tx, tt
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[0]: fp32, batch 1, 1x512x512 -- latency of one image through the module (device-resident input,
+    # CUDA events) and through the ORT-shaped session call (host buffers); the CPU batch-1 number is cpu_baseline.batch1_ms
+    latency_n1 = None
+    if rank == 0 and not args.no_extras:
+        latency_n1 = {}
+        x1 = torch.rand(1, 1, H, W, generator=torch.Generator().manual_seed(7)).to(dev)
+        for storage in ("fp32", args.storage):
+            n1 = dg.LightweightUNet(storage=storage, path=args.path)
+            n1.load_state_dict(sd, strict=True)
+            n1 = n1.to(dev).eval()
+            with torch.no_grad():
+                for _ in range(5):
+                    n1(x1)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                torch.cuda.synchronize()
+                ev[0].record()
+                for _ in range(50):
+                    n1(x1)
+                ev[1].record()
+                torch.cuda.synchronize()
+            s1 = InferenceSession(n1, chunk=1)
+            xh = x1.cpu().numpy()
+            for _ in range(3):
+                s1.run(["output"], {"input": xh})
+            tl = time.perf_counter()
+            for _ in range(20):
+                s1.run(["output"], {"input": xh})
+            latency_n1[storage] = {"device_ms": ev[0].elapsed_time(ev[1]) / 50, "session_run_ms": (time.perf_counter() - tl) / 20 * 1e3}
+            del n1, s1
+        latency_n1["what"] = ("one 1x1x512x512 image: device_ms = module forward with the input resident in HBM (CUDA events, mean of 50); "
+                              "session_run_ms = InferenceSession.run from a pageable numpy array and back (api/app.py:171 call shape)")
+
+    # ---- BASELINE.json configs[4]: the wide variant LightweightUNet(features_start=64), 31.0 M parameters, 384.7 GFLOP per
+    # 512x512 image: every conv with C_out >= 32 and every ConvTranspose on the tcgen05 kernel (conv3x3_t5.cu)
+    wide = None
+    if rank == 0 and not args.no_extras:
+        torch.manual_seed(42)
+        wb = 4
+        wnet = dg.LightweightUNet(features_start=64, storage=args.storage, path=args.path).to(dev).eval()
+        wx = torch.rand(wb, 1, H, W, generator=torch.Generator().manual_seed(3)).to(dev)
+        with torch.no_grad():
+            for _ in range(3):
+                wnet(wx)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(5):
+                wnet(wx)
+            ev[1].record()
+            torch.cuda.synchronize()
+        wms = ev[0].elapsed_time(ev[1]) / 5
+        flop = 384.7e9 * (H * W) / (512 * 512)
+        peaks_w = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks_w = json.load(f)
+        except OSError:
+            pass
+        tpeak = float(peaks_w.get("bf16_tflops_sustained", 1400.0))
+        wide = {"model": "LightweightUNet(features_start=64)", "params": dg.count_parameters(wnet), "batch": wb, "ms_per_step": wms,
+                "value": wb / (wms * 1e-3), "unit": UNIT, "tflops": flop * wb / (wms * 1e-3) / 1e12,
+                "roofline": {"bound": "tensor", "achieved": flop * wb / (wms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                             "frac": flop * wb / (wms * 1e-3) / 1e12 / tpeak,
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks_w else "fallback 1400"},
+                "what": "inference forward, random-init weights (no checkpoint exists for this width), CUDA events, mean of 5"}
+        del wnet, wx
         torch.cuda.empty_cache()
 
     # ---- per-kernel device times (CUDA events on the launching stream) -> roofline of the dominant kernel
@@ -367,10 +491,13 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # rank 0 at N = 1 only (the other ranks would idle behind it)
         reps = 3
-        rate, cores, times = cpu_reference_rate(args.ref_batch, reps, H, W)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        rate, cores, times, kind = cpu_reference_rate(args.ref_batch, reps, H, W)
+        rate1, _, times1, _ = cpu_reference_rate(1, 3, H, W) if H * W <= 512 * 512 else (None, None, [], None)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
                         "sample": f"median of {len(times)} forwards of {args.ref_batch} x 1x{H}x{W} fp32 images, torch CPU, "
-                                  f"{cores} threads ({sum(times):.1f} s of CPU work)"}
+                                  f"{cores} threads ({sum(times):.1f} s of CPU work)",
+                        "batch1_ms": (1e3 / rate1 if rate1 else None),
+                        "onnxruntime_cpu": onnxruntime_status()}
 
     if rank == 0:
         print(json.dumps({
@@ -392,6 +519,8 @@ def main():
                        "steps": e2e_steps, "api": "InferenceSession.run_pinned_u8 -> dg_lw_infer_host_u8 (uint8 pixels in and out, "
                                                   "/255 and clip*255 on the GPU as api/app.py:153,190-193 do on the host)"},
             "train_step": train_step,
+            "latency_n1": latency_n1,
+            "wide": wide,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

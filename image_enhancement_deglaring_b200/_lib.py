@@ -90,11 +90,11 @@ SYMBOLS = {
     "dg_lw_host_scratch_bytes": (C.c_int, [C.POINTER(DgLwParams), C.c_int32, C.c_int32, C.c_int32,
                                            C.POINTER(C.c_size_t)]),
     "dg_lw_infer_host": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_int32, C.c_void_p, C.c_size_t]),
+                                   C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dg_lw_forward_u8": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "dg_lw_infer_host_u8": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                      C.c_int32, C.c_void_p, C.c_size_t]),
+                                      C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dg_tc_conv3x3_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "dg_pack_conv3x3_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_tc_convt2x2_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),

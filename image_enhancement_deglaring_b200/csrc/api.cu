@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -602,13 +603,20 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
 // ---- host-buffer pipeline state --------------------------------------------------------------
 struct HostPipe {
     bool ready = false;
+    cudaEvent_t start;   // recorded on the CALLER's stream: weight packing etc. enqueued there is ordered before the pipeline
     static constexpr int NS = 4;  // chunks in flight (measured: 4 x 8-image chunks 2.84 ms per 64 images, 8 in flight 2.98, 2 in flight 3.3): compute streams, staging buffers and workspaces
     cudaStream_t s_in, s_cmp[NS], s_out;
     cudaEvent_t in_done[NS], cmp_done[NS], out_done[NS];
 };
-static HostPipe g_pipe;
+static HostPipe g_pipes[16];   // one pipeline (streams, events) per device ordinal
+static std::mutex g_pipe_mutex;  // the *_host entry points serialise: they share the pipeline and the caller's scratch
 
-static int pipe_init() {
+static int pipe_init(HostPipe** out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) { set_error("infer_host: device ordinal %d out of range", dev); return 2; }
+    HostPipe& g_pipe = g_pipes[dev];
+    *out = &g_pipe;
     if (g_pipe.ready) return 0;
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&g_pipe.s_in, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -624,6 +632,10 @@ static int pipe_init() {
         cudaEventCreateWithFlags(&g_pipe.in_done[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g_pipe.cmp_done[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g_pipe.out_done[i], cudaEventDisableTiming);
+    }
+    if ((e = cudaEventCreateWithFlags(&g_pipe.start, cudaEventDisableTiming)) != cudaSuccess) {
+        set_error("event create: %s", cudaGetErrorString(e));
+        return 10;
     }
     g_pipe.ready = true;
     return 0;
@@ -850,7 +862,7 @@ int dg_lw_host_scratch_bytes(const dg_lw_params* p, int32_t chunk, int32_t H, in
 // Chunk i: H2D on s_in -> forward on s_cmp[i % NS] with workspace i % NS -> D2H on s_out.  Several compute streams let the
 // under-filled deep layers of one chunk (16 images x 8 tiles < 148 SMs) overlap the next chunk's wide layers.
 static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host_y, int N, int H, int W, int chunk,
-                           void* dev_ws, size_t dev_ws_bytes, int io) {
+                           void* dev_ws, size_t dev_ws_bytes, int io, cudaStream_t caller) {
     if (chunk < 1) { set_error("infer_host: chunk %d", chunk); return 2; }
     if (chunk > N) chunk = N;
     LwPlan pl;
@@ -860,7 +872,9 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
     dg_lw_host_scratch_bytes(p, chunk, H, W, &need);
     if (dev_ws == nullptr || dev_ws_bytes < need) { set_error("infer_host: scratch %zu < %zu", dev_ws_bytes, need); return 4; }
     if (host_x == nullptr || host_y == nullptr) { set_error("infer_host: null host buffer"); return 2; }
-    if ((rc = dg::pipe_init())) return rc;
+    std::lock_guard<std::mutex> lock(dg::g_pipe_mutex);
+    dg::HostPipe* pipe = nullptr;
+    if ((rc = dg::pipe_init(&pipe))) return rc;
     const size_t esz_in = (io & 1) ? 1 : sizeof(float), esz_out = (io & 2) ? 1 : sizeof(float);
     const size_t in_img = (size_t)p->in_channels * H * W, out_img = (size_t)p->out_channels * H * W;
     const size_t in_b = align_up(chunk * in_img * sizeof(float), 256);
@@ -874,7 +888,12 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
         dy[k] = base + NS * in_b + k * out_b;
         ws[k] = base + NS * (in_b + out_b) + k * ws_b;
     }
-    dg::HostPipe& P = dg::g_pipe;
+    dg::HostPipe& P = *pipe;
+    // everything the caller enqueued on ITS stream (weight packing after a parameter update, the previous consumer of dev_ws) is
+    // ordered before the first kernel of the pipeline
+    cudaError_t ce = cudaEventRecord(P.start, caller);
+    for (int k = 0; k < NS && ce == cudaSuccess; ++k) ce = cudaStreamWaitEvent(P.s_cmp[k], P.start, 0);
+    if (ce != cudaSuccess) { set_error("infer_host: %s", cudaGetErrorString(ce)); return 10; }
     const char* hx = static_cast<const char*>(host_x);
     char* hy = static_cast<char*>(host_y);
     // chunk schedule: a half-size first and last chunk shorten the pipeline fill (first H2D) and drain (last D2H)
@@ -888,7 +907,8 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
         if (head && (i == 0 || i == nchunks - 1)) nn = head;
         else { const int left = N - head - n0; nn = left < chunk ? left : chunk; }  // body: what the tail chunk leaves
         if (i >= NS) cudaStreamWaitEvent(P.s_in, P.cmp_done[b], 0);  // dx[b] consumed by chunk i-NS
-        cudaMemcpyAsync(dx[b], hx + (size_t)n0 * in_img * esz_in, nn * in_img * esz_in, cudaMemcpyHostToDevice, P.s_in);
+        ce = cudaMemcpyAsync(dx[b], hx + (size_t)n0 * in_img * esz_in, nn * in_img * esz_in, cudaMemcpyHostToDevice, P.s_in);
+        if (ce != cudaSuccess) { cudaDeviceSynchronize(); set_error("infer_host: H2D copy: %s", cudaGetErrorString(ce)); return 10; }
         cudaEventRecord(P.in_done[b], P.s_in);
         cudaStreamWaitEvent(P.s_cmp[b], P.in_done[b], 0);
         if (i >= NS) cudaStreamWaitEvent(P.s_cmp[b], P.out_done[b], 0);  // dy[b] drained by chunk i-NS
@@ -896,7 +916,8 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
         if (rc) { cudaDeviceSynchronize(); return rc; }
         cudaEventRecord(P.cmp_done[b], P.s_cmp[b]);
         cudaStreamWaitEvent(P.s_out, P.cmp_done[b], 0);
-        cudaMemcpyAsync(hy + (size_t)n0 * out_img * esz_out, dy[b], nn * out_img * esz_out, cudaMemcpyDeviceToHost, P.s_out);
+        ce = cudaMemcpyAsync(hy + (size_t)n0 * out_img * esz_out, dy[b], nn * out_img * esz_out, cudaMemcpyDeviceToHost, P.s_out);
+        if (ce != cudaSuccess) { cudaDeviceSynchronize(); set_error("infer_host: D2H copy: %s", cudaGetErrorString(ce)); return 10; }
         cudaEventRecord(P.out_done[b], P.s_out);
         n0 += nn;
     }
@@ -907,13 +928,13 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
 }
 
 int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, int32_t N, int32_t H, int32_t W,
-                     int32_t chunk, void* dev_ws, size_t dev_ws_bytes) {
-    return infer_host_impl(p, host_x, host_y, N, H, W, chunk, dev_ws, dev_ws_bytes, 0);
+                     int32_t chunk, void* dev_ws, size_t dev_ws_bytes, dg_stream_t stream) {
+    return infer_host_impl(p, host_x, host_y, N, H, W, chunk, dev_ws, dev_ws_bytes, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dg_lw_infer_host_u8(const dg_lw_params* p, const uint8_t* host_x, uint8_t* host_y, int32_t N, int32_t H, int32_t W,
-                        int32_t chunk, void* dev_ws, size_t dev_ws_bytes) {
-    return infer_host_impl(p, host_x, host_y, N, H, W, chunk, dev_ws, dev_ws_bytes, 3);
+                        int32_t chunk, void* dev_ws, size_t dev_ws_bytes, dg_stream_t stream) {
+    return infer_host_impl(p, host_x, host_y, N, H, W, chunk, dev_ws, dev_ws_bytes, 3, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dg_lw_forward_u8(const dg_lw_params* p, const uint8_t* x, uint8_t* y, int32_t N, int32_t H, int32_t W, void* workspace,

@@ -178,11 +178,12 @@ class LightweightUNet(nn.Module):
             return lightweight_forward_train(self, x)
         x = x.detach().float().contiguous()
         N, _, H, W = x.shape
-        pc = self._refresh()
-        ws = self._workspace(N, H, W, x.device)
-        y = torch.empty((N, self.out_channels, H, W), dtype=torch.float32, device=x.device)
-        _lib.check(lib.dg_lw_forward(C.byref(pc), x.data_ptr(), y.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
-                                     None, None, torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(x.device):   # the library launches on the CURRENT device's stream: make it the tensors' device
+            pc = self._refresh()
+            ws = self._workspace(N, H, W, x.device)
+            y = torch.empty((N, self.out_channels, H, W), dtype=torch.float32, device=x.device)
+            _lib.check(lib.dg_lw_forward(C.byref(pc), x.data_ptr(), y.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
+                                         None, None, torch.cuda.current_stream().cuda_stream))
         return y
 
     def forward_u8(self, x):
@@ -196,11 +197,12 @@ class LightweightUNet(nn.Module):
             raise RuntimeError(f"expected input [N,{self.in_channels},H,W], got {tuple(x.shape)}")
         x = x.contiguous()
         N, _, H, W = x.shape
-        pc = self._refresh()
-        ws = self._workspace(N, H, W, x.device)
-        y = torch.empty((N, self.out_channels, H, W), dtype=torch.uint8, device=x.device)
-        _lib.check(lib.dg_lw_forward_u8(C.byref(pc), x.data_ptr(), y.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
-                                        torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(x.device):
+            pc = self._refresh()
+            ws = self._workspace(N, H, W, x.device)
+            y = torch.empty((N, self.out_channels, H, W), dtype=torch.uint8, device=x.device)
+            _lib.check(lib.dg_lw_forward_u8(C.byref(pc), x.data_ptr(), y.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
+                                            torch.cuda.current_stream().cuda_stream))
         return y
 
     # ---- debugging / test hooks ----------------------------------------------------------------------

@@ -78,7 +78,8 @@ class InferenceSession:
         scratch = self._scratch_for(chunk, H, W)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().dg_lw_infer_host(C.byref(self.model.c_params()), x_host.data_ptr(), y_host.data_ptr(),
-                                                    N, H, W, chunk, scratch.data_ptr(), scratch.numel()))
+                                                    N, H, W, chunk, scratch.data_ptr(), scratch.numel(),
+                                                    torch.cuda.current_stream().cuda_stream))
         return y_host
 
     def run_pinned_u8(self, x_host, y_host):
@@ -91,7 +92,8 @@ class InferenceSession:
         scratch = self._scratch_for(chunk, H, W)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().dg_lw_infer_host_u8(C.byref(self.model.c_params()), x_host.data_ptr(), y_host.data_ptr(),
-                                                       N, H, W, chunk, scratch.data_ptr(), scratch.numel()))
+                                                       N, H, W, chunk, scratch.data_ptr(), scratch.numel(),
+                                                       torch.cuda.current_stream().cuda_stream))
         return y_host
 
     def run_u8(self, images):

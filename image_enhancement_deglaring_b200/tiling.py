@@ -33,19 +33,25 @@ def merge_tiles(tiles, grid):
     return tiles.reshape(gh, gw, C, th, tw).permute(2, 0, 3, 1, 4).reshape(C, gh * th, gw * tw).contiguous()
 
 
-def infer_tiled(forward, image, tile=512, rank=0, world=1, group=None, gather=True, batch=64):
+def infer_tiled(forward, image, tile=512, rank=0, world=1, group=None, gather=True, batch=64, out_channels=None, out_dtype=None):
     """Run `forward` (a callable [n, C, tile, tile] -> [n, C', tile, tile]: the drop-in module, `forward_u8`, ...) over the
     tiles of `image` that belong to `rank` (contiguous shard of the row-major tile list), `batch` tiles per call.
 
     gather=True: every rank returns the full [C', H, W] result (one all_gather of the finished tiles over `group`).
-    gather=False: returns (tiles of this rank, (first, last) tile index, grid) and never communicates."""
+    gather=False: returns (tiles of this rank, (first, last) tile index, grid) and never communicates.
+    out_channels / out_dtype: shape of `forward`'s output per tile if it differs from the input's (C' != C, a float callable fed a
+    uint8 image, ...); only needed by a rank that owns NO tile (more ranks than tiles) -- every rank must hand all_gather the same
+    shape and dtype.  When omitted such a rank runs `forward` on one zero tile to learn them."""
     tiles, grid = split_tiles(image, tile)
     lo, hi = shard_range(tiles.shape[0], rank, world)
     outs = [forward(tiles[i:min(i + batch, hi)]) for i in range(lo, hi, batch)]
     if outs:
         mine = torch.cat(outs, 0)
-    else:  # more ranks than tiles: shape the empty shard from a dry description of one tile
-        mine = tiles.new_zeros((0,) + tuple(tiles.shape[1:]))
+    else:  # more ranks than tiles: an empty shard with the OUTPUT's channel count and dtype (not the input's)
+        if out_channels is None or out_dtype is None:
+            probe = forward(torch.zeros_like(tiles[:1]))
+            out_channels, out_dtype = probe.shape[1], probe.dtype
+        mine = torch.zeros((0, out_channels) + tuple(tiles.shape[2:]), dtype=out_dtype, device=tiles.device)
     if not gather:
         return mine, (lo, hi), grid
     if world > 1:

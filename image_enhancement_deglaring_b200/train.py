@@ -116,7 +116,6 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self._scratch = torch.zeros(1, dtype=torch.float64, device=dev)
         self._step = 0
-        self._step_t = torch.tensor(0.0)      # shared by every parameter's state entry (AdamW keeps `step` as a CPU float tensor)
         off = 0
         with torch.no_grad():
             for p in ps:
@@ -143,7 +142,9 @@ class FusedAdamW(torch.optim.Optimizer):
         off = 0
         for p in self._ps:
             k = p.numel()
-            self.state[p] = {"step": self._step_t, "exp_avg": self.exp_avg[off:off + k].view_as(p),
+            # one `step` tensor PER parameter (torch.optim.AdamW increments each entry in place: a shared tensor would be bumped
+            # once per parameter after a reload)
+            self.state[p] = {"step": torch.tensor(float(self._step)), "exp_avg": self.exp_avg[off:off + k].view_as(p),
                              "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p)}
             off += k
 
@@ -174,7 +175,6 @@ class FusedAdamW(torch.optim.Optimizer):
         if len(steps) != 1:
             raise ValueError(f"FusedAdamW needs one common step count, checkpoint has {sorted(steps)}")
         self._step = steps.pop()
-        self._step_t = torch.tensor(float(self._step))
         if self._step > 0:
             self._publish_state()
         else:
@@ -205,7 +205,6 @@ class FusedAdamW(torch.optim.Optimizer):
         self._gather()
         g = self.param_groups[0]
         self._step += 1
-        self._step_t.fill_(float(self._step))
         _lib.check(_lib.load().dg_adamw_step(
             self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
             self.flat_p.numel(), self._scratch.data_ptr(), float(g["max_grad_norm"]), float(g["lr"]), float(g["betas"][0]),

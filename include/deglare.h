@@ -235,10 +235,12 @@ int dg_lw_profile(const dg_lw_params* p, const float* x, float* y, int32_t N, in
  * copy over `chunk`-image slices on private streams (up to four chunks in flight on their own compute streams,
  * with a workspace each); returns when host_y is complete.
  * host_x/host_y should be pinned for full PCIe rate.  `dev_ws` is caller-owned device scratch of
- * dg_lw_host_scratch_bytes() bytes. */
+ * dg_lw_host_scratch_bytes() bytes.  `stream` is the CALLER's stream: the pipeline's private streams wait for everything
+ * enqueued on it so far (e.g. the packing kernels of freshly updated weights) before their first kernel.  One pipeline per
+ * device; concurrent calls are serialised. */
 int dg_lw_host_scratch_bytes(const dg_lw_params* p, int32_t chunk, int32_t H, int32_t W, size_t* bytes);
 int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, int32_t N, int32_t H,
-                     int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes);
+                     int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes, dg_stream_t stream);
 
 /* uint8 in / uint8 out: what api/app.py:153-193 does around `ort_session.run` -- `img.astype(float32) / 255.0`
  * before, `(np.clip(y, 0, 1) * 255).astype(np.uint8)` after -- folded into the first and the last kernel, so a quarter of
@@ -247,7 +249,7 @@ int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, 
 int dg_lw_forward_u8(const dg_lw_params* p, const uint8_t* x, uint8_t* y, int32_t N, int32_t H, int32_t W,
                      void* workspace, size_t workspace_bytes, dg_stream_t stream);
 int dg_lw_infer_host_u8(const dg_lw_params* p, const uint8_t* host_x, uint8_t* host_y, int32_t N, int32_t H,
-                        int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes);
+                        int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes, dg_stream_t stream);
 
 /* ---- tensor-core weight packing (16-bit storage types) ---------------------------------
  * The HMMA implicit-GEMM kernels read B operands as ldmatrix-ready tiles

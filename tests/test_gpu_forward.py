@@ -306,3 +306,47 @@ def test_4096_square_image_as_64_tiles(best_sd):
             assert torch.equal(out[:, r * 512:(r + 1) * 512, c * 512:(c + 1) * 512], alone), (r, c)
         # the marked (constant-input) tile is not confused with its random neighbours
         assert not torch.equal(out[:, 3 * 512:4 * 512, 5 * 512:6 * 512], out[:, 3 * 512:4 * 512, 4 * 512:5 * 512])
+
+
+def test_headline_config_batch64_512_fp16_matches_oracle(best_sd):
+    """The configuration bench.py quotes -- batch 64 x 1x512x512, fp16 storage, default two-stream split, every persistent kernel on
+    full grids -- against the oracle on the same seeded inputs: max-abs <= 5e-3 and PSNR >= 50 dB per image (north_star)."""
+    net = _net(best_sd, storage="fp16")
+    x = _rand((64, 1, 512, 512), 77)
+    with torch.no_grad():
+        y = net(x.cuda()).cpu()
+        y2 = net(x.cuda()).cpu()
+    assert torch.equal(y, y2)                       # run-to-run reproducible
+    torch.set_num_threads(os.cpu_count() or 1)
+    worst, worst_psnr = 0.0, 1e9
+    with torch.no_grad():
+        for i in range(0, 64, 8):
+            ref = tpo.lightweight_forward(x[i:i + 8], best_sd)
+            for j in range(8):
+                a, b = y[i + j, 0].numpy(), ref[j, 0].numpy()
+                worst = max(worst, float(np.abs(a - b).max()))
+                worst_psnr = min(worst_psnr, psnr(a, b))
+    print(f"batch 64 fp16: worst max-abs {worst:.3e}, worst PSNR {worst_psnr:.1f} dB")
+    assert worst <= 5e-3, worst
+    assert worst_psnr >= 50.0, worst_psnr
+    # ... and the batch is bit-identical to its images run alone (GroupNorm is per sample; statistics are batch-invariant)
+    with torch.no_grad():
+        for i in (0, 31, 32, 63):
+            assert torch.equal(net(x[i:i + 1].cuda()).cpu(), y[i:i + 1]), i
+
+
+def test_session_sees_weight_update_immediately(best_sd):
+    """the host pipeline runs on library-private streams; packing kernels of freshly changed weights are enqueued on the
+    caller's stream.  dg_lw_infer_host orders its streams after the caller's, so run() right after an in-place update is correct."""
+    from image_enhancement_deglaring_b200.session import InferenceSession
+    net = _net(best_sd, storage="fp16")
+    sess = InferenceSession(net, chunk=4)
+    x = _rand((8, 1, 64, 96), 5).numpy()
+    for step in range(4):
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(1.0 + 0.01 * (step + 1))      # bumps the version counters -> re-pack on the next call
+        out = sess.run(["output"], {"input": x})[0]
+        with torch.no_grad():
+            want = net(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.array_equal(out, want), step

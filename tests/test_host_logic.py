@@ -167,6 +167,11 @@ def test_tiles_roundtrip_and_order():
         split_tiles(torch.zeros(10, 12), tile=4)
 
 
+def _fake_forward_2ch(t):
+    f = t.float() / 255.0
+    return torch.cat((f, 1.0 - f), 1)
+
+
 def _tile_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -178,6 +183,17 @@ def _tile_worker(rank, world, port, out):
         res[name] = infer_tiled(_fake_forward, img, tile=4, rank=rank, world=world)
         part, span, _ = infer_tiled(_fake_forward, img, tile=4, rank=rank, world=world, gather=False)
         assert part.shape[0] == span[1] - span[0]
+    # more ranks than tiles AND a forward that changes dtype and channel count (uint8 in -> 2 float channels out): the empty
+    # shard must take the OUTPUT's shape / dtype or all_gather mismatches across ranks
+    u8 = (torch.arange(16, dtype=torch.float32).reshape(4, 4)).to(torch.uint8)
+    res["u8_to_2ch_float"] = infer_tiled(_fake_forward_2ch, u8, tile=4, rank=rank, world=world)
+    res["u8_to_2ch_float_declared"] = infer_tiled(_fake_forward_2ch, u8, tile=4, rank=rank, world=world, out_channels=2,
+                                                  out_dtype=torch.float32)
+    # data-parallel gradient exchange: mean over ranks of the flat bucket (train.sync_gradients; gloo has no AVG -> sum + scale)
+    from image_enhancement_deglaring_b200.train import sync_gradients
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    res["sync"] = sync_gradients(flat.clone())
+    res["nosync"] = sync_gradients(flat.clone(), enabled=False)
     torch.save(res, f"{out}.{rank}")
     dist.destroy_process_group()
 
@@ -192,6 +208,14 @@ def test_tiled_inference_sharded_world2(tmp_path):
         img = torch.arange(h * w, dtype=torch.float32).reshape(h, w) / 7.0
         want = infer_tiled(_fake_forward, img, tile=4)
         assert torch.equal(r0[name], want) and torch.equal(r1[name], want), name
+    u8 = (torch.arange(16, dtype=torch.float32).reshape(4, 4)).to(torch.uint8)
+    want = infer_tiled(_fake_forward_2ch, u8, tile=4)
+    for key in ("u8_to_2ch_float", "u8_to_2ch_float_declared"):
+        assert want.dtype == torch.float32 and want.shape == (2, 4, 4)
+        assert torch.equal(r0[key], want) and torch.equal(r1[key], want), key
+    base = torch.arange(10, dtype=torch.float32)
+    assert torch.allclose(r0["sync"], base * 1.5) and torch.allclose(r1["sync"], base * 1.5)      # mean of (1x, 2x)
+    assert torch.equal(r0["nosync"], base) and torch.equal(r1["nosync"], base * 2)
 
 
 def test_bench_reference_arm_contract():
@@ -207,5 +231,8 @@ def test_bench_reference_arm_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "unet_deglare_512x512_images_per_sec" and d["unit"] == "images/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" = the unmodified reference module from oracle/_ref (oracle/build_ref.py, build container -> GPU box), else the port
+    want_kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "model.py")) else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["onnxruntime_cpu"].startswith("onnxruntime")
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
