@@ -34,7 +34,7 @@ class DgConv3x3Args(C.Structure):
         ("weight", C.c_void_p), ("weight_tc", C.c_void_p), ("out", C.c_void_p), ("out_stats", C.c_void_p),
         ("act_sum", C.c_void_p), ("out_coef", C.c_void_p), ("out_counter", C.c_void_p), ("out_gamma", C.c_void_p),
         ("out_beta", C.c_void_p), ("out_groups", C.c_int32), ("reserved", C.c_int32), ("eps", C.c_float),
-        ("path", C.c_int32),
+        ("path", C.c_int32), ("weight_comp", C.c_void_p),
     ]
 
 
@@ -56,6 +56,7 @@ class DgLwParams(C.Structure):
         ("conv_w_flip", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w_t", C.c_void_p * 4),
         ("up_w_tc_bf16", C.c_void_p * 4), ("conv_w_tc_bf16", (C.c_void_p * 2) * DG_MAX_BLOCKS),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("path", C.c_int32), ("reserved", C.c_int32),
+        ("dec_comp", C.c_void_p * 4),
     ]
 
 
@@ -99,6 +100,8 @@ SYMBOLS = {
     "dg_pack_conv3x3_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_tc_convt2x2_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "dg_pack_convt2x2_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "dg_dec_composite_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "dg_pack_dec_composite": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_last_error_string": (C.c_char_p, []),
     "dg_version": (C.c_int, []),
     "dg_set_pdl": (C.c_int, [C.c_int]),

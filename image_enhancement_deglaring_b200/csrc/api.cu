@@ -177,6 +177,7 @@ static int lw_forward_range(const dg_lw_params* p, const LwPlan& pl, char* ws, c
             a.src[0].ct_cout = pl.f[lvl];
             a.src[1] = gn_src(p, pl, ws, 2 * lvl + 1, DG_X_SAME, n0);  // skip: torch.cat((up, skip), 1)
             a.nsrc = 2;
+            a.weight_comp = p->dec_comp[u];
             // deep levels (upconv4, upconv3; upconv2 with path bit 5): run the transposed conv as its own tensor-core GEMM and
             // feed its output as an identity source -- see convt_tc.cu for why this beats fusing there
             const bool unfuse = p->dtype != DG_F32 && (p->path & 3) != 1 && lw_up_materialised(p, pl, u);
@@ -686,6 +687,9 @@ int dg_conv3x3_fused(const dg_conv3x3_args* a, dg_stream_t stream) {
         rc = conv3x3_umma_launch(*a, st, &handled);   // round-1 tcgen05 kernel (opt-in, path bit 6)
         if (rc) return rc;
         if (handled) return 0;
+        rc = conv3x3_dec_launch(*a, st, &handled);    // upconv1 + dec1.0 with the ConvTranspose folded into the conv taps
+        if (rc) return rc;
+        if (handled) return 0;
         rc = conv3x3_ring_launch(*a, st, &handled);   // persistent TMA-fed kernel for the 8 -> 8 full-resolution layers
         if (rc) return rc;
         if (handled) return 0;
@@ -745,6 +749,16 @@ int dg_tc_convt2x2_bytes(int32_t cin, int32_t cout, size_t* bytes) {
 int dg_pack_convt2x2_tc(const float* w, void* out, int32_t cin, int32_t cout, int32_t dtype, dg_stream_t stream) {
     if (w == nullptr || out == nullptr) { set_error("pack: null pointer"); return 2; }
     return pack_convt_tc(w, out, cin, cout, dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_dec_composite_bytes(int32_t cl, int32_t cu, size_t* bytes) {
+    if (bytes == nullptr) { set_error("null bytes"); return 2; }
+    return dec_composite_bytes(cl, cu, bytes);
+}
+int dg_pack_dec_composite(const float* ct_w, const float* ct_b, const float* conv_w, void* out, int32_t cl, int32_t cu,
+                          int32_t dtype, dg_stream_t stream) {
+    if (!ct_w || !ct_b || !conv_w || !out) { set_error("pack: null pointer"); return 2; }
+    return pack_dec_composite(ct_w, ct_b, conv_w, out, cl, cu, dtype, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dg_lw_workspace_bytes(const dg_lw_params* p, int32_t N, int32_t H, int32_t W, size_t* bytes) {

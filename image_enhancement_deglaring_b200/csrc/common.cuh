@@ -186,6 +186,9 @@ int conv_first_tc_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* ha
 int conv3x3_umma_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int conv3x3_t5_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
 int conv3x3_ring_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
+int conv3x3_dec_launch(const dg_conv3x3_args& a, cudaStream_t stream, bool* handled);
+int dec_composite_bytes(int cl, int cu, size_t* bytes);
+int pack_dec_composite(const float* ct_w, const float* ct_b, const float* conv_w, void* out, int cl, int cu, int dtype, cudaStream_t st);
 int convt_t5_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, float eps, int path, cudaStream_t st, bool* handled);
 int head_launch(const dg_head_args& a, cudaStream_t stream);
 int convt_tc_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, float eps, int path, cudaStream_t st,

@@ -137,7 +137,13 @@ class LightweightUNet(nn.Module):
             if tc_bwd:
                 wbf = wtc if pc.dtype == ops.DG_BF16 else ops.pack_convt2x2_tc(w, ops.DG_BF16)
             pc.up_w_tc_bf16[u] = None if wbf is None else wbf.data_ptr()
-            keep += [w, bt, wtc, wtt, wbf]
+            # composite decoder taps (ConvTranspose folded into the consuming conv, conv3x3_dec.cu) where that kernel has coverage
+            comp = None
+            if self.path != 1 and pc.dtype != ops.DG_F32:
+                dblk = getattr(self, _BLOCKS[5 + u])
+                comp = ops.pack_dec_composite(w, bt, ops.pack_conv3x3(dblk[0].weight), pc.dtype)
+            pc.dec_comp[u] = None if comp is None else comp.data_ptr()
+            keep += [w, bt, wtc, wtt, wbf, comp]
             pc.up_w_tc[u] = None if wtc is None else wtc.data_ptr()
             pc.up_w[u] = w.data_ptr()
             pc.up_b[u] = bt.data_ptr()

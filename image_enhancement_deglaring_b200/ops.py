@@ -58,6 +58,20 @@ def pack_convt2x2_tc(w_packed, dtype, stream=None):
     return out
 
 
+def pack_dec_composite(ct_w_packed, ct_b, conv_w_packed, dtype, stream=None):
+    """ConvTranspose2d(2,2)+bias folded into the taps of the 3x3 conv that consumes cat((up, skip)) (dg_pack_dec_composite);
+    ct_w_packed fp32 [2,2,Cl,Cu], ct_b [Cu], conv_w_packed fp32 [3,3,2Cu,Cu].  None where the composite kernel has no coverage."""
+    lib = _lib.load()
+    cl, cu = int(ct_w_packed.shape[2]), int(ct_w_packed.shape[3])
+    n = C.c_size_t(0)
+    if dtype == DG_F32 or lib.dg_dec_composite_bytes(cl, cu, C.byref(n)) != 0:
+        return None
+    out = torch.empty(n.value, dtype=torch.uint8, device=ct_w_packed.device)
+    _lib.check(lib.dg_pack_dec_composite(ct_w_packed.data_ptr(), ct_b.data_ptr(), conv_w_packed.data_ptr(), out.data_ptr(), cl, cu,
+                                         dtype, _stream(stream)))
+    return out
+
+
 def make_src(raw, channels, xform=DG_X_SAME, stats=None, gamma=None, beta=None, groups=1, silu=True,
              scale=None, ct_w=None, ct_b=None, ct_cout=0, ct_w_tc=None):
     _require_cuda(raw, stats, gamma, beta, scale, ct_w, ct_b, ct_w_tc)
@@ -87,7 +101,7 @@ def _stream(stream):
 
 
 def conv3x3_fused(srcs, weight, cout, N, H, W, dtype, out=None, out_stats=None, act_sum=None, path=0, stream=None,
-                  eps=1e-5, weight_tc=None):
+                  eps=1e-5, weight_tc=None, weight_comp=None):
     """Fused 3x3 conv over the concat of `srcs` (list of DgSrc).  Returns (raw NHWC out, stats [N,cout,2] f64)."""
     lib = _lib.load()
     dev = weight.device
@@ -103,6 +117,7 @@ def conv3x3_fused(srcs, weight, cout, N, H, W, dtype, out=None, out_stats=None, 
     a.N, a.H, a.W, a.cout = N, H, W, cout
     a.weight = _ptr(weight)
     a.weight_tc = _ptr(weight_tc)
+    a.weight_comp = _ptr(weight_comp)
     a.out = _ptr(out)
     a.out_stats = _ptr(out_stats)
     a.act_sum = _ptr(act_sum)

@@ -103,7 +103,11 @@ typedef struct {
     int32_t path;         /* bits 0-1: 0 = auto, 1 = force generic CUDA-core path, 2 = force tensor-core path;
                              bits 2-3: SiLU flavour of the tensor-core prologue (0 tanh.approx, 1 exact ex2/rcp, 2 half2);
                              bit 4: producer-side GroupNorm finalisation; bit 5: un-fuse upconv2 as well;
-                             bit 6: use the tcgen05/TMEM kernel where it exists (deep 64-channel layers; measured at parity)                      */
+                             bit 6: round-1 tcgen05 kernel (opt-in); bit 7: do not use the round-2 tcgen05 kernel (conv3x3_t5.cu);
+                             bit 8: insist on it (tests); bit 9 / bit 10: do not use the persistent TMA-fed 8 -> 8 kernel
+                             (conv3x3_ring.cu) / the composite decoder kernel (conv3x3_dec.cu)                                  */
+    const void* weight_comp;  /* optional, decoder conv over (DG_X_CONVT2 low, DG_X_SAME skip) only: dg_pack_dec_composite blob --
+                                 the ConvTranspose folded into the conv's taps (conv3x3_dec.cu); NULL = stage `up` in the CTA  */
 } dg_conv3x3_args;
 
 int dg_conv3x3_fused(const dg_conv3x3_args* args, dg_stream_t stream);
@@ -186,6 +190,9 @@ typedef struct {
     const float* head_b;
     int32_t path;                           /* 0 auto, 1 generic, 2 tensor-core            */
     int32_t reserved;
+    const void* dec_comp[4];                /* optional: dg_pack_dec_composite blobs of (upconv4..1, dec4..1 `.0`) for the
+                                               levels the composite decoder kernel covers (upconv1 + dec1.0 of the shipped
+                                               model); NULL elsewhere                                                  */
 } dg_lw_params;
 
 /* Bytes of workspace dg_lw_forward needs for an [N,in,H,W] batch (raw activations of all 18
@@ -260,6 +267,13 @@ int dg_tc_conv3x3_bytes(int32_t cin, int32_t cout, size_t* bytes);
 int dg_pack_conv3x3_tc(const float* w, void* out, int32_t cin, int32_t cout, int32_t dtype, dg_stream_t stream);
 int dg_tc_convt2x2_bytes(int32_t cin, int32_t cout, size_t* bytes);
 int dg_pack_convt2x2_tc(const float* w, void* out, int32_t cin, int32_t cout, int32_t dtype, dg_stream_t stream);
+
+/* Composite decoder taps (conv3x3_dec.cu): ConvTranspose2d(k=2, s=2)+bias folded into the 3x3 conv that consumes cat((up, skip)).
+ * ct_w fp32 [2][2][cl][cu], ct_b [cu], conv_w fp32 [3][3][2 cu][cu] (the packings dg_conv3x3_fused takes); out = blob of
+ * *bytes bytes in `dtype`.  Covers (cl, cu) = (16, 8) -- upconv1 + dec1.0 of LightweightUNet(features_start=8), src/model.py:53,54. */
+int dg_dec_composite_bytes(int32_t cl, int32_t cu, size_t* bytes);
+int dg_pack_dec_composite(const float* ct_w, const float* ct_b, const float* conv_w, void* out, int32_t cl, int32_t cu,
+                          int32_t dtype, dg_stream_t stream);
 
 /* ---- misc --------------------------------------------------------------------------- */
 const char* dg_last_error_string(void);

@@ -500,6 +500,45 @@ def test_ring_tma_kernel_matches_per_tile_kernel(dtype, N, H, W):
     assert float((s_ring.cpu() - want).abs().max() / max(1.0, float(want.abs().max()))) <= 6e-4
 
 
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("N,H,W", [(2, 64, 128), (3, 48, 80), (1, 16, 64), (2, 16, 16), (2, 2, 2), (3, 34, 66), (1, 512, 512)])
+def test_composite_decoder_kernel(dtype, N, H, W):
+    """upconv1 + dec1.0 with the ConvTranspose folded into the conv taps (conv3x3_dec.cu: 2x2 composite taps per output parity
+    class, border-corrected bias, TMA-fed) vs the oracle's ConvTranspose -> cat -> conv and vs the round-1 fused kernel."""
+    rs = _rs(29)
+    c = 8
+    low = torch.from_numpy((rs.standard_normal((N, 2 * c, H // 2, W // 2)) * 2).astype(np.float32))
+    skip = torch.from_numpy((rs.standard_normal((N, c, H, W)) * 2 + 0.3).astype(np.float32))
+    ql, seen_l = _nhwc(low, dtype)
+    qs, seen_s = _nhwc(skip, dtype)
+    g1, b1 = _gn_params(rs, 2 * c)
+    g2, b2 = _gn_params(rs, c)
+    ctw = torch.from_numpy((rs.standard_normal((2 * c, c, 2, 2)) * (1.0 / np.sqrt(2 * c))).astype(np.float32))
+    ctb = torch.from_numpy((rs.standard_normal(c) * 0.5).astype(np.float32))     # a bias large enough to expose border mistakes
+    w = torch.from_numpy((rs.standard_normal((c, 2 * c, 3, 3)) * (1.0 / np.sqrt(18 * c))).astype(np.float32))
+    wp = ops.pack_conv3x3(w.cuda())
+    ctp = ops.pack_convt2x2(ctw.cuda())
+    s0 = ops.make_src(ql, 2 * c, xform=ops.DG_X_CONVT2, stats=_stats(seen_l), gamma=g1.cuda(), beta=b1.cuda(),
+                      groups=8, ct_w=ctp, ct_b=ctb.cuda(), ct_cout=c, ct_w_tc=ops.pack_convt2x2_tc(ctp, dtype))
+    s1 = ops.make_src(qs, c, stats=_stats(seen_s), gamma=g2.cuda(), beta=b2.cuda(), groups=8)
+    comp = ops.pack_dec_composite(ctp, ctb.cuda(), wp, dtype)
+    assert comp is not None
+    wtc = ops.pack_conv3x3_tc(wp, dtype)
+    o_c, s_c = ops.conv3x3_fused([s0, s1], wp, c, N, H, W, dtype, path=2, weight_tc=wtc, weight_comp=comp)
+    o_h, s_h = ops.conv3x3_fused([s0, s1], wp, c, N, H, W, dtype, path=2 | 1024, weight_tc=wtc, weight_comp=comp)
+    torch.cuda.synchronize()
+    up = F.conv_transpose2d(tpo.gn_silu(seen_l, 8, g1, b1), ctw, ctb, stride=2)
+    ref = F.conv2d(torch.cat((up, tpo.gn_silu(seen_s, 8, g2, b2)), 1), w, None, 1, 1)
+    scale = max(1.0, float(ref.abs().max()))
+    tol = (6e-3 if dtype == ops.DG_F16 else 4e-2) * scale
+    got = o_c.float().cpu().permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) <= tol, f"composite vs oracle {float((got - ref).abs().max()):.3e} (scale {scale:.2f})"
+    assert float((o_c.float() - o_h.float()).abs().max()) <= tol
+    want = torch.stack((got.double().sum(dim=(2, 3)), (got.double() ** 2).sum(dim=(2, 3))), dim=2)
+    assert float((s_c.cpu() - want).abs().max() / max(1.0, float(want.abs().max()))) <= 6e-4
+    assert not torch.equal(o_c, o_h) or H * W <= 4      # really two different kernels
+
+
 def test_tc_path_refuses_unsupported():
     w = torch.zeros(3, 3, 24, 24, device="cuda")
     raw = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.float16)
