@@ -328,13 +328,13 @@ def main():
     # same storage tier; data parallel = one flat-gradient all-reduce inside FusedAdamW.step.  Reported beside the headline.
     train_step = None
     if not args.no_train:
-        from image_enhancement_deglaring_b200.train import FusedAdamW
+        from image_enhancement_deglaring_b200.train import FusedAdamW, L1Loss
         tb = 32
         tnet = dg.LightweightUNet(storage=args.storage, path=args.path)
         tnet.load_state_dict(sd, strict=True)
         tnet = tnet.to(dev).train()
         opt = FusedAdamW(tnet.parameters(), lr=0.002362532125818593, weight_decay=6.753784966611083e-05, max_grad_norm=1.0)
-        crit = torch.nn.L1Loss()
+        crit = L1Loss()   # drop-in for nn.L1Loss: seed generated inside the head backward, gradients written into the flat bucket
         tx = torch.rand(tb, 1, H, W, generator=torch.Generator().manual_seed(10 + rank)).to(dev)
         tt = torch.rand(tb, 1, H, W, generator=torch.Generator().manual_seed(110 + rank)).to(dev)
 

@@ -5,3 +5,6 @@ __all__ = ["LightweightUNet", "count_parameters", "get_model_size_mb"]
 from .model_optimized import OptimizedUNet  # noqa: E402,F401
 
 __all__.append("OptimizedUNet")
+from .train import FusedAdamW, L1Loss  # noqa: E402,F401
+
+__all__ += ["FusedAdamW", "L1Loss"]

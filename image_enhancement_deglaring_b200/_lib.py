@@ -84,6 +84,9 @@ SYMBOLS = {
                                                  C.POINTER(C.c_size_t)]),
     "dg_lw_backward": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "dg_l1_loss_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "dg_lw_backward_l1": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "dg_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p]),
     "dg_lw_profile": (C.c_int, [C.POINTER(DgLwParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -385,12 +385,15 @@ static void fwd_conv_args(const dg_lw_params* p, const LwPlan& pl, char* ws, con
     }
 }
 
+// nn.L1Loss backward fused into the head backward: forward output, target, device scalar dLoss (NULL = 1) and 1 / numel
+struct L1Seed { const float* y; const float* target; const float* scale; float inv_numel; };
+
 static int lw_backward_range(const dg_lw_params* p, const struct LwPlan& pl, const struct BwdPlan& bp, const struct GradLayout& gl,
                              const float* x, const float* grad_y, int n0, int N, int H, int W, char* fw, char* bw, float* grads,
-                             cudaStream_t st);
+                             cudaStream_t st, const L1Seed* l1);
 
 static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_y, int N, int H, int W, void* fwd_ws,
-                       size_t fwd_bytes, void* bwd_ws, size_t bwd_bytes, float* grads, cudaStream_t st) {
+                       size_t fwd_bytes, void* bwd_ws, size_t bwd_bytes, float* grads, cudaStream_t st, const L1Seed* l1 = nullptr) {
     LwPlan pl;
     int rc = make_plan(p, N, H, W, &pl);
     if (rc) return rc;
@@ -402,7 +405,7 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
         set_error("backward: workspace too small (fwd %zu/%zu, bwd %zu/%zu)", fwd_bytes, pl.total_bytes, bwd_bytes, bp.total);
         return 4;
     }
-    if (x == nullptr || grad_y == nullptr || grads == nullptr) { set_error("backward: null pointer"); return 2; }
+    if (x == nullptr || (grad_y == nullptr && l1 == nullptr) || grads == nullptr) { set_error("backward: null pointer"); return 2; }
     // conv_w_flip / up_w_t feed the CUDA-core data-gradient kernels only: required where a tensor-core packing is absent
     for (int b = 0; b < 9; ++b)
         for (int j = 0; j < 2; ++j)
@@ -425,20 +428,21 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
         const int half = N / 2;
         for (int k = 0; k < 2; ++k) {
             cudaStreamWaitEvent(F.s[k], F.fork, 0);
-            rc = lw_backward_range(p, pl, bp, gl, x, grad_y, k ? half : 0, k ? N - half : half, H, W, fw, bw, grads, F.s[k]);
+            rc = lw_backward_range(p, pl, bp, gl, x, grad_y, k ? half : 0, k ? N - half : half, H, W, fw, bw, grads, F.s[k], l1);
             cudaEventRecord(F.join[k], F.s[k]);
             cudaStreamWaitEvent(st, F.join[k], 0);
             if (rc) return rc;
         }
         return 0;
     }
-    return lw_backward_range(p, pl, bp, gl, x, grad_y, 0, N, H, W, fw, bw, grads, st);
+    return lw_backward_range(p, pl, bp, gl, x, grad_y, 0, N, H, W, fw, bw, grads, st, l1);
 }
 
 // Backward over images [n0, n0 + N) of a batch of N_total; every buffer was laid out for the whole batch (`N` below is the
 // sub-batch size).  Parameter gradients are accumulated atomically, so concurrent sub-batches add up.
 static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdPlan& bp, const GradLayout& gl, const float* x,
-                             const float* grad_y, int n0, int N, int H, int W, char* fw, char* bw, float* grads, cudaStream_t st) {
+                             const float* grad_y, int n0, int N, int H, int W, char* fw, char* bw, float* grads, cudaStream_t st,
+                             const L1Seed* l1) {
     int rc = 0;
     const size_t esz = dtype_size(p->dtype);
     bool t_split[18] = {};   // decoder conv i: T(i) holds the two halves of the concat gradient as two compact tensors
@@ -453,9 +457,11 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
                               P(j), N, pl.conv_h[j], pl.conv_w[j], pl.conv_c[j], p->groups[j / 2], 1e-5f, st);
     };
     // head: src/model.py:131 backward
+    const size_t o0 = (size_t)n0 * p->out_channels * H * W;
     rc = head_bwd_launch(p->dtype, raw(17), stats(17), p->gn_w[8][1], p->gn_b[8][1],
-                         grad_y + (size_t)n0 * p->out_channels * H * W, p->head_w, G(17), P(17),
-                         grads + gl.head_w, grads + gl.head_b, N, H, W, pl.conv_c[17], p->out_channels, p->groups[8], 1e-5f, st);
+                         grad_y ? grad_y + o0 : nullptr, p->head_w, G(17), P(17),
+                         grads + gl.head_w, grads + gl.head_b, N, H, W, pl.conv_c[17], p->out_channels, p->groups[8], 1e-5f, st,
+                         l1 ? l1->y + o0 : nullptr, l1 ? l1->target + o0 : nullptr, l1 ? l1->scale : nullptr, l1 ? l1->inv_numel : 0.f);
     if (rc) return rc;
     for (int i = 17; i >= 0; --i) {
         const int b = i / 2, j = i % 2, C = pl.conv_c[i], Hi = pl.conv_h[i], Wi = pl.conv_w[i];
@@ -835,6 +841,21 @@ int dg_lw_backward(const dg_lw_params* p, const float* x, const float* grad_y, i
                    dg_stream_t stream) {
     return lw_backward(p, x, grad_y, N, H, W, fwd_workspace, fwd_bytes, bwd_workspace, bwd_bytes, grads,
                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_lw_backward_l1(const dg_lw_params* p, const float* x, const float* y, const float* target, const float* loss_grad,
+                      int32_t N, int32_t H, int32_t W, void* fwd_workspace, size_t fwd_bytes, void* bwd_workspace, size_t bwd_bytes,
+                      float* grads, dg_stream_t stream) {
+    if (y == nullptr || target == nullptr) { set_error("backward_l1: null output / target"); return 2; }
+    if (p == nullptr) { set_error("null params"); return 2; }
+    L1Seed l1{y, target, loss_grad, 1.0f / ((float)N * (float)p->out_channels * (float)H * (float)W)};
+    return lw_backward(p, x, nullptr, N, H, W, fwd_workspace, fwd_bytes, bwd_workspace, bwd_bytes, grads,
+                       reinterpret_cast<cudaStream_t>(stream), &l1);
+}
+
+int dg_l1_loss_sum(const float* y, const float* target, size_t count, double* sum, dg_stream_t stream) {
+    if (!y || !target || !sum || count == 0) { set_error("l1_loss_sum: bad arguments"); return 2; }
+    return l1_sum_launch(y, target, count, sum, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t count, double* scratch,

@@ -324,7 +324,12 @@ struct HeadBwdArgs {
     float* G; double* P;  // [N,H,W,C], [N,C,2]
     float* dW; float* dB; // [OC][C], [OC] accumulated atomically (zero on entry)
     int N, H, W, C, OC, groups; float eps;
+    // nn.L1Loss backward fused (optimized_train.py:439,210/226): when `target` is set, dOut is not read at all -- the seed
+    // sign(y - target) * (*scale) * inv_numel is generated here from the forward output y (sign(0) = 0, as torch)
+    const float* y; const float* target; const float* scale; float inv_numel;
 };
+
+__device__ __forceinline__ float l1_seed(float y, float t, float s) { return y > t ? s : (y < t ? -s : 0.f); }
 
 template <typename T>
 __global__ void __launch_bounds__(BW_THREADS) head_bwd_kernel(const HeadBwdArgs p) {
@@ -351,7 +356,10 @@ __global__ void __launch_bounds__(BW_THREADS) head_bwd_kernel(const HeadBwdArgs 
         const bool live = pix < HW;
         float dO[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < OC; ++j) {
-            if (live) dO[j] = p.dOut[((size_t)n * OC + j) * HW + pix];
+            if (live) {
+                const size_t oi = ((size_t)n * OC + j) * HW + pix;
+                dO[j] = p.target ? l1_seed(p.y[oi], p.target[oi], (p.scale ? __ldg(p.scale) : 1.f) * p.inv_numel) : p.dOut[oi];
+            }
             const float t = warp_sum(dO[j]);
             if (lane == 0) atomicAdd(&wacc[OC * C + j], (double)t);
         }
@@ -591,8 +599,11 @@ __global__ void __launch_bounds__(BW_THREADS) head_bwd_fast_kernel(const HeadBwd
     const T* raw = reinterpret_cast<const T*>(p.raw) + (size_t)n * HW * C;
     float* G = p.G + (size_t)n * HW * C;
     const float* dOut = p.dOut + (size_t)n * HW;
+    const float* yo = p.y + (size_t)n * HW;
+    const float* tg = p.target + (size_t)n * HW;
+    const float seed = p.target ? (p.scale ? __ldg(p.scale) : 1.f) * p.inv_numel : 0.f;
     for (int pix = blockIdx.x * BW_THREADS + threadIdx.x; pix < HW; pix += gridDim.x * BW_THREADS) {
-        const float d = __ldg(dOut + pix);
+        const float d = p.target ? l1_seed(__ldg(yo + pix), __ldg(tg + pix), seed) : __ldg(dOut + pix);
         db += d;
         float r[C];
 #pragma unroll
@@ -782,11 +793,42 @@ int gn_bwd_apply_launch(int dtype, const void* raw, const double* stats, const f
     return check_launch("gn_bwd_apply");
 }
 
+// nn.L1Loss forward (optimized_train.py:439,207/223): sum |y - t| in double, one atomic per CTA
+__global__ void __launch_bounds__(BW_THREADS) l1_sum_kernel(const float* __restrict__ y, const float* __restrict__ t, size_t n, double* out) {
+    __shared__ double red[BW_THREADS / 32];
+    float acc = 0.f;
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * BW_THREADS) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(y) + i), b = __ldg(reinterpret_cast<const float4*>(t) + i);
+        acc += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = 4 * n4 + threadIdx.x; i < n; i += BW_THREADS) acc += fabsf(y[i] - t[i]);
+    double d = (double)warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < BW_THREADS / 32; ++k) s += red[k];
+        atomicAdd(out, s);
+    }
+}
+
+int l1_sum_launch(const float* y, const float* t, size_t n, double* out, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(t)) & 15) { set_error("l1: pointers must be 16-byte aligned"); return 2; }
+    size_t blocks = (n / 4 + BW_THREADS * 8 - 1) / (BW_THREADS * 8);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1184) blocks = 1184;
+    l1_sum_kernel<<<(unsigned)blocks, BW_THREADS, 0, st>>>(y, t, n, out);
+    count_launch();
+    return check_launch("l1_sum");
+}
+
 int head_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dOut,
                     const float* w, float* G, double* P, float* dW, float* dB, int N, int H, int W, int C, int OC, int groups,
-                    float eps, cudaStream_t st) {
+                    float eps, cudaStream_t st, const float* l1_y, const float* l1_target, const float* l1_scale, float l1_inv_numel) {
     if (OC > 4) { set_error("head backward: out_channels %d > 4", OC); return 3; }
-    HeadBwdArgs a{raw, stats, gamma, beta, dOut, w, G, P, dW, dB, N, H, W, C, OC, groups, eps};
+    HeadBwdArgs a{raw, stats, gamma, beta, dOut, w, G, P, dW, dB, N, H, W, C, OC, groups, eps, l1_y, l1_target, l1_scale, l1_inv_numel};
     if (OC == 1 && (C == 8 || C == 16) && aligned16(G) && aligned_raw(dtype, raw) && N <= 65535) {
         int fx = (H * W + BW_THREADS * 16 - 1) / (BW_THREADS * 16);
         if (fx < 1) fx = 1;

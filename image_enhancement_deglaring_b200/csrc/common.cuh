@@ -223,7 +223,9 @@ int gn_bwd_apply_launch(int dtype, const void* raw, const double* stats, const f
                         float* dgamma, float* dbeta, int N, int H, int W, int C, int groups, float eps, cudaStream_t st, void* dRb = nullptr, bool* wrote_bf16 = nullptr);
 int head_bwd_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* dOut,
                     const float* w, float* G, double* P, float* dW, float* dB, int N, int H, int W, int C, int OC, int groups,
-                    float eps, cudaStream_t st);
+                    float eps, cudaStream_t st, const float* l1_y = nullptr, const float* l1_target = nullptr,
+                    const float* l1_scale = nullptr, float l1_inv_numel = 0.f);
+int l1_sum_launch(const float* y, const float* t, size_t n, double* out, cudaStream_t st);
 int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low, const double* stats,
                      const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias, float* coefbuf, int N,
                      int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st, const void* wtc_bf16 = nullptr, const DgradAct* act = nullptr, bool* act_fused = nullptr);

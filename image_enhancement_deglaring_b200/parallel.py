@@ -73,6 +73,8 @@ class FlatGradBucket:
 
     def zero_(self):
         self.flat.zero_()
+        self.flat._dg_zero_version = self.flat._version   # lets the fused backward write straight into the bucket (train._flat_grad_sink)
+        self.attach()
 
     def allreduce_mean(self, group=None):
         if dist.is_available() and dist.is_initialized():

@@ -21,48 +21,132 @@ import torch
 from . import _lib
 
 
+class _TrainCtx:
+    """Side channel between the module's autograd node and `L1Loss` below: when the loss of the step is the fused L1, its backward
+    leaves (target, dL/dloss) here and the module's backward generates the gradient seed inside the head-backward kernel."""
+    __slots__ = ("y", "l1_target", "l1_scale", "l1_marker")
+
+    def __init__(self):
+        self.y = self.l1_target = self.l1_scale = self.l1_marker = None
+
+
+def _flat_grad_sink(params):
+    """The flat fp32 buffer all `.grad`s are views of (FusedAdamW / FlatGradBucket layout, parameters() order) if it is known to be
+    all-zero since its last zero_grad and nothing else would observe the per-parameter accumulation; else None."""
+    g0 = params[0].grad
+    if g0 is None:
+        return None
+    base = g0._base if g0._base is not None else g0
+    if getattr(base, "_dg_zero_version", None) != base._version or base.dtype != torch.float32 or not base.is_contiguous():
+        return None
+    off = 0
+    for p in params:
+        g = p.grad
+        if g is None or not p.requires_grad or g.data_ptr() != base.data_ptr() + 4 * off or g.numel() != p.numel():
+            return None
+        if p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None):
+            return None     # wandb.watch and friends hook the per-parameter accumulation: keep the ordinary autograd path
+        off += p.numel()
+    return base if off == base.numel() else None
+
+
 class _LightweightUNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, *params):
+    def forward(ctx, module, tctx, x, *params):
         lib = _lib.load()
         x = x.detach().float().contiguous()
         N, _, H, W = x.shape
-        pc = module._refresh(train=True)
-        ws = torch.empty(module.workspace_bytes(N, H, W), dtype=torch.uint8, device=x.device)  # kept for backward
-        y = torch.empty((N, module.out_channels, H, W), dtype=torch.float32, device=x.device)
-        _lib.check(lib.dg_lw_forward(C.byref(pc), x.data_ptr(), y.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
-                                     None, None, torch.cuda.current_stream().cuda_stream))
-        ctx.module, ctx.ws, ctx.x = module, ws, x
+        with torch.cuda.device(x.device):
+            pc = module._refresh(train=True)
+            ws = torch.empty(module.workspace_bytes(N, H, W), dtype=torch.uint8, device=x.device)  # kept for backward
+            y = torch.empty((N, module.out_channels, H, W), dtype=torch.float32, device=x.device)
+            _lib.check(lib.dg_lw_forward(C.byref(pc), x.data_ptr(), y.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
+                                         None, None, torch.cuda.current_stream().cuda_stream))
+        ctx.module, ctx.ws, ctx.x, ctx.tctx = module, ws, x, tctx
+        tctx.y = y
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
         lib = _lib.load()
-        module, x = ctx.module, ctx.x
+        module, x, tctx = ctx.module, ctx.x, ctx.tctx
         N, _, H, W = x.shape
-        grad_y = grad_y.detach().float().contiguous()
-        pc = module._refresh(train=True)
-        nb = C.c_size_t(0)
-        _lib.check(lib.dg_lw_backward_workspace_bytes(C.byref(pc), N, H, W, C.byref(nb)))
-        bws = torch.empty(nb.value, dtype=torch.uint8, device=x.device)
         params = list(module.parameters())
         total = sum(p.numel() for p in params)
-        cnt = C.c_size_t(0)
-        _lib.check(lib.dg_lw_num_params(C.byref(pc), C.byref(cnt)))
-        if cnt.value != total:
-            raise RuntimeError(f"gradient layout mismatch: library {cnt.value} vs module {total}")
-        flat = torch.empty(total, dtype=torch.float32, device=x.device)
-        _lib.check(lib.dg_lw_backward(C.byref(pc), x.data_ptr(), grad_y.data_ptr(), N, H, W, ctx.ws.data_ptr(),
-                                      ctx.ws.numel(), bws.data_ptr(), bws.numel(), flat.data_ptr(),
-                                      torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(x.device):
+            pc = module._refresh(train=True)
+            nb = C.c_size_t(0)
+            _lib.check(lib.dg_lw_backward_workspace_bytes(C.byref(pc), N, H, W, C.byref(nb)))
+            bws = torch.empty(nb.value, dtype=torch.uint8, device=x.device)
+            cnt = C.c_size_t(0)
+            _lib.check(lib.dg_lw_num_params(C.byref(pc), C.byref(cnt)))
+            if cnt.value != total:
+                raise RuntimeError(f"gradient layout mismatch: library {cnt.value} vs module {total}")
+            # gradients go straight into the optimizer's flat bucket when that is safe (fresh after zero_grad, no hooks): no
+            # per-parameter accumulate kernels, no temporary
+            sink = _flat_grad_sink(params) if total > 0 else None
+            flat = sink if sink is not None else torch.empty(total, dtype=torch.float32, device=x.device)
+            stream = torch.cuda.current_stream().cuda_stream
+            fused_l1 = (tctx.l1_target is not None and tctx.l1_marker is not None and grad_y.data_ptr() == tctx.l1_marker.data_ptr()
+                        and all(s == 0 for s in grad_y.stride()))
+            if fused_l1:   # loss = L1Loss (below): the seed sign(y - t) * dloss / numel is generated inside the head backward
+                _lib.check(lib.dg_lw_backward_l1(C.byref(pc), x.data_ptr(), tctx.y.data_ptr(), tctx.l1_target.data_ptr(),
+                                                 tctx.l1_scale.data_ptr(), N, H, W, ctx.ws.data_ptr(), ctx.ws.numel(),
+                                                 bws.data_ptr(), bws.numel(), flat.data_ptr(), stream))
+            else:
+                grad_y = grad_y.detach().float().contiguous()
+                _lib.check(lib.dg_lw_backward(C.byref(pc), x.data_ptr(), grad_y.data_ptr(), N, H, W, ctx.ws.data_ptr(),
+                                              ctx.ws.numel(), bws.data_ptr(), bws.numel(), flat.data_ptr(), stream))
         ctx.ws = None
+        tctx.y = tctx.l1_target = tctx.l1_scale = tctx.l1_marker = None
         sync_gradients(flat, getattr(module, "ddp_sync", True))
+        if sink is not None:
+            sink._dg_zero_version = None      # the bucket now holds a gradient: a second backward must accumulate the ordinary way
+            return (None, None, None) + (None,) * len(params)
         grads, off = [], 0
         for p in params:
             n = p.numel()
             grads.append(flat[off:off + n].view_as(p) if p.requires_grad else None)
             off += n
-        return (None, None, *grads)
+        return (None, None, None, *grads)
+
+
+class _FusedL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, outputs, targets, tctx):
+        acc = torch.zeros(1, dtype=torch.float64, device=outputs.device)
+        with torch.cuda.device(outputs.device):
+            _lib.check(_lib.load().dg_l1_loss_sum(outputs.data_ptr(), targets.data_ptr(), outputs.numel(), acc.data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream))
+        ctx.tctx, ctx.targets, ctx.shape = tctx, targets, outputs.shape
+        return (acc / outputs.numel()).to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        tctx = ctx.tctx
+        scale = grad_loss.detach().float().reshape(1).contiguous()
+        tctx.l1_target, tctx.l1_scale = ctx.targets, scale
+        tctx.l1_marker = scale.expand(ctx.shape)     # stride-0 view: no kernel; the module's backward recognises it by pointer
+        return tctx.l1_marker, None, None
+
+
+class L1Loss(torch.nn.Module):
+    """Drop-in for the `nn.L1Loss()` of optimized_train.py:439.  On an output of this package's module in training it is the fused
+    L1: the loss value is one reduction kernel, and backward never materialises sign(o - t) / numel -- the head
+    backward kernel generates it from the forward output and the target.  Anything else (other reductions, other tensors, CPU)
+    falls through to torch.nn.functional.l1_loss with identical semantics."""
+
+    def __init__(self, size_average=None, reduce=None, reduction="mean"):
+        super().__init__()
+        self.reduction = reduction
+
+    def forward(self, outputs, targets):
+        tctx = getattr(outputs, "_dg_train_ctx", None)
+        if (tctx is None or self.reduction != "mean" or not torch.is_grad_enabled() or not outputs.requires_grad
+                or targets.requires_grad or outputs.shape != targets.shape or not targets.is_cuda
+                or targets.dtype != torch.float32 or tctx.y is None or outputs.data_ptr() != tctx.y.data_ptr()):
+            return torch.nn.functional.l1_loss(outputs, targets, reduction=self.reduction)
+        return _FusedL1.apply(outputs, targets.contiguous(), tctx)
 
 
 def sync_gradients(flat, enabled=True, group=None):
@@ -85,7 +169,10 @@ def sync_gradients(flat, enabled=True, group=None):
 def lightweight_forward_train(module, x):
     if x.requires_grad:
         raise NotImplementedError("gradient w.r.t. the input image is not implemented (the reference never needs it)")
-    return _LightweightUNetFn.apply(module, x, *module.parameters())
+    tctx = _TrainCtx()
+    y = _LightweightUNetFn.apply(module, tctx, x, *module.parameters())
+    y._dg_train_ctx = tctx
+    return y
 
 
 class FusedAdamW(torch.optim.Optimizer):
@@ -183,6 +270,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=True):
         # the reference calls zero_grad(set_to_none=True) (optimized_train.py:201); keep the flat aliasing instead
         self.flat_g.zero_()
+        self.flat_g._dg_zero_version = self.flat_g._version   # all-zero as of this version: backward may write into it directly
         self._attach_grads()
 
     def _gather(self):

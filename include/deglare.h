@@ -224,6 +224,16 @@ int dg_lw_backward(const dg_lw_params* p, const float* x, const float* grad_y, i
                    void* fwd_workspace, size_t fwd_bytes, void* bwd_workspace, size_t bwd_bytes, float* grads,
                    dg_stream_t stream);
 
+/* nn.L1Loss (optimized_train.py:439) fused into the training path.
+ * dg_l1_loss_sum: *sum += sum_i |y_i - target_i| (double, zero on entry); the mean is sum / count.
+ * dg_lw_backward_l1: dg_lw_backward for loss = mean |y - target| without a gradient tensor at the output: the head backward
+ * generates sign(y - target) * (*loss_grad) / numel itself from the forward output `y` (fp32 [N,out,H,W]) and `target`;
+ * `loss_grad` = device pointer to dL/dloss (the GradScaler scale; NULL = 1).  sign(0) = 0 as in torch. */
+int dg_l1_loss_sum(const float* y, const float* target, size_t count, double* sum, dg_stream_t stream);
+int dg_lw_backward_l1(const dg_lw_params* p, const float* x, const float* y, const float* target, const float* loss_grad,
+                      int32_t N, int32_t H, int32_t W, void* fwd_workspace, size_t fwd_bytes, void* bwd_workspace, size_t bwd_bytes,
+                      float* grads, dg_stream_t stream);
+
 /* Fused optimizer tail over flat buffers: torch.nn.utils.clip_grad_norm_(max_norm) (skipped if max_norm <= 0) followed by
  * torch.optim.AdamW (optimized_train.py:215-218,230-233,440-446).  grads are first multiplied by grad_scale (1/world after a
  * sum all-reduce).  `scratch` = one device double.  `step` counts from 1. */

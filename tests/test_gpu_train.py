@@ -246,7 +246,10 @@ def test_fused_adamw_checkpoint_roundtrip_with_torch_adamw(best_sd):
     oa = FusedAdamW(a.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
     for _ in range(2):
         step(a, oa)
-    ck = {"model_state_dict": {k: v.detach().clone() for k, v in a.state_dict().items()}, "optimizer_state_dict": oa.state_dict()}
+    import copy
+    # save_model (optimized_train.py:63-73) serialises right away; here the "file" is a deep copy (state_dict() hands out live views)
+    ck = {"model_state_dict": {k: v.detach().clone() for k, v in a.state_dict().items()},
+          "optimizer_state_dict": copy.deepcopy(oa.state_dict())}
     st = ck["optimizer_state_dict"]["state"]
     assert len(st) == 64 and all(set(v) == {"step", "exp_avg", "exp_avg_sq"} and float(v["step"]) == 2.0 for v in st.values())
     step(a, oa)                                             # the uninterrupted third step
@@ -262,7 +265,7 @@ def test_fused_adamw_checkpoint_roundtrip_with_torch_adamw(best_sd):
     step(c, oc)
     d = _net({k: v.detach().clone() for k, v in b.state_dict().items()}, path=1)
     od = FusedAdamW(d.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
-    od.load_state_dict(ob.state_dict())
+    od.load_state_dict(copy.deepcopy(ob.state_dict()))
     assert od._step == 3
     for (k, pa), pb, pc in zip(a.named_parameters(), b.parameters(), c.parameters()):
         assert float((pa - pb).abs().max()) <= 2e-6, k
@@ -322,3 +325,46 @@ def test_fp16_tier_tracks_fp32_oracle_loss_trajectory(best_sd):
     assert ref[-1] < ref[0]                                  # the oracle does learn on this batch
     assert np.abs(ours - ref).max() <= 0.02 * ref[0], (ours, ref)
     assert abs(ours[-1] - ref[-1]) <= 0.05 * abs(ref[0] - ref[-1]) + 1e-3
+
+
+@pytest.mark.parametrize("storage", ["fp32", "fp16"])
+def test_fused_l1_loss_and_direct_gradient_sink(best_sd, storage):
+    """`dg.L1Loss` (drop-in for optimized_train.py:439) computes the loss with one reduction kernel and lets the
+    head backward generate sign(o - t) / numel itself; with FusedAdamW the gradients land in the flat bucket without per-parameter
+    accumulate kernels.  Same loss and gradients as nn.L1Loss through ordinary autograd; a second backward before zero_grad
+    accumulates; the AMP loss scale reaches the kernel through a device pointer."""
+    from image_enhancement_deglaring_b200.train import FusedAdamW, L1Loss
+    x, t = _rand((3, 1, 64, 96), 31).cuda(), _rand((3, 1, 64, 96), 32).cuda()
+    ref = _net(best_sd, storage=storage)
+    loss_ref = torch.nn.L1Loss()(ref(x), t)
+    loss_ref.backward()
+    gref = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+    total = float(torch.sqrt(sum((v.double() ** 2).sum() for v in gref.values())))
+
+    def close(net, scale=1.0):
+        for k, p in net.named_parameters():   # fp32 atomics: summation-order noise only
+            assert float((p.grad - scale * gref[k]).norm()) <= 2e-5 * scale * float(gref[k].norm()) + 5e-7 * scale * total, k
+
+    # (1) fused loss, plain autograd accumulation
+    a = _net(best_sd, storage=storage)
+    la = L1Loss()(a(x), t)
+    assert abs(float(la) - float(loss_ref)) <= 1e-6
+    la.backward()
+    close(a)
+    # (2) fused loss + FusedAdamW: direct sink; then a second backward accumulates (2x); zero_grad resets
+    b = _net(best_sd, storage=storage)
+    opt = FusedAdamW(b.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    opt.zero_grad(set_to_none=True)
+    L1Loss()(b(x), t).backward()
+    assert all(p.grad.data_ptr() == opt.flat_g.data_ptr() + 4 * o for p, o in zip(b.parameters(), np.cumsum([0] + [q.numel() for q in b.parameters()][:-1])))
+    close(b)
+    L1Loss()(b(x), t).backward()
+    close(b, 2.0)
+    opt.zero_grad(set_to_none=True)
+    (L1Loss()(b(x), t) * 8.0).backward()           # dL/dloss = 8 reaches the head backward through a device scalar
+    close(b, 8.0)
+    # (3) anything that is not the module's own training output falls through to torch
+    y = torch.rand(2, 1, 8, 8, device="cuda", requires_grad=True)
+    z = torch.rand(2, 1, 8, 8, device="cuda")
+    assert torch.equal(L1Loss()(y, z), torch.nn.functional.l1_loss(y, z))
+    assert torch.equal(L1Loss(reduction="sum")(y, z), torch.nn.functional.l1_loss(y, z, reduction="sum"))
