@@ -2,8 +2,11 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
 
@@ -29,6 +32,21 @@ int check_launch(const char* what) {
     }
     return 0;
 }
+
+// NVTX ranges per fused kernel of the forward / backward (the reference has no tracing at all).  NVTX v3 is
+// header-only and a no-op unless a tool (Nsight Systems / Compute) injects itself; DG_NVTX=0 turns the calls off entirely.
+static bool nvtx_on() {
+    static const bool on = [] { const char* e = getenv("DG_NVTX"); return !(e && e[0] == '0'); }();
+    return on;
+}
+struct NvtxRange {
+    bool live;
+    explicit NvtxRange(const char* name) : live(nvtx_on()) { if (live) nvtxRangePushA(name); }
+    ~NvtxRange() { if (live) nvtxRangePop(); }
+};
+static const char* const kConvNames[18] = {"enc1.0", "enc1.3", "enc2.0", "enc2.3", "enc3.0", "enc3.3", "enc4.0", "enc4.3", "bottleneck.0",
+                                           "bottleneck.3", "up4+dec4.0", "dec4.3", "up3+dec3.0", "dec3.3", "up2+dec2.0", "dec2.3",
+                                           "up1+dec1.0", "dec1.3"};
 
 static int validate_src(const dg_src& s, const char* who) {
     if (s.raw == nullptr) { set_error("%s: null source pointer", who); return 2; }
@@ -141,6 +159,7 @@ static int lw_forward_range(const dg_lw_params* p, const LwPlan& pl, char* ws, c
     if (evs) cudaEventRecord(evs[0], stream);
     for (int i = 0; i < 18; ++i) {
         const int b = i / 2;
+        NvtxRange range(kConvNames[i]);
         dg_conv3x3_args a;
         memset(&a, 0, sizeof(a));
         a.dtype = p->dtype;
@@ -199,6 +218,7 @@ static int lw_forward_range(const dg_lw_params* p, const LwPlan& pl, char* ws, c
         if (rc) return rc;
         if (evs) cudaEventRecord(evs[i + 1], stream);
     }
+    NvtxRange head_range("head");
     dg_head_args h;
     memset(&h, 0, sizeof(h));
     h.src = gn_src(p, pl, ws, 17, DG_X_SAME, n0);
@@ -465,6 +485,9 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
     if (rc) return rc;
     for (int i = 17; i >= 0; --i) {
         const int b = i / 2, j = i % 2, C = pl.conv_c[i], Hi = pl.conv_h[i], Wi = pl.conv_w[i];
+        char rname[32];
+        snprintf(rname, sizeof(rname), "bwd %s", kConvNames[i]);
+        NvtxRange range(rname);
         // dW_i: same sources as the forward conv, correlated with dR_i; written in the parameter's [Co][Ci][3][3] layout
         dg_conv3x3_args a;
         fwd_conv_args(p, pl, fw, x, N, i, &a, n0);

@@ -256,20 +256,20 @@ def test_fused_adamw_checkpoint_roundtrip_with_torch_adamw(best_sd):
     # resume into torch.optim.AdamW ...
     b = _net(ck["model_state_dict"], path=1)
     ob = torch.optim.AdamW(b.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
-    ob.load_state_dict(ck["optimizer_state_dict"])
-    step(b, ob)
+    ob.load_state_dict(copy.deepcopy(ck["optimizer_state_dict"]))   # torch.load would hand out fresh tensors; load_state_dict
+    step(b, ob)                                                     # adopts the given ones and AdamW then updates them in place
     # ... and into a fresh FusedAdamW (from its own checkpoint and from the plain AdamW's)
     c = _net(ck["model_state_dict"], path=1)
     oc = FusedAdamW(c.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
-    oc.load_state_dict(ck["optimizer_state_dict"])
+    oc.load_state_dict(copy.deepcopy(ck["optimizer_state_dict"]))
     step(c, oc)
     d = _net({k: v.detach().clone() for k, v in b.state_dict().items()}, path=1)
     od = FusedAdamW(d.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
     od.load_state_dict(copy.deepcopy(ob.state_dict()))
     assert od._step == 3
     for (k, pa), pb, pc in zip(a.named_parameters(), b.parameters(), c.parameters()):
-        assert float((pa - pb).abs().max()) <= 2e-6, k
-        assert float((pa - pc).abs().max()) <= 2e-6, k
+        assert float((pa - pb).abs().max()) <= 2e-6, f"{k}: resumed torch.optim.AdamW vs uninterrupted"
+        assert float((pa - pc).abs().max()) <= 2e-6, f"{k}: resumed FusedAdamW vs uninterrupted"
     with pytest.raises(ValueError, match="single param group"):
         ps = list(_net(best_sd, path=1).parameters())
         FusedAdamW([{"params": ps[:10]}, {"params": ps[10:], "lr": 1e-4}])
