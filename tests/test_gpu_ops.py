@@ -407,7 +407,9 @@ T5_CASES = [("pool", 16, 32, 128, 128), ("same", 32, 32, 128, 128), ("cat2", 64,
             ("same", 32, 32, 16, 16), ("same", 64, 64, 12, 40), ("pool", 32, 64, 6, 10), ("cat2", 64, 32, 10, 36),
             ("same", 128, 128, 2, 2), ("pool", 64, 128, 1, 1), ("same", 64, 64, 48, 80),
             ("same", 256, 256, 16, 16), ("pool", 128, 256, 16, 32), ("cat2", 512, 256, 16, 16), ("same", 512, 512, 8, 8),
-            ("pool", 512, 1024, 4, 4), ("same", 1024, 1024, 4, 8), ("cat2", 1024, 512, 8, 8)]
+            ("pool", 512, 1024, 4, 4), ("same", 1024, 1024, 4, 8), ("cat2", 1024, 512, 8, 8),
+            # images wider than 128 columns are cut into column strips of 126 (+ 2 halo) columns: wide variant levels 1-2
+            ("same", 64, 64, 24, 272), ("pool", 64, 128, 8, 160), ("cat2", 128, 64, 6, 130), ("same", 64, 64, 512, 512)]
 
 
 @pytest.mark.parametrize("dtype", TC_DTYPES)
@@ -434,7 +436,7 @@ def test_t5_warp_specialised_tcgen05_conv(dtype, mode, cin, cout, H, W):
 
 @pytest.mark.parametrize("dtype", TC_DTYPES)
 @pytest.mark.parametrize("c,H,W", [(64, 16, 32), (32, 16, 32), (64, 2, 2), (32, 6, 10), (128, 32, 32), (256, 16, 16), (512, 8, 8),
-                                     (64, 128, 128)])
+                                     (64, 128, 128), (64, 8, 520), (64, 512, 512)])
 def test_t5_convtranspose(dtype, c, H, W):
     """ConvTranspose2d(2c -> c, k=2, s=2) + bias of the activated low-resolution tensor on the tcgen05 kernel (1-tap GEMM, N = 4c):
     upconv4 / upconv3 of the shipped model and every up-convolution of the wide variant."""

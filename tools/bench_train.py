@@ -31,13 +31,13 @@ a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 sd = torch.load(os.path.join(ROOT, "weights", "best_model.pth"))
 net = dg.LightweightUNet(storage=a.storage)
 net.load_state_dict(sd, strict=True)
 net = net.cuda().train()
 opt = FusedAdamW(net.parameters(), lr=0.002362532125818593, weight_decay=6.753784966611083e-05, max_grad_norm=1.0)
-crit = torch.nn.L1Loss()
+crit = dg.L1Loss()   # drop-in for nn.L1Loss (fused seed)
 x = torch.rand(a.batch, 1, a.hw, a.hw, generator=torch.Generator().manual_seed(rank)).cuda()
 t = torch.rand(a.batch, 1, a.hw, a.hw, generator=torch.Generator().manual_seed(100 + rank)).cuda()
 
