@@ -26,13 +26,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.dg_launch_count() == 0  # nothing may launch without a GPU
 
 
-def test_struct_layouts_match_header_sizes():
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """The ctypes mirrors must have the size the C compiler gives the structs of include/deglare.h (gcc compiles the header as C)."""
     import ctypes as C
+    import subprocess
     from image_enhancement_deglaring_b200 import _lib
-    # 8 pointers + 6 int32; 2 srcs + 6 int32 + 5 pointers + float + int32; ...
+    src = tmp_path / "sz.c"
+    src.write_text('#include "deglare.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(dg_src), '
+                   'sizeof(dg_conv3x3_args), sizeof(dg_head_args), sizeof(dg_lw_params)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    assert sizes == [C.sizeof(_lib.DgSrc), C.sizeof(_lib.DgConv3x3Args), C.sizeof(_lib.DgHeadArgs), C.sizeof(_lib.DgLwParams)]
     assert C.sizeof(_lib.DgSrc) == 9 * 8 + 6 * 4
-    assert C.sizeof(_lib.DgConv3x3Args) == 2 * C.sizeof(_lib.DgSrc) + 6 * 4 + 9 * 8 + 8 + 8
-    assert C.sizeof(_lib.DgHeadArgs) == C.sizeof(_lib.DgSrc) + 5 * 4 + 4 + 5 * 8 + 8
 
 
 def test_module_surface_matches_reference_contract(best_sd, golden):
