@@ -394,6 +394,25 @@ def main():
                     n1(x1)
                 ev[1].record()
                 torch.cuda.synchronize()
+                # the same forward captured once and replayed as a CUDA graph (launch overhead off the critical path)
+                graph_ms = None
+                try:
+                    g1, gs = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+                    with torch.cuda.stream(gs):
+                        with torch.cuda.graph(g1, stream=gs):
+                            n1(x1)
+                    g1.replay()
+                    gev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                    torch.cuda.synchronize()
+                    gev[0].record()
+                    for _ in range(50):
+                        g1.replay()
+                    gev[1].record()
+                    torch.cuda.synchronize()
+                    graph_ms = gev[0].elapsed_time(gev[1]) / 50
+                    del g1
+                except RuntimeError as e:   # reported, not hidden
+                    graph_ms = f"capture failed: {str(e)[:80]}"
             s1 = InferenceSession(n1, chunk=1)
             xh = x1.cpu().numpy()
             for _ in range(3):
@@ -401,9 +420,11 @@ def main():
             tl = time.perf_counter()
             for _ in range(20):
                 s1.run(["output"], {"input": xh})
-            latency_n1[storage] = {"device_ms": ev[0].elapsed_time(ev[1]) / 50, "session_run_ms": (time.perf_counter() - tl) / 20 * 1e3}
+            latency_n1[storage] = {"device_ms": ev[0].elapsed_time(ev[1]) / 50, "graph_replay_ms": graph_ms,
+                                   "session_run_ms": (time.perf_counter() - tl) / 20 * 1e3}
             del n1, s1
         latency_n1["what"] = ("one 1x1x512x512 image: device_ms = module forward with the input resident in HBM (CUDA events, mean of 50); "
+                              "graph_replay_ms = the same forward replayed from a captured CUDA graph; "
                               "session_run_ms = InferenceSession.run from a pageable numpy array and back (api/app.py:171 call shape)")
 
     # ---- BASELINE.json configs[4]: the wide variant LightweightUNet(features_start=64), 31.0 M parameters, 384.7 GFLOP per

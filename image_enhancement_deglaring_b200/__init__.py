@@ -8,3 +8,6 @@ __all__.append("OptimizedUNet")
 from .train import FusedAdamW, L1Loss  # noqa: E402,F401
 
 __all__ += ["FusedAdamW", "L1Loss"]
+from . import imageops  # noqa: E402,F401  (device-side PIL / OpenCV pre- and post-processing)
+
+__all__.append("imageops")

@@ -110,6 +110,19 @@ class InferenceSession:
         self.run_pinned_u8(*self._pin8)
         return self._pin8[1].numpy().copy()
 
+    def infer_image(self, image, size=512):
+        """Everything api/app.py:136-203 computes between PNG decode and PNG encode, on the device: `image` = the decoded upload as
+        a uint8 ndarray [H,W] (mode L) or [H,W,3|4] (RGB / RGBA) -> uint8 ndarray [H,W], the enhanced image at the upload's size
+        (PIL convert('L') + LANCZOS to size x size, /255, the network, clip * 255 -> uint8, LANCZOS back; imageops.infer_image).
+        Bit-identical to running those PIL calls on the host around `run_u8`."""
+        from . import imageops
+        img = np.ascontiguousarray(image)
+        if img.dtype != np.uint8 or img.ndim not in (2, 3):
+            raise RuntimeError(f"expected a uint8 image [H,W] or [H,W,C], got {img.dtype} {img.shape}")
+        with torch.cuda.device(self.device):
+            out = imageops.infer_image(self.model, torch.from_numpy(img).to(self.device, non_blocking=True), size)
+        return out[0].cpu().numpy()
+
     def run(self, output_names, input_feed, run_options=None):
         x = input_feed[self._in.name]
         x = np.ascontiguousarray(x, dtype=np.float32)

@@ -285,6 +285,37 @@ int dg_dec_composite_bytes(int32_t cl, int32_t cu, size_t* bytes);
 int dg_pack_dec_composite(const float* ct_w, const float* ct_b, const float* conv_w, void* out, int32_t cl, int32_t cu,
                           int32_t dtype, dg_stream_t stream);
 
+/* ---- image pre/post-processing on the device ------------------- */
+/* Replaces the host calls of api/app.py:143-150 -- `Image.fromarray(img).convert('L')` and `.resize((512, 512), Image.LANCZOS)` -- and
+ * of api/app.py:199-203 (resize of the uint8 result back to the upload's size), bit-exactly: Pillow's rgb2l (16-bit fixed point) and
+ * its two-pass resampler with 22-bit fixed-point taps and uint8 rounding after each pass (libImaging/Convert.c, Resample.c).
+ * src: uint8 [N][in_h][in_w][channels], channels 1 (L), 3 (RGB) or 4 (RGBA, alpha ignored);  dst: uint8 [N][out_h][out_w].
+ * bounds_* int32 [out][2] = (first source index, tap count), kk_* int32 [out][ksize_*]: Pillow's precompute_coeffs +
+ * normalize_coeffs_8bpc tables (device memory; the host binding computes them, imageops.pil_lanczos_tables).  A pass whose size does
+ * not change is skipped as in Pillow (its tables may be NULL).  [row0, row0 + rows) = the source rows the vertical pass reads
+ * (Pillow's ybox); tmp holds the horizontal result, N * rows * out_w bytes. */
+int dg_pil_resize_u8(const uint8_t* src, int32_t channels, int32_t N, int32_t in_h, int32_t in_w, uint8_t* dst, int32_t out_h,
+                     int32_t out_w, const int32_t* bounds_h, const int32_t* kk_h, int32_t ksize_h, const int32_t* bounds_v,
+                     const int32_t* kk_v, int32_t ksize_v, int32_t row0, int32_t rows, uint8_t* tmp, size_t tmp_bytes,
+                     dg_stream_t stream);
+
+/* Replaces src/optimized_dataset.py:104-123 (and :56-82): the triptych split is the column panel [x_off, x_off + in_w) of an image of
+ * width in_w_full (`img[:, :third]`, `img[:, third:2*third]`), then cv2.cvtColor(COLOR_RGB2GRAY) (15-bit fixed point) when
+ * channels == 3 and cv2.resize(..., (out_w, out_h)) (INTER_LINEAR on uint8: 11-bit taps; exact 2x down-scaling takes the library's
+ * INTER_AREA fast path), bit-exactly.  xofs / yofs int32 [out], xab / yab int32 [out][2]: source index and the two taps per
+ * destination index (imageops.cv2_linear_tables).  src uint8 [N][in_h][in_w_full][channels], dst uint8 [N][out_h][out_w]. */
+int dg_cv2_resize_u8(const uint8_t* src, int32_t channels, int32_t N, int32_t in_h, int32_t in_w_full, int32_t x_off, int32_t in_w,
+                     uint8_t* dst, int32_t out_h, int32_t out_w, const int32_t* xofs, const int32_t* xab, const int32_t* yofs,
+                     const int32_t* yab, dg_stream_t stream);
+
+/* Replaces the per-sample albumentations pipeline of src/optimized_dataset.py:126-127,159-172 given the SAMPLED parameters:
+ * image / mask uint8 [N][H][W] -> float32 [N][1][H][W] = x / 255; HorizontalFlip of both; on the image only
+ * RandomBrightnessContrast = clip(alpha x + beta, 0, 1) and GaussNoise = clip(x + N(0, sigma), 0, 1).
+ * params float32 [N][4] = (flip != 0, alpha, beta, sigma); alpha = 1, beta = 0, sigma = 0 switch a transform off.  The noise field
+ * comes from a counter-based generator keyed on (seed, sample, pixel) -- not albumentations' stream.  mask / mask_out may be NULL. */
+int dg_augment(const uint8_t* image, const uint8_t* mask, float* image_out, float* mask_out, int32_t N, int32_t H, int32_t W,
+               const float* params, uint64_t seed, dg_stream_t stream);
+
 /* ---- misc --------------------------------------------------------------------------- */
 const char* dg_last_error_string(void);
 int dg_version(void);

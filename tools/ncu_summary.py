@@ -1,10 +1,14 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (raw page) into one line per kernel launch: time, DRAM bytes, pipe utilisation, stalls.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--names a,b,c] > profiles/xxx.txt
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--names a,b,c] [--json launches.json] > profiles/xxx.txt
+
+--json also writes [{"kernel", "us", "read", "write"}] per launch (DRAM bytes), the input of profiles/ncu_traffic.json.  Run it on the
+GPU box right after the capture and delete the .ncu-rep there: a --set full report of one forward is larger than what gpurun copies back.
 """
 import csv
 import io
+import json
 import subprocess
 import sys
 
@@ -45,3 +49,8 @@ for i, r in enumerate(data):
           f"{f(r, 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'):5.1f} "
           f"{f(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'):6.1f} {r[ix['launch__registers_per_thread']]:>4s} "
           f"{f(r, 'smsp__inst_executed.sum') / 1e6:7.1f}  " + " ".join(f"{n}={v:.1f}" for v, n in st))
+
+if "--json" in sys.argv:
+    with open(sys.argv[sys.argv.index("--json") + 1], "w") as fh:
+        json.dump([{"kernel": r[ix["Kernel Name"]], "us": tounit(r, "gpu__time_duration.sum", 1e-6),
+                    "read": tounit(r, "dram__bytes_read.sum", 1.0), "write": tounit(r, "dram__bytes_write.sum", 1.0)} for r in data], fh, indent=1)
