@@ -199,7 +199,10 @@ static int lw_forward_range(const dg_lw_params* p, const LwPlan& pl, char* ws, c
             a.weight_comp = p->dec_comp[u];
             // deep levels (upconv4, upconv3; upconv2 with path bit 5): run the transposed conv as its own tensor-core GEMM and
             // feed its output as an identity source -- see convt_tc.cu for why this beats fusing there
-            const bool unfuse = p->dtype != DG_F32 && (p->path & 3) != 1 && lw_up_materialised(p, pl, u);
+            // composite weights present for a level the tcgen05 decoder mode covers (C_up >= 16): ConvTranspose, concat and conv run
+            // as one low-resolution conv in conv3x3_t5.cu -- no stand-alone ConvTranspose, no `up` tensor
+            const bool dec_t5 = p->dec_comp[u] != nullptr && !(p->path & (128 | 1024)) && pl.f[lvl] >= 16;
+            const bool unfuse = p->dtype != DG_F32 && (p->path & 3) != 1 && lw_up_materialised(p, pl, u) && !dec_t5;
             if (unfuse) {
                 bool handled = false;
                 void* up = ws + pl.up_off[u] + (size_t)n0 * a.H * a.W * pl.f[lvl] * esz;

@@ -138,8 +138,12 @@ class LightweightUNet(nn.Module):
                 wbf = wtc if pc.dtype == ops.DG_BF16 else ops.pack_convt2x2_tc(w, ops.DG_BF16)
             pc.up_w_tc_bf16[u] = None if wbf is None else wbf.data_ptr()
             # composite decoder taps (ConvTranspose folded into the consuming conv, conv3x3_dec.cu) where that kernel has coverage
+            # level 1 (16 -> 8): conv3x3_dec.cu's kernel, forward of both modes.  Levels 2-4 (32 -> 16, 64 -> 32, 128 -> 64) have the
+            # tcgen05 decoder mode of conv3x3_t5.cu (ConvTranspose + cat + conv as one low-resolution conv): correct but measured
+            # slower than the default kernels, so it is opt-in with path bit 11 (2048), inference only
             comp = None
-            if self.path != 1 and pc.dtype != ops.DG_F32:
+            cu_ = int(w.shape[3])
+            if self.path != 1 and pc.dtype != ops.DG_F32 and (cu_ == 8 or ((self.path & 2048) and not train)):
                 dblk = getattr(self, _BLOCKS[5 + u])
                 comp = ops.pack_dec_composite(w, bt, ops.pack_conv3x3(dblk[0].weight), pc.dtype)
             pc.dec_comp[u] = None if comp is None else comp.data_ptr()

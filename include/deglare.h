@@ -105,7 +105,8 @@ typedef struct {
                              bit 4: producer-side GroupNorm finalisation; bit 5: un-fuse upconv2 as well;
                              bit 6: round-1 tcgen05 kernel (opt-in); bit 7: do not use the round-2 tcgen05 kernel (conv3x3_t5.cu);
                              bit 8: insist on it (tests); bit 9 / bit 10: do not use the persistent TMA-fed 8 -> 8 kernel
-                             (conv3x3_ring.cu) / the composite decoder kernel (conv3x3_dec.cu)                                  */
+                             (conv3x3_ring.cu) / the composite decoder kernels (conv3x3_dec.cu, conv3x3_t5.cu decoder mode);
+                             bit 11 (module level): also pack the composite blobs of the 32 -> 16 ... 128 -> 64 decoders           */
     const void* weight_comp;  /* optional, decoder conv over (DG_X_CONVT2 low, DG_X_SAME skip) only: dg_pack_dec_composite blob --
                                  the ConvTranspose folded into the conv's taps (conv3x3_dec.cu); NULL = stage `up` in the CTA  */
 } dg_conv3x3_args;
@@ -280,7 +281,10 @@ int dg_pack_convt2x2_tc(const float* w, void* out, int32_t cin, int32_t cout, in
 
 /* Composite decoder taps (conv3x3_dec.cu): ConvTranspose2d(k=2, s=2)+bias folded into the 3x3 conv that consumes cat((up, skip)).
  * ct_w fp32 [2][2][cl][cu], ct_b [cu], conv_w fp32 [3][3][2 cu][cu] (the packings dg_conv3x3_fused takes); out = blob of
- * *bytes bytes in `dtype`.  Covers (cl, cu) = (16, 8) -- upconv1 + dec1.0 of LightweightUNet(features_start=8), src/model.py:53,54. */
+ * *bytes bytes in `dtype`.  Covers (cl, cu) = (16, 8) -- upconv1 + dec1.0 of LightweightUNet(features_start=8), src/model.py:53,54 --
+ * for the kernel of conv3x3_dec.cu, and (32, 16), (64, 32), (128, 64) for the tcgen05 decoder mode of conv3x3_t5.cu (the three
+ * layers as ONE 3x3 conv on the low-resolution grid: fp32 [3][3][3 cl][4 cu] composite taps in the tensor-core packing followed by
+ * the 9 border-kind bias vectors [9][cu]); dg_conv3x3_fused uses whichever blob `weight_comp` holds for the channel set. */
 int dg_dec_composite_bytes(int32_t cl, int32_t cu, size_t* bytes);
 int dg_pack_dec_composite(const float* ct_w, const float* ct_b, const float* conv_w, void* out, int32_t cl, int32_t cu,
                           int32_t dtype, dg_stream_t stream);
