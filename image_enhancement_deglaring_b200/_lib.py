@@ -65,6 +65,10 @@ SYMBOLS = {
     "dg_conv3x3_fused": (C.c_int, [C.POINTER(DgConv3x3Args), C.c_void_p]),
     "dg_conv3x3_wgrad": (C.c_int, [C.POINTER(DgConv3x3Args), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p]),
+    "dg_conv3x3_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p]),
+    "dg_convt2x2_dgrad": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p]),
     "dg_head1x1": (C.c_int, [C.POINTER(DgHeadArgs), C.c_void_p]),
     "dg_pil_resize_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -751,6 +751,24 @@ int dg_conv3x3_wgrad(const dg_conv3x3_args* a, const float* dR, float* dW, int32
     return conv3x3_wgrad_launch(*a, dR, dW, s_tap, s_ci, s_co, st);
 }
 
+int dg_conv3x3_dgrad(const float* dR, const void* weight_tc_bf16, float* dX, int32_t N, int32_t H, int32_t W, int32_t cin,
+                     int32_t cout, dg_stream_t stream) {
+    if (dR == nullptr || weight_tc_bf16 == nullptr || dX == nullptr) { set_error("dgrad: null pointer"); return 2; }
+    bool handled = false;
+    int rc = conv3x3_dgrad_tc_launch(dR, weight_tc_bf16, dX, N, H, W, cout, cin, reinterpret_cast<cudaStream_t>(stream), &handled);
+    if (rc == 0 && !handled) { set_error("dgrad: no tensor-core kernel for %d -> %d channels (or unaligned pointers)", cin, cout); return 3; }
+    return rc;
+}
+
+int dg_convt2x2_dgrad(const float* dCat, int32_t stride, const void* ct_w_tc_bf16, float* dLow, int32_t N, int32_t H, int32_t W,
+                      int32_t cl, int32_t cu, dg_stream_t stream) {
+    if (dCat == nullptr || ct_w_tc_bf16 == nullptr || dLow == nullptr) { set_error("convT dgrad: null pointer"); return 2; }
+    bool handled = false;
+    int rc = convt_dgrad_tc_launch(dCat, stride, ct_w_tc_bf16, dLow, N, H, W, cl, cu, reinterpret_cast<cudaStream_t>(stream), &handled);
+    if (rc == 0 && !handled) { set_error("convT dgrad: no tensor-core kernel for %d -> %d channels / this shape", cl, cu); return 3; }
+    return rc;
+}
+
 int dg_image_metrics(const float* output, const float* target, int32_t N, int32_t H, int32_t W, int32_t clip01, double data_range,
                      double* acc, dg_stream_t stream) {
     if (output == nullptr || target == nullptr || acc == nullptr) { set_error("metrics: null pointer"); return 2; }

@@ -144,6 +144,26 @@ def conv3x3_wgrad(srcs, dR, cin_total, cout, N, H, W, dtype, path=0, stream=None
     return dW
 
 
+def conv3x3_dgrad(dR, weight_tc_bf16, cin, cout, stream=None):
+    """Data gradient of the 3x3 conv on the tensor cores (dg_conv3x3_dgrad): dR fp32 NHWC [N,H,W,cout] -> dX fp32 NHWC [N,H,W,cin];
+    weight_tc_bf16 = pack_conv3x3_tc(pack_conv3x3(weight), DG_BF16) of the FORWARD weights."""
+    _require_cuda(dR, weight_tc_bf16)
+    N, H, W, _ = dR.shape
+    dX = torch.empty((N, H, W, cin), dtype=torch.float32, device=dR.device)
+    _lib.check(_lib.load().dg_conv3x3_dgrad(_ptr(dR), _ptr(weight_tc_bf16), _ptr(dX), N, H, W, cin, cout, _stream(stream)))
+    return dX
+
+
+def convt2x2_dgrad(dCat, ct_w_tc_bf16, cl, cu, stream=None):
+    """Data gradient of ConvTranspose2d(2,2) on the tensor cores (dg_convt2x2_dgrad): the first cu channels of dCat fp32 NHWC
+    [N,H,W,stride] -> dLow fp32 NHWC [N,H/2,W/2,cl]; ct_w_tc_bf16 = pack_convt2x2_tc(pack_convt2x2(weight), DG_BF16)."""
+    _require_cuda(dCat, ct_w_tc_bf16)
+    N, H, W, stride = dCat.shape
+    dLow = torch.empty((N, H // 2, W // 2, cl), dtype=torch.float32, device=dCat.device)
+    _lib.check(_lib.load().dg_convt2x2_dgrad(_ptr(dCat), stride, _ptr(ct_w_tc_bf16), _ptr(dLow), N, H, W, cl, cu, _stream(stream)))
+    return dLow
+
+
 def head1x1(src, weight, bias, N, H, W, dtype, out=None, target=None, l1_sum=None, stream=None, eps=1e-5):
     lib = _lib.load()
     cout = weight.shape[0]

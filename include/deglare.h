@@ -122,6 +122,18 @@ int dg_conv3x3_fused(const dg_conv3x3_args* args, dg_stream_t stream);
 int dg_conv3x3_wgrad(const dg_conv3x3_args* args, const float* dR, float* dW, int32_t s_tap, int32_t s_ci, int32_t s_co,
                      dg_stream_t stream);
 
+/* Data gradients on the tensor cores (16-bit tiers of dg_lw_backward; exposed for per-op tests), bf16 operands, fp32 accumulate:
+ *   dg_conv3x3_dgrad:  dX[n,y,x,ci] = sum_{ky,kx,co} dR[n, y+1-ky, x+1-kx, co] * W[co][ci][ky][kx]  (autograd of src/model.py:93,96
+ *     w.r.t. the conv INPUT); dR fp32 NHWC [N,H,W,cout], dX fp32 NHWC [N,H,W,cin]; weight_tc_bf16 = the FORWARD weights in
+ *     dg_pack_conv3x3_tc(..., DG_BF16) packing (read transposed, no second layout).  Covers the (cin, cout) pairs of
+ *     LightweightUNet(features_start=8) except the first layer; returns 3 otherwise.
+ *   dg_convt2x2_dgrad: dLow[n,i,j,ci] = sum_{a,b,co} dCat[n, 2i+a, 2j+b, co] * Wt[ci][co][a][b] (autograd of src/model.py:47-53) from
+ *     the first cu channels of dCat fp32 [N,H,W,stride]; dLow fp32 [N,H/2,W/2,cl]; ct_w_tc_bf16 = dg_pack_convt2x2_tc(..., DG_BF16). */
+int dg_conv3x3_dgrad(const float* dR, const void* weight_tc_bf16, float* dX, int32_t N, int32_t H, int32_t W, int32_t cin,
+                     int32_t cout, dg_stream_t stream);
+int dg_convt2x2_dgrad(const float* dCat, int32_t stride, const void* ct_w_tc_bf16, float* dLow, int32_t N, int32_t H, int32_t W,
+                      int32_t cl, int32_t cu, dg_stream_t stream);
+
 /* Output head: GroupNorm+SiLU of the last block, then nn.Conv2d(C, out_channels, 1) + bias
  * (src/model.py:57,131; src/optimized_model.py:74,158).  fp32 (or quantised uint8) NCHW output.  If `target` is
  * given, also accumulates sum|out-target| into *l1_sum (nn.L1Loss forward, optimized_train.py:439). */

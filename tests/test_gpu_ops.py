@@ -585,6 +585,65 @@ def test_t5_decoder_mode(dtype, c, N, H, W):
         assert not torch.equal(o_c, o_h)
 
 
+DGRAD_CASES = [(8, 8), (8, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128), (128, 64), (64, 32), (32, 16), (16, 8)]
+
+
+@pytest.mark.parametrize("cin,cout", DGRAD_CASES)
+@pytest.mark.parametrize("N,H,W", [(2, 32, 64), (3, 24, 40), (1, 8, 8)])
+def test_dgrad_tc_matches_autograd(cin, cout, N, H, W):
+    """dg_conv3x3_dgrad (dgrad_tc.cu: reads the forward weights' tensor-core packing transposed, bf16 operands) vs autograd of
+    F.conv2d w.r.t. its input (src/model.py:93,96), every (C_in, C_out) pair of the shipped network."""
+    rs = _rs(41 + cin + cout)
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) / np.sqrt(9 * cin)).astype(np.float32))
+    dR = torch.from_numpy(rs.standard_normal((N, cout, H, W)).astype(np.float32))
+    x = torch.zeros(N, cin, H, W, requires_grad=True)
+    F.conv2d(x, w, None, 1, 1).backward(dR)
+    ref = x.grad
+    wtc = ops.pack_conv3x3_tc(ops.pack_conv3x3(w.cuda()), ops.DG_BF16)
+    got = ops.conv3x3_dgrad(dR.permute(0, 2, 3, 1).contiguous().cuda(), wtc, cin, cout).cpu().permute(0, 3, 1, 2)
+    # bf16 rounding of both operands: relative 2^-8 per product, sqrt(9 cout) products per sum
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 1.5e-2 * scale, f"{float((got - ref).abs().max()):.3e} vs scale {scale:.3e}"
+    rel = float((got - ref).norm() / ref.norm())
+    assert rel <= 5e-3, rel
+    # against the same product with operands rounded the way the kernel rounds them: tight
+    xq = torch.zeros(N, cin, H, W, requires_grad=True)
+    F.conv2d(xq, w.bfloat16().float(), None, 1, 1).backward(dR.bfloat16().float())
+    assert float((got - xq.grad).abs().max()) <= 2e-5 * max(1.0, scale) * np.sqrt(9 * cout)
+
+
+@pytest.mark.parametrize("cl,cu", [(128, 64), (64, 32), (32, 16), (16, 8)])
+@pytest.mark.parametrize("N,H,W,interleaved", [(2, 32, 64, True), (3, 16, 24, False), (1, 8, 8, True)])
+def test_convt_dgrad_tc_matches_autograd(cl, cu, N, H, W, interleaved):
+    """dg_convt2x2_dgrad vs autograd of F.conv_transpose2d w.r.t. its input (src/model.py:47-53); the up-half gradient is read from
+    the concat gradient either interleaved with the skip half (stride 2 C) or compact (stride C)."""
+    rs = _rs(43 + cl)
+    wt = torch.from_numpy((rs.standard_normal((cl, cu, 2, 2)) / np.sqrt(cl)).astype(np.float32))
+    dUp = torch.from_numpy(rs.standard_normal((N, cu, H, W)).astype(np.float32))
+    low = torch.zeros(N, cl, H // 2, W // 2, requires_grad=True)
+    F.conv_transpose2d(low, wt, None, stride=2).backward(dUp)
+    ref = low.grad
+    nhwc = dUp.permute(0, 2, 3, 1).contiguous()
+    dCat = torch.cat((nhwc, torch.full_like(nhwc, 7.0)), 3).contiguous() if interleaved else nhwc   # the skip half must be ignored
+    wtc = ops.pack_convt2x2_tc(ops.pack_convt2x2(wt.cuda()), ops.DG_BF16)
+    got = ops.convt2x2_dgrad(dCat.cuda(), wtc, cl, cu).cpu().permute(0, 3, 1, 2)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 1.5e-2 * scale
+    assert float((got - ref).norm() / ref.norm()) <= 5e-3
+    lq = torch.zeros(N, cl, H // 2, W // 2, requires_grad=True)
+    F.conv_transpose2d(lq, wt.bfloat16().float(), None, stride=2).backward(dUp.bfloat16().float())
+    assert float((got - lq.grad).abs().max()) <= 2e-5 * max(1.0, scale) * np.sqrt(4 * cu)
+
+
+def test_dgrad_refuses_uncovered_channel_sets():
+    dR = torch.zeros(1, 8, 8, 24, device="cuda")
+    w = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="no tensor-core kernel"):
+        ops.conv3x3_dgrad(dR, w, 24, 24)
+    with pytest.raises(RuntimeError, match="no tensor-core kernel"):
+        ops.convt2x2_dgrad(dR, w, 48, 24)
+
+
 def test_tc_path_refuses_unsupported():
     w = torch.zeros(3, 3, 24, 24, device="cuda")
     raw = torch.zeros(1, 8, 8, 24, device="cuda", dtype=torch.float16)
