@@ -175,6 +175,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     batch = args.ref_batch
+    if batch <= 0:   # the GPU arm's per-step batch when the whole run stays within a few minutes, else a bounded sample of it
+        batch = args.batch if (args.steps + args.warmup) * args.batch <= 4096 else max(1, 4096 // (args.steps + args.warmup))
     t0 = time.perf_counter()
     import torch
     cores = os.cpu_count() or 1
@@ -189,17 +191,18 @@ def run_reference(args, rank, world):
             fwd(x)
         dt = time.perf_counter() - t
     rate = batch * args.steps / dt
-    sample = (f"{args.steps} steps x {batch} images of 1x{args.hw}x{args.hw}, fp32, torch CPU {cores} threads; a bounded sample of the "
-              f"configs[1] workload (the GPU arm runs batch {args.batch} x 1x{args.hw}x{args.hw} in 16-bit storage: per-image CPU cost is flat in "
-              "the batch size, measured 8 vs 1)")
+    sample = (f"{args.steps} steps x {batch} images of 1x{args.hw}x{args.hw}, fp32, torch CPU {cores} threads"
+              + ("" if batch == args.batch else f"; a bounded sample of the GPU arm's batch of {args.batch} (per-image CPU cost is flat in "
+                                                "the batch size, measured 8 vs 1)"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"best_model.pth LightweightUNet inference, bounded sample of batch {batch} x 1x{args.hw}x{args.hw} "
-                               "(configs[1] shape), reference PyTorch-CPU path ("
-                               + ("the unmodified reference module, oracle/_ref" if kind == "reference" else "pinned oracle port") + ")",
-                   "batch": batch, "l2": "n/a (CPU)", "onnxruntime_cpu": onnxruntime_status()},
+        "config": {"workload": f"best_model.pth LightweightUNet (486,409 params) batched inference, batch {args.batch} x 1x{args.hw}x{args.hw} "
+                               "per GPU (BASELINE.json configs[1])",
+                   "arm": "reference PyTorch-CPU path, fp32 (" + ("the unmodified reference module, oracle/_ref" if kind == "reference"
+                                                                   else "pinned oracle port") + ")",
+                   "batch_per_step": batch, "l2": "n/a (CPU)", "onnxruntime_cpu": onnxruntime_status()},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -215,7 +218,7 @@ def main():
     ap.add_argument("--storage", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--hw", type=int, default=512)
-    ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--ref-batch", type=int, default=0, help="images per step of the CPU reference arm (0 = the GPU arm's batch, reduced only if steps x batch would exceed ~4096 images = a few minutes of CPU work)")
     ap.add_argument("--path", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[3] training-step measurement")
@@ -512,10 +515,11 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # rank 0 at N = 1 only (the other ranks would idle behind it)
         reps = 3
-        rate, cores, times, kind = cpu_reference_rate(args.ref_batch, reps, H, W)
+        cb = args.ref_batch if args.ref_batch > 0 else 8   # bounded sample: ~10 s of CPU work at 512x512
+        rate, cores, times, kind = cpu_reference_rate(cb, reps, H, W)
         rate1, _, times1, _ = cpu_reference_rate(1, 3, H, W) if H * W <= 512 * 512 else (None, None, [], None)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": f"median of {len(times)} forwards of {args.ref_batch} x 1x{H}x{W} fp32 images, torch CPU, "
+                        "sample": f"median of {len(times)} forwards of {cb} x 1x{H}x{W} fp32 images, torch CPU, "
                                   f"{cores} threads ({sum(times):.1f} s of CPU work)",
                         "batch1_ms": (1e3 / rate1 if rate1 else None),
                         "onnxruntime_cpu": onnxruntime_status()}
