@@ -326,6 +326,29 @@ def test_4096_square_image_as_64_tiles(best_sd):
         assert not torch.equal(out[:, 3 * 512:4 * 512, 5 * 512:6 * 512], out[:, 3 * 512:4 * 512, 4 * 512:5 * 512])
 
 
+def test_whole_image_4096_exact_groupnorm_on_one_gpu(best_sd):
+    """SURVEY 8e "definition B": the network applied to the WHOLE 4096x4096 image (GroupNorm statistics over the full image, receptive
+    fields across what would be tile borders) -- one dg_lw_forward call with N = 1, H = W = 4096 (2.1 GB of fp16 workspace, every
+    kernel on image-wide grids, the tcgen05 kernel on column strips) against the oracle; and it differs from the tiled result."""
+    from image_enhancement_deglaring_b200.tiling import infer_tiled
+    x = _rand((1, 1, 4096, 4096), 91)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = tpo.lightweight_forward(x, best_sd)
+    for storage, tol in (("fp16", 5e-3), ("fp32", 2e-4)):
+        net = _net(best_sd, storage=storage)
+        with torch.no_grad():
+            y = net(x.cuda())
+            err = float((y.cpu() - ref).abs().max())
+            assert err <= tol, f"{storage}: whole-image max-abs {err:.3e}"
+            if storage == "fp16":
+                assert psnr(y.cpu().numpy(), ref.numpy()) >= 50.0
+                tiled = infer_tiled(net, x[0, 0].cuda(), tile=512, batch=16)
+                assert float((tiled - y[0]).abs().max()) > 1e-3          # tiling is a different function (definition A)
+        del net, y
+        torch.cuda.empty_cache()
+
+
 def test_headline_config_batch64_512_fp16_matches_oracle(best_sd):
     """The configuration bench.py quotes -- batch 64 x 1x512x512, fp16 storage, default two-stream split, every persistent kernel on
     full grids -- against the oracle on the same seeded inputs: max-abs <= 5e-3 and PSNR >= 50 dB per image (north_star)."""
