@@ -282,6 +282,32 @@ def forward_band(net, x_band, comm, H_total, backend=None):
     return y[:, ht:ht + Hb]
 
 
+class BandGraph:
+    """forward_band captured ONCE in a CUDA graph (kernels, the small statistics / affine ops and the NCCL all-reduces and
+    send/recv pairs alike) and replayed per image: a band's forward is ~60 kernels of a few microseconds each plus ~35 tiny
+    collectives, i.e. host-launch bound when issued from Python.  Fixed shape; weights are read at capture time."""
+
+    def __init__(self, net, comm, H_total, W, backend=None, warmup=2):
+        be = backend or KernelBackend(net)
+        r0, r1 = band_rows(H_total, comm.rank, comm.world)
+        rows = (r1 - r0) + (HALO if comm.rank > 0 else 0) + (HALO if comm.rank < comm.world - 1 else 0)
+        self.x = torch.zeros((rows, W), dtype=torch.float32, device=be.device)
+        side = torch.cuda.Stream(device=be.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():      # lazy initialisations (kernel attributes, NCCL channels) outside capture
+            for _ in range(warmup):
+                forward_band(net, self.x, comm, H_total, be)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.y = forward_band(net, self.x, comm, H_total, be)
+
+    def __call__(self, x_band):
+        self.x.copy_(x_band)
+        self.graph.replay()
+        return self.y
+
+
 def infer_whole_sharded(net, image, group=None, gather=True, backend=None):
     """`net` on the whole `image` [H, W] (float32, H a multiple of 32 x world, W of 16), rows sharded over the ranks of `group`
     (torch.distributed, one process per GPU).  Every rank passes the same image (or at least its own `band_with_halo` rows of
