@@ -8,8 +8,9 @@
 A step = one forward pass of the 486,409-parameter best_model UNet over one batch of 64 synthetic
 1x512x512 grayscale images per GPU (BASELINE.json configs[1]); batches shard over GPUs with no
 collective (weak scaling).  `value` is device-resident throughput (CUDA events, max over ranks);
-`e2e` goes through the ORT-shaped `InferenceSession.run_pinned` -> `dg_lw_infer_host` C-ABI call with
-pinned HOST buffers, H2D + D2H inside the timed region (`e2e_u8`: the uint8-in / uint8-out twin).  `train_step` is one
+`e2e` goes through the session API with pinned HOST buffers, every step's H2D + D2H inside the timed region:
+`InferenceSession.submit` / `wait` -> `dg_lw_infer_host_submit` / `_wait` with two batches in flight (the service shape; `e2e.blocking`
+is the one-batch-at-a-time `run_pinned` -> `dg_lw_infer_host` call; `e2e_u8`: the uint8-in / uint8-out twins).  `train_step` is one
 BASELINE.json configs[3] training step (batch 32 per GPU) in the same storage tier; `latency_n1` is configs[0] (fp32, batch 1) and
 `wide` configs[4] (features_start=64 on the tcgen05 kernel), both rank 0 only.  `roofline` is for the dominant kernel,
 timed live with CUDA events by `dg_lw_profile` (whole batch on one stream; the timed steps themselves run the batch as two
@@ -294,38 +295,62 @@ def main():
     value = world * B * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the reference-facing session API, host buffers in and out ------------
+    # Two flavours, both with every step's H2D copy of its inputs and D2H copy of its result inside the timed region:
+    #   blocking  -- InferenceSession.run_pinned per batch (returns when the result is in host memory; chunk 8)
+    #   pipelined -- InferenceSession.submit / wait with THREE batches in flight on three pinned buffer pairs, each batch one
+    #                chunk: the service shape (several requests outstanding) -- the H2D copy of batch k+2, the forward of batch k+1
+    #                and the D2H copy of batch k overlap (tools/e2e_sweep.py: chunk 8..32 or two in flight 27.5-29k img/s, this 31-33k)
     sess = InferenceSession(net, chunk=8)
-    hx, hy = sess.pinned_buffers(B, H, W)
-    hx.copy_(x.cpu())
-    for _ in range(2):
-        sess.run_pinned(hx, hy)
-    barrier()
-    te = time.perf_counter()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        sess.run_pinned(hx, hy)
-    barrier()
-    e2e_s = time.perf_counter() - te
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
-    e2e_err = float((hy.to(dev) - y).abs().max())
+    e2e_steps = max(6, min(args.steps, 12))
+    x2 = torch.flip(x, dims=(0,))
+    with torch.no_grad():
+        y2 = net(x2)
 
+    def host_pairs(dtype):
+        xs = []
+        for src in (x, x2, x):
+            h = (src * 255).to(torch.uint8).cpu() if dtype == torch.uint8 else src.cpu()
+            xs.append((h.pin_memory(), torch.empty((B, 1, H, W), dtype=dtype).pin_memory()))
+        return xs
+
+    def rate(step_fn, drain):
+        for i in range(3):
+            step_fn(i)
+        drain()
+        barrier()
+        te = time.perf_counter()
+        for i in range(e2e_steps):
+            step_fn(i)
+        drain()
+        barrier()
+        t = torch.tensor([time.perf_counter() - te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * e2e_steps / float(t.item())
+
+    def measure(dtype):
+        pairs = host_pairs(dtype)
+        run = sess.run_pinned_u8 if dtype == torch.uint8 else sess.run_pinned
+        blocking = rate(lambda i: run(*pairs[i % 3]), lambda: None)
+        pending = []
+
+        def step(i):
+            if len(pending) == 3:
+                sess.wait(pending.pop(0))
+            pending.append(sess.submit(*pairs[i % 3], chunk=B))
+
+        def drain():
+            while pending:
+                sess.wait(pending.pop(0))
+
+        pipelined = rate(step, drain)
+        return blocking, pipelined, pairs
+
+    e2e_blocking, e2e_value, pairs32 = measure(torch.float32)
+    e2e_err = max(float((pairs32[0][1].to(dev) - y).abs().max()), float((pairs32[1][1].to(dev) - y2).abs().max()))
     # ---- the same, uint8 images in / uint8 images out (api/app.py:153,190-193 folded into the kernels)
-    hx8 = (hx * 255).to(torch.uint8).pin_memory()
-    hy8 = torch.empty((B, 1, H, W), dtype=torch.uint8).pin_memory()
-    for _ in range(2):
-        sess.run_pinned_u8(hx8, hy8)
-    barrier()
-    te = time.perf_counter()
-    for _ in range(e2e_steps):
-        sess.run_pinned_u8(hx8, hy8)
-    barrier()
-    t = torch.tensor([time.perf_counter() - te], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_u8_value = world * B * e2e_steps / float(t.item())
+    e2e_u8_blocking, e2e_u8_value, pairs8 = measure(torch.uint8)
+    del pairs32, pairs8
 
     # ---- BASELINE.json configs[3]: one optimized_train.py step (forward + L1 + backward + clip 1.0 + AdamW), batch 32 per GPU,
     # same storage tier; data parallel = one flat-gradient all-reduce inside FusedAdamW.step.  Reported beside the headline.
@@ -376,6 +401,56 @@ def main():
                               "for 16-bit storage, CUDA events, max over ranks"}
         del tnet, opt, tx, tt
         torch.cuda.empty_cache()
+        # the same step captured in ONE CUDA graph (train.GraphedTrainStep: forward, loss, backward, all-reduce, clip, AdamW; step
+        # count and learning rate in device memory) at 32 and at 4 images per GPU -- the latter is the reference's own global batch
+        # of 32 on 8 GPUs, where the eager step is host-launch bound
+        # (single-process runs only: tools/bench_train.py --graph times it under torchrun, where a captured NCCL all-reduce is involved)
+        if not args.no_extras and world == 1:
+            from image_enhancement_deglaring_b200.train import GraphedTrainStep
+            graphed = {}
+            for gb in (tb, 4):
+                try:
+                    gnet = dg.LightweightUNet(storage=args.storage, path=args.path)
+                    gnet.load_state_dict(sd, strict=True)
+                    gnet = gnet.to(dev).train()
+                    gopt = FusedAdamW(gnet.parameters(), lr=0.002362532125818593, weight_decay=6.753784966611083e-05, max_grad_norm=1.0,
+                                      capturable=True)
+                    gx = torch.rand(gb, 1, H, W, generator=torch.Generator().manual_seed(10 + rank)).to(dev)
+                    gt = torch.rand(gb, 1, H, W, generator=torch.Generator().manual_seed(110 + rank)).to(dev)
+                    eager_ms = None
+                    if gb != tb:      # eager time at this batch for comparison (batch 32 is the line above)
+                        def estep():
+                            gopt.zero_grad(set_to_none=True)
+                            crit(gnet(gx), gt).backward()
+                            gopt.step()
+                        for _ in range(3):
+                            estep()
+                        barrier()
+                        e0.record()
+                        for _ in range(tsteps):
+                            estep()
+                        e1.record()
+                        torch.cuda.synchronize()
+                        eager_ms = e0.elapsed_time(e1) / tsteps
+                    gstep = GraphedTrainStep(gnet, gopt, crit, gx.shape)
+                    for _ in range(3):
+                        gstep(gx, gt)
+                    barrier()
+                    e0.record()
+                    for _ in range(tsteps):
+                        gloss = gstep(gx, gt)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    tg = torch.tensor([e0.elapsed_time(e1) / tsteps], dtype=torch.float64, device=dev)
+                    if world > 1:
+                        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+                    graphed[f"batch_{gb}_per_gpu"] = {"ms_per_step": float(tg.item()), "value": world * gb / (float(tg.item()) * 1e-3),
+                                                      "unit": UNIT, "eager_ms_per_step": eager_ms, "loss": float(gloss)}
+                    del gstep, gnet, gopt, gx, gt
+                except Exception as e:   # noqa: BLE001 -- an extra: report instead of losing the line
+                    graphed[f"batch_{gb}_per_gpu"] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+            train_step["cuda_graph"] = graphed
 
     # ---- BASELINE.json configs[0]: fp32, batch 1, 1x512x512 -- latency of one image through the module (device-resident input,
     # CUDA events) and through the ORT-shaped session call (host buffers); the CPU batch-1 number is cpu_baseline.batch1_ms
@@ -466,6 +541,32 @@ def main():
         del wnet, wx
         torch.cuda.empty_cache()
 
+    # ---- src/optimized_model.py:OptimizedUNet (north_star's module file): inference at batch 16, random-init
+    # weights (no checkpoint ships for it), 16.35 GMAC per 512x512 image
+    optimized = None
+    if rank == 0 and not args.no_extras:
+        torch.manual_seed(7)
+        ob = 16
+        onet = dg.OptimizedUNet(storage=args.storage).to(dev).eval()
+        ox = torch.rand(ob, 1, H, W, generator=torch.Generator().manual_seed(4)).to(dev)
+        with torch.no_grad():
+            for _ in range(3):
+                onet(ox)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(5):
+                onet(ox)
+            ev[1].record()
+            torch.cuda.synchronize()
+        oms = ev[0].elapsed_time(ev[1]) / 5
+        oflop = 2 * 16.35e9 * (H * W) / (512 * 512)
+        optimized = {"model": "OptimizedUNet()", "params": dg.count_parameters(onet), "batch": ob, "ms_per_step": oms,
+                     "value": ob / (oms * 1e-3), "unit": UNIT, "tflops": oflop * ob / (oms * 1e-3) / 1e12,
+                     "what": "inference forward (nearest-up + ChannelAttention variant), random-init weights, CUDA events, mean of 5"}
+        del onet, ox
+        torch.cuda.empty_cache()
+
     # ---- per-kernel device times (CUDA events on the launching stream) -> roofline of the dominant kernel
     roofline = None
     if rank == 0:
@@ -538,14 +639,18 @@ def main():
                        "l2": f"inputs+intermediates per step ({sum(algorithmic_bytes_per_image(H, W)) * B / 2**20:.0f} MiB) exceed the 126 MB L2; no flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 4, "d2h_bytes_per_step": B * H * W * 4,
-                    "steps": e2e_steps, "api": "InferenceSession.run_pinned -> dg_lw_infer_host (pinned host buffers)",
-                    "max_abs_vs_device_path": e2e_err},
+                    "steps": e2e_steps, "api": "InferenceSession.submit / wait -> dg_lw_infer_host_submit / _wait (pinned host buffers, "
+                    "three batches in flight, one chunk per batch)", "max_abs_vs_device_path": e2e_err,
+                    "blocking": {"value": e2e_blocking, "api": "InferenceSession.run_pinned -> dg_lw_infer_host, one batch at a time"}},
             "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": B * H * W,
-                       "steps": e2e_steps, "api": "InferenceSession.run_pinned_u8 -> dg_lw_infer_host_u8 (uint8 pixels in and out, "
-                                                  "/255 and clip*255 on the GPU as api/app.py:153,190-193 do on the host)"},
+                       "steps": e2e_steps, "api": "InferenceSession.submit / wait on uint8 buffers -> dg_lw_infer_host_submit (uint8 pixels "
+                                                  "in and out, /255 and clip*255 on the GPU as api/app.py:153,190-193 do on the host; "
+                                                  "three batches in flight)",
+                       "blocking": {"value": e2e_u8_blocking, "api": "InferenceSession.run_pinned_u8 -> dg_lw_infer_host_u8"}},
             "train_step": train_step,
             "latency_n1": latency_n1,
             "wide": wide,
+            "optimized": optimized,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -640,6 +640,13 @@ struct HostPipe {
     static constexpr int NS = 4;  // chunks in flight (measured: 4 x 8-image chunks 2.84 ms per 64 images, 8 in flight 2.98, 2 in flight 3.3): compute streams, staging buffers and workspaces
     cudaStream_t s_in, s_cmp[NS], s_out;
     cudaEvent_t in_done[NS], cmp_done[NS], out_done[NS];
+    // asynchronous submissions (dg_lw_infer_host_submit / _wait): the chunk counter runs ACROSS calls, so the first chunks of
+    // call k+1 are copied in and computed while the last chunks of call k are still computing / being copied out
+    static constexpr int NT = 8;  // tickets (calls) that may be outstanding
+    unsigned long long seq = 0, tickets = 0;
+    cudaEvent_t ticket_done[NT];
+    const void* ws_in_flight = nullptr;   // scratch / geometry of the calls in flight: a different one drains the pipeline first
+    int chunk_in_flight = 0, h_in_flight = 0, w_in_flight = 0;
 };
 static HostPipe g_pipes[16];   // one pipeline (streams, events) per device ordinal
 static std::mutex g_pipe_mutex;  // the *_host entry points serialise: they share the pipeline and the caller's scratch
@@ -670,6 +677,11 @@ static int pipe_init(HostPipe** out) {
         set_error("event create: %s", cudaGetErrorString(e));
         return 10;
     }
+    for (int i = 0; i < HostPipe::NT; ++i)
+        if ((e = cudaEventCreateWithFlags(&g_pipe.ticket_done[i], cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) {
+            set_error("event create: %s", cudaGetErrorString(e));
+            return 10;
+        }
     g_pipe.ready = true;
     return 0;
 }
@@ -913,6 +925,17 @@ int dg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_
                         step, grad_scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int dg_adamw_step_graph(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t count, double* scratch,
+                        float max_norm, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                        int32_t* step_dev, float grad_scale, dg_stream_t stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !scratch || !lr_dev || !step_dev || count == 0) {
+        set_error("adamw (device step): bad arguments");
+        return 2;
+    }
+    return adamw_dev_launch(params, grads, exp_avg, exp_avg_sq, count, scratch, max_norm, lr_dev, beta1, beta2, eps, weight_decay,
+                            step_dev, grad_scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int dg_lw_profile(const dg_lw_params* p, const float* x, float* y, int32_t N, int32_t H, int32_t W, void* workspace,
                   size_t workspace_bytes, dg_stream_t stream, float* ms19) {
     if (ms19 == nullptr) { set_error("profile: null output"); return 2; }
@@ -940,8 +963,10 @@ int dg_lw_host_scratch_bytes(const dg_lw_params* p, int32_t chunk, int32_t H, in
 
 // Chunk i: H2D on s_in -> forward on s_cmp[i % NS] with workspace i % NS -> D2H on s_out.  Several compute streams let the
 // under-filled deep layers of one chunk (16 images x 8 tiles < 148 SMs) overlap the next chunk's wide layers.
+// ticket == nullptr: blocking call (returns when host_y is complete).  ticket != nullptr: everything is enqueued, *ticket names
+// the call for dg_lw_infer_host_wait, and the pipeline keeps running across calls.
 static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host_y, int N, int H, int W, int chunk,
-                           void* dev_ws, size_t dev_ws_bytes, int io, cudaStream_t caller) {
+                           void* dev_ws, size_t dev_ws_bytes, int io, cudaStream_t caller, int64_t* ticket = nullptr) {
     if (chunk < 1) { set_error("infer_host: chunk %d", chunk); return 2; }
     if (chunk > N) chunk = N;
     LwPlan pl;
@@ -968,6 +993,13 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
         ws[k] = base + NS * (in_b + out_b) + k * ws_b;
     }
     dg::HostPipe& P = *pipe;
+    if (P.ws_in_flight != dev_ws || P.chunk_in_flight != chunk || P.h_in_flight != H || P.w_in_flight != W) {
+        // other scratch or geometry than the calls still in flight: their slots are not ours -- drain first
+        cudaStreamSynchronize(P.s_out);
+        for (int k = 0; k < NS; ++k) cudaStreamSynchronize(P.s_cmp[k]);
+        P.seq = 0;
+        P.ws_in_flight = dev_ws; P.chunk_in_flight = chunk; P.h_in_flight = H; P.w_in_flight = W;
+    }
     // everything the caller enqueued on ITS stream (weight packing after a parameter update, the previous consumer of dev_ws) is
     // ordered before the first kernel of the pipeline
     cudaError_t ce = cudaEventRecord(P.start, caller);
@@ -976,21 +1008,22 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
     const char* hx = static_cast<const char*>(host_x);
     char* hy = static_cast<char*>(host_y);
     // chunk schedule: a half-size first and last chunk shorten the pipeline fill (first H2D) and drain (last D2H)
-    const int head = (N >= 3 * chunk && chunk >= 2) ? chunk / 2 : 0;
+    const int head = (ticket == nullptr && N >= 3 * chunk && chunk >= 2) ? chunk / 2 : 0;
     const int body = N - 2 * head;
     const int nchunks = (body + chunk - 1) / chunk + (head ? 2 : 0);
     int n0 = 0;
-    for (int i = 0; i < nchunks; ++i) {
-        const int b = i % NS;
+    for (int i = 0; i < nchunks; ++i, ++P.seq) {
+        const int b = (int)(P.seq % NS);
+        const bool reuse = P.seq >= (unsigned long long)NS;   // slot b was used by chunk seq - NS (possibly of an earlier call)
         int nn;
         if (head && (i == 0 || i == nchunks - 1)) nn = head;
         else { const int left = N - head - n0; nn = left < chunk ? left : chunk; }  // body: what the tail chunk leaves
-        if (i >= NS) cudaStreamWaitEvent(P.s_in, P.cmp_done[b], 0);  // dx[b] consumed by chunk i-NS
+        if (reuse) cudaStreamWaitEvent(P.s_in, P.cmp_done[b], 0);  // dx[b] consumed by chunk seq-NS
         ce = cudaMemcpyAsync(dx[b], hx + (size_t)n0 * in_img * esz_in, nn * in_img * esz_in, cudaMemcpyHostToDevice, P.s_in);
         if (ce != cudaSuccess) { cudaDeviceSynchronize(); set_error("infer_host: H2D copy: %s", cudaGetErrorString(ce)); return 10; }
         cudaEventRecord(P.in_done[b], P.s_in);
         cudaStreamWaitEvent(P.s_cmp[b], P.in_done[b], 0);
-        if (i >= NS) cudaStreamWaitEvent(P.s_cmp[b], P.out_done[b], 0);  // dy[b] drained by chunk i-NS
+        if (reuse) cudaStreamWaitEvent(P.s_cmp[b], P.out_done[b], 0);  // dy[b] drained by chunk seq-NS
         rc = dg::lw_forward(p, dx[b], dy[b], nn, H, W, ws[b], pl.total_bytes, nullptr, nullptr, P.s_cmp[b], nullptr, io, 1 + b);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         cudaEventRecord(P.cmp_done[b], P.s_cmp[b]);
@@ -999,6 +1032,13 @@ static int infer_host_impl(const dg_lw_params* p, const void* host_x, void* host
         if (ce != cudaSuccess) { cudaDeviceSynchronize(); set_error("infer_host: D2H copy: %s", cudaGetErrorString(ce)); return 10; }
         cudaEventRecord(P.out_done[b], P.s_out);
         n0 += nn;
+    }
+    if (ticket != nullptr) {   // s_out is one stream: its last copy done = every chunk of this call computed and copied out
+        const unsigned long long t = P.tickets++;
+        ce = cudaEventRecord(P.ticket_done[t % dg::HostPipe::NT], P.s_out);
+        if (ce != cudaSuccess) { cudaDeviceSynchronize(); set_error("infer_host: %s", cudaGetErrorString(ce)); return 10; }
+        *ticket = (int64_t)t;
+        return 0;
     }
     cudaError_t e = cudaStreamSynchronize(P.s_out);
     for (int k = 0; k < NS && e == cudaSuccess; ++k) e = cudaStreamSynchronize(P.s_cmp[k]);
@@ -1014,6 +1054,30 @@ int dg_lw_infer_host(const dg_lw_params* p, const float* host_x, float* host_y, 
 int dg_lw_infer_host_u8(const dg_lw_params* p, const uint8_t* host_x, uint8_t* host_y, int32_t N, int32_t H, int32_t W,
                         int32_t chunk, void* dev_ws, size_t dev_ws_bytes, dg_stream_t stream) {
     return infer_host_impl(p, host_x, host_y, N, H, W, chunk, dev_ws, dev_ws_bytes, 3, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_lw_infer_host_submit(const dg_lw_params* p, const void* host_x, void* host_y, int32_t N, int32_t H, int32_t W, int32_t chunk,
+                            void* dev_ws, size_t dev_ws_bytes, int32_t u8, dg_stream_t stream, int64_t* ticket) {
+    if (ticket == nullptr) { set_error("infer_host_submit: null ticket"); return 2; }
+    {   // at most NT calls outstanding: the event about to be re-recorded must have completed
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 16 && dg::g_pipes[dev].ready && dg::g_pipes[dev].tickets >= (unsigned long long)dg::HostPipe::NT)
+            cudaEventSynchronize(dg::g_pipes[dev].ticket_done[dg::g_pipes[dev].tickets % dg::HostPipe::NT]);
+    }
+    return infer_host_impl(p, host_x, host_y, N, H, W, chunk, dev_ws, dev_ws_bytes, u8 ? 3 : 0, reinterpret_cast<cudaStream_t>(stream), ticket);
+}
+
+int dg_lw_infer_host_wait(int64_t ticket) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16 || !dg::g_pipes[dev].ready) { set_error("infer_host_wait: no pipeline on this device"); return 2; }
+    dg::HostPipe& P = dg::g_pipes[dev];
+    if (ticket < 0 || (unsigned long long)ticket >= P.tickets) { set_error("infer_host_wait: unknown ticket %lld", (long long)ticket); return 2; }
+    if (P.tickets - (unsigned long long)ticket > (unsigned long long)dg::HostPipe::NT) return 0;   // long retired (submit waited on it)
+    cudaError_t e = cudaEventSynchronize(P.ticket_done[(unsigned long long)ticket % dg::HostPipe::NT]);
+    if (e != cudaSuccess) { set_error("infer_host_wait: %s", cudaGetErrorString(e)); return 10; }
+    return 0;
 }
 
 int dg_lw_forward_u8(const dg_lw_params* p, const uint8_t* x, uint8_t* y, int32_t N, int32_t H, int32_t W, void* workspace,

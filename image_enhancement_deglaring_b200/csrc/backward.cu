@@ -564,6 +564,38 @@ __global__ void __launch_bounds__(BW_THREADS) adamw_kernel(const AdamwArgs a) {
     }
 }
 
+// CUDA-graph-capturable flavour: the step count and the learning rate live in device memory, so a captured training step can be
+// replayed with nothing baked in -- `step_bump_kernel` increments the counter, the update kernel derives the bias corrections.
+__global__ void step_bump_kernel(int32_t* step) { *step += 1; }
+
+struct AdamwDevArgs {
+    float* p; const float* g; float* m; float* v; size_t n;
+    const double* sumsq; const int32_t* step; const float* lr;
+    float max_norm, beta1, beta2, eps, weight_decay, grad_scale;
+};
+
+__global__ void __launch_bounds__(BW_THREADS) adamw_dev_kernel(const AdamwDevArgs a) {
+    float coef = a.grad_scale;
+    if (a.max_norm > 0.f) {
+        const float total = (float)sqrt(*a.sumsq) * a.grad_scale;
+        coef *= fminf(1.f, a.max_norm / (total + 1e-6f));
+    }
+    const int step = *a.step;
+    const float lr = *a.lr;
+    const float bc1 = (float)(1.0 - pow((double)a.beta1, (double)step));         // same double-precision corrections as the host flavour
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, (double)step));
+    for (size_t i = (size_t)blockIdx.x * BW_THREADS + threadIdx.x; i < a.n; i += (size_t)gridDim.x * BW_THREADS) {
+        const float g = a.g[i] * coef;
+        float p = a.p[i] * (1.f - lr * a.weight_decay);
+        const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+        const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+        a.m[i] = m;
+        a.v[i] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+        a.p[i] = p - (lr / bc1) * (m / denom);
+    }
+}
+
 inline int ew_blocks(size_t elems, int C) {
     // element-wise kernels keep a thread on one channel across its stride loop only if the stride is a multiple of C
     size_t b = (elems + BW_THREADS - 1) / BW_THREADS;
@@ -933,6 +965,22 @@ int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double*
     adamw_kernel<<<blocks, BW_THREADS, 0, st>>>(a);
     count_launch();
     return check_launch("adamw");
+}
+
+int adamw_dev_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, const float* lr_dev,
+                     float beta1, float beta2, float eps, float weight_decay, int32_t* step_dev, float grad_scale, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), st);
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 10; }
+    int blocks = (int)((n + BW_THREADS - 1) / BW_THREADS);
+    if (blocks > 592) blocks = 592;
+    step_bump_kernel<<<1, 1, 0, st>>>(step_dev);
+    count_launch();
+    sumsq_kernel<<<blocks, BW_THREADS, 0, st>>>(g, n, sumsq_scratch);
+    count_launch();
+    AdamwDevArgs a{p, g, m, v, n, sumsq_scratch, step_dev, lr_dev, max_norm, beta1, beta2, eps, weight_decay, grad_scale};
+    adamw_dev_kernel<<<blocks, BW_THREADS, 0, st>>>(a);
+    count_launch();
+    return check_launch("adamw (device step)");
 }
 
 }  // namespace dg

@@ -186,8 +186,9 @@ class FusedAdamW(torch.optim.Optimizer):
     round-trips with a plain AdamW in either direction.  The data-parallel gradient exchange is NOT here: it happens at the
     end of backward (see the module docstring), before any clipping or inf check."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0, capturable=False):
         params = [p for p in params]
+        self.capturable = capturable
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm))
         if len(self.param_groups) != 1:
             raise ValueError("FusedAdamW keeps one flat buffer: pass a single param group (per-group hyper-parameters are not supported)")
@@ -203,6 +204,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self._scratch = torch.zeros(1, dtype=torch.float64, device=dev)
         self._step = 0
+        # capturable: step count and learning rate in device memory (dg_adamw_step_graph), so that step() can sit inside a CUDA graph
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev) if capturable else None
+        self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev) if capturable else None
         off = 0
         with torch.no_grad():
             for p in ps:
@@ -235,7 +239,18 @@ class FusedAdamW(torch.optim.Optimizer):
                              "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p)}
             off += k
 
+    def _sync_step(self):
+        if self.capturable:
+            self._step = int(self._step_dev.item())
+
+    def push_hyperparameters(self):
+        """capturable only: copy param_groups[0]['lr'] (an LR scheduler writes it on the host) to the device scalar the captured
+        step reads.  Call before replaying a graph that contains step()."""
+        if self.capturable:
+            self._lr_dev.fill_(float(self.param_groups[0]["lr"]))
+
     def state_dict(self):
+        self._sync_step()
         if self._step > 0:
             self._publish_state()
         return super().state_dict()
@@ -262,6 +277,8 @@ class FusedAdamW(torch.optim.Optimizer):
         if len(steps) != 1:
             raise ValueError(f"FusedAdamW needs one common step count, checkpoint has {sorted(steps)}")
         self._step = steps.pop()
+        if self.capturable:
+            self._step_dev.fill_(self._step)
         if self._step > 0:
             self._publish_state()
         else:
@@ -292,6 +309,16 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         self._gather()
         g = self.param_groups[0]
+        if self.capturable:
+            if not torch.cuda.is_current_stream_capturing():
+                self._lr_dev.fill_(float(g["lr"]))
+            _lib.check(_lib.load().dg_adamw_step_graph(
+                self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                self.flat_p.numel(), self._scratch.data_ptr(), float(g["max_grad_norm"]), self._lr_dev.data_ptr(),
+                float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self._step_dev.data_ptr(),
+                1.0, torch.cuda.current_stream().cuda_stream))
+            _lib.bump_generation()
+            return loss
         self._step += 1
         _lib.check(_lib.load().dg_adamw_step(
             self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
@@ -304,3 +331,60 @@ class FusedAdamW(torch.optim.Optimizer):
     def grad_norm(self):
         """Total L2 norm of the gradient seen by the last step (the value clip_grad_norm_ returns)."""
         return float(self._scratch.sqrt().item())
+
+
+class GraphedTrainStep:
+    """One training step of the reference loop (optimized_train.py:201-233: zero_grad, forward, L1, backward -- with the data-parallel
+    all-reduce at its end -- clip, AdamW) captured ONCE in a CUDA graph and replayed per batch.
+
+    Why: at the reference's own configuration (global batch 32 = 4 images per GPU on 8 GPUs) a step is ~75 kernels of 10-50 us
+    plus the packing kernels of the updated weights; issued from Python the host launch rate bounds it, not the GPU.
+    Needs a `FusedAdamW(..., capturable=True)` (step count and learning rate in device memory) and fixed batch shapes.
+
+        step = GraphedTrainStep(net, opt, criterion, inputs.shape)
+        for inputs, targets in loader: loss = step(inputs, targets)      # loss: 0-d device tensor, valid until the next call
+    """
+
+    def __init__(self, module, optimizer, criterion, shape, warmup=3, clip_grad_norm=None):
+        if not getattr(optimizer, "capturable", False):
+            raise RuntimeError("GraphedTrainStep needs FusedAdamW(..., capturable=True)")
+        dev = next(module.parameters()).device
+        self.module, self.optimizer, self.criterion, self.clip = module, optimizer, criterion, clip_grad_norm
+        self.x = torch.zeros(shape, dtype=torch.float32, device=dev)
+        self.t = torch.zeros((shape[0], module.out_channels) + tuple(shape[2:]), dtype=torch.float32, device=dev)
+        # the warm-up steps run on zeros with lr = 0 and weight decay 0 against saved moments: they must not train
+        g = optimizer.param_groups[0]
+        saved = (g["lr"], g["weight_decay"], optimizer.exp_avg.clone(), optimizer.exp_avg_sq.clone(), optimizer._step_dev.clone())
+        g["lr"], g["weight_decay"] = 0.0, 0.0
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        # restore what the warm-up touched BEFORE capturing: weight decay, betas, eps and the clip norm are launch arguments and are
+        # baked into the graph (only the step count and the learning rate are read from device memory)
+        g["lr"], g["weight_decay"] = saved[0], saved[1]
+        optimizer.exp_avg.copy_(saved[2]); optimizer.exp_avg_sq.copy_(saved[3]); optimizer._step_dev.copy_(saved[4])
+        optimizer.push_hyperparameters()
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+
+    def _eager(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.criterion(self.module(self.x), self.t)
+        loss.backward()
+        if self.clip:
+            torch.nn.utils.clip_grad_norm_(self.module.parameters(), max_norm=self.clip)
+        self.optimizer.step()
+        return loss.detach()
+
+    def __call__(self, inputs, targets):
+        self.x.copy_(inputs, non_blocking=True)
+        self.t.copy_(targets, non_blocking=True)
+        self.optimizer.push_hyperparameters()
+        self.graph.replay()
+        _lib.bump_generation()   # the weights changed inside the graph: eager forwards after this must re-pack their caches
+        return self.loss

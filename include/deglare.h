@@ -254,6 +254,14 @@ int dg_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                   float grad_scale, dg_stream_t stream);
 
+/* The same optimizer tail with nothing baked into the launch: the step count (incremented by the call) and the learning rate are
+ * read from DEVICE memory, so a whole training step -- forward, loss, backward, gradient all-reduce, clip, AdamW -- can be captured
+ * in a CUDA graph once and replayed (train.GraphedTrainStep): at the reference's own configuration of 4 images per GPU on 8 GPUs
+ * (optimized_train.py:383-446 with global batch 32) the step is ~75 launches of 10-50 us kernels and is host-launch bound otherwise. */
+int dg_adamw_step_graph(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t count, double* scratch,
+                        float max_norm, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                        int32_t* step_dev, float grad_scale, dg_stream_t stream);
+
 /* One forward with a CUDA-event pair around each of its 19 kernels (18 fused convs + head), recorded on
  * `stream`; synchronises the stream and writes the per-kernel milliseconds to ms19[19].  For bench.py's
  * roofline line -- the events add launch gaps, so use dg_lw_forward for throughput. */
@@ -280,6 +288,18 @@ int dg_lw_forward_u8(const dg_lw_params* p, const uint8_t* x, uint8_t* y, int32_
                      void* workspace, size_t workspace_bytes, dg_stream_t stream);
 int dg_lw_infer_host_u8(const dg_lw_params* p, const uint8_t* host_x, uint8_t* host_y, int32_t N, int32_t H,
                         int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes, dg_stream_t stream);
+
+/* Asynchronous twin of dg_lw_infer_host / dg_lw_infer_host_u8 (`u8` != 0) for a service with several requests in flight
+ * (uvicorn workers in front of api/app.py:171, evaluate.py:245's loop over batches): _submit enqueues the whole call -- H2D
+ * copies, forwards, D2H copies -- and returns a ticket at once; _wait blocks until that call's host_y is complete.  The chunk
+ * pipeline runs ACROSS calls (call k+1's first chunks are copied in and computed while call k's last chunks are still being
+ * computed / copied out), so with two calls in flight the fill and drain of the pipeline are hidden and larger chunks (which
+ * run the kernels at better efficiency) cost no latency.  Calls in flight must share `dev_ws`, `chunk`, H and W (a different
+ * combination drains the pipeline first); host_x / host_y must stay valid and untouched until _wait returns; at most 8 calls
+ * outstanding (_submit blocks on the oldest).  Tickets are per device. */
+int dg_lw_infer_host_submit(const dg_lw_params* p, const void* host_x, void* host_y, int32_t N, int32_t H, int32_t W,
+                            int32_t chunk, void* dev_ws, size_t dev_ws_bytes, int32_t u8, dg_stream_t stream, int64_t* ticket);
+int dg_lw_infer_host_wait(int64_t ticket);
 
 /* ---- tensor-core weight packing (16-bit storage types) ---------------------------------
  * The HMMA implicit-GEMM kernels read B operands as ldmatrix-ready tiles

@@ -266,6 +266,47 @@ def test_infer_host_many_chunks_two_compute_streams(best_sd):
         assert np.array_equal(out, y), f"chunk {chunk}"
 
 
+def test_submit_wait_pipeline_across_calls(best_sd):
+    """dg_lw_infer_host_submit / _wait: several calls in flight share the chunk pipeline (slots are reused ACROSS calls), float and
+    uint8, batch sizes that are not a multiple of the chunk, more calls than tickets, a geometry change that drains the pipeline --
+    every result equals the device-resident forward of the same batch, and a blocking call may follow at once."""
+    from image_enhancement_deglaring_b200.session import InferenceSession
+    net = _net(best_sd, storage="fp16")
+    sess = InferenceSession(net, chunk=2)
+    xs = [_rand((n, 1, 64, 96), 40 + i) for i, n in enumerate((5, 7, 2, 9, 1, 6, 3, 8, 5, 4, 7))]      # 11 calls > 8 tickets
+    with torch.no_grad():
+        want = [net(x.cuda()).cpu() for x in xs]
+    pins = [(x.pin_memory(), torch.empty_like(x).pin_memory()) for x in xs]
+    tickets = [sess.submit(px, py, chunk=2) for px, py in pins]
+    for t in reversed(tickets):          # any order; early tickets may already be retired
+        sess.wait(t)
+    for (px, py), w in zip(pins, want):
+        assert torch.equal(py, w)
+    # uint8 twin, two in flight as bench.py does, then another image size (drains), then the blocking call
+    us = [(torch.rand(6, 1, 64, 96, generator=torch.Generator().manual_seed(60 + i)) * 255).to(torch.uint8) for i in range(4)]
+    pins8 = [(u.pin_memory(), torch.empty_like(u).pin_memory()) for u in us]
+    pending = []
+    for px, py in pins8:
+        if len(pending) == 2:
+            sess.wait(pending.pop(0))
+        pending.append(sess.submit(px, py, chunk=4))
+    big = _rand((3, 1, 128, 64), 77)
+    pbig = (big.pin_memory(), torch.empty_like(big).pin_memory())
+    pending.append(sess.submit(*pbig, chunk=4))
+    for t in pending:
+        sess.wait(t)
+    for (px, py), u in zip(pins8, us):
+        assert torch.equal(py, net.forward_u8(u.cuda()).cpu())
+    with torch.no_grad():
+        assert torch.equal(pbig[1], net(big.cuda()).cpu())
+    out = sess.run(["output"], {"input": xs[0].numpy()})[0]
+    assert np.array_equal(out, want[0].numpy())
+    with pytest.raises(RuntimeError):
+        sess.wait(10 ** 6)                # unknown ticket
+    with pytest.raises(RuntimeError):
+        sess.submit(pins[0][0], pins8[0][1])   # mixed dtypes
+
+
 def test_tiled_high_resolution_equals_per_tile_forward(best_sd):
     """BASELINE.json configs[2] (definition A of SURVEY 8e): a 1024x1536 image as six independent 512x512 tiles equals the
     module applied to each tile on its own -- float and uint8 entry points."""

@@ -368,3 +368,53 @@ def test_fused_l1_loss_and_direct_gradient_sink(best_sd, storage):
     z = torch.rand(2, 1, 8, 8, device="cuda")
     assert torch.equal(L1Loss()(y, z), torch.nn.functional.l1_loss(y, z))
     assert torch.equal(L1Loss(reduction="sum")(y, z), torch.nn.functional.l1_loss(y, z, reduction="sum"))
+
+
+@pytest.mark.parametrize("storage", ["fp32", "fp16"])
+def test_cuda_graph_training_step_equals_eager_loop(best_sd, storage):
+    """train.GraphedTrainStep: the reference loop's step (zero_grad, forward, L1, backward, clip 1.0, AdamW; optimized_train.py:201-233)
+    captured once and replayed must walk the same trajectory as the eager loop -- losses and parameters after 4 steps on 4 different
+    batches, with a learning-rate change in between (the scheduler writes param_groups on the host; the graph reads it from device
+    memory), and the checkpointed step count must follow the replays.  Eager forwards after replays see the updated weights."""
+    from image_enhancement_deglaring_b200.train import FusedAdamW, GraphedTrainStep, L1Loss
+    xs = [_rand((4, 1, 64, 96), 70 + i).cuda() for i in range(4)]
+    ts = [_rand((4, 1, 64, 96), 80 + i).cuda() for i in range(4)]
+    lrs = [TRAIN_LR, TRAIN_LR, TRAIN_LR * 0.5, TRAIN_LR * 0.5]
+
+    def run(graphed):
+        net = _net(best_sd, storage=storage)
+        opt = FusedAdamW(net.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD, max_grad_norm=1.0, capturable=graphed)
+        crit = L1Loss()
+        step = GraphedTrainStep(net, opt, crit, xs[0].shape) if graphed else None
+        losses = []
+        for x, t, lr in zip(xs, ts, lrs):
+            opt.param_groups[0]["lr"] = lr
+            if graphed:
+                losses.append(float(step(x, t)))
+            else:
+                opt.zero_grad(set_to_none=True)
+                loss = crit(net(x), t)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss))
+        net.eval()
+        with torch.no_grad():
+            y = net(xs[0]).cpu()
+        return losses, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}, opt.state_dict(), y
+
+    la, pa, sa, ya = run(False)
+    lb, pb, sb, yb = run(True)
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 2e-5 * abs(a), (la, lb)
+    for k in pa:   # same arithmetic; fp32 atomics give summation-order noise, amplified by Adam's g / (|g| + eps) on tiny gradients
+        d = (pa[k] - pb[k]).abs()
+        assert float(d.max()) <= 2 * TRAIN_LR, k
+        assert float((d > 2e-5).float().mean()) <= 2e-3, k
+    assert int(float(sb["state"][0]["step"])) == 4 == int(float(sa["state"][0]["step"]))
+    assert float((ya - yb).abs().max()) <= 2e-3
+    # the untrained network gives a visibly different output: the eager forward after the replays used the updated weights
+    with torch.no_grad():
+        y0 = _net(best_sd, storage=storage).eval()(xs[0]).cpu()
+    assert float((yb - y0).abs().max()) > 10 * float((ya - yb).abs().max()) + 1e-4
+    with pytest.raises(RuntimeError):
+        GraphedTrainStep(_net(best_sd), FusedAdamW(_net(best_sd).parameters()), L1Loss(), xs[0].shape)

@@ -29,3 +29,22 @@ for chunk in (4, 8, 16, 32, 64):
     for _ in range(10): sess.run_pinned(hx, hy)
     dt = (time.perf_counter() - t) / 10
     print(f"e2e chunk {chunk:2d}: {dt*1e3:.2f} ms/batch64  {B/dt:.0f} img/s")
+# asynchronous submit / wait (dg_lw_infer_host_submit): `depth` batches in flight, fp32 and uint8 host buffers
+for dtype in (torch.float32, torch.uint8):
+    pairs = [((torch.rand(B, 1, H, W) * (255 if dtype == torch.uint8 else 1)).to(dtype).pin_memory(),
+              torch.empty(B, 1, H, W, dtype=dtype).pin_memory()) for _ in range(3)]
+    for chunk in (8, 16, 32, 64):
+        for depth in (2, 3):
+            sess = InferenceSession(net, chunk=chunk)
+            pend = []
+            def step(i):
+                if len(pend) == depth: sess.wait(pend.pop(0))
+                pend.append(sess.submit(*pairs[i % 3], chunk=chunk))
+            def drain():
+                while pend: sess.wait(pend.pop(0))
+            for i in range(4): step(i)
+            drain(); t = time.perf_counter()
+            for i in range(12): step(i)
+            drain(); dt = (time.perf_counter() - t) / 12
+            print(f"submit/wait {str(dtype)[6:]:7s} chunk {chunk:2d} depth {depth}: {dt*1e3:.2f} ms/batch64  {B/dt:.0f} img/s")
+            del sess
