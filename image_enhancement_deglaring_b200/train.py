@@ -63,6 +63,8 @@ class _LightweightUNetFn(torch.autograd.Function):
             _lib.check(lib.dg_lw_forward(C.byref(pc), x.data_ptr(), y.data_ptr(), N, H, W, ws.data_ptr(), ws.numel(),
                                          None, None, torch.cuda.current_stream().cuda_stream))
         ctx.module, ctx.ws, ctx.x, ctx.tctx = module, ws, x, tctx
+        ctx.n_inputs = len(params)
+        ctx.direct = getattr(module, "_dg_direct_grads", False)
         tctx.y = y
         return y
 
@@ -85,6 +87,9 @@ class _LightweightUNetFn(torch.autograd.Function):
             # gradients go straight into the optimizer's flat bucket when that is safe (fresh after zero_grad, no hooks): no
             # per-parameter accumulate kernels, no temporary
             sink = _flat_grad_sink(params) if total > 0 else None
+            if ctx.direct and sink is None:
+                raise RuntimeError("GraphedTrainStep: the gradients must land in the optimizer's flat bucket (FusedAdamW.zero_grad "
+                                   "inside the step, no per-parameter hooks)")
             flat = sink if sink is not None else torch.empty(total, dtype=torch.float32, device=x.device)
             stream = torch.cuda.current_stream().cuda_stream
             fused_l1 = (tctx.l1_target is not None and tctx.l1_marker is not None and grad_y.data_ptr() == tctx.l1_marker.data_ptr()
@@ -102,7 +107,7 @@ class _LightweightUNetFn(torch.autograd.Function):
         sync_gradients(flat, getattr(module, "ddp_sync", True))
         if sink is not None:
             sink._dg_zero_version = None      # the bucket now holds a gradient: a second backward must accumulate the ordinary way
-            return (None, None, None) + (None,) * len(params)
+            return (None, None, None) + (None,) * ctx.n_inputs
         grads, off = [], 0
         for p in params:
             n = p.numel()
@@ -170,6 +175,15 @@ def lightweight_forward_train(module, x):
     if x.requires_grad:
         raise NotImplementedError("gradient w.r.t. the input image is not implemented (the reference never needs it)")
     tctx = _TrainCtx()
+    if getattr(module, "_dg_direct_grads", False):
+        # GraphedTrainStep: the parameters are NOT autograd inputs -- their AccumulateGrad nodes carry the stream they were created
+        # on (the default stream if an eager step's graph is still alive), and the engine would synchronise the capturing stream
+        # with it at the end of backward (cudaErrorStreamCaptureIsolation).  A fresh leaf anchors the node instead; the gradients
+        # go straight into the optimizer's flat bucket.
+        anchor = torch.zeros((), device=x.device, requires_grad=True)
+        y = _LightweightUNetFn.apply(module, tctx, x, anchor)
+        y._dg_train_ctx = tctx
+        return y
     y = _LightweightUNetFn.apply(module, tctx, x, *module.parameters())
     y._dg_train_ctx = tctx
     return y
@@ -374,7 +388,11 @@ class GraphedTrainStep:
 
     def _eager(self):
         self.optimizer.zero_grad(set_to_none=True)
-        loss = self.criterion(self.module(self.x), self.t)
+        self.module._dg_direct_grads = True
+        try:
+            loss = self.criterion(self.module(self.x), self.t)
+        finally:
+            self.module._dg_direct_grads = False
         loss.backward()
         if self.clip:
             torch.nn.utils.clip_grad_norm_(self.module.parameters(), max_norm=self.clip)
