@@ -418,7 +418,12 @@ def test_cuda_graph_training_step_equals_eager_loop(best_sd, storage):
     for k in pa:   # same arithmetic; fp32 atomics give summation-order noise, amplified by Adam's g / (|g| + eps) on tiny gradients
         d = (pa[k] - pb[k]).abs()
         assert float(d.max()) <= 2 * TRAIN_LR, k
-        assert float((d > 2e-5).float().mean()) <= 2e-3, k
+        if storage == "fp32":
+            assert float((d > 2e-5).float().mean()) <= 2e-3, k
+        # both runs moved the same way: their distance is a small fraction of the distance travelled in 4 steps (the 16-bit tier's
+        # gradients carry more summation-order noise, and Adam turns noise on a near-zero gradient into a step of up to lr)
+        moved = float((pa[k] - best_sd[k]).norm())
+        assert float((pa[k] - pb[k]).norm()) <= (0.02 if storage == "fp32" else 0.1) * moved + 1e-6, k
     assert int(float(sb["state"][0]["step"])) == 4 == int(float(sa["state"][0]["step"]))
     assert float((ya - yb).abs().max()) <= 2e-3
     # the untrained network gives a visibly different output: the eager forward after the replays used the updated weights
