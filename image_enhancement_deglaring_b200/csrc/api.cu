@@ -863,6 +863,21 @@ int dg_convt2x2_fused(const dg_src* src, int32_t dtype, int32_t N, int32_t H, in
     return 0;
 }
 
+int dg_band_stats(const double* kernel_stats, const void* rows, int32_t dtype, int32_t W, int32_t C, int32_t halo_top0, int32_t own0,
+                  int32_t own1, int32_t halo_bottom1, double* out, dg_stream_t stream) {
+    if (!kernel_stats || !rows || !out || W < 1 || halo_top0 < 0 || halo_top0 > own0 || own0 > own1 || own1 > halo_bottom1) {
+        set_error("band_stats: bad arguments");
+        return 2;
+    }
+    return band_stats_launch(kernel_stats, rows, dtype, W, C, halo_top0, own0, own1, halo_bottom1, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_gn_affine(const double* stats, const float* gamma, const float* beta, int32_t C, int32_t groups, double plane, float eps,
+                 float* coef, dg_stream_t stream) {
+    if (!stats || !gamma || !beta || !coef || C < 1 || groups < 1 || C % groups || plane <= 0) { set_error("gn_affine: bad arguments"); return 2; }
+    return gn_affine_launch(stats, gamma, beta, C, groups, plane, eps, coef, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int dg_channel_attention(const double* act_sum, double plane, const float* w1, const float* w2, int32_t N, int32_t C,
                          int32_t hidden, float* scale, dg_stream_t stream) {
     if (!act_sum || !w1 || !w2 || !scale || N < 1 || C < 1 || hidden < 1 || plane <= 0) {

@@ -231,6 +231,10 @@ int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, 
                      int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st, const void* wtc_bf16 = nullptr, const DgradAct* act = nullptr, bool* act_fused = nullptr);
 int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, float lr,
                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t st);
+int band_stats_launch(const double* kstats, const void* t, int dtype, int W, int C, int a0, int a1, int b0, int b1, double* out,
+                      cudaStream_t st);
+int gn_affine_launch(const double* stats, const float* gamma, const float* beta, int C, int groups, double plane, float eps, float* coef,
+                     cudaStream_t st);
 int adamw_dev_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, const float* lr_dev,
                      float beta1, float beta2, float eps, float weight_decay, int32_t* step_dev, float grad_scale, cudaStream_t st);
 int tc_conv3x3_bytes(int cin, int cout, size_t* bytes);

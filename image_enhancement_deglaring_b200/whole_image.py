@@ -196,6 +196,25 @@ class KernelBackend:
         _lib.check(lib.dg_conv3x3_fused(C.byref(a), stream))
         return stats
 
+    def band_stats(self, stats, t, c0, own0, own1, c1):
+        """Partial sums of the rows the band owns: `stats` (the conv's epilogue sums over the computed rows [c0, c1) of t) minus the
+        computed halo rows [c0, own0) and [own1, c1) -- one launch (dg_band_stats)."""
+        if t.shape[-1] > 1024:
+            return None      # the driver's tensor-op path
+        out = torch.empty_like(stats)
+        _lib.check(_lib.load().dg_band_stats(stats.data_ptr(), t.data_ptr(), self.pc.dtype, t.shape[1], t.shape[2], c0, own0, own1, c1,
+                                             out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def gn_affine(self, stats, i, plane):
+        """All-reduced statistics of conv `i`'s output -> its GroupNorm's finished affine [C, 2] -- one launch (dg_gn_affine)."""
+        b, j = divmod(i, 2)
+        c = stats.shape[0]
+        coef = torch.empty((c, 2), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.load().dg_gn_affine(stats.data_ptr(), self.pc.gn_w[b][j], self.pc.gn_b[b][j], c, self.net._block_groups[b],
+                                            float(plane), 1e-5, coef.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return coef
+
     def head(self, t, coef, out):
         """GroupNorm + SiLU + 1x1 conv + bias of raw [H, W, C] -> fp32 [out_channels, H, W]."""
         h = DgHeadArgs()
@@ -247,11 +266,17 @@ def forward_band(net, x_band, comm, H_total, backend=None):
     def finish(i, lvl, stats, c0, c1, exchange=True):
         """Rows [c0, c1) of T[i] were just computed.  Whole-image statistics -> coef[i]; neighbours' rows -> halo rows."""
         t, hb_l = T[i], Hb >> lvl
-        stats = stats - _row_stats(t[c0:ht]) - _row_stats(t[ht + hb_l:c1])
-        comm.all_reduce_sum(stats)
+        own = be.band_stats(stats, t, c0, ht, ht + hb_l, c1) if hasattr(be, "band_stats") else None
+        if own is None:      # backends without the fused step (the CPU stand-in of the tests; > 1024 channels)
+            own = stats - _row_stats(t[c0:ht]) - _row_stats(t[ht + hb_l:c1])
+        stats = comm.all_reduce_sum(own)
         b, j = divmod(i, 2)
-        gn = getattr(net, _BLOCKS[b])[1 if j == 0 else 4]
-        coef[i] = _gn_coef(stats, gn.weight.detach(), gn.bias.detach(), net._block_groups[b], (H_total >> lvl) * (W >> lvl))
+        plane = (H_total >> lvl) * (W >> lvl)
+        if hasattr(be, "gn_affine"):
+            coef[i] = be.gn_affine(stats, i, plane)
+        else:
+            gn = getattr(net, _BLOCKS[b])[1 if j == 0 else 4]
+            coef[i] = _gn_coef(stats, gn.weight.detach(), gn.bias.detach(), net._block_groups[b], plane)
         if exchange and world > 1:
             comm.exchange(t[ht:ht + HALO], t[0:ht], t[ht + hb_l - HALO:ht + hb_l], t[ht + hb_l:ht + hb_l + hb])
 
