@@ -117,7 +117,8 @@ SYMBOLS = {
     "dg_lw_infer_host_wait": (C.c_int, [C.c_int64]),
     "dg_band_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p]),
-    "dg_gn_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_float, C.c_void_p, C.c_void_p]),
+    "dg_gn_affine": (C.c_int, [C.c_void_p, C.c_int32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_float,
+                               C.c_void_p, C.c_void_p]),
     "dg_tc_conv3x3_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "dg_pack_conv3x3_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_tc_convt2x2_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),

@@ -872,10 +872,14 @@ int dg_band_stats(const double* kernel_stats, const void* rows, int32_t dtype, i
     return band_stats_launch(kernel_stats, rows, dtype, W, C, halo_top0, own0, own1, halo_bottom1, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int dg_gn_affine(const double* stats, const float* gamma, const float* beta, int32_t C, int32_t groups, double plane, float eps,
-                 float* coef, dg_stream_t stream) {
-    if (!stats || !gamma || !beta || !coef || C < 1 || groups < 1 || C % groups || plane <= 0) { set_error("gn_affine: bad arguments"); return 2; }
-    return gn_affine_launch(stats, gamma, beta, C, groups, plane, eps, coef, reinterpret_cast<cudaStream_t>(stream));
+int dg_gn_affine(const double* parts, int32_t nparts, size_t part_stride, const float* gamma, const float* beta, int32_t C, int32_t groups,
+                 double plane, float eps, float* coef, dg_stream_t stream) {
+    if (!parts || nparts < 1 || !gamma || !beta || !coef || C < 1 || groups < 1 || C % groups || plane <= 0 ||
+        (nparts > 1 && part_stride < (size_t)2 * C)) {
+        set_error("gn_affine: bad arguments");
+        return 2;
+    }
+    return gn_affine_launch(parts, nparts, part_stride, gamma, beta, C, groups, plane, eps, coef, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dg_channel_attention(const double* act_sum, double plane, const float* w1, const float* w2, int32_t N, int32_t C,

@@ -3,7 +3,7 @@
 //   band_stats : partial sums of the rows a band OWNS = the conv kernel's epilogue statistics (over every row it computed) minus
 //                the halo rows it computed as well -- nn.GroupNorm (src/model.py:94,97) normalises over the whole image, each
 //                rank contributes the rows it owns exactly once
-//   gn_affine  : all-reduced (sum, sum of squares) -> the finished per-channel affine (a, b) consumers take as dg_src.coef,
+//   gn_affine  : every rank's partial (sum, sum of squares), added in rank order -> the finished per-channel affine (a, b) consumers take as dg_src.coef,
 //                with the SAME double-precision chain the kernels run themselves (common.cuh:gn_coef)
 // One CTA each, fixed summation order: the result does not depend on the launch.
 #include "common.cuh"
@@ -44,11 +44,18 @@ __global__ void __launch_bounds__(BS_THREADS) band_stats_kernel(const double* __
     }
 }
 
-__global__ void gn_affine_kernel(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int C,
-                                 int groups, double plane, float eps, float* __restrict__ coef) {
+__global__ void gn_affine_kernel(const double* __restrict__ parts, int nparts, size_t stride, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int C, int groups, double plane, float eps, float* __restrict__ coef) {
+    extern __shared__ double tot[];   // [C][2]: the partial sums of all ranks, added in rank order (the same bits on every rank)
+    for (int k = threadIdx.x; k < 2 * C; k += blockDim.x) {
+        double v = 0.0;
+        for (int r = 0; r < nparts; ++r) v += parts[(size_t)r * stride + k];
+        tot[k] = v;
+    }
+    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a, b;
-        gn_coef(stats, gamma, beta, 0, C, groups, c, plane, eps, a, b);
+        gn_coef(tot, gamma, beta, 0, C, groups, c, plane, eps, a, b);
         coef[2 * c] = a;
         coef[2 * c + 1] = b;
     }
@@ -70,9 +77,11 @@ int band_stats_launch(const double* kstats, const void* t, int dtype, int W, int
     return check_launch("band_stats");
 }
 
-int gn_affine_launch(const double* stats, const float* gamma, const float* beta, int C, int groups, double plane, float eps, float* coef,
-                     cudaStream_t st) {
-    gn_affine_kernel<<<1, C < 256 ? ((C + 31) / 32) * 32 : 256, 0, st>>>(stats, gamma, beta, C, groups, plane, eps, coef);
+int gn_affine_launch(const double* parts, int nparts, size_t stride, const float* gamma, const float* beta, int C, int groups, double plane,
+                     float eps, float* coef, cudaStream_t st) {
+    if (C > 2048) { set_error("gn_affine: %d channels (<= 2048 supported)", C); return 3; }
+    gn_affine_kernel<<<1, C < 256 ? ((C + 31) / 32) * 32 : 256, (size_t)C * 2 * sizeof(double), st>>>(parts, nparts, stride, gamma, beta, C,
+                                                                                                     groups, plane, eps, coef);
     count_launch();
     return check_launch("gn_affine");
 }

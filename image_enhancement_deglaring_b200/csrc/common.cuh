@@ -233,8 +233,8 @@ int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double*
                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t st);
 int band_stats_launch(const double* kstats, const void* t, int dtype, int W, int C, int a0, int a1, int b0, int b1, double* out,
                       cudaStream_t st);
-int gn_affine_launch(const double* stats, const float* gamma, const float* beta, int C, int groups, double plane, float eps, float* coef,
-                     cudaStream_t st);
+int gn_affine_launch(const double* parts, int nparts, size_t stride, const float* gamma, const float* beta, int C, int groups, double plane,
+                     float eps, float* coef, cudaStream_t st);
 int adamw_dev_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, const float* lr_dev,
                      float beta1, float beta2, float eps, float weight_decay, int32_t* step_dev, float grad_scale, cudaStream_t st);
 int tc_conv3x3_bytes(int cin, int cout, size_t* bytes);

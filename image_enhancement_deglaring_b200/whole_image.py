@@ -10,9 +10,12 @@ see across what would be tile borders.  Here the function is the reference's `fo
     where the kernels' own zero padding of the activated tensor applies): one row feeds a 3x3 conv, two rows feed the
     2x2 pool in front of the next level's conv, two rows of `up` come from one halo row of the low-resolution tensor;
   * after each of the 18 convs (a) the band's GroupNorm partial sums -- the producing kernel's epilogue statistics minus
-    the contribution of the halo rows it also computed -- are SUMMED OVER RANKS (one all-reduce of [C, 2] doubles) and
-    turned into the per-channel affine (a, b) that the consumer kernels take ready-made (`dg_src.coef`), and (b) the two
-    outermost owned rows are exchanged with both neighbours (one send/recv pair each way) into their halo rows.
+    the contribution of the halo rows it also computed -- are summed over ranks and turned into the per-channel affine
+    (a, b) that the consumer kernels take ready-made (`dg_src.coef`), and (b) the two outermost owned rows go to both
+    neighbours' halo rows.  Both exchanges ride on ONE all-gather per conv (packet = [C x 2 doubles | 2 top rows | 2 bottom
+    rows], 0.26 MB per rank at any level of a 4096-wide image): the band forward is latency-bound (35 separate small
+    collectives cost more than the convolutions), and adding the gathered partial sums in rank order gives every rank the
+    same bits.
 
 So the data path has exactly the two exchange steps per layer SURVEY 8e names; everything else is the per-op C-ABI
 (`dg_conv3x3_fused`, `dg_convt2x2_fused`, `dg_head1x1`) on band-sized tensors.  The arithmetic backend is pluggable only so
@@ -55,22 +58,16 @@ class DistComm:
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
 
-    def all_reduce_sum(self, t):
-        if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
-        return t
-
-    def exchange(self, send_up, recv_up, send_down, recv_down):
-        """send_up -> rank-1's recv_down, send_down -> rank+1's recv_up (contiguous row slices; None at the image border)."""
-        d, ops = self.dist, []
-        peer = lambda r: r if self.group is None else d.get_global_rank(self.group, r)
-        if self.rank > 0:
-            ops += [d.P2POp(d.isend, send_up, peer(self.rank - 1), self.group), d.P2POp(d.irecv, recv_up, peer(self.rank - 1), self.group)]
-        if self.rank < self.world - 1:
-            ops += [d.P2POp(d.isend, send_down, peer(self.rank + 1), self.group), d.P2POp(d.irecv, recv_down, peer(self.rank + 1), self.group)]
-        if ops:
-            for w in d.batch_isend_irecv(ops):
-                w.wait()
+    def gather(self, packed):
+        """packed: contiguous 1-D uint8 tensor, the same length on every rank -> [world, n] (every rank's packet, rank order)."""
+        out = torch.empty((self.world, packed.numel()), dtype=packed.dtype, device=packed.device)
+        if self.world == 1:
+            out[0].copy_(packed)
+        elif self.dist.get_backend(self.group) == "nccl":
+            self.dist.all_gather_into_tensor(out, packed, group=self.group)
+        else:
+            self.dist.all_gather(list(out.unbind(0)), packed, group=self.group)
+        return out
 
     def gather_rows(self, band):
         parts = [torch.empty_like(band) for _ in range(self.world)]
@@ -89,8 +86,6 @@ class LocalBands:
         self.world = world
         self.barrier = threading.Barrier(world)
         self.slots = [None] * world
-        self.up = [None] * world
-        self.down = [None] * world
 
     def comm(self, rank):
         return _LocalComm(self, rank)
@@ -100,27 +95,13 @@ class _LocalComm:
     def __init__(self, shared, rank):
         self.s, self.rank, self.world = shared, rank, shared.world
 
-    def all_reduce_sum(self, t):
+    def gather(self, packed):
         s = self.s
-        s.slots[self.rank] = t.clone()
+        s.slots[self.rank] = packed
         s.barrier.wait()
-        total = s.slots[0].clone()
-        for r in range(1, self.world):   # rank order: every band computes the same sum, bit for bit
-            total += s.slots[r]
+        out = torch.stack(list(s.slots), 0)
         s.barrier.wait()
-        t.copy_(total)
-        return t
-
-    def exchange(self, send_up, recv_up, send_down, recv_down):
-        s = self.s
-        s.up[self.rank] = None if self.rank == 0 else send_up.clone()
-        s.down[self.rank] = None if self.rank == self.world - 1 else send_down.clone()
-        s.barrier.wait()
-        if self.rank > 0:
-            recv_up.copy_(s.down[self.rank - 1])
-        if self.rank < self.world - 1:
-            recv_down.copy_(s.up[self.rank + 1])
-        s.barrier.wait()
+        return out
 
     def gather_rows(self, band):
         s = self.s
@@ -196,23 +177,23 @@ class KernelBackend:
         _lib.check(lib.dg_conv3x3_fused(C.byref(a), stream))
         return stats
 
-    def band_stats(self, stats, t, c0, own0, own1, c1):
-        """Partial sums of the rows the band owns: `stats` (the conv's epilogue sums over the computed rows [c0, c1) of t) minus the
-        computed halo rows [c0, own0) and [own1, c1) -- one launch (dg_band_stats)."""
+    def band_stats(self, stats, t, c0, own0, own1, c1, out):
+        """Partial sums of the rows the band owns, written to `out` (float64 [C, 2] view of the packet): `stats` (the conv's epilogue
+        sums over the computed rows [c0, c1) of t) minus the computed halo rows [c0, own0) and [own1, c1) -- one launch."""
         if t.shape[-1] > 1024:
-            return None      # the driver's tensor-op path
-        out = torch.empty_like(stats)
+            return False     # the driver's tensor-op path
         _lib.check(_lib.load().dg_band_stats(stats.data_ptr(), t.data_ptr(), self.pc.dtype, t.shape[1], t.shape[2], c0, own0, own1, c1,
                                              out.data_ptr(), torch.cuda.current_stream().cuda_stream))
-        return out
+        return True
 
-    def gn_affine(self, stats, i, plane):
-        """All-reduced statistics of conv `i`'s output -> its GroupNorm's finished affine [C, 2] -- one launch (dg_gn_affine)."""
+    def gn_affine(self, parts, stride_bytes, c, i, plane):
+        """Every rank's partial sums of conv `i`'s output (`parts`: the gathered packets, one every `stride_bytes`, the [C, 2]
+        doubles at their start) -> summed in rank order -> its GroupNorm's finished affine [C, 2] -- one launch (dg_gn_affine)."""
         b, j = divmod(i, 2)
-        c = stats.shape[0]
         coef = torch.empty((c, 2), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.load().dg_gn_affine(stats.data_ptr(), self.pc.gn_w[b][j], self.pc.gn_b[b][j], c, self.net._block_groups[b],
-                                            float(plane), 1e-5, coef.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        _lib.check(_lib.load().dg_gn_affine(parts.data_ptr(), parts.shape[0], stride_bytes // 8, self.pc.gn_w[b][j], self.pc.gn_b[b][j], c,
+                                            self.net._block_groups[b], float(plane), 1e-5, coef.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
         return coef
 
     def head(self, t, coef, out):
@@ -264,21 +245,35 @@ def forward_band(net, x_band, comm, H_total, backend=None):
     T, coef = [None] * 18, [None] * 18
 
     def finish(i, lvl, stats, c0, c1, exchange=True):
-        """Rows [c0, c1) of T[i] were just computed.  Whole-image statistics -> coef[i]; neighbours' rows -> halo rows."""
+        """Rows [c0, c1) of T[i] were just computed.  ONE all-gather carries both exchanges of SURVEY 8e: every rank's packet is
+        [its partial sums (C x 2 doubles) | its two top-most owned rows | its two bottom-most owned rows]; afterwards the sums are
+        added in rank order (the same bits on every rank) -> coef[i], and the neighbours' rows land in the halo rows."""
         t, hb_l = T[i], Hb >> lvl
-        own = be.band_stats(stats, t, c0, ht, ht + hb_l, c1) if hasattr(be, "band_stats") else None
-        if own is None:      # backends without the fused step (the CPU stand-in of the tests; > 1024 channels)
-            own = stats - _row_stats(t[c0:ht]) - _row_stats(t[ht + hb_l:c1])
-        stats = comm.all_reduce_sum(own)
+        c = t.shape[-1]
+        exchange = exchange and world > 1
+        sb = 16 * c                                              # statistics bytes
+        rb = HALO * t.shape[1] * c * t.element_size() if exchange else 0   # bytes of two rows
+        packet = torch.empty(sb + 2 * rb, dtype=torch.uint8, device=t.device)
+        own = packet[:sb].view(torch.float64).view(c, 2)
+        if not (hasattr(be, "band_stats") and be.band_stats(stats, t, c0, ht, ht + hb_l, c1, own)):
+            own.copy_(stats - _row_stats(t[c0:ht]) - _row_stats(t[ht + hb_l:c1]))   # backends without the fused step
+        if exchange:
+            packet[sb:sb + rb].view(t.dtype).copy_(t[ht:ht + HALO].reshape(-1))
+            packet[sb + rb:].view(t.dtype).copy_(t[ht + hb_l - HALO:ht + hb_l].reshape(-1))
+        allp = comm.gather(packet)
         b, j = divmod(i, 2)
         plane = (H_total >> lvl) * (W >> lvl)
         if hasattr(be, "gn_affine"):
-            coef[i] = be.gn_affine(stats, i, plane)
+            coef[i] = be.gn_affine(allp, allp.shape[1], c, i, plane)
         else:
+            total = allp[:, :sb].contiguous().view(torch.float64).view(world, c, 2).sum(0)
             gn = getattr(net, _BLOCKS[b])[1 if j == 0 else 4]
-            coef[i] = _gn_coef(stats, gn.weight.detach(), gn.bias.detach(), net._block_groups[b], plane)
-        if exchange and world > 1:
-            comm.exchange(t[ht:ht + HALO], t[0:ht], t[ht + hb_l - HALO:ht + hb_l], t[ht + hb_l:ht + hb_l + hb])
+            coef[i] = _gn_coef(total, gn.weight.detach(), gn.bias.detach(), net._block_groups[b], plane)
+        if exchange:
+            if rank > 0:                 # the upper neighbour's bottom rows
+                t[0:ht].reshape(-1).copy_(allp[rank - 1, sb + rb:].view(t.dtype))
+            if rank < world - 1:         # the lower neighbour's top rows
+                t[ht + hb_l:].reshape(-1).copy_(allp[rank + 1, sb:sb + rb].view(t.dtype))
 
     for b in range(9):
         lvl = b if b < 5 else 8 - b

@@ -290,17 +290,19 @@ int dg_lw_infer_host_u8(const dg_lw_params* p, const uint8_t* host_x, uint8_t* h
                         int32_t W, int32_t chunk, void* dev_ws, size_t dev_ws_bytes, dg_stream_t stream);
 
 /* Row-sharded whole-image inference (SURVEY 8e definition B; whole_image.py): nn.GroupNorm (src/model.py:94,97) normalises over the
- * WHOLE image, so a rank that holds a band of rows contributes the partial sums of the rows it owns, the sums are all-reduced, and the
- * consumers take the finished affine through dg_src.coef.
+ * WHOLE image, so a rank that holds a band of rows contributes the partial sums of the rows it owns, the partial sums of all ranks are
+ * exchanged (one all-gather per conv, which carries the halo rows as well), and the consumers take the finished affine through
+ * dg_src.coef.
  *  dg_band_stats: `rows` = NHWC [R, W, C] band tensor (N = 1) of which the producing conv computed rows [halo_top0, halo_bottom1) and
  *    the band owns [own0, own1); out[C][2] = kernel_stats[C][2] (the conv's out_stats over every computed row) minus the (sum, sum of
  *    squares) of the computed halo rows.  C <= 1024.
- *  dg_gn_affine: stats[C][2] summed over ranks, `plane` = H_total * W of the whole image at this level ->
- *    coef[C][2] = (a, b), y = x * a + b, by the same double-precision chain the conv kernels run on their own statistics. */
+ *  dg_gn_affine: `nparts` blocks of [C][2] partial sums, one every `part_stride` doubles (the gathered packets of all ranks), are added in
+ *    block order; `plane` = H_total * W of the whole image at this level -> coef[C][2] = (a, b), y = x * a + b, by the same
+ *    double-precision chain the conv kernels run on their own statistics.  C <= 2048. */
 int dg_band_stats(const double* kernel_stats, const void* rows, int32_t dtype, int32_t W, int32_t C, int32_t halo_top0, int32_t own0,
                   int32_t own1, int32_t halo_bottom1, double* out, dg_stream_t stream);
-int dg_gn_affine(const double* stats, const float* gamma, const float* beta, int32_t C, int32_t groups, double plane, float eps,
-                 float* coef, dg_stream_t stream);
+int dg_gn_affine(const double* parts, int32_t nparts, size_t part_stride, const float* gamma, const float* beta, int32_t C, int32_t groups,
+                 double plane, float eps, float* coef, dg_stream_t stream);
 
 /* Asynchronous twin of dg_lw_infer_host / dg_lw_infer_host_u8 (`u8` != 0) for a service with several requests in flight
  * (uvicorn workers in front of api/app.py:171, evaluate.py:245's loop over batches): _submit enqueues the whole call -- H2D

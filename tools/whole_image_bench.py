@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """BASELINE.json configs[2], definition B: ONE 4096x4096 image through the network exactly (whole-image GroupNorm), rows sharded
-over the ranks (whole_image.py: per-conv GroupNorm partial-sum all-reduce + 2-row halo exchange).
+over the ranks (whole_image.py: per conv ONE all-gather carrying the GroupNorm partial sums and the 2-row halos).
 
     python tools/whole_image_bench.py [--size 4096] [--storage fp16]                 # 1 GPU: the single-call forward AND 1 band
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/whole_image_bench.py
@@ -65,7 +65,7 @@ with torch.no_grad():
     full = comm.gather_rows(y.permute(1, 0, 2).contiguous()).permute(1, 0, 2)
     line = {"what": f"one {S}x{S} image, exact whole-image GroupNorm, rows sharded over ranks (SURVEY 8e definition B)",
             "n_gpus": world, "storage": args.storage, "ms_per_image_sharded": ms_sharded,
-            "exchanges_per_image": {"allreduce_of_C_x_2_doubles": 18, "halo_send_recv_pairs_per_neighbour": 17}}
+            "exchanges_per_image": {"all_gathers": 18, "packet": "C x 2 doubles of GroupNorm partial sums + 2 top rows + 2 bottom rows"}}
     try:   # the same band forward replayed from a CUDA graph (kernels + NCCL in one graph)
         g = BandGraph(net, comm, S, S, be)
         line["ms_per_image_sharded_cuda_graph"] = timed(lambda: g(band))
