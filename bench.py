@@ -69,16 +69,54 @@ def training_algorithmic_bytes_per_image(H, W, fs=8, esize=2):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML polled every few milliseconds
+    from a thread (the timed region of the default run is tens of milliseconds, nvidia-smi's 100 ms loop gave it 2-3 samples);
+    `nvidia-smi -lms 100` is the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []     # (time, sm_mhz, reasons bitmask)
+        self.smax = None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            props = torch.cuda.get_device_properties(self.index)
+            bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
+
+    def _poll(self):
+        nv, h = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+            except Exception:
+                pass
+            self._stop.wait(0.004)
 
     def start(self):
+        try:
+            self.nvml = self._nvml_handle()
+            nv, h = self.nvml
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -93,6 +131,16 @@ class ClockSampler:
             self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1)
+            rows = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+            sm = [s[1] for s in rows]
+            mask = 0
+            for s in rows:
+                mask |= s[2]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(nm for nm, bit in self.REASONS if mask & bit), "samples": len(sm), "source": "nvml, 4 ms poll"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -117,7 +165,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 ORT_NOTE = "onnxruntime unavailable \u2014 not installed, no network"
@@ -274,7 +322,8 @@ def main():
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-            time.sleep(0.25)
+            if sampler.nvml is None:
+                time.sleep(0.25)   # nvidia-smi needs a moment to produce its first line
         barrier()
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
