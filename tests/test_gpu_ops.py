@@ -736,3 +736,81 @@ def test_wgrad_tc_refuses_what_it_does_not_cover():
     with pytest.raises(RuntimeError):
         ops.conv3x3_wgrad([src], dR, 24, 24, 1, 16, 16, ops.DG_F16, path=2)
     ops.conv3x3_wgrad([src], dR, 24, 24, 1, 16, 16, ops.DG_F16, path=0)   # auto falls back to the generic kernel
+
+
+# ---- the two device steps of the row-sharded whole-image path and the graph-capturable optimizer tail -----------------------------
+@pytest.mark.parametrize("tdtype,code", [(torch.float32, 0), (torch.float16, 1), (torch.bfloat16, 2)])
+@pytest.mark.parametrize("C,W,rows,c0,own0,own1,c1", [(8, 64, 20, 0, 2, 18, 20), (16, 48, 11, 1, 2, 10, 10), (12, 32, 9, 0, 0, 7, 9),
+                                                     (128, 16, 6, 1, 2, 4, 5), (1024, 4, 5, 0, 1, 4, 5)])
+def test_band_stats_subtracts_the_computed_halo_rows(tdtype, code, C, W, rows, c0, own0, own1, c1):
+    """dg_band_stats: kernel statistics over the computed rows [c0, c1) minus the halo rows [c0, own0) and [own1, c1) = the sums
+    over the owned rows, in double (whole_image.py; nn.GroupNorm over the whole image, src/model.py:94,97)."""
+    import ctypes as C_
+    from image_enhancement_deglaring_b200 import _lib
+    g = torch.Generator().manual_seed(C + rows)
+    t = (torch.randn(rows, W, C, generator=g) * 2).to(tdtype).cuda()
+    d = t.double()
+    full = torch.stack((d[c0:c1].sum((0, 1)), (d[c0:c1] ** 2).sum((0, 1))), -1)        # what the conv epilogue hands over
+    want = torch.stack((d[own0:own1].sum((0, 1)), (d[own0:own1] ** 2).sum((0, 1))), -1)
+    out = torch.empty_like(full)
+    _lib.check(_lib.load().dg_band_stats(full.data_ptr(), t.data_ptr(), code, W, C, c0, own0, own1, c1, out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+    assert float((out - want).abs().max()) <= 1e-9 * max(1.0, float(full.abs().max()))
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.load().dg_band_stats(full.data_ptr(), t.data_ptr(), code, W, C, 3, 2, own1, c1, out.data_ptr(), None))
+
+
+@pytest.mark.parametrize("C,groups,parts", [(8, 8, 1), (16, 8, 2), (12, 6, 3), (128, 8, 8), (1024, 8, 2)])
+def test_gn_affine_from_gathered_partial_sums(C, groups, parts):
+    """dg_gn_affine: partial (sum, sum of squares) blocks of all ranks, one every `stride` doubles, added in block order -> the
+    GroupNorm affine (a, b) with y = x * a + b equal to F.group_norm on the full tensor."""
+    from image_enhancement_deglaring_b200 import _lib
+    g = torch.Generator().manual_seed(C + parts)
+    H, W = 6 * parts, 10
+    x = torch.randn(1, C, H, W, generator=g) * 1.5 + 0.3
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    want = F.group_norm(x, groups, gamma, beta, 1e-5)
+    stride = 2 * C + 24                                   # packets carry rows behind the statistics
+    buf = torch.zeros(parts, stride, dtype=torch.float64)
+    for r in range(parts):
+        band = x[0, :, r * 6:(r + 1) * 6].double()
+        buf[r, :2 * C] = torch.stack((band.sum((1, 2)), (band ** 2).sum((1, 2))), -1).reshape(-1)
+    buf[:, 2 * C:] = 1e30                                  # must not be read
+    coef = torch.empty(C, 2, dtype=torch.float32, device="cuda")
+    dbuf, dgamma, dbeta = buf.cuda(), gamma.cuda(), beta.cuda()      # named: the library only borrows the pointers
+    _lib.check(_lib.load().dg_gn_affine(dbuf.data_ptr(), parts, stride, dgamma.data_ptr(), dbeta.data_ptr(), C, groups,
+                                        float(H * W), 1e-5, coef.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    c = coef.cpu()
+    got = x * c[:, 0].view(1, C, 1, 1) + c[:, 1].view(1, C, 1, 1)
+    assert float((got - want).abs().max()) <= 2e-5
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.load().dg_gn_affine(buf.data_ptr(), parts, stride, gamma.data_ptr(), beta.data_ptr(), C, 5 if C % 5 else 7, float(H * W),
+                                            1e-5, coef.data_ptr(), None))
+
+
+def test_adamw_step_graph_equals_host_step_flavour():
+    """dg_adamw_step_graph (step count and learning rate in device memory) performs exactly the update of dg_adamw_step, step after step."""
+    from image_enhancement_deglaring_b200 import _lib
+    lib = _lib.load()
+    n = 10007
+    g0 = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=g0)
+    pa, pb = p0.clone().cuda(), p0.clone().cuda()
+    ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
+    sa, sb = torch.zeros(1, dtype=torch.float64, device="cuda"), torch.zeros(1, dtype=torch.float64, device="cuda")
+    step_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lr_dev = torch.zeros(1, dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for step, lr in enumerate((1e-3, 1e-3, 5e-4, 2e-3), start=1):
+        gr = (torch.randn(n, generator=g0) * (10.0 if step == 2 else 0.01)).cuda()     # step 2 is clipped
+        _lib.check(lib.dg_adamw_step(pa.data_ptr(), gr.data_ptr(), ma.data_ptr(), va.data_ptr(), n, sa.data_ptr(), 1.0, lr, 0.9, 0.999, 1e-8,
+                                     0.01, step, 1.0, st))
+        lr_dev.fill_(lr)
+        _lib.check(lib.dg_adamw_step_graph(pb.data_ptr(), gr.data_ptr(), mb.data_ptr(), vb.data_ptr(), n, sb.data_ptr(), 1.0, lr_dev.data_ptr(),
+                                           0.9, 0.999, 1e-8, 0.01, step_dev.data_ptr(), 1.0, st))
+        assert int(step_dev.item()) == step
+        # the gradient's sum of squares is reduced with double atomics (order noise ~1e-16), so the clip factor may move by an ulp
+        assert float((pa - pb).abs().max()) <= 1e-7
+        assert torch.allclose(ma, mb, rtol=1e-6, atol=0) and torch.allclose(va, vb, rtol=1e-6, atol=0)
+        assert abs(float(sa.item()) - float(sb.item())) <= 1e-12 * float(sa.item())
