@@ -247,10 +247,11 @@ static int lw_forward_range(const dg_lw_params* p, const LwPlan& pl, char* ws, c
 // 2.25 -> 2.09 ms per forward (two streams; four: 2.12); batch 32: 1.20 -> 1.08 ms, batch 16: 0.675 -> 0.599 ms, batch 8: no
 // change (hence the default threshold of 16).  Outputs are bit-identical (nothing depends on the batch size).
 struct FwdFork {
+    static constexpr int MAXF = 4;
     bool ready = false;
     int device = -1;
-    cudaStream_t s[2];
-    cudaEvent_t fork, join[2];
+    cudaStream_t s[MAXF];
+    cudaEvent_t fork, join[MAXF];
 };
 // slot 0: calls on the caller's stream (dg_lw_forward / dg_lw_backward); slots 1..4: the chunks in flight of the host pipeline,
 // which must not share fork streams (that would serialise the chunks again)
@@ -263,9 +264,9 @@ static int fork_init(int slot = 0) {
     cudaGetDevice(&dev);
     if (g_fork.ready && g_fork.device == dev) return 0;
     cudaError_t e = cudaSuccess;
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&g_fork.s[k], cudaStreamNonBlocking);
+    for (int k = 0; k < FwdFork::MAXF && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&g_fork.s[k], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_fork.fork, cudaEventDisableTiming);
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&g_fork.join[k], cudaEventDisableTiming);
+    for (int k = 0; k < FwdFork::MAXF && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&g_fork.join[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("forward fork streams: %s", cudaGetErrorString(e)); return 10; }
     g_fork.ready = true;
     g_fork.device = dev;
@@ -444,16 +445,20 @@ static int lw_backward(const dg_lw_params* p, const float* x, const float* grad_
     if (e == cudaSuccess) e = cudaMemsetAsync(grads, 0, gl.total * sizeof(float), st);
     if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return 10; }
     const int split = g_split.load();
-    if (split > 0 && N >= split && N >= 2) {   // two concurrent halves, as in lw_forward
+    if (split > 0 && N >= split && N >= 2) {   // concurrent sub-batches, as in lw_forward (DG_BWD_FORKS = 2..4 of them; default 2)
         if ((rc = fork_init())) return rc;
         FwdFork& F = g_forks[0];
+        static const int want = [] { const char* e = getenv("DG_BWD_FORKS"); const int v = e ? atoi(e) : 2; return v < 2 ? 2 : (v > FwdFork::MAXF ? FwdFork::MAXF : v); }();
+        const int nf = N >= 8 * want ? want : 2;
         cudaEventRecord(F.fork, st);
-        const int half = N / 2;
-        for (int k = 0; k < 2; ++k) {
+        int n0 = 0;
+        for (int k = 0; k < nf; ++k) {
+            const int nn = (N - n0) / (nf - k);
             cudaStreamWaitEvent(F.s[k], F.fork, 0);
-            rc = lw_backward_range(p, pl, bp, gl, x, grad_y, k ? half : 0, k ? N - half : half, H, W, fw, bw, grads, F.s[k], l1);
+            rc = lw_backward_range(p, pl, bp, gl, x, grad_y, n0, nn, H, W, fw, bw, grads, F.s[k], l1);
             cudaEventRecord(F.join[k], F.s[k]);
             cudaStreamWaitEvent(st, F.join[k], 0);
+            n0 += nn;
             if (rc) return rc;
         }
         return 0;
