@@ -896,6 +896,95 @@ int dg_channel_attention(const double* act_sum, double plane, const float* w1, c
     return se_scale_launch(act_sum, plane, w1, w2, N, C, hidden, scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ---- per-op backward entry points (OptimizedUNet training is orchestrated above the C-ABI from these) ----------------------
+static int check_gn(const char* who, const void* raw, const double* stats, const float* gamma, const float* beta, int N, int H, int W,
+                    int C, int groups) {
+    if (raw == nullptr || stats == nullptr || gamma == nullptr || beta == nullptr) { set_error("%s: null pointer", who); return 2; }
+    if (N < 1 || H < 1 || W < 1 || C < 1) { set_error("%s: bad shape", who); return 3; }
+    if (groups < 1 || C % groups != 0) { set_error("%s: %d channels not divisible into %d groups", who, C, groups); return 2; }
+    return 0;
+}
+
+int dg_head1x1_bwd(const dg_head_args* a, const float* grad_y, float* G, double* P, float* dW, float* dB, dg_stream_t stream) {
+    if (a == nullptr || grad_y == nullptr || G == nullptr || P == nullptr || dW == nullptr || dB == nullptr) {
+        set_error("head backward: null pointer");
+        return 2;
+    }
+    int rc = validate_src(a->src, "head backward");
+    if (rc) return rc;
+    if (a->src.xform != DG_X_SAME || a->src.stats == nullptr || !a->src.silu || a->src.scale != nullptr || a->src.coef != nullptr) {
+        set_error("head backward: the source must be a same-resolution GroupNorm + SiLU tensor described by its statistics");
+        return 3;
+    }
+    if (a->weight == nullptr) { set_error("head backward: null weight"); return 2; }
+    return head_bwd_launch(a->dtype, a->src.raw, a->src.stats, a->src.gamma, a->src.beta, grad_y, a->weight, G, P, dW, dB, a->N, a->H,
+                           a->W, a->src.channels, a->cout, a->src.groups, a->eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_act_bwd(int32_t dtype, const void* raw, const double* stats, const float* gamma, const float* beta, int32_t groups,
+               const float* dA_a, int32_t stride_a, int32_t off_a, const float* dA_b, int32_t stride_b, int32_t off_b, float* G,
+               double* P, int32_t N, int32_t H, int32_t W, int32_t C, float eps, dg_stream_t stream) {
+    int rc = check_gn("act backward", raw, stats, gamma, beta, N, H, W, C, groups);
+    if (rc) return rc;
+    if (G == nullptr || P == nullptr || (dA_a == nullptr && dA_b == nullptr)) { set_error("act backward: null pointer"); return 2; }
+    if (dA_b != nullptr && ((H | W) & 1)) { set_error("act backward: pooled gradient needs even H, W"); return 3; }
+    if ((dA_a != nullptr && (off_a < 0 || off_a + C > stride_a)) || (dA_b != nullptr && (off_b < 0 || off_b + C > stride_b))) {
+        set_error("act backward: channel window outside the gradient tensor");
+        return 3;
+    }
+    return act_bwd_launch(dtype, raw, stats, gamma, beta, dA_a, stride_a, off_a, dA_b, stride_b, off_b, G, P, N, H, W, C, groups, eps,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_gn_bwd_apply(int32_t dtype, const void* raw, const double* stats, const float* gamma, int32_t groups, const double* P, float* G,
+                    float* dgamma, float* dbeta, int32_t N, int32_t H, int32_t W, int32_t C, float eps, dg_stream_t stream) {
+    int rc = check_gn("GroupNorm backward", raw, stats, gamma, gamma, N, H, W, C, groups);
+    if (rc) return rc;
+    if (P == nullptr || G == nullptr || (dgamma == nullptr) != (dbeta == nullptr)) { set_error("GroupNorm backward: null pointer"); return 2; }
+    return gn_bwd_apply_launch(dtype, raw, stats, gamma, P, G, dgamma, dbeta, N, H, W, C, groups, eps,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_grad_gather(const float* a, int32_t stride_a, int32_t off_a, const float* a_scale, const float* b, int32_t stride_b,
+                   int32_t off_b, const float* u, int32_t stride_u, int32_t off_u, const float* add, float* out, int32_t N, int32_t H,
+                   int32_t W, int32_t C, dg_stream_t stream) {
+    if (out == nullptr || (a == nullptr && b == nullptr && u == nullptr)) { set_error("grad gather: null pointer"); return 2; }
+    if (N < 1 || H < 1 || W < 1 || C < 1) { set_error("grad gather: bad shape"); return 3; }
+    if (b != nullptr && ((H | W) & 1)) { set_error("grad gather: pooled gradient needs even H, W"); return 3; }
+    if ((a != nullptr && (off_a < 0 || off_a + C > stride_a)) || (b != nullptr && (off_b < 0 || off_b + C > stride_b)) ||
+        (u != nullptr && (off_u < 0 || off_u + C > stride_u)) || (a == nullptr && a_scale != nullptr)) {
+        set_error("grad gather: channel window outside a gradient tensor");
+        return 3;
+    }
+    return grad_gather_launch(a, stride_a, off_a, a_scale, b, stride_b, off_b, u, stride_u, off_u, add, out, N, H, W, C,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_scale_bwd_sum(int32_t dtype, const void* raw, const double* stats, const float* gamma, const float* beta, int32_t groups,
+                     const float* d, int32_t stride_d, int32_t off_d, double* dscale, int32_t N, int32_t H, int32_t W, int32_t C,
+                     float eps, dg_stream_t stream) {
+    int rc = check_gn("scale backward", raw, stats, gamma, beta, N, H, W, C, groups);
+    if (rc) return rc;
+    if (d == nullptr || dscale == nullptr) { set_error("scale backward: null pointer"); return 2; }
+    if (off_d < 0 || off_d + C > stride_d) { set_error("scale backward: channel window outside the gradient tensor"); return 3; }
+    if (C > 2048) { set_error("scale backward: %d channels > 2048", C); return 3; }
+    return scale_bwd_sum_launch(dtype, raw, stats, gamma, beta, d, stride_d, off_d, dscale, N, H, W, C, groups, eps,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dg_channel_attention_bwd(const double* act_sum, double plane, const float* w1, const float* w2, const double* dscale, int32_t N,
+                             int32_t C, int32_t hidden, float* add, float* dw1, float* dw2, dg_stream_t stream) {
+    if (act_sum == nullptr || w1 == nullptr || w2 == nullptr || dscale == nullptr || add == nullptr || dw1 == nullptr || dw2 == nullptr) {
+        set_error("attention backward: null pointer");
+        return 2;
+    }
+    if (N < 1 || C < 1 || hidden < 1 || plane <= 0.0 || (size_t)(2 * C + 3 * hidden) * sizeof(float) > 48 * 1024) {
+        set_error("attention backward: bad shape");
+        return 3;
+    }
+    return se_bwd_launch(act_sum, plane, w1, w2, dscale, N, C, hidden, add, dw1, dw2, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int dg_lw_num_params(const dg_lw_params* p, size_t* count) {
     LwPlan pl;
     int rc = make_plan(p, 1, 16, 16, &pl);

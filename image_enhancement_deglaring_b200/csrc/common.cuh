@@ -237,6 +237,13 @@ int gn_affine_launch(const double* parts, int nparts, size_t stride, const float
                      float eps, float* coef, cudaStream_t st);
 int adamw_dev_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, const float* lr_dev,
                      float beta1, float beta2, float eps, float weight_decay, int32_t* step_dev, float grad_scale, cudaStream_t st);
+// OptimizedUNet-only backward pieces (opt_bwd.cu)
+int grad_gather_launch(const float* a, int sa, int oa, const float* a_scale, const float* b, int sb, int ob, const float* u, int su,
+                       int ou, const float* add, float* out, int N, int H, int W, int C, cudaStream_t st);
+int scale_bwd_sum_launch(int dtype, const void* raw, const double* stats, const float* gamma, const float* beta, const float* d,
+                         int sd, int od, double* out, int N, int H, int W, int C, int groups, float eps, cudaStream_t st);
+int se_bwd_launch(const double* act_sum, double plane, const float* w1, const float* w2, const double* dscale, int N, int C,
+                  int hidden, float* add, float* dw1, float* dw2, cudaStream_t st);
 int tc_conv3x3_bytes(int cin, int cout, size_t* bytes);
 int tc_convt_bytes(int cl, int cu, size_t* bytes);
 int pack_conv3x3_tc(const float* w, void* out, int cin, int cout, int dtype, cudaStream_t st);

@@ -11,13 +11,18 @@ Mapping onto the fused 3x3 conv (include/deglare.h):
                                   two tiny mat-vecs (dg_channel_attention), scale applied on load (dg_src.scale) :185-202
   torch.cat((up, skip*att))    -> two-source conv, never materialised                                    :140-156
 """
-import ctypes as C
+import contextlib
 
 import torch
 import torch.nn as nn
 
 from . import _lib, ops
 from ._lib import DTYPE_CODES
+
+
+def _on_device_of(t):
+    """Make t's GPU the current one for the launches below (the public forward has already refused CPU tensors)."""
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
 class ChannelAttention(nn.Module):
@@ -86,8 +91,6 @@ class OptimizedUNet(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.storage, self.path, _lib.generation())
         if key == self._pack_key:
             return self._pk
-        if self.output.weight.device.type != "cuda":
-            raise RuntimeError("OptimizedUNet (B200) needs its parameters on a CUDA device; there is no CPU fallback")
         dt = DTYPE_CODES[self.storage]
         pk = {}
 
@@ -112,22 +115,50 @@ class OptimizedUNet(nn.Module):
         self._pk, self._pack_key = pk, key
         return pk
 
+    def _packs_bwd(self):
+        """Backward-only weight copies: taps-flipped [3,3,Co,Ci] fp32 for the CUDA-core data gradient and, in the 16-bit tiers,
+        the bf16 tensor-core packing of the forward weights the tensor-core data gradient reads transposed."""
+        pk = self._packs()
+        if pk.get("_bwd") is None:
+            bk = {}
+            for name, v in list(pk.items()):
+                if not (isinstance(v, tuple) and len(v) == 2 and name[-2:] in (".0", ".3", ".1") and "attention" not in name):
+                    continue
+                blk, idx = name.rsplit(".", 1)
+                w = getattr(self, blk)[int(idx)].weight
+                tc = None
+                if self.storage != "fp32" and (self.path & 3) != 1:
+                    tc = ops.pack_conv3x3_tc(v[0], ops.DG_BF16)
+                bk[name] = (ops.flip_conv3x3(w), tc)
+            pk["_bwd"] = bk
+        return pk["_bwd"]
+
     def forward(self, x):
-        lib = _lib.load()
+        _lib.load()
         if not x.is_cuda:
             raise RuntimeError("OptimizedUNet (B200) runs on CUDA tensors only; there is no CPU fallback")
+        if self.output.weight.device.type != "cuda":
+            raise RuntimeError("OptimizedUNet (B200) needs its parameters on a CUDA device; there is no CPU fallback")
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise RuntimeError(f"expected input [N,{self.in_channels},H,W], got {tuple(x.shape)}")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("OptimizedUNet training is not implemented yet: call under torch.no_grad()")
         N, _, H, W = x.shape
         if H % 16 or W % 16 or H < 16 or W < 16:
             raise RuntimeError(f"input {N}x{H}x{W}: H and W must be positive multiples of 16")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if x.requires_grad:
+                raise NotImplementedError("gradient w.r.t. the input image is not implemented (the reference never needs it)")
+            return _OptimizedUNetFn.apply(self, x, *self.parameters())
+        with _on_device_of(x):
+            return self._run(x)
+
+    def _run(self, x, keep=None):
+        """The forward of src/optimized_model.py:118-158 on the fused ops.  `keep` (training): filled with everything backward
+        re-reads -- per conv its raw output, statistics and source descriptions, per attention its squeeze sums and scales."""
+        N, _, H, W = x.shape
         x = x.detach().float().contiguous()
         pk = self._packs()
         dt = DTYPE_CODES[self.storage]
         dev = x.device
-        stream = torch.cuda.current_stream().cuda_stream
 
         def src(t, gnname, xform=ops.DG_X_SAME, scale=None):
             raw, stats, c = t
@@ -137,14 +168,15 @@ class OptimizedUNet(nn.Module):
         def conv(name, srcs, cout, h, w, act_sum=None):
             wp, wtc = pk[name]
             raw, stats = ops.conv3x3_fused(srcs, wp, cout, N, h, w, dt, act_sum=act_sum, path=self.path, weight_tc=wtc)
+            if keep is not None:
+                keep[name] = dict(raw=raw, stats=stats, c=cout, h=h, w=w, srcs=srcs, cin=int(wp.shape[2]))
             return raw, stats, cout
 
         def attention(name, t, act_sum, h, w):
             w1, w2 = pk[name]
-            c = t[2]
-            scale = torch.empty((N, c), dtype=torch.float32, device=dev)
-            _lib.check(lib.dg_channel_attention(act_sum.data_ptr(), float(h * w), w1.data_ptr(), w2.data_ptr(), N, c,
-                                                w1.shape[0], scale.data_ptr(), stream))
+            scale = ops.channel_attention(act_sum, float(h * w), w1, w2)
+            if keep is not None:
+                keep[name] = dict(act_sum=act_sum, scale=scale, plane=float(h * w))
             return scale
 
         f = self.init_features
@@ -173,4 +205,130 @@ class OptimizedUNet(nn.Module):
             d = conv(f"dec{k}.3", [src(d, f"dec{k}.1")], chans[lvl], *hw[lvl])
             dname = f"dec{k}.4"
         hw_, hb = pk["head"]
-        return ops.head1x1(src(d, dname), hw_, hb, N, H, W, dt)
+        hsrc = src(d, dname)
+        if keep is not None:
+            keep["head"] = hsrc
+        return ops.head1x1(hsrc, hw_, hb, N, H, W, dt)
+
+    # ---- training: autograd of the forward above (optimized_train.py:210/226 drives it through loss.backward()) ----------------
+    _tc_dgrad_ok = {}   # (cin, cout) -> does the tensor-core data gradient cover the pair (probed once per process)
+
+    def _backward(self, keep, grad_y, flat):
+        """All 76 parameter gradients into `flat` (zero on entry; parameters() order, the parameters' own layouts)."""
+        pk, bk = self._packs(), self._packs_bwd()
+        dt = DTYPE_CODES[self.storage]
+        N, _, H, W = grad_y.shape
+        dev = grad_y.device
+        views, off = {}, 0
+        for name, p in self.named_parameters():
+            views[name] = flat[off:off + p.numel()]
+            off += p.numel()
+        T = {}   # conv name -> gradient at the conv's input grid, fp32 NHWC [N,h,w,cin_total]
+
+        def gn_of(name):
+            blk, idx = name.rsplit(".", 1)
+            return f"{blk}.{int(idx) + 1}"
+
+        def dgrad(name, dR):
+            L = keep[name]
+            wflip, wtc = bk[name]
+            key = (L["cin"], L["c"])
+            if wtc is not None and OptimizedUNet._tc_dgrad_ok.get(key, True):
+                try:
+                    return ops.conv3x3_dgrad(dR, wtc, L["cin"], L["c"])
+                except RuntimeError as e:   # rc 3 is raised before any launch: the pair is outside the tensor-core kernel's table
+                    if "no tensor-core kernel" not in str(e):
+                        raise
+                    OptimizedUNet._tc_dgrad_ok[key] = False
+            return ops.conv3x3_dgrad_generic(dR, wflip, L["cin"], N, L["h"], L["w"])
+
+        def finish(name, G, P):
+            """G = dL/dy of conv `name` -> dR in place; GroupNorm / conv parameter gradients; the conv's input gradient."""
+            L = keep[name]
+            gn = gn_of(name)
+            g, _, groups = pk[gn]
+            ops.gn_bwd_apply(L["raw"], L["stats"], g, groups, dt, N, L["h"], L["w"], L["c"], P, G, views[gn + ".weight"],
+                             views[gn + ".bias"])
+            ops.conv3x3_wgrad(L["srcs"], G, L["cin"], L["c"], N, L["h"], L["w"], dt, path=self.path & 3,
+                              out=views[name + ".weight"])
+            if name != "enc1.0":
+                T[name] = dgrad(name, G)
+
+        def act(name, dA, off_a=0):
+            L = keep[name]
+            g, b, groups = pk[gn_of(name)]
+            G = torch.empty((N, L["h"], L["w"], L["c"]), dtype=torch.float32, device=dev)
+            P = torch.zeros((N, L["c"], 2), dtype=torch.float64, device=dev)
+            ops.act_bwd(L["raw"], L["stats"], g, b, groups, dt, N, L["h"], L["w"], L["c"], G, P, dA_a=dA, off_a=off_a)
+            finish(name, G, P)
+
+        # head (src/optimized_model.py:158) and the last conv's activation
+        L = keep["dec1.3"]
+        G = torch.empty((N, H, W, L["c"]), dtype=torch.float32, device=dev)
+        P = torch.zeros((N, L["c"], 2), dtype=torch.float64, device=dev)
+        ops.head1x1_bwd(keep["head"], pk["head"][0], grad_y, N, H, W, dt, G, P, views["output.weight"], views["output.bias"])
+        finish("dec1.3", G, P)
+        # decoder, top level first (:138-156 backwards)
+        for k in (1, 2, 3, 4):
+            act(f"dec{k}.0", T.pop(f"dec{k}.3"))
+            act(f"upconv{k}.1", T[f"dec{k}.0"], 0)                    # first half of torch.cat((dec, enc * att))
+            prod = f"dec{k + 1}.3" if k < 4 else "bottleneck.3"       # nn.Upsample(x2, nearest) backward: 2x2 sums
+            Lp = keep[prod]
+            act(prod, ops.grad_gather(N, Lp["h"], Lp["w"], Lp["c"], u=T.pop(f"upconv{k}.1")))
+        act("bottleneck.0", T.pop("bottleneck.3"))
+        # encoder: each skip tensor feeds the decoder concat (x att), the next level's pool and the attention squeeze
+        for lvl in (4, 3, 2, 1):
+            name = f"enc{lvl}.3"
+            nxt = "bottleneck.0" if lvl == 4 else f"enc{lvl + 1}.0"
+            L = keep[name]
+            g, b, groups = pk[gn_of(name)]
+            att = keep[f"attention{lvl}"]
+            w1, w2 = pk[f"attention{lvl}"]
+            tdec = T.pop(f"dec{lvl}.0")
+            dscale = ops.scale_bwd_sum(L["raw"], L["stats"], g, b, groups, dt, N, L["h"], L["w"], L["c"], tdec, L["c"])
+            add = ops.channel_attention_bwd(att["act_sum"], att["plane"], w1, w2, dscale, views[f"attention{lvl}.fc.0.weight"],
+                                            views[f"attention{lvl}.fc.2.weight"])
+            dA = ops.grad_gather(N, L["h"], L["w"], L["c"], a=tdec, off_a=L["c"], a_scale=att["scale"], b=T.pop(nxt), add=add)
+            del tdec
+            act(name, dA)
+            del dA
+            act(f"enc{lvl}.0", T.pop(name))
+
+
+class _OptimizedUNetFn(torch.autograd.Function):
+    """Autograd bridge of OptimizedUNet: forward keeps the raw activations, backward writes every parameter gradient into one
+    flat buffer (the optimizer's own bucket when FusedAdamW / FlatGradBucket own `.grad` and it is fresh after zero_grad) and
+    ends with the data-parallel mean all-reduce, exactly like the LightweightUNet bridge (train._LightweightUNetFn)."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        keep = {}
+        with _on_device_of(x):
+            y = module._run(x, keep)
+        ctx.module, ctx.keep, ctx.n_inputs = module, keep, len(params)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        from .train import _flat_grad_sink, sync_gradients
+        module, keep = ctx.module, ctx.keep
+        if keep is None:
+            raise RuntimeError("OptimizedUNet: backward through the same forward twice (the saved activations were released)")
+        params = list(module.parameters())
+        total = sum(p.numel() for p in params)
+        grad_y = grad_y.detach().float().contiguous()
+        with _on_device_of(grad_y):
+            sink = _flat_grad_sink(params)
+            flat = sink if sink is not None else torch.zeros(total, dtype=torch.float32, device=grad_y.device)
+            module._backward(keep, grad_y, flat)
+        ctx.keep = None
+        sync_gradients(flat, getattr(module, "ddp_sync", True))
+        if sink is not None:
+            sink._dg_zero_version = None
+            return (None, None) + (None,) * ctx.n_inputs
+        grads, off = [], 0
+        for p in params:
+            n = p.numel()
+            grads.append(flat[off:off + n].view_as(p) if p.requires_grad else None)
+            off += n
+        return (None, None, *grads)

@@ -101,13 +101,14 @@ def _stream(stream):
 
 
 def conv3x3_fused(srcs, weight, cout, N, H, W, dtype, out=None, out_stats=None, act_sum=None, path=0, stream=None,
-                  eps=1e-5, weight_tc=None, weight_comp=None):
-    """Fused 3x3 conv over the concat of `srcs` (list of DgSrc).  Returns (raw NHWC out, stats [N,cout,2] f64)."""
+                  eps=1e-5, weight_tc=None, weight_comp=None, want_stats=True):
+    """Fused 3x3 conv over the concat of `srcs` (list of DgSrc).  Returns (raw NHWC out, stats [N,cout,2] f64);
+    want_stats=False (generic path only, e.g. a data gradient) skips the statistics epilogue and returns None for them."""
     lib = _lib.load()
     dev = weight.device
     if out is None:
         out = torch.empty((N, H, W, cout), dtype=TORCH_DTYPE[dtype], device=dev)
-    if out_stats is None:
+    if out_stats is None and want_stats:
         out_stats = torch.zeros((N, cout, 2), dtype=torch.float64, device=dev)
     a = DgConv3x3Args()
     for i, s in enumerate(srcs):
@@ -127,11 +128,14 @@ def conv3x3_fused(srcs, weight, cout, N, H, W, dtype, out=None, out_stats=None, 
     return out, out_stats
 
 
-def conv3x3_wgrad(srcs, dR, cin_total, cout, N, H, W, dtype, path=0, stream=None, eps=1e-5):
+def conv3x3_wgrad(srcs, dR, cin_total, cout, N, H, W, dtype, path=0, stream=None, eps=1e-5, out=None):
     """Weight gradient of conv3x3_fused's conv: dW [cout, cin_total, 3, 3] fp32 (the nn.Conv2d.weight layout) from the same
-    source descriptions and dR = fp32 NHWC [N,H,W,cout] gradient at the raw conv output."""
+    source descriptions and dR = fp32 NHWC [N,H,W,cout] gradient at the raw conv output.  `out` (contiguous, that many
+    elements) is ACCUMULATED into -- e.g. a zeroed window of a flat gradient bucket."""
     lib = _lib.load()
-    dW = torch.zeros((cout, cin_total, 3, 3), dtype=torch.float32, device=dR.device)
+    dW = torch.zeros((cout, cin_total, 3, 3), dtype=torch.float32, device=dR.device) if out is None else out
+    if dW.numel() != cout * cin_total * 9 or dW.dtype != torch.float32 or not dW.is_contiguous():
+        raise RuntimeError("conv3x3_wgrad: `out` must be a contiguous fp32 tensor of cout*cin*9 elements")
     a = DgConv3x3Args()
     for i, s in enumerate(srcs):
         a.src[i] = s
@@ -183,6 +187,17 @@ def head1x1(src, weight, bias, N, H, W, dtype, out=None, target=None, l1_sum=Non
     return out
 
 
+def channel_attention(act_sum, plane, w1, w2, stream=None):
+    """ChannelAttention weights (dg_channel_attention): act_sum [N,C] f64 = pixel sums of the activated tensor (the `act_sum`
+    epilogue of the conv that pools it), plane = H*W, w1 [hidden,C], w2 [C,hidden] -> scale [N,C] fp32 (feeds dg_src.scale)."""
+    _require_cuda(act_sum, w1, w2)
+    N, channels = act_sum.shape
+    scale = torch.empty((N, channels), dtype=torch.float32, device=act_sum.device)
+    _lib.check(_lib.load().dg_channel_attention(_ptr(act_sum), float(plane), _ptr(w1), _ptr(w2), N, channels, int(w1.shape[0]),
+                                                _ptr(scale), _stream(stream)))
+    return scale
+
+
 def convt2x2_fused(src, N, H, W, dtype, out=None, path=0, stream=None, eps=1e-5):
     """Stand-alone tensor-core ConvTranspose2d(2,2)+bias of the activated low-res source -> NHWC [N,H,W,ct_cout]."""
     lib = _lib.load()
@@ -190,3 +205,76 @@ def convt2x2_fused(src, N, H, W, dtype, out=None, path=0, stream=None, eps=1e-5)
         out = torch.empty((N, H, W, src.ct_cout), dtype=TORCH_DTYPE[dtype], device=src._keep[0].device)
     _lib.check(lib.dg_convt2x2_fused(C.byref(src), dtype, N, H, W, _ptr(out), eps, path, _stream(stream)))
     return out
+
+
+# ---- per-op backward (OptimizedUNet training; include/deglare.h "per-op backward") ------------------------------------------
+def conv3x3_dgrad_generic(dR, weight_flip, cin, N, H, W, out=None, stream=None):
+    """Data gradient of a 3x3 conv as the forward generic kernel on an identity fp32 source: dR fp32 NHWC [N,H,W,cout] ->
+    dX fp32 NHWC [N,H,W,cin]; weight_flip = flip_conv3x3(weight) ([3,3,cout,cin], taps flipped)."""
+    src = make_src(dR, int(dR.shape[-1]), xform=DG_X_SAME, silu=False)
+    dX, _ = conv3x3_fused([src], weight_flip, cin, N, H, W, DG_F32, out=out, path=1, stream=stream, want_stats=False)
+    return dX
+
+
+def flip_conv3x3(w):
+    """nn.Conv2d weight [Co,Ci,3,3] -> [3,3,Co,Ci] fp32 with the taps flipped: the data gradient is a forward conv with it."""
+    return w.detach().float().flip(2, 3).permute(2, 3, 0, 1).contiguous()
+
+
+def head1x1_bwd(src, weight, grad_y, N, H, W, dtype, G, P, dW, dB, stream=None, eps=1e-5):
+    a = DgHeadArgs()
+    a.src = src
+    a.dtype = dtype
+    a.N, a.H, a.W, a.cout = N, H, W, int(weight.shape[0])
+    a.weight = _ptr(weight)
+    a.eps = eps
+    _require_cuda(grad_y, G, P, dW, dB)
+    _lib.check(_lib.load().dg_head1x1_bwd(C.byref(a), _ptr(grad_y), _ptr(G), _ptr(P), _ptr(dW), _ptr(dB), _stream(stream)))
+
+
+def act_bwd(raw, stats, gamma, beta, groups, dtype, N, H, W, channels, G, P, dA_a=None, off_a=0, dA_b=None, off_b=0, stream=None,
+            eps=1e-5):
+    """G = (dA_a[..., off_a:off_a+C] + 0.25 * replicate2x2(dA_b[..., off_b:off_b+C])) * SiLU'(GN(raw)); P += (sum G, sum G*xhat)."""
+    _require_cuda(raw, stats, gamma, beta, dA_a, dA_b, G, P)
+    sa = int(dA_a.shape[-1]) if dA_a is not None else 0
+    sb = int(dA_b.shape[-1]) if dA_b is not None else 0
+    _lib.check(_lib.load().dg_act_bwd(dtype, _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), groups, _ptr(dA_a), sa, off_a,
+                                      _ptr(dA_b), sb, off_b, _ptr(G), _ptr(P), N, H, W, channels, eps, _stream(stream)))
+
+
+def gn_bwd_apply(raw, stats, gamma, groups, dtype, N, H, W, channels, P, G, dgamma, dbeta, stream=None, eps=1e-5):
+    """In place G -> dR (nn.GroupNorm backward), dgamma / dbeta accumulated."""
+    _require_cuda(raw, stats, gamma, P, G, dgamma, dbeta)
+    _lib.check(_lib.load().dg_gn_bwd_apply(dtype, _ptr(raw), _ptr(stats), _ptr(gamma), groups, _ptr(P), _ptr(G), _ptr(dgamma),
+                                           _ptr(dbeta), N, H, W, channels, eps, _stream(stream)))
+
+
+def grad_gather(N, H, W, channels, a=None, off_a=0, a_scale=None, b=None, off_b=0, u=None, off_u=0, add=None, out=None, stream=None):
+    """Dense fp32 [N,H,W,C] gradient at an activated tensor from its consumers' input gradients (dg_grad_gather)."""
+    _require_cuda(a, a_scale, b, u, add, out)
+    ref = a if a is not None else (b if b is not None else u)
+    if out is None:
+        out = torch.empty((N, H, W, channels), dtype=torch.float32, device=ref.device)
+    st = lambda t: int(t.shape[-1]) if t is not None else 0
+    _lib.check(_lib.load().dg_grad_gather(_ptr(a), st(a), off_a, _ptr(a_scale), _ptr(b), st(b), off_b, _ptr(u), st(u), off_u,
+                                          _ptr(add), _ptr(out), N, H, W, channels, _stream(stream)))
+    return out
+
+
+def scale_bwd_sum(raw, stats, gamma, beta, groups, dtype, N, H, W, channels, d, off_d, stream=None, eps=1e-5):
+    """dscale [N,C] f64 = sum over pixels of d[..., off_d:off_d+C] * SiLU(GN(raw)) (dg_scale_bwd_sum)."""
+    _require_cuda(raw, stats, gamma, beta, d)
+    out = torch.zeros((N, channels), dtype=torch.float64, device=d.device)
+    _lib.check(_lib.load().dg_scale_bwd_sum(dtype, _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), groups, _ptr(d),
+                                            int(d.shape[-1]), off_d, _ptr(out), N, H, W, channels, eps, _stream(stream)))
+    return out
+
+
+def channel_attention_bwd(act_sum, plane, w1, w2, dscale, dw1, dw2, stream=None):
+    """ChannelAttention backward (dg_channel_attention_bwd): accumulates dw1 / dw2, returns add [N,C] fp32."""
+    _require_cuda(act_sum, w1, w2, dscale, dw1, dw2)
+    N, channels = act_sum.shape
+    add = torch.empty((N, channels), dtype=torch.float32, device=act_sum.device)
+    _lib.check(_lib.load().dg_channel_attention_bwd(_ptr(act_sum), float(plane), _ptr(w1), _ptr(w2), _ptr(dscale), N, channels,
+                                                    int(w1.shape[0]), _ptr(add), _ptr(dw1), _ptr(dw2), _stream(stream)))
+    return add

@@ -176,6 +176,48 @@ int dg_convt2x2_fused(const dg_src* src, int32_t dtype, int32_t N, int32_t H, in
 int dg_channel_attention(const double* act_sum, double plane, const float* w1, const float* w2, int32_t N, int32_t C,
                          int32_t hidden, float* scale, dg_stream_t stream);
 
+/* ---- per-op backward (autograd of the pieces above; OptimizedUNet training, src/optimized_model.py:118-158 under
+ * optimized_train.py:210/226, is orchestrated above the C-ABI from these; LightweightUNet uses dg_lw_backward) --------
+ * Notation per conv i: R = its raw output, y = GroupNorm(R), A = SiLU(y).  Gradient tensors are fp32 NHWC.
+ *
+ * dg_head1x1_bwd: backward of dg_head1x1 (src/optimized_model.py:74,158) for grad_y = dL/d(out) fp32 [N,cout,H,W] (cout <= 4):
+ *   G [N,H,W,C] = dL/dy of the head's source conv, P [N,C,2] += per-(n, c) (sum G, sum G*xhat) (zero on entry),
+ *   dW [cout][C] and dB [cout] += the 1x1 conv's parameter gradients (zero on entry, or a running sum).  `a` is the forward
+ *   call's argument block (out / target / l1_sum ignored).
+ * dg_act_bwd: G = (dA_a + 0.25 * replicate2x2(dA_b)) * SiLU'(y) and P += (sum G, sum G*xhat).  dA_a = same-resolution gradient
+ *   [N,H,W,stride_a], channels off_a .. off_a+C (one half of a concat gradient is a window of it); dA_b = optional gradient
+ *   of the 2x2 average pool of A, [N,H/2,W/2,stride_b] (nn.AvgPool2d backward).  Either may be NULL, not both.
+ * dg_gn_bwd_apply: in place G -> dR = rstd * (gamma*G - mean_g(gamma*G) - xhat * mean_g(gamma*G*xhat)) (nn.GroupNorm backward
+ *   from the sums P), and dgamma[c] += sum_n P[n][c][1], dbeta[c] += sum_n P[n][c][0] (both NULL = skip). */
+int dg_head1x1_bwd(const dg_head_args* a, const float* grad_y, float* G, double* P, float* dW, float* dB, dg_stream_t stream);
+int dg_act_bwd(int32_t dtype, const void* raw, const double* stats, const float* gamma, const float* beta, int32_t groups,
+               const float* dA_a, int32_t stride_a, int32_t off_a, const float* dA_b, int32_t stride_b, int32_t off_b, float* G,
+               double* P, int32_t N, int32_t H, int32_t W, int32_t C, float eps, dg_stream_t stream);
+int dg_gn_bwd_apply(int32_t dtype, const void* raw, const double* stats, const float* gamma, int32_t groups, const double* P, float* G,
+                    float* dgamma, float* dbeta, int32_t N, int32_t H, int32_t W, int32_t C, float eps, dg_stream_t stream);
+
+/* dg_grad_gather: the gradient at an ACTIVATED tensor A [N,H,W,C] collected from its consumers' input gradients into one dense
+ * fp32 tensor:  out = a[.., off_a + c] * a_scale[n][c]  (the skip half of torch.cat((dec, enc * att)), src/optimized_model.py:141-156)
+ *                   + 0.25 * b[n, y/2, x/2, off_b + c]   (nn.AvgPool2d(2, 2) backward, :131-135)
+ *                   + sum_{dy,dx} u[n, 2y+dy, 2x+dx, off_u + c]   (nn.Upsample(x2, nearest) backward, :112)
+ *                   + add[n][c]                          (gradient of ChannelAttention's global mean, dg_channel_attention_bwd)
+ * every term optional (a_scale needs a); a [N,H,W,stride_a], b [N,H/2,W/2,stride_b], u [N,2H,2W,stride_u], a_scale / add [N,C]. */
+int dg_grad_gather(const float* a, int32_t stride_a, int32_t off_a, const float* a_scale, const float* b, int32_t stride_b,
+                   int32_t off_b, const float* u, int32_t stride_u, int32_t off_u, const float* add, float* out, int32_t N, int32_t H,
+                   int32_t W, int32_t C, dg_stream_t stream);
+
+/* ChannelAttention backward (src/optimized_model.py:185-202: `x * weights`, weights = fc(avg_pool(x))).
+ * dg_scale_bwd_sum: dscale[n][c] += sum_pixels d[n, y, x, off_d + c] * A[n, y, x, c] with A rebuilt from (raw, stats, gamma, beta)
+ *   as the forward does; d = the consumer's input gradient [N,H,W,stride_d]; dscale [N,C] double, zero on entry.
+ * dg_channel_attention_bwd: from the forward's act_sum / plane / w1 / w2 (dg_channel_attention) and dscale:
+ *   dw1 [hidden][C], dw2 [C][hidden] += the two nn.Linear weight gradients summed over the batch (zero on entry or a running
+ *   sum); add[n][c] = dL/dmean[n][c] / plane, the constant every pixel of A receives through the global average. */
+int dg_scale_bwd_sum(int32_t dtype, const void* raw, const double* stats, const float* gamma, const float* beta, int32_t groups,
+                     const float* d, int32_t stride_d, int32_t off_d, double* dscale, int32_t N, int32_t H, int32_t W, int32_t C,
+                     float eps, dg_stream_t stream);
+int dg_channel_attention_bwd(const double* act_sum, double plane, const float* w1, const float* w2, const double* dscale, int32_t N,
+                             int32_t C, int32_t hidden, float* add, float* dw1, float* dw2, dg_stream_t stream);
+
 /* ---- whole-network entry points (native orchestrator) ------------------------------- */
 
 #define DG_MAX_BLOCKS 10  /* enc1-4, bottleneck, dec4-1 */

@@ -130,6 +130,43 @@ def test_train_step_oracle_matches_reference(best_sd, golden):
         assert np.abs(r["new_params"][k].numpy() - g["new/" + k]).max() <= 2e-6, k
 
 
+def _opt_sd(golden):
+    g = golden("opt_rand.npz")
+    tmpl = {k: tuple(int(s) for s in sh.split(",")) for k, sh in zip(g["keys"], g["shapes"])}
+    return {k: torch.from_numpy(v) for k, v in det_state_dict(tmpl, seed=1234).items()}
+
+
+def test_optimized_train_step_oracle_matches_reference(golden):
+    """tests/golden/make_opt_train_golden.py: the reference OptimizedUNet through optimized_train.py:220-233 (L1, backward, clip 1.0,
+    AdamW) and through backward(gy) with an explicit output gradient."""
+    g = golden("opt_train.npz")
+    sd = _opt_sd(golden)
+    x, t = _rand((2, 1, 64, 64), 7), _rand((2, 1, 64, 64), 8)
+    r = tpo.train_step(sd, x, t, forward=tpo.optimized_forward, lr=TRAIN_LR, weight_decay=TRAIN_WD, max_norm=1.0)
+    assert abs(r["loss"] - float(g["loss"])) <= 2e-6 * max(1.0, abs(float(g["loss"])))
+    assert np.abs(r["out"].numpy() - g["y"]).max() <= 1e-4 * max(1.0, np.abs(g["y"]).max())
+    assert abs(r["total_norm"] - float(g["total_norm"])) <= 1e-4 * float(g["total_norm"])
+    for k in sd:
+        got = r["grads"][k].numpy().reshape(-1)
+        norm = float(g["gnorm/" + k])
+        assert abs(np.sqrt((got.astype(np.float64) ** 2).sum()) - norm) <= 1e-4 * norm + 1e-7, k
+        assert np.abs(got[:32] - g["ghead/" + k]).max() <= 1e-5 + 1e-3 * np.abs(g["ghead/" + k]).max(), k
+        if "grad/" + k in g.files:
+            ref = g["grad/" + k].reshape(-1)
+            assert np.abs(got - ref).max() <= 1e-5 + 1e-3 * np.abs(ref).max(), k
+        new = r["new_params"][k].numpy().reshape(-1)
+        assert np.abs(new[:32] - g["newhead/" + k]).max() <= 2e-5, k
+    # explicit output gradient
+    gy = torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(9)) / (2 * 64 * 64)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    grads = torch.autograd.grad((tpo.optimized_forward(x, params) * gy).sum(), list(params.values()))
+    for k, gr in zip(params, grads):
+        got = gr.numpy().reshape(-1)
+        norm = float(g["gy_gnorm/" + k])
+        assert abs(np.sqrt((got.astype(np.float64) ** 2).sum()) - norm) <= 1e-4 * norm + 1e-9, k
+        assert np.abs(got[:32] - g["gy_ghead/" + k]).max() <= 1e-9 + 1e-3 * np.abs(g["gy_ghead/" + k]).max(), k
+
+
 def test_l1_grad_restatement():
     o = np.array([[0.2, 0.5], [0.7, 0.1]])
     t = np.array([[0.5, 0.5], [0.1, 0.4]])
