@@ -4,7 +4,7 @@ The reference has no whole-image path for a 4096x4096 input: its model is traine
 (api/app.py:149 resizes, src/preprocess.py crops), so what a user of the repo can do today is run the network on every
 512x512 tile.  GroupNorm statistics are per sample, so tiles are independent units: they are one batch, sharded over
 ranks with no data-path collective (parallel.shard_range); only the finished tiles are gathered, and only if asked.
-This is NOT the whole-image function (GroupNorm + receptive field couple tiles; SURVEY 8e definition B, not built).
+This is NOT the whole-image function (GroupNorm + receptive field couple tiles): that is SURVEY 8e definition B, whole_image.py.
 """
 import torch
 

@@ -145,6 +145,41 @@ def test_optimized_reference_loop_step_fp32(golden):
     assert float((y2 - ref2).abs().max()) <= 2e-4 * max(1.0, float(ref2.abs().max()))
 
 
+def test_optimized_reference_amp_gradscaler_branch_verbatim(golden):
+    """optimized_train.py:201-219 (the branch the reference takes on every CUDA device) with the reference's own torch.optim.AdamW:
+    autocast + GradScaler.scale / unscale_ / step / update + clip_grad_norm_ run unchanged on the drop-in OptimizedUNet and land on
+    the reference module's fp32 step (the module keeps its own precision under autocast; the power-of-two loss scale cancels)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import TRAIN_LR, TRAIN_WD
+    g = golden("opt_train.npz")
+    _, sd = _sd(golden)
+    net = _train_net(sd)
+    opt = torch.optim.AdamW(net.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD)
+    scaler = torch.amp.GradScaler("cuda")
+    crit = torch.nn.L1Loss()
+    x, t = _rand((2, 1, 64, 64), 7).cuda(), _rand((2, 1, 64, 64), 8).cuda()
+    opt.zero_grad(set_to_none=True)                       # :201
+    with torch.amp.autocast("cuda"):                      # :205
+        outputs = net(x)                                  # :206
+        loss = crit(outputs, t)                           # :207
+    scaler.scale(loss).backward()                         # :210
+    scaler.unscale_(opt)                                  # :214
+    total = torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)   # :215
+    scaler.step(opt)                                      # :218
+    scaler.update()                                       # :219
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * max(1.0, float(g["loss"]))
+    assert abs(float(total) - float(g["total_norm"])) <= 2e-3 * float(g["total_norm"])
+    loose = n = 0
+    for k, p in net.named_parameters():
+        got = p.detach().cpu().numpy().reshape(-1)
+        err = np.abs(got[:32] - g["newhead/" + k])
+        assert err.max() <= 2 * TRAIN_LR, k
+        loose += int((err > 2e-5).sum())
+        n += err.size
+        assert abs(float(got.astype(np.float64).sum()) - float(g["newsum/" + k])) <= 2e-5 * got.size ** 0.5 + 2 * TRAIN_LR, k
+    assert loose <= 2e-3 * n, (loose, n)
+
+
 @pytest.mark.parametrize("storage,global_tol", [("fp16", 1.5e-2), ("bf16", 6e-2)])
 def test_optimized_backward_16bit_storage_is_close(golden, storage, global_tol):
     """16-bit storage of the saved activations; tensor-core weight / data gradients (bf16 operands, fp32 accumulate) where the
