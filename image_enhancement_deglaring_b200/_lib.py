@@ -56,7 +56,7 @@ class DgLwParams(C.Structure):
         ("conv_w_flip", (C.c_void_p * 2) * DG_MAX_BLOCKS), ("up_w_t", C.c_void_p * 4),
         ("up_w_tc_bf16", C.c_void_p * 4), ("conv_w_tc_bf16", (C.c_void_p * 2) * DG_MAX_BLOCKS),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("path", C.c_int32), ("reserved", C.c_int32),
-        ("dec_comp", C.c_void_p * 4),
+        ("dec_comp", C.c_void_p * 4), ("conv_w_flip_tc_bf16", (C.c_void_p * 2) * DG_MAX_BLOCKS),
     ]
 
 
@@ -69,6 +69,8 @@ SYMBOLS = {
                                    C.c_void_p]),
     "dg_convt2x2_dgrad": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p]),
+    "dg_conv3x3_dgrad_wide": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_void_p]),
     "dg_head1x1": (C.c_int, [C.POINTER(DgHeadArgs), C.c_void_p]),
     "dg_pil_resize_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

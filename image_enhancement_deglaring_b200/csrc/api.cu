@@ -583,6 +583,13 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
                 if (rc) return rc;
             }
         }
+        // ... the tcgen05 kernel where the mma.sync data gradient has no instance (wider variants): dR rounded to bf16, the
+        // taps-flipped weights in the tensor-core packing, fp32 result (conv3x3_t5.cu, T5_IDENT) ...
+        if (!dg_done && dRb_in == nullptr && p->dtype != DG_F32 && (p->path & 3) != 1 && p->conv_w_flip_tc_bf16[b][j] != nullptr) {
+            rc = conv3x3_dgrad_t5_launch(G(i), nullptr, bw + bp.gb_off[i] + (size_t)n0 * hwc(i, C) * 2, p->conv_w_flip_tc_bf16[b][j], T(i),
+                                         N, Hi, Wi, C, bp.cin_tot[i], st, &dg_done);
+            if (rc) return rc;
+        }
         // ... else the forward generic kernel on an identity fp32 source
         dg_conv3x3_args d;
         memset(&d, 0, sizeof(d));
@@ -783,6 +790,17 @@ int dg_convt2x2_dgrad(const float* dCat, int32_t stride, const void* ct_w_tc_bf1
     bool handled = false;
     int rc = convt_dgrad_tc_launch(dCat, stride, ct_w_tc_bf16, dLow, N, H, W, cl, cu, reinterpret_cast<cudaStream_t>(stream), &handled);
     if (rc == 0 && !handled) { set_error("convT dgrad: no tensor-core kernel for %d -> %d channels / this shape", cl, cu); return 3; }
+    return rc;
+}
+
+int dg_conv3x3_dgrad_wide(const float* dR, const void* weight_flip_tc_bf16, float* dX, void* scratch_bf16, int32_t N, int32_t H,
+                          int32_t W, int32_t cin, int32_t cout, dg_stream_t stream) {
+    if (dR == nullptr || weight_flip_tc_bf16 == nullptr || dX == nullptr || scratch_bf16 == nullptr) { set_error("wide dgrad: null pointer"); return 2; }
+    if (N < 1 || H < 1 || W < 1) { set_error("wide dgrad: bad shape"); return 3; }
+    bool handled = false;
+    int rc = conv3x3_dgrad_t5_launch(dR, nullptr, scratch_bf16, weight_flip_tc_bf16, dX, N, H, W, cout, cin,
+                                     reinterpret_cast<cudaStream_t>(stream), &handled);
+    if (rc == 0 && !handled) { set_error("wide dgrad: no tcgen05 plan for %d -> %d channels at %dx%d (or unaligned pointers)", cin, cout, H, W); return 3; }
     return rc;
 }
 

@@ -205,6 +205,9 @@ int conv3x3_dgrad_tc_launch(const float* dR, const void* wtc_bf16, float* out, i
                             bool dry = false, float* out2 = nullptr);
 int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, float* dLow, int N, int H, int W, int Cl, int Cu,
                           cudaStream_t st, bool* handled, const DgradAct* act = nullptr);
+// data gradient of the wide layers on the tcgen05 kernel (conv3x3_t5.cu, T5_IDENT): dR fp32 (converted into scratch_bf16) or bf16
+int conv3x3_dgrad_t5_launch(const float* dR, const void* dR_bf16, void* scratch_bf16, const void* wflip_tc_bf16, float* out, int N,
+                            int H, int W, int ck, int cn, cudaStream_t st, bool* handled);
 int image_metrics_launch(const float* out, const float* tgt, int N, int H, int W, int clip01, double data_range, double* acc,
                          cudaStream_t st);
 int first_wgrad_launch(const float* x, const float* dR, float* dW, int N, int H, int W, int CO, cudaStream_t st, bool* handled);

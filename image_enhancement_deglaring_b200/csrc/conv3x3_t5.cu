@@ -31,7 +31,10 @@ namespace dg {
 
 namespace {
 
-enum { T5_SAME = 0, T5_POOL = 1, T5_CAT2 = 3, T5_CONVT = 4, T5_DEC = 5 };   // T5_CONVT: ConvTranspose2d(2,2)+bias as a 1-tap GEMM with N = 4*C_up
+enum { T5_SAME = 0, T5_POOL = 1, T5_CAT2 = 3, T5_CONVT = 4, T5_DEC = 5, T5_IDENT = 6 };   // T5_CONVT: ConvTranspose2d(2,2)+bias as a 1-tap GEMM with N = 4*C_up
+// T5_IDENT: the conv DATA GRADIENT of the wide layers (dgrad = a 3x3 conv of dR with the taps-flipped, transposed weights): the one
+// source is an identity bf16 tensor (no GroupNorm, no SiLU: chunks are copied), the epilogue stores the fp32 accumulators as fp32
+// [N,H,W,cout] and keeps no statistics.
 // T5_DEC: ConvTranspose2d(2,2) + torch.cat + 3x3 conv (src/model.py:116-128 + :93) as ONE 3x3 conv on the LOW-resolution grid:
 //   input channels  = CL activated low channels + the activated skip tensor in space-to-depth form (4 parities x CU channels),
 //   output channels = 4 output-pixel parities x CU channels (scattered to the full-resolution tensor by the epilogue),
@@ -420,6 +423,18 @@ __global__ void __launch_bounds__(T5_THREADS, 1) conv3x3_t5_kernel(const __grid_
                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                             : "r"(trow + (uint32_t)(c * 32)));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if constexpr (MODE == T5_IDENT) {
+                            // data gradient: fp32 out, 32 consecutive channels of this lane's pixel = eight 128-bit stores
+                            if (valid) {
+                                float4* of = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                                                       ((size_t)(it.n * p.H + y) * p.W + x) * p.cout + it.nbk * p.nb + c * 32);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    of[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                                        __uint_as_float(r[4 * j + 3]));
+                            }
+                            continue;
+                        }
                         if constexpr (MODE == T5_CONVT) {
                             // ConvTranspose2d(2,2): column n = pos * cu + co of low pixel (y, x) is channel co of output pixel
                             // (2y + pos/2, 2x + pos%2); + bias, no statistics (the consumer treats `up` as an identity source)
@@ -551,7 +566,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) conv3x3_t5_kernel(const __grid_
                 }
                 return jb;
             }
-            jb.ident = MODE == T5_CAT2 && cg < p.cout;                // `up` half of the concat: plain copy
+            jb.ident = (MODE == T5_CAT2 && cg < p.cout) || MODE == T5_IDENT;   // `up` half of the concat / a gradient tensor: plain copy
             jb.cs = (MODE == T5_CAT2 && !jb.ident) ? cg - p.cout : cg;
             jb.src = reinterpret_cast<const unsigned char*>((MODE == T5_CAT2 && !jb.ident) ? p.src1 : p.src0) +
                      (size_t)it.n * Hs * Ws * Cs * 2 + (size_t)jb.cs * 2;
@@ -639,6 +654,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) conv3x3_t5_kernel(const __grid_
             }
         };
         auto ensure_coefs = [&](int n, int& coef_n) {
+            if constexpr (MODE == T5_IDENT) return;   // nothing to normalise
             if (n == coef_n) return;
             stager_bar();   // every stager is done with the previous image's coefficients
             const double plane = (double)Hs * Ws;
@@ -932,6 +948,52 @@ int convt_t5_launch(const dg_src& s, int dtype, int N, int H, int W, void* out, 
     if (dtype == DG_F16)
         return flavour == 1 ? dispatch_t5<__half, ACT_EXACT>(t, T5_CONVT, st) : dispatch_t5<__half, ACT_TANH>(t, T5_CONVT, st);
     return flavour == 1 ? dispatch_t5<__nv_bfloat16, ACT_EXACT>(t, T5_CONVT, st) : dispatch_t5<__nv_bfloat16, ACT_TANH>(t, T5_CONVT, st);
+}
+
+
+// ---- data gradient of a 3x3 conv on the tcgen05 kernel (wide variant, BASELINE.json configs[4]) ----------------------------------------
+//   dX[n,y,x,ci] = sum_{ky,kx,co} dR[n, y+1-ky, x+1-kx, co] * W[co][ci][ky][kx]   (autograd of src/model.py:93,96 w.r.t. the conv input)
+// = conv3x3(dR, flipped / transposed W): ck = channels of dR (GEMM K side), cn = channels of dX (N side, >= 32), wflip_tc_bf16 =
+// dg_pack_conv3x3_tc of the fp32 [3][3][ck][cn] taps-flipped weights in DG_BF16.  dR comes as fp32 (converted into `scratch_bf16`,
+// N*H*W*ck bf16, by one element-wise kernel) or already as bf16 (dR_bf16, e.g. gn_bwd_apply's second output form).
+namespace {
+__global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n8) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2<__nv_bfloat16>(a.x, a.y), pack2<__nv_bfloat16>(a.z, a.w),
+                                                      pack2<__nv_bfloat16>(b.x, b.y), pack2<__nv_bfloat16>(b.z, b.w));
+    }
+}
+}  // namespace
+
+int conv3x3_dgrad_t5_launch(const float* dR, const void* dR_bf16, void* scratch_bf16, const void* wflip_tc_bf16, float* out, int N,
+                            int H, int W, int ck, int cn, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (wflip_tc_bf16 == nullptr || out == nullptr || (dR_bf16 == nullptr && (dR == nullptr || scratch_bf16 == nullptr))) return 0;
+    const void* src = dR_bf16 != nullptr ? dR_bf16 : scratch_bf16;
+    if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(wflip_tc_bf16) |
+         reinterpret_cast<uintptr_t>(dR)) & 15)
+        return 0;
+    T5Args t;
+    memset(&t, 0, sizeof(t));
+    t.src0 = src;
+    t.wgt = wflip_tc_bf16;
+    t.out = out; t.out_stats = nullptr;
+    t.N = N; t.H = H; t.W = W; t.eps = 1e-5f;
+    t.cin = ck;
+    t.cout = cn;
+    if (!t5_plan(t, T5_IDENT)) return 0;
+    if (dR_bf16 == nullptr) {
+        const size_t n8 = (size_t)N * H * W * ck / 8;   // ck % 16 == 0 (t5_plan)
+        size_t blocks = (n8 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        cvt_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(dR, static_cast<__nv_bfloat16*>(scratch_bf16), n8);
+        count_launch();
+        int rc = check_launch("cvt_f32_bf16");
+        if (rc) return rc;
+    }
+    *handled = true;
+    return launch_t5<__nv_bfloat16, T5_IDENT, ACT_TANH>(t, st);
 }
 
 }  // namespace dg

@@ -129,7 +129,11 @@ wgrad_tc_kernel(const WgArgs p) {
         if (n != cur_n) {
             cur_n = n;
             // GroupNorm affine (a, b) per activated source channel, pre-halved for silu(y) = h + h tanh(h)
-            for (int c = tid; c < G::NCOEF; c += WG_THREADS) {
+            // only the channels this CTA stages: its CIB-channel block (CAT2: the part of the block that lies in the skip half).
+            // Each coefficient sums a whole group's statistics in double: all CI of them per image per CTA was ~260 k loads at 1024 channels
+            constexpr int CHALF = MODE == WG_CAT2 ? CI / 2 : 0;
+            const int c_lo = ci0 - CHALF > 0 ? ci0 - CHALF : 0, c_hi = ci0 + CIB - CHALF;
+            for (int c = c_lo + tid; c < c_hi; c += WG_THREADS) {
                 float a, b;
                 if constexpr (MODE == WG_CAT2) {
                     gn_coef(p.st1, p.g1, p.b1, n, CI / 2, p.groups1, c, (double)H * W, p.eps, a, b);
@@ -343,6 +347,18 @@ int dispatch_wg(const WgArgs& a, int ci, int co, int mode, cudaStream_t st, bool
     DG_WG(64, 32, WG_CAT2, 8, 32, 32, 4)      // dec3.0
     DG_WG(32, 16, WG_CAT2, 16, 32, 16, 2)     // dec2.0
     DG_WG(16, 8, WG_CAT2, 16, 64, 16, 1)      // dec1.0
+    // wider variants (features_start = 16 / 32 / 64, BASELINE.json configs[4]): same CTA block (32 input x 64 output channels, all
+    // nine taps) as the 128-channel layers -- shared memory and registers depend on the block, not on CI / CO; the grid just gets
+    // more (ci-block, co-block) columns and each persistent CTA walks all tiles of its column
+    DG_WG(128, 256, WG_POOL, 8, 32, 16, 16)
+    DG_WG(256, 256, WG_SAME, 8, 32, 32, 8)
+    DG_WG(256, 512, WG_POOL, 8, 32, 16, 16)
+    DG_WG(512, 512, WG_SAME, 8, 32, 32, 8)
+    DG_WG(512, 1024, WG_POOL, 8, 32, 16, 16)
+    DG_WG(1024, 1024, WG_SAME, 8, 32, 32, 8)
+    DG_WG(256, 128, WG_CAT2, 8, 32, 32, 8)
+    DG_WG(512, 256, WG_CAT2, 8, 32, 32, 8)
+    DG_WG(1024, 512, WG_CAT2, 8, 32, 32, 8)
 #undef DG_WG
     *handled = false;
     return 0;

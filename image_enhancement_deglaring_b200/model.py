@@ -110,17 +110,23 @@ class LightweightUNet(nn.Module):
                 g = blk[gi].weight.detach().float().contiguous()
                 bt = blk[gi].bias.detach().float().contiguous()
                 wtc = ops.pack_conv3x3_tc(w, pc.dtype) if self.path != 1 else None
-                # backward only, CUDA-core tier: dgrad runs as a forward conv with the taps flipped and Cin/Cout swapped
-                # (the tensor-core tier reads the bf16 packing below instead; it covers the features_start = 8 channel sets)
-                tc_bwd = train and self.path != 1 and pc.dtype != ops.DG_F32 and self.features_start == 8
-                wfl = blk[ci].weight.detach().float().flip(2, 3).permute(2, 3, 0, 1).contiguous() if (train and not tc_bwd) else None
+                # backward only.  Tensor-core tier (16-bit storage): the mma.sync data gradient reads the bf16 packing of the
+                # FORWARD weights transposed (bf16 because dR underflows fp16); it has an instance for every layer of the shipped
+                # widths (features_start = 8).  Wider variants (configs[4]) also get the taps-flipped weights in the tensor-core
+                # packing for the tcgen05 data gradient (conv3x3_t5.cu, T5_IDENT), and the fp32 flipped weights as the CUDA-core
+                # fallback of whatever neither covers.  CUDA-core tier: dgrad = the forward generic conv on the flipped weights.
+                tc_tier = train and self.path != 1 and pc.dtype != ops.DG_F32
+                tc_only = tc_tier and self.features_start == 8
+                wfl = blk[ci].weight.detach().float().flip(2, 3).permute(2, 3, 0, 1).contiguous() if (train and not tc_only) else None
                 pc.conv_w_flip[b][j] = None if wfl is None else wfl.data_ptr()
-                # tensor-core dgrad: bf16 packing of the forward weights (read transposed; bf16 because dR underflows fp16)
-                wbf = None
-                if tc_bwd and (b, j) != (0, 0):
-                    wbf = wtc if pc.dtype == ops.DG_BF16 else ops.pack_conv3x3_tc(w, ops.DG_BF16)
+                wbf = wflt = None
+                if tc_tier and (b, j) != (0, 0):
+                    wbf = wtc if (pc.dtype == ops.DG_BF16 and wtc is not None) else ops.pack_conv3x3_tc(w, ops.DG_BF16)
+                    if not tc_only:
+                        wflt = ops.pack_conv3x3_tc(wfl, ops.DG_BF16)
                 pc.conv_w_tc_bf16[b][j] = None if wbf is None else wbf.data_ptr()
-                keep += [w, g, bt, wtc, wfl, wbf]
+                pc.conv_w_flip_tc_bf16[b][j] = None if wflt is None else wflt.data_ptr()
+                keep += [w, g, bt, wtc, wfl, wbf, wflt]
                 pc.conv_w_tc[b][j] = None if wtc is None else wtc.data_ptr()
                 pc.conv_w[b][j] = w.data_ptr()
                 pc.gn_w[b][j] = g.data_ptr()
@@ -130,12 +136,13 @@ class LightweightUNet(nn.Module):
             w = ops.pack_convt2x2(m.weight)
             bt = m.bias.detach().float().contiguous()
             wtc = ops.pack_convt2x2_tc(w, pc.dtype) if self.path != 1 else None
-            tc_bwd = train and self.path != 1 and pc.dtype != ops.DG_F32 and self.features_start == 8
-            wtt = m.weight.detach().float().permute(2, 3, 1, 0).contiguous() if (train and not tc_bwd) else None   # [2,2,Co,Ci]
+            tc_tier = train and self.path != 1 and pc.dtype != ops.DG_F32
+            tc_only = tc_tier and self.features_start == 8
+            wtt = m.weight.detach().float().permute(2, 3, 1, 0).contiguous() if (train and not tc_only) else None   # [2,2,Co,Ci]
             pc.up_w_t[u] = None if wtt is None else wtt.data_ptr()
             wbf = None
-            if tc_bwd:
-                wbf = wtc if pc.dtype == ops.DG_BF16 else ops.pack_convt2x2_tc(w, ops.DG_BF16)
+            if tc_tier:
+                wbf = wtc if (pc.dtype == ops.DG_BF16 and wtc is not None) else ops.pack_convt2x2_tc(w, ops.DG_BF16)
             pc.up_w_tc_bf16[u] = None if wbf is None else wbf.data_ptr()
             # composite decoder taps (ConvTranspose folded into the consuming conv, conv3x3_dec.cu) where that kernel has coverage
             # level 1 (16 -> 8): conv3x3_dec.cu's kernel, forward of both modes.  Levels 2-4 (32 -> 16, 64 -> 32, 128 -> 64) have the

@@ -126,10 +126,12 @@ class OptimizedUNet(nn.Module):
                     continue
                 blk, idx = name.rsplit(".", 1)
                 w = getattr(self, blk)[int(idx)].weight
-                tc = None
+                tc = tcf = None
+                wflip = ops.flip_conv3x3(w)
                 if self.storage != "fp32" and (self.path & 3) != 1:
                     tc = ops.pack_conv3x3_tc(v[0], ops.DG_BF16)
-                bk[name] = (ops.flip_conv3x3(w), tc)
+                    tcf = ops.pack_conv3x3_tc(wflip, ops.DG_BF16)   # for the tcgen05 data gradient of the pairs mma.sync lacks
+                bk[name] = (wflip, tc, tcf)
             pk["_bwd"] = bk
         return pk["_bwd"]
 
@@ -211,7 +213,8 @@ class OptimizedUNet(nn.Module):
         return ops.head1x1(hsrc, hw_, hb, N, H, W, dt)
 
     # ---- training: autograd of the forward above (optimized_train.py:210/226 drives it through loss.backward()) ----------------
-    _tc_dgrad_ok = {}   # (cin, cout) -> does the tensor-core data gradient cover the pair (probed once per process)
+    _tc_dgrad_ok = {}   # (cin, cout) -> does the mma.sync data gradient cover the pair (probed once per process)
+    _t5_dgrad_ok = {}   # (cin, cout, h, w) -> does the tcgen05 data gradient have a plan
 
     def _backward(self, keep, grad_y, flat):
         """All 76 parameter gradients into `flat` (zero on entry; parameters() order, the parameters' own layouts)."""
@@ -231,7 +234,7 @@ class OptimizedUNet(nn.Module):
 
         def dgrad(name, dR):
             L = keep[name]
-            wflip, wtc = bk[name]
+            wflip, wtc, wtcf = bk[name]
             key = (L["cin"], L["c"])
             if wtc is not None and OptimizedUNet._tc_dgrad_ok.get(key, True):
                 try:
@@ -240,6 +243,14 @@ class OptimizedUNet(nn.Module):
                     if "no tensor-core kernel" not in str(e):
                         raise
                     OptimizedUNet._tc_dgrad_ok[key] = False
+            wkey = key + (L["h"], L["w"])
+            if wtcf is not None and OptimizedUNet._t5_dgrad_ok.get(wkey, True):
+                try:
+                    return ops.conv3x3_dgrad_wide(dR, wtcf, L["cin"], L["c"])
+                except RuntimeError as e:   # likewise: no plan for this shape, nothing was launched
+                    if "no tcgen05 plan" not in str(e):
+                        raise
+                    OptimizedUNet._t5_dgrad_ok[wkey] = False
             return ops.conv3x3_dgrad_generic(dR, wflip, L["cin"], N, L["h"], L["w"])
 
         def finish(name, G, P):

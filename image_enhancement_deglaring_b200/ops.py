@@ -158,6 +158,18 @@ def conv3x3_dgrad(dR, weight_tc_bf16, cin, cout, stream=None):
     return dX
 
 
+def conv3x3_dgrad_wide(dR, weight_flip_tc_bf16, cin, cout, stream=None):
+    """Data gradient of the 3x3 conv as a tcgen05 implicit GEMM (dg_conv3x3_dgrad_wide; cin >= 32): dR fp32 NHWC [N,H,W,cout] -> dX fp32
+    NHWC [N,H,W,cin]; weight_flip_tc_bf16 = pack_conv3x3_tc(flip_conv3x3(weight), DG_BF16)."""
+    _require_cuda(dR, weight_flip_tc_bf16)
+    N, H, W, _ = dR.shape
+    dX = torch.empty((N, H, W, cin), dtype=torch.float32, device=dR.device)
+    scratch = torch.empty(dR.numel(), dtype=torch.bfloat16, device=dR.device)
+    _lib.check(_lib.load().dg_conv3x3_dgrad_wide(_ptr(dR), _ptr(weight_flip_tc_bf16), _ptr(dX), _ptr(scratch), N, H, W, cin, cout,
+                                                 _stream(stream)))
+    return dX
+
+
 def convt2x2_dgrad(dCat, ct_w_tc_bf16, cl, cu, stream=None):
     """Data gradient of ConvTranspose2d(2,2) on the tensor cores (dg_convt2x2_dgrad): the first cu channels of dCat fp32 NHWC
     [N,H,W,stride] -> dLow fp32 NHWC [N,H/2,W/2,cl]; ct_w_tc_bf16 = pack_convt2x2_tc(pack_convt2x2(weight), DG_BF16)."""

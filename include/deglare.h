@@ -133,6 +133,12 @@ int dg_conv3x3_dgrad(const float* dR, const void* weight_tc_bf16, float* dX, int
                      int32_t cout, dg_stream_t stream);
 int dg_convt2x2_dgrad(const float* dCat, int32_t stride, const void* ct_w_tc_bf16, float* dLow, int32_t N, int32_t H, int32_t W,
                       int32_t cl, int32_t cu, dg_stream_t stream);
+/* dg_conv3x3_dgrad_wide: the same data gradient as dg_conv3x3_dgrad for the wide layers (cin >= 32, cin % 32 == 0, cout % 16 == 0;
+ * LightweightUNet(features_start=64), BASELINE.json configs[4]) as a tcgen05 implicit GEMM: dR is rounded to bf16 into
+ * `scratch_bf16` (N*H*W*cout bf16, caller-owned) and convolved with weight_flip_tc_bf16 = dg_pack_conv3x3_tc of the fp32
+ * [3][3][cout][cin] taps-flipped weights (w.flip(2,3).permute(2,3,0,1)) in DG_BF16; dX fp32.  Returns 3 where it has no plan. */
+int dg_conv3x3_dgrad_wide(const float* dR, const void* weight_flip_tc_bf16, float* dX, void* scratch_bf16, int32_t N, int32_t H,
+                          int32_t W, int32_t cin, int32_t cout, dg_stream_t stream);
 
 /* Output head: GroupNorm+SiLU of the last block, then nn.Conv2d(C, out_channels, 1) + bias
  * (src/model.py:57,131; src/optimized_model.py:74,158).  fp32 (or quantised uint8) NCHW output.  If `target` is
@@ -248,6 +254,9 @@ typedef struct {
     const void* dec_comp[4];                /* optional: dg_pack_dec_composite blobs of (upconv4..1, dec4..1 `.0`) for the
                                                levels the composite decoder kernel covers (upconv1 + dec1.0 of the shipped
                                                model); NULL elsewhere                                                  */
+    const void* conv_w_flip_tc_bf16[DG_MAX_BLOCKS][2]; /* backward only, optional: dg_pack_conv3x3_tc(conv_w_flip, DG_BF16) -- the
+                                               taps-flipped weights in the tensor-core packing: the data gradient of the layers the
+                                               mma.sync dgrad does not cover (wider variants, configs[4]) runs as a tcgen05 conv  */
 } dg_lw_params;
 
 /* Bytes of workspace dg_lw_forward needs for an [N,in,H,W] batch (raw activations of all 18

@@ -635,6 +635,34 @@ def test_convt_dgrad_tc_matches_autograd(cl, cu, N, H, W, interleaved):
     assert float((got - lq.grad).abs().max()) <= 2e-5 * max(1.0, scale) * np.sqrt(4 * cu)
 
 
+@pytest.mark.parametrize("cin,cout,N,H,W", [(64, 64, 2, 32, 64), (128, 64, 1, 16, 32), (256, 128, 2, 8, 8), (256, 256, 1, 24, 40),
+                                              (512, 1024, 1, 4, 4), (1024, 512, 2, 2, 2), (64, 128, 1, 16, 160), (32, 16, 1, 8, 8)])
+def test_dgrad_wide_tcgen05_matches_autograd(cin, cout, N, H, W):
+    """dg_conv3x3_dgrad_wide (conv3x3_t5.cu T5_IDENT: dR rounded to bf16, taps-flipped weights in the tensor-core packing, tcgen05
+    implicit GEMM, fp32 out) vs autograd of F.conv2d w.r.t. its input (src/model.py:93,96) on the wide variant's channel sets."""
+    rs = _rs(47 + cin + cout)
+    w = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) / np.sqrt(9 * cin)).astype(np.float32))
+    dR = torch.from_numpy(rs.standard_normal((N, cout, H, W)).astype(np.float32))
+    x = torch.zeros(N, cin, H, W, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x, w.double(), None, 1, 1).backward(dR.double())
+    ref = x.grad.float()
+    wflip_tc = ops.pack_conv3x3_tc(ops.flip_conv3x3(w.cuda()), ops.DG_BF16)
+    got = ops.conv3x3_dgrad_wide(dR.permute(0, 2, 3, 1).contiguous().cuda(), wflip_tc, cin, cout).cpu().permute(0, 3, 1, 2)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 1.5e-2 * scale, f"{float((got - ref).abs().max()):.3e} vs scale {scale:.3e}"
+    assert float((got - ref).norm() / ref.norm()) <= 5e-3
+    xq = torch.zeros(N, cin, H, W, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xq, w.bfloat16().double(), None, 1, 1).backward(dR.bfloat16().double())
+    assert float((got - xq.grad.float()).abs().max()) <= 2e-5 * max(1.0, scale) * np.sqrt(9 * cout)
+
+
+def test_dgrad_wide_refuses_what_it_has_no_plan_for():
+    dR = torch.zeros(1, 8, 8, 32, device="cuda")
+    w = torch.zeros(9 * 32 * 16 * 2, dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="no tcgen05 plan"):
+        ops.conv3x3_dgrad_wide(dR, w, 16, 32)        # 16 result channels: below the N = 32 minimum of the tcgen05 tile
+
+
 def test_dgrad_refuses_uncovered_channel_sets():
     dR = torch.zeros(1, 8, 8, 24, device="cuda")
     w = torch.zeros(4096, dtype=torch.uint8, device="cuda")
@@ -673,7 +701,8 @@ def _wgrad_check(dw_tc, dw_gen, ref, what):
 
 @pytest.mark.parametrize("dtype", TC_DTYPES)
 @pytest.mark.parametrize("cin,cout,H,W", [(8, 8, 64, 128), (16, 16, 32, 64), (32, 32, 32, 32), (64, 64, 16, 32),
-                                            (128, 128, 8, 32), (8, 8, 48, 80), (32, 32, 6, 10)])
+                                            (128, 128, 8, 32), (8, 8, 48, 80), (32, 32, 6, 10),
+                                            (256, 256, 8, 32), (512, 512, 4, 8), (1024, 1024, 2, 4)])   # wider variants (configs[4])
 def test_wgrad_tc_same(dtype, cin, cout, H, W):
     rs = _rs(41)
     N = 3
@@ -690,7 +719,8 @@ def test_wgrad_tc_same(dtype, cin, cout, H, W):
 
 
 @pytest.mark.parametrize("dtype", TC_DTYPES)
-@pytest.mark.parametrize("cin,cout,H,W", [(8, 16, 32, 64), (16, 32, 16, 32), (32, 64, 16, 32), (64, 128, 8, 32), (8, 16, 24, 40)])
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 16, 32, 64), (16, 32, 16, 32), (32, 64, 16, 32), (64, 128, 8, 32), (8, 16, 24, 40),
+                                            (128, 256, 8, 32), (256, 512, 4, 8), (512, 1024, 2, 4)])
 def test_wgrad_tc_pool(dtype, cin, cout, H, W):
     rs = _rs(42)
     N = 2
@@ -707,7 +737,8 @@ def test_wgrad_tc_pool(dtype, cin, cout, H, W):
 
 
 @pytest.mark.parametrize("dtype", TC_DTYPES)
-@pytest.mark.parametrize("c,H,W", [(8, 64, 128), (16, 32, 64), (32, 16, 32), (64, 16, 32), (8, 48, 80)])
+@pytest.mark.parametrize("c,H,W", [(8, 64, 128), (16, 32, 64), (32, 16, 32), (64, 16, 32), (8, 48, 80), (128, 8, 32), (256, 4, 8),
+                                   (512, 2, 4)])
 def test_wgrad_tc_cat(dtype, c, H, W):
     """Decoder conv: input = cat(materialised ConvTranspose output, activated skip)."""
     rs = _rs(43)

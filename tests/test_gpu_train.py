@@ -432,3 +432,42 @@ def test_cuda_graph_training_step_equals_eager_loop(best_sd, storage):
     assert float((yb - y0).abs().max()) > 10 * float((ya - yb).abs().max()) + 1e-4
     with pytest.raises(RuntimeError):
         GraphedTrainStep(_net(best_sd), FusedAdamW(_net(best_sd).parameters()), L1Loss(), xs[0].shape)
+
+
+# ---- wider variants (constructor argument features_start; BASELINE.json configs[4]) on the tensor-core backward ----------------------
+@pytest.mark.parametrize("fs,shape", [(16, (2, 1, 64, 64)), (64, (2, 1, 32, 32)), (64, (1, 1, 48, 160))])
+def test_wide_variant_training_tensor_core_backward(golden, fs, shape):
+    """LightweightUNet(features_start=16 / 64) in the 16-bit tiers: weight gradients on wgrad_tc.cu's wide instances, data gradients
+    on dgrad_tc.cu where it has the pair and on the tcgen05 kernel (conv3x3_t5.cu T5_IDENT) elsewhere, ConvTranspose gradients on
+    the CUDA-core kernels; every parameter gradient against the autograd oracle for an explicit output gradient, and the
+    CUDA-core backward (path=1) of the same tier beside it."""
+    from make_golden import det_state_dict
+    g = golden("lw_variants.npz")
+    tmpl = {k: tuple(int(v) for v in sh.split(",")) for k, sh in zip(g[f"keys_fs{fs}"], g[f"shapes_fs{fs}"])}
+    sd = {k: torch.from_numpy(v) for k, v in det_state_dict(tmpl, seed=100 + fs).items()}
+    x = _rand(shape, 21)
+    gy = torch.randn(*shape, generator=torch.Generator().manual_seed(22)) / x.numel()
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    out = tpo.lightweight_forward(x, params)
+    ref = dict(zip(params, torch.autograd.grad((out * gy).sum(), list(params.values()))))
+    den = sum(float((r.double() ** 2).sum()) for r in ref.values())
+
+    def run(storage, path):
+        net = dg.LightweightUNet(features_start=fs, storage=storage, path=path)
+        net.load_state_dict(sd, strict=True)
+        net = net.cuda().train()
+        net(x.cuda()).backward(gy.cuda())
+        num, worst = 0.0, ("", 0.0)
+        for k, p in net.named_parameters():
+            d = float(((p.grad.cpu().double() - ref[k].double()) ** 2).sum())
+            n = float((ref[k].double() ** 2).sum())
+            num += d
+            if n > 0 and (d / n) ** 0.5 > worst[1]:
+                worst = (k, (d / n) ** 0.5)
+        return (num / den) ** 0.5, worst
+
+    for storage, tol in (("fp16", 1.5e-2), ("bf16", 6e-2)):
+        e_tc, w_tc = run(storage, 0)
+        assert e_tc <= tol, (storage, e_tc, w_tc)
+    e_gen, w_gen = run("fp16", 1)
+    assert e_gen <= 1.5e-2, (e_gen, w_gen)
