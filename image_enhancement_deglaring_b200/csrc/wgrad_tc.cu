@@ -378,10 +378,14 @@ struct CtWgArgs {
     int tiles_x, tiles_y;
 };
 
-template <typename T, int CL, int CU, int TH, int TW, int POSG>
+// A CTA owns the dWt block of CLB input x CUB output channels x POSG positions: grid = (persistent CTAs, 4 / POSG, (CL / CLB) * (CU / CUB)).
+// The shipped widths use one block (CLB = CL, CUB = CU); the wider variants (configs[4]: 256 -> 128 ... 1024 -> 512) tile the
+// proven 128 x 64 block over grid.z -- shared memory and accumulators depend on the block only.
+template <typename T, int CL, int CU, int CLB, int CUB, int TH, int TW, int POSG>
 __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgArgs p) {
     using BF = __nv_bfloat16;
-    constexpr int NC8 = CL / 8, NTW = CU / 8, MT = CL / 16, ITEMS = POSG * MT, IPW = (ITEMS + 7) / 8, SEGS = TW / 16;
+    constexpr int NC8 = CLB / 8, NTW = CUB / 8, MT = CLB / 16, ITEMS = POSG * MT, IPW = (ITEMS + 7) / 8, SEGS = TW / 16;
+    static_assert(CL % CLB == 0 && CU % CUB == 0, "channel blocks");
     constexpr int APLANE = wg_pad_plane(TH * TW, NC8), DPLANE = wg_pad_plane(TH * TW, NTW);
     constexpr int A_BYTES = NC8 * APLANE * 16, D_BYTES = POSG * NTW * DPLANE * 16;
     static_assert(IPW * NTW * 4 <= 64 && (NTW == 1 || NTW % 2 == 0) && TW % 16 == 0, "shape");
@@ -390,11 +394,12 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
     unsigned char* act = smem;
     unsigned char* dsm = smem + A_BYTES;
     float2* coef = reinterpret_cast<float2*>(smem + A_BYTES + D_BYTES);
-    float* bias_sm = reinterpret_cast<float*>(coef + CL);   // [CU]
+    float* bias_sm = reinterpret_cast<float*>(coef + CLB);   // [CUB]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pos0 = blockIdx.y * POSG;
+    const int ci0 = (blockIdx.z % (CL / CLB)) * CLB, co0 = (blockIdx.z / (CL / CLB)) * CUB;   // this CTA's channel block
     float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias gradient partials of this thread's 8 output channels
-    for (int c = tid; c < CU; c += WG_THREADS) bias_sm[c] = 0.f;
+    for (int c = tid; c < CUB; c += WG_THREADS) bias_sm[c] = 0.f;
     const int Hl = p.Hl, Wl = p.Wl, H = 2 * Hl, W = 2 * Wl;
     const int tiles_per_img = p.tiles_x * p.tiles_y, ntiles = tiles_per_img * p.N;
     float acc[IPW][NTW][4];
@@ -412,9 +417,9 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
         __syncthreads();
         if (n != cur_n) {
             cur_n = n;
-            for (int c = tid; c < CL; c += WG_THREADS) {
+            for (int c = tid; c < CLB; c += WG_THREADS) {
                 float a, b;
-                gn_coef(p.stats, p.gamma, p.beta, n, CL, p.groups, c, (double)Hl * Wl, p.eps, a, b);
+                gn_coef(p.stats, p.gamma, p.beta, n, CL, p.groups, ci0 + c, (double)Hl * Wl, p.eps, a, b);
                 coef[c] = make_float2(0.5f * a, 0.5f * b);
             }
             __syncthreads();
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
             float2 cf[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) cf[k] = coef[c8 * 8 + k];
-            const unsigned char* base = reinterpret_cast<const unsigned char*>(p.raw_low) + (size_t)n * Hl * Wl * CL * 2 + c8 * 16;
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(p.raw_low) + (size_t)n * Hl * Wl * CL * 2 + (ci0 / 8 + c8) * 16;
             unsigned char* dst = act + (size_t)c8 * APLANE * 16;
             for (int pix = tid / NC8; pix < TH * TW; pix += WG_THREADS / NC8) {
                 const int r = pix / TW, c = pix - r * TW;
@@ -440,7 +445,7 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
         }
         {   // gradient of the up half, one plane set per kernel position
             const int j8 = tid % NTW;
-            const float* gsrc = p.dCat + (size_t)n * H * W * p.stride + j8 * 8;
+            const float* gsrc = p.dCat + (size_t)n * H * W * p.stride + co0 + j8 * 8;
             for (int it = tid / NTW; it < POSG * TH * TW; it += WG_THREADS / NTW) {
                 const int ps = it / (TH * TW), pix = it - ps * (TH * TW);
                 const int pos = pos0 + ps;
@@ -490,12 +495,12 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
             }
         }
     }
-    if (p.dBias != nullptr) {
+    if (p.dBias != nullptr && ci0 == 0) {   // every up-half gradient element is staged once per input-channel block: count it once
         const int j8 = tid % NTW;
 #pragma unroll
         for (int k = 0; k < 8; ++k) atomicAdd(&bias_sm[j8 * 8 + k], bsum[k]);
         __syncthreads();
-        for (int c = tid; c < CU; c += WG_THREADS) atomicAdd(p.dBias + c, bias_sm[c]);
+        for (int c = tid; c < CUB; c += WG_THREADS) atomicAdd(p.dBias + co0 + c, bias_sm[c]);
     }
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
@@ -505,10 +510,10 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
         const int pos = pos0 + item / MT, mt = item % MT;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-            const int ci = mt * 16 + g + 8 * hf;
+            const int ci = ci0 + mt * 16 + g + 8 * hf;
 #pragma unroll
             for (int j = 0; j < NTW; ++j) {
-                const int co = j * 8 + 2 * q;
+                const int co = co0 + j * 8 + 2 * q;
                 atomicAdd(p.dWt + ((size_t)ci * CU + co) * 4 + pos, acc[s][j][2 * hf]);
                 atomicAdd(p.dWt + ((size_t)ci * CU + co + 1) * 4 + pos, acc[s][j][2 * hf + 1]);
             }
@@ -516,12 +521,12 @@ __global__ void __launch_bounds__(WG_THREADS) convt_wgrad_tc_kernel(const CtWgAr
     }
 }
 
-template <typename T, int CL, int CU, int POSG>
+template <typename T, int CL, int CU, int POSG, int CLB = CL, int CUB = CU>
 int launch_ctwg(CtWgArgs a, cudaStream_t st) {
     constexpr int TH = 8, TW = 32;
-    constexpr int NC8 = CL / 8, NTW = CU / 8;
-    constexpr int SMEM = NC8 * wg_pad_plane(TH * TW, NC8) * 16 + POSG * NTW * wg_pad_plane(TH * TW, NTW) * 16 + CL * 8 + CU * 4;
-    auto kern = convt_wgrad_tc_kernel<T, CL, CU, TH, TW, POSG>;
+    constexpr int NC8 = CLB / 8, NTW = CUB / 8;
+    constexpr int SMEM = NC8 * wg_pad_plane(TH * TW, NC8) * 16 + POSG * NTW * wg_pad_plane(TH * TW, NTW) * 16 + CLB * 8 + CUB * 4;
+    auto kern = convt_wgrad_tc_kernel<T, CL, CU, CLB, CUB, TH, TW, POSG>;
     static bool done = false;
     if (!done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -531,12 +536,12 @@ int launch_ctwg(CtWgArgs a, cudaStream_t st) {
     a.tiles_x = (a.Wl + TW - 1) / TW;
     a.tiles_y = (a.Hl + TH - 1) / TH;
     const int ntiles = a.tiles_x * a.tiles_y * a.N;
-    constexpr int GY = 4 / POSG;
+    constexpr int GY = 4 / POSG, GZ = (CL / CLB) * (CU / CUB);
     constexpr int RES = (227 * 1024) / (SMEM + 1024) >= 2 ? 2 : 1;
-    int gx = (148 * RES + GY - 1) / GY;
+    int gx = (148 * RES + GY * GZ - 1) / (GY * GZ);
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
-    kern<<<dim3(gx, GY), WG_THREADS, SMEM, st>>>(a);
+    kern<<<dim3(gx, GY, GZ), WG_THREADS, SMEM, st>>>(a);
     count_launch();
     return check_launch("convt_wgrad_tc");
 }
@@ -548,6 +553,9 @@ int dispatch_ctwg(const CtWgArgs& a, int cl, int cu, cudaStream_t st, bool* hand
     if (cl == 64 && cu == 32) return launch_ctwg<T, 64, 32, 4>(a, st);
     if (cl == 32 && cu == 16) return launch_ctwg<T, 32, 16, 4>(a, st);
     if (cl == 16 && cu == 8) return launch_ctwg<T, 16, 8, 4>(a, st);
+    if (cl == 256 && cu == 128) return launch_ctwg<T, 256, 128, 1, 128, 64>(a, st);     // wider variants: 128 x 64 blocks over grid.z
+    if (cl == 512 && cu == 256) return launch_ctwg<T, 512, 256, 1, 128, 64>(a, st);
+    if (cl == 1024 && cu == 512) return launch_ctwg<T, 1024, 512, 1, 128, 64>(a, st);
     *handled = false;
     return 0;
 }
