@@ -587,6 +587,39 @@ def main():
                              "frac": flop * wb / (wms * 1e-3) / 1e12 / tpeak,
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks_w else "fallback 1400"},
                 "what": "inference forward, random-init weights (no checkpoint exists for this width), CUDA events, mean of 5"}
+        # configs[4] asks for "training + inference": one training step of the same width (forward + L1 + backward + clip 1.0 +
+        # AdamW), tensor-core backward (wgrad_tc wide instances, tcgen05 data gradient, blocked ConvTranspose weight gradient);
+        # 3 x the forward FLOPs per step
+        try:
+            from image_enhancement_deglaring_b200.train import FusedAdamW, L1Loss
+            wnet.train()
+            wopt = FusedAdamW(wnet.parameters(), lr=2.3e-3, weight_decay=6.75e-5, max_grad_norm=1.0)
+            wcrit = L1Loss()
+            wt = torch.rand(wb, 1, H, W, generator=torch.Generator().manual_seed(6)).to(dev)
+
+            def wstep():
+                wopt.zero_grad(set_to_none=True)
+                l = wcrit(wnet(wx), wt)
+                l.backward()
+                wopt.step()
+                return l
+            for _ in range(3):
+                wstep()
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(5):
+                wl = wstep()
+            ev[1].record()
+            torch.cuda.synchronize()
+            wtms = ev[0].elapsed_time(ev[1]) / 5
+            wide["train_step"] = {"batch": wb, "ms_per_step": wtms, "value": wb / (wtms * 1e-3), "unit": UNIT,
+                                  "tflops": 3 * flop * wb / (wtms * 1e-3) / 1e12, "frac": 3 * flop * wb / (wtms * 1e-3) / 1e12 / tpeak,
+                                  "loss": float(wl),
+                                  "what": "forward + L1 + backward + clip 1.0 + AdamW (FusedAdamW), tensor-core backward; "
+                                          "ConvTranspose data gradient, GroupNorm / activation backward above 128 channels on CUDA cores"}
+            del wopt, wt
+        except Exception as e:  # a side measurement must never take the headline line down
+            wide["train_step"] = {"error": repr(e)[:200]}
         del wnet, wx
         torch.cuda.empty_cache()
 

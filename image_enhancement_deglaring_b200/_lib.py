@@ -57,6 +57,7 @@ class DgLwParams(C.Structure):
         ("up_w_tc_bf16", C.c_void_p * 4), ("conv_w_tc_bf16", (C.c_void_p * 2) * DG_MAX_BLOCKS),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("path", C.c_int32), ("reserved", C.c_int32),
         ("dec_comp", C.c_void_p * 4), ("conv_w_flip_tc_bf16", (C.c_void_p * 2) * DG_MAX_BLOCKS),
+        ("up_w_dgrad_tc_bf16", C.c_void_p * 4),
     ]
 
 

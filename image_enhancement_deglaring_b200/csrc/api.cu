@@ -630,7 +630,9 @@ static int lw_backward_range(const dg_lw_params* p, const LwPlan& pl, const BwdP
                                   p->gn_b[b - 1][1], try_fuse ? G(i - 1) : dlow, grads + gl.up_w[u], grads + gl.up_b[u],
                                   reinterpret_cast<float*>(bw + bp.coef_off) + (size_t)n0 * bp.maxc * 2, N, Hi, Wi, pl.f[lvl + 1], pl.f[lvl],
                                   p->groups[b - 1], 1e-5f, st, (p->path & 3) != 1 ? p->up_w_tc_bf16[u] : nullptr,
-                                  try_fuse ? &lact : nullptr, try_fuse ? &low_fused : nullptr);
+                                  try_fuse ? &lact : nullptr, try_fuse ? &low_fused : nullptr,
+                                  (p->path & 3) != 1 ? p->up_w_dgrad_tc_bf16[u] : nullptr,
+                                  p->dtype != DG_F32 ? bw + bp.gb_off[i] + (size_t)n0 * hwc(i, C) * 2 : nullptr);   // conv i's bf16 dR scratch is free again
             if (rc) return rc;
             if (low_fused) continue;   // G(i-1), P(i-1) are done
             if (try_fuse) {            // the kernel declined: G(i-1) holds the plain gradient; act_bwd works in place on it

@@ -882,7 +882,7 @@ int head_bwd_launch(int dtype, const void* raw, const double* stats, const float
 int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low,
                      const double* stats, const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias,
                      float* coefbuf, int N, int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st,
-                     const void* wtc_bf16, const DgradAct* act, bool* act_fused) {
+                     const void* wtc_bf16, const DgradAct* act, bool* act_fused, const void* w2_tc_bf16, void* scratch_bf16) {
     if (act_fused) *act_fused = false;
     if (Cu % 4 || (stride % 4) || (reinterpret_cast<uintptr_t>(dCat) & 15)) { set_error("convT backward: unaligned gradient"); return 3; }
     ConvtBwdArgs a{dCat, stride, wt, wt_t, raw_low, stats, gamma, beta, dAlow, dWt, nullptr, coefbuf, N, H, W, Cl, Cu, groups, eps};
@@ -901,6 +901,10 @@ int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, 
             rc = convt_dgrad_tc_launch(dCat, stride, wtc_bf16, dAlow, N, H, W, Cl, Cu, st, &data_done);
             if (rc) return rc;
         }
+    }
+    if (!data_done && dtype != DG_F32 && w2_tc_bf16 != nullptr && scratch_bf16 != nullptr) {   // wider variants: tcgen05 GEMM (conv3x3_t5.cu)
+        rc = convt_dgrad_t5_launch(dCat, stride, scratch_bf16, w2_tc_bf16, dAlow, N, H, W, Cl, Cu, st, &data_done);
+        if (rc) return rc;
     }
     if (!data_done) {
         if (wt_t == nullptr) { set_error("convT backward: the CUDA-core data gradient needs up_w_t"); return 2; }

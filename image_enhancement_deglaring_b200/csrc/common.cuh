@@ -208,6 +208,10 @@ int convt_dgrad_tc_launch(const float* dCat, int stride, const void* wtc_bf16, f
 // data gradient of the wide layers on the tcgen05 kernel (conv3x3_t5.cu, T5_IDENT): dR fp32 (converted into scratch_bf16) or bf16
 int conv3x3_dgrad_t5_launch(const float* dR, const void* dR_bf16, void* scratch_bf16, const void* wflip_tc_bf16, float* out, int N,
                             int H, int W, int ck, int cn, cudaStream_t st, bool* handled);
+// ConvTranspose2d(2,2) data gradient of the wide layers on the tcgen05 kernel: gather of the up half per position (bf16 scratch of
+// N*H*W*Cu elements) + one-tap T5_IDENT GEMM with K = 4 Cu, N = Cl
+int convt_dgrad_t5_launch(const float* dCat, int stride, void* scratch_bf16, const void* w2_tc_bf16, float* dLow, int N, int H, int W,
+                          int Cl, int Cu, cudaStream_t st, bool* handled);
 int image_metrics_launch(const float* out, const float* tgt, int N, int H, int W, int clip01, double data_range, double* acc,
                          cudaStream_t st);
 int first_wgrad_launch(const float* x, const float* dR, float* dW, int N, int H, int W, int CO, cudaStream_t st, bool* handled);
@@ -231,7 +235,8 @@ int head_bwd_launch(int dtype, const void* raw, const double* stats, const float
 int l1_sum_launch(const float* y, const float* t, size_t n, double* out, cudaStream_t st);
 int convt_bwd_launch(int dtype, const float* dCat, int stride, const float* wt, const float* wt_t, const void* raw_low, const double* stats,
                      const float* gamma, const float* beta, float* dAlow, float* dWt, float* dBias, float* coefbuf, int N,
-                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st, const void* wtc_bf16 = nullptr, const DgradAct* act = nullptr, bool* act_fused = nullptr);
+                     int H, int W, int Cl, int Cu, int groups, float eps, cudaStream_t st, const void* wtc_bf16 = nullptr, const DgradAct* act = nullptr, bool* act_fused = nullptr,
+                     const void* w2_tc_bf16 = nullptr, void* scratch_bf16 = nullptr);
 int adamw_launch(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float max_norm, float lr,
                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t st);
 int band_stats_launch(const double* kstats, const void* t, int dtype, int W, int C, int a0, int a1, int b0, int b1, double* out,

@@ -728,7 +728,7 @@ int t5_sm_count() {
 }
 
 // Geometry / shared-memory plan.  Returns false when the configuration does not fit (caller falls back to mma.sync).
-bool t5_plan(T5Args& t, int mode) {
+bool t5_plan(T5Args& t, int mode, int ntaps = 0) {
     const int cin = t.cin, cout = t.cout;
     if (cin < 16 || cin % 16 || cout < 32 || cout % 32) return false;
     t.nb = cout <= 128 ? cout : 128;
@@ -736,7 +736,7 @@ bool t5_plan(T5Args& t, int mode) {
     if (t.nb == 96) return false;   // keep N a power of two (TMEM stage arithmetic)
     t.nnb = cout / t.nb;
     const int csrc = mode == T5_CAT2 ? cout : (mode == T5_DEC ? t.cl : cin);   // channels of one source tensor
-    t.ntaps = mode == T5_CONVT ? 1 : 9;
+    t.ntaps = ntaps ? ntaps : (mode == T5_CONVT ? 1 : 9);   // ntaps = 1 with T5_IDENT: a plain GEMM over pixels (centre tap)
     t.kc = csrc >= 64 ? 64 : csrc;
     if (t.kc != 16 && t.kc != 32 && t.kc != 64) return false;
     if (csrc % t.kc || cin % t.kc) return false;
@@ -965,6 +965,61 @@ __global__ void __launch_bounds__(256) cvt_f32_bf16_kernel(const float* __restri
     }
 }
 }  // namespace
+
+// ---- data gradient of ConvTranspose2d(k=2, s=2) on the tcgen05 kernel (wide variant) -------------------------------------------------
+//   dLow[n,i,j,ci] = sum_{a,b,co} dUp[n, 2i+a, 2j+b, co] * Wt[ci][co][a][b]     (autograd of src/model.py:47-53 w.r.t. its input)
+// = a plain GEMM over low-resolution pixels with K = (position, co) = 4 Cu and N = ci: the up half of the concat gradient is gathered
+// per position into a bf16 tensor D [N,Hl,Wl,4 Cu] (one element-wise kernel), then T5_IDENT with ONE tap.  w2_tc_bf16 = the [4 Cu][Cl]
+// matrix W2[(2a+b) Cu + co][ci] = Wt[ci][co][a][b] in the [K/16][k-half][N][8] packing (dg_pack_convt2x2_tc of its re-blocked view).
+namespace {
+__global__ void __launch_bounds__(256) up_half_pos_bf16_kernel(const float* __restrict__ dCat, int stride, __nv_bfloat16* __restrict__ D,
+                                                               int N, int Hl, int Wl, int Cu) {
+    const int c8n = Cu >> 3;
+    const size_t items = (size_t)N * Hl * Wl * 4 * c8n;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < items; e += (size_t)gridDim.x * 256) {
+        const int c8 = (int)(e % c8n);
+        const size_t r = e / c8n;
+        const int pos = (int)(r & 3);
+        const size_t pix = r >> 2;                  // (n*Hl + i)*Wl + j
+        const int j = (int)(pix % Wl);
+        const size_t row = pix / Wl;                // n*Hl + i
+        const int i = (int)(row % Hl);
+        const size_t n = row / Hl;
+        const float* q = dCat + ((n * (2 * Hl) + 2 * i + (pos >> 1)) * (size_t)(2 * Wl) + 2 * j + (pos & 1)) * stride + c8 * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(q)), b = __ldg(reinterpret_cast<const float4*>(q) + 1);
+        *reinterpret_cast<uint4*>(D + (pix * 4 + pos) * Cu + c8 * 8) =
+            make_uint4(pack2<__nv_bfloat16>(a.x, a.y), pack2<__nv_bfloat16>(a.z, a.w), pack2<__nv_bfloat16>(b.x, b.y), pack2<__nv_bfloat16>(b.z, b.w));
+    }
+}
+}  // namespace
+
+int convt_dgrad_t5_launch(const float* dCat, int stride, void* scratch_bf16, const void* w2_tc_bf16, float* dLow, int N, int H, int W,
+                          int Cl, int Cu, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (dCat == nullptr || scratch_bf16 == nullptr || w2_tc_bf16 == nullptr || dLow == nullptr || ((H | W) & 1)) return 0;
+    if ((Cu & 7) || (stride & 3) ||
+        ((reinterpret_cast<uintptr_t>(dCat) | reinterpret_cast<uintptr_t>(scratch_bf16) | reinterpret_cast<uintptr_t>(w2_tc_bf16) |
+          reinterpret_cast<uintptr_t>(dLow)) & 15))
+        return 0;
+    T5Args t;
+    memset(&t, 0, sizeof(t));
+    t.src0 = scratch_bf16;
+    t.wgt = w2_tc_bf16;
+    t.out = dLow; t.out_stats = nullptr;
+    t.N = N; t.H = H / 2; t.W = W / 2; t.eps = 1e-5f;
+    t.cin = 4 * Cu;
+    t.cout = Cl;
+    if (!t5_plan(t, T5_IDENT, 1)) return 0;
+    const size_t items = (size_t)N * (H / 2) * (W / 2) * 4 * (Cu / 8);
+    size_t blocks = (items + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    up_half_pos_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(dCat, stride, static_cast<__nv_bfloat16*>(scratch_bf16), N, H / 2, W / 2, Cu);
+    count_launch();
+    int rc = check_launch("up_half_pos_bf16");
+    if (rc) return rc;
+    *handled = true;
+    return launch_t5<__nv_bfloat16, T5_IDENT, ACT_TANH>(t, st);
+}
 
 int conv3x3_dgrad_t5_launch(const float* dR, const void* dR_bf16, void* scratch_bf16, const void* wflip_tc_bf16, float* out, int N,
                             int H, int W, int ck, int cn, cudaStream_t st, bool* handled) {

@@ -144,6 +144,15 @@ class LightweightUNet(nn.Module):
             if tc_tier:
                 wbf = wtc if (pc.dtype == ops.DG_BF16 and wtc is not None) else ops.pack_convt2x2_tc(w, ops.DG_BF16)
             pc.up_w_tc_bf16[u] = None if wbf is None else wbf.data_ptr()
+            # wider variants: the data gradient as a one-tap tcgen05 GEMM with K = (position, co), N = ci (conv3x3_t5.cu)
+            w2t = None
+            if tc_tier and not tc_only and m.weight.shape[0] % 32 == 0:
+                ci_, co_ = int(m.weight.shape[0]), int(m.weight.shape[1])
+                w2 = m.weight.detach().float().permute(2, 3, 1, 0).reshape(4 * co_, ci_)              # [(2a+b) Co + co][ci]
+                w2 = w2.reshape(4 * co_, 4, ci_ // 4).permute(1, 0, 2).contiguous().reshape(2, 2, 4 * co_, ci_ // 4)
+                w2t = ops.pack_convt2x2_tc(w2, ops.DG_BF16)
+            pc.up_w_dgrad_tc_bf16[u] = None if w2t is None else w2t.data_ptr()
+            keep.append(w2t)
             # composite decoder taps (ConvTranspose folded into the consuming conv, conv3x3_dec.cu) where that kernel has coverage
             # level 1 (16 -> 8): conv3x3_dec.cu's kernel, forward of both modes.  Levels 2-4 (32 -> 16, 64 -> 32, 128 -> 64) have the
             # tcgen05 decoder mode of conv3x3_t5.cu (ConvTranspose + cat + conv as one low-resolution conv): correct but measured

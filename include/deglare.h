@@ -257,6 +257,10 @@ typedef struct {
     const void* conv_w_flip_tc_bf16[DG_MAX_BLOCKS][2]; /* backward only, optional: dg_pack_conv3x3_tc(conv_w_flip, DG_BF16) -- the
                                                taps-flipped weights in the tensor-core packing: the data gradient of the layers the
                                                mma.sync dgrad does not cover (wider variants, configs[4]) runs as a tcgen05 conv  */
+    const void* up_w_dgrad_tc_bf16[4];      /* backward only, optional: the ConvTranspose weights as the [4 Cout][Cin] matrix
+                                               W2[(2a+b) Cout + co][ci] = w[ci][co][a][b] in the [K/16][k-half][N][8] tensor-core packing
+                                               (dg_pack_convt2x2_tc of its [2][2][4 Cout][Cin/4] view, DG_BF16): the ConvTranspose data
+                                               gradient of the wider variants runs as a one-tap tcgen05 GEMM                     */
 } dg_lw_params;
 
 /* Bytes of workspace dg_lw_forward needs for an [N,in,H,W] batch (raw activations of all 18
