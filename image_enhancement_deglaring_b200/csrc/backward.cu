@@ -48,6 +48,47 @@ __device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, i
     rstd = (float)r;
 }
 
+// (mean, rstd) from a group's (sum, sumsq): the arithmetic of gn_mean_rstd above
+__device__ __forceinline__ void mean_rstd_of(double s1, double s2, double cnt, float eps, float& mean, float& rstd) {
+    double inv = (double)__frcp_rn((float)cnt);
+    inv = inv * (2.0 - cnt * inv);
+    inv = inv * (2.0 - cnt * inv);
+    const double m = s1 * inv;
+    double var = fma(s2, inv, -m * m);
+    if (var < 0.0) var = 0.0;
+    const double x = var + (double)eps;
+    double r = (double)rsqrtf((float)x);
+    r = r * (1.5 - 0.5 * x * r * r);
+    r = r * (1.5 - 0.5 * x * r * r);
+    mean = (float)m;
+    rstd = (float)r;
+}
+
+// Wide layers (C > 128, groups of 32..128 channels): the per-channel prologue above re-sums a whole group per channel -- 2 cpg
+// double loads for each of C channels in EVERY CTA (524 k loads at C = 1024).  Here one warp sums one group (lanes stride over its
+// channels, shuffle tree, fixed order), lane 0 leaves the K sums in gq[g][K]; callers derive the per-channel values from them.
+// w(c, k) = k-th summand of channel c.  Must be called by the whole CTA; ends with a barrier.
+template <int K, typename F>
+__device__ __forceinline__ void group_sums(double* gq, int C, int groups, F w) {
+    const int cpg = C / groups, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < groups; g += nwarps) {
+        double acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.0;
+        for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] += w(c, k);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            if (lane == 0) gq[g * K + k] = acc[k];
+        }
+    }
+    __syncthreads();
+}
+
 // ---- G = (dA_a + 0.25 * up2(dA_b)) * silu'(y);  P[n][c] += (sum G, sum G*xhat) -------------------------------------
 struct ActBwdArgs {
     const void* raw; const double* stats; const float* gamma; const float* beta;
@@ -180,10 +221,24 @@ __global__ void __launch_bounds__(BW_THREADS) act_bwd_vec_kernel(const ActBwdArg
     float* slot = coef + 4 * C;                        // [8 warps][C][2]
     const int n = blockIdx.y;
     const int HW = p.H * p.W;
-    for (int c = threadIdx.x; c < C; c += BW_THREADS) {
-        float m, r;
-        gn_mean_rstd(p.stats, n, C, p.groups, c, (double)HW, p.eps, m, r);
-        coef[4 * c] = m; coef[4 * c + 1] = r; coef[4 * c + 2] = p.gamma[c]; coef[4 * c + 3] = p.beta[c];
+    if (C4 > 32) {
+        // wide layers: per-group sums by warps; a warp holds only 32 of the C4 chunks, so the slots start at zero
+        double* gq = reinterpret_cast<double*>(slot + (BW_THREADS / 32) * C * 2);   // [groups][2]
+        const double* st = p.stats + (size_t)n * C * 2;
+        group_sums<2>(gq, C, p.groups, [&](int c, int k) { return st[2 * c + k]; });
+        const int cpg = C / p.groups;
+        for (int c = threadIdx.x; c < C; c += BW_THREADS) {
+            float m, r;
+            mean_rstd_of(gq[(c / cpg) * 2], gq[(c / cpg) * 2 + 1], (double)HW * cpg, p.eps, m, r);
+            coef[4 * c] = m; coef[4 * c + 1] = r; coef[4 * c + 2] = p.gamma[c]; coef[4 * c + 3] = p.beta[c];
+        }
+        for (int i = threadIdx.x; i < (BW_THREADS / 32) * C * 2; i += BW_THREADS) slot[i] = 0.f;
+    } else {
+        for (int c = threadIdx.x; c < C; c += BW_THREADS) {
+            float m, r;
+            gn_mean_rstd(p.stats, n, C, p.groups, c, (double)HW, p.eps, m, r);
+            coef[4 * c] = m; coef[4 * c + 1] = r; coef[4 * c + 2] = p.gamma[c]; coef[4 * c + 3] = p.beta[c];
+        }
     }
     __syncthreads();
     const int items = HW * C4;
@@ -243,7 +298,7 @@ __global__ void __launch_bounds__(BW_THREADS) act_bwd_vec_kernel(const ActBwdArg
         }
     }
     __syncthreads();
-    // C4 <= 32: every warp holds every chunk (32 % C4 == 0) -> sum the 8 warp slots in a fixed order
+    // C4 <= 32: every warp holds every chunk (32 % C4 == 0); C4 > 32: the other warps' slots are zero -> sum the 8 warp slots in a fixed order
     for (int i = threadIdx.x; i < 2 * C; i += BW_THREADS) {
         double t = 0.0;
 #pragma unroll
@@ -257,6 +312,20 @@ __global__ void __launch_bounds__(BW_THREADS) gn_bwd_apply_vec_kernel(const GnBw
     extern __shared__ float gsm[];  // [C][5] mean, rstd, gamma, m1, m2
     const int C = p.C, C4 = C >> 2, n = blockIdx.y, HW = p.H * p.W;
     const int cpg = C / p.groups;
+    if (C4 > 32) {   // wide layers: the four per-group sums once per CTA (see group_sums)
+        double* gq = reinterpret_cast<double*>(gsm + 5 * C + (C & 1));   // [groups][4], 8-byte aligned behind the 5 C floats
+        const double* st = p.stats + (size_t)n * C * 2;
+        const double* P = p.P + (size_t)n * C * 2;
+        group_sums<4>(gq, C, p.groups, [&](int c, int k) { return k < 2 ? st[2 * c + k] : (double)p.gamma[c] * P[2 * c + (k - 2)]; });
+        const double cnt = (double)HW * cpg;
+        for (int c = threadIdx.x; c < C; c += BW_THREADS) {
+            const double* q = gq + (c / cpg) * 4;
+            float m, r;
+            mean_rstd_of(q[0], q[1], cnt, p.eps, m, r);
+            gsm[5 * c] = m; gsm[5 * c + 1] = r; gsm[5 * c + 2] = p.gamma[c];
+            gsm[5 * c + 3] = (float)(q[2] / cnt); gsm[5 * c + 4] = (float)(q[3] / cnt);
+        }
+    } else
     for (int c = threadIdx.x; c < C; c += BW_THREADS) {
         float m, r;
         gn_mean_rstd(p.stats, n, C, p.groups, c, (double)HW, p.eps, m, r);
@@ -744,10 +813,20 @@ __global__ void __launch_bounds__(BW_THREADS) first_wgrad_kernel(const float* __
 }
 
 // vector path: (pixel, 4-channel) items; C/4 a power of two <= 32 keeps a thread on one chunk and lets a warp cover all chunks
+// vector kernels: C a power of two, 4 .. 128 (the shipped widths) and -- with the per-group prologue -- 256 .. 1024 (wider variants,
+// groups of at most 32 warps' worth of work: groups <= C / 32 is not required, any divisor works)
 inline bool ew_vec_ok(int dtype, int C, int H, int W) {
     (void)dtype;
     const int c4 = C / 4;
-    return C % 4 == 0 && c4 >= 1 && c4 <= 32 && (c4 & (c4 - 1)) == 0 && (size_t)H * W * c4 < (size_t)1 << 30;
+    return C % 4 == 0 && c4 >= 1 && c4 <= 256 && (c4 & (c4 - 1)) == 0 && (size_t)H * W * c4 < (size_t)1 << 30;
+}
+template <typename K>
+inline int ew_allow_smem(K kern, size_t bytes, bool* done) {
+    if (bytes <= 48 * 1024 || *done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(element-wise backward): %s", cudaGetErrorString(e)); return 4; }
+    *done = true;
+    return 0;
 }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool aligned_raw(int dtype, const void* p) { return (reinterpret_cast<uintptr_t>(p) & (dtype == DG_F32 ? 15 : 7)) == 0; }
@@ -775,7 +854,11 @@ int act_bwd_launch(int dtype, const void* raw, const double* stats, const float*
     if (ew_vec_ok(dtype, C, H, W) && aligned16(G) && aligned16(dA_a) && aligned16(dA_b) && (stride_a & 3) == 0 &&
         (off_a & 3) == 0 && (stride_b & 3) == 0 && (off_b & 3) == 0 && aligned_raw(dtype, raw)) {
         dim3 vgrid(ew_vec_blocks((size_t)H * W * (C / 4)), N);
-        const size_t vsmem = (size_t)C * 4 * sizeof(float) + (size_t)(BW_THREADS / 32) * C * 2 * sizeof(float);
+        const size_t vsmem = (size_t)C * 4 * sizeof(float) + (size_t)(BW_THREADS / 32) * C * 2 * sizeof(float) +
+                             (C > 128 ? (size_t)groups * 2 * sizeof(double) : 0);
+        if (vsmem > 96 * 1024) { set_error("act backward: %d channels need %zu B of shared memory", C, vsmem); return 3; }
+        static bool attr[3] = {false, false, false};
+        { int rc = 0; DG_BY_DTYPE(dtype, (rc = ew_allow_smem(act_bwd_vec_kernel<T>, vsmem, &attr[dtype]))); if (rc) return rc; }
         DG_BY_DTYPE(dtype, (act_bwd_vec_kernel<T><<<vgrid, BW_THREADS, vsmem, st>>>(a)));
         count_launch();
         return check_launch("act_bwd_vec");
@@ -814,7 +897,8 @@ int gn_bwd_apply_launch(int dtype, const void* raw, const double* stats, const f
             *wrote_bf16 = true;
         }
         dim3 vgrid(ew_vec_blocks((size_t)H * W * (C / 4)), N);
-        DG_BY_DTYPE(dtype, (gn_bwd_apply_vec_kernel<T><<<vgrid, BW_THREADS, (size_t)C * 5 * sizeof(float), st>>>(a)));
+        const size_t gsmem = (size_t)(C * 5 + (C & 1)) * sizeof(float) + (C > 128 ? (size_t)groups * 4 * sizeof(double) : 0);
+        DG_BY_DTYPE(dtype, (gn_bwd_apply_vec_kernel<T><<<vgrid, BW_THREADS, gsmem, st>>>(a)));
         count_launch();
         return check_launch("gn_bwd_apply_vec");
     }

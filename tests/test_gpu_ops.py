@@ -769,6 +769,38 @@ def test_wgrad_tc_refuses_what_it_does_not_cover():
     ops.conv3x3_wgrad([src], dR, 24, 24, 1, 16, 16, ops.DG_F16, path=0)   # auto falls back to the generic kernel
 
 
+# ---- per-op backward of GroupNorm + SiLU (dg_act_bwd, dg_gn_bwd_apply): shipped widths and the wide variant's (per-group prologue) ----
+@pytest.mark.parametrize("dtype", [ops.DG_F32, ops.DG_F16])
+@pytest.mark.parametrize("C,groups,H,W,pooled", [(16, 8, 16, 24, True), (128, 8, 8, 8, False), (256, 8, 8, 12, True), (1024, 8, 4, 4, False),
+                                                   (512, 4, 6, 10, False), (12, 6, 8, 8, False)])
+def test_act_and_groupnorm_backward_ops(dtype, C, groups, H, W, pooled):
+    """G = (dA_a + AvgPool2d-backward(dA_b)) * SiLU'(y), P sums, then dR / dgamma / dbeta in place, against autograd of
+    F.silu(F.group_norm(raw)) (src/model.py:94-98) consumed same-resolution and (optionally) through nn.AvgPool2d(2, 2)."""
+    gen = torch.Generator().manual_seed(5 + C)
+    N = 2
+    raw = (torch.randn(N, H, W, C, generator=gen) * 1.5 + 0.3).to(ops.TORCH_DTYPE[dtype]).cuda()
+    gamma = (1 + 0.2 * torch.randn(C, generator=gen)).cuda().requires_grad_(True)
+    beta = (0.2 * torch.randn(C, generator=gen)).cuda().requires_grad_(True)
+    dA = torch.randn(N, H, W, 2 * C, generator=gen).cuda()                 # one half of a concat gradient: channels C .. 2C
+    dB = torch.randn(N, H // 2, W // 2, C, generator=gen).cuda() if pooled else None
+    r = raw.float().requires_grad_(True)
+    act = F.silu(F.group_norm(r.permute(0, 3, 1, 2), groups, gamma, beta, 1e-5))
+    loss = (act * dA[..., C:].permute(0, 3, 1, 2)).sum()
+    if pooled:
+        loss = loss + (F.avg_pool2d(act, 2, 2) * dB.permute(0, 3, 1, 2)).sum()
+    loss.backward()
+    stats = torch.stack((raw.double().sum(dim=(1, 2)), (raw.double() ** 2).sum(dim=(1, 2))), dim=-1).contiguous()
+    G = torch.empty(N, H, W, C, device="cuda")
+    P = torch.zeros(N, C, 2, dtype=torch.float64, device="cuda")
+    g, b = gamma.detach(), beta.detach()
+    ops.act_bwd(raw, stats, g, b, groups, dtype, N, H, W, C, G, P, dA_a=dA, off_a=C, dA_b=dB)
+    dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.gn_bwd_apply(raw, stats, g, groups, dtype, N, H, W, C, P, G, dgamma, dbeta)
+    for got, ref, what in ((G, r.grad, "dR"), (dgamma, gamma.grad, "dgamma"), (dbeta, beta.grad, "dbeta")):
+        err = float((got - ref).abs().max())
+        assert err <= 2e-4 * float(ref.abs().max()) + 1e-6, (what, err, float(ref.abs().max()))
+
+
 # ---- the two device steps of the row-sharded whole-image path and the graph-capturable optimizer tail -----------------------------
 @pytest.mark.parametrize("tdtype,code", [(torch.float32, 0), (torch.float16, 1), (torch.bfloat16, 2)])
 @pytest.mark.parametrize("C,W,rows,c0,own0,own1,c1", [(8, 64, 20, 0, 2, 18, 20), (16, 48, 11, 1, 2, 10, 10), (12, 32, 9, 0, 0, 7, 9),
