@@ -25,7 +25,8 @@ def main():
     t = torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(2)).cuda()
     crit = torch.nn.L1Loss()
     grads, per = {}, {}
-    for path in (0, 1):
+    paths = tuple(int(v) for v in os.environ.get("DG_DIAG_PATHS", "0,1").split(","))
+    for path in paths:
         net = dg.LightweightUNet(features_start=64, storage="fp16", path=path)
         net.load_state_dict(sd, strict=True)
         net = net.cuda().train()
@@ -73,6 +74,8 @@ def main():
         print(f"one step, {tot / 1e3:.2f} ms of kernels:")
         for name, r in sorted(rows.items(), key=lambda kv: -kv[1][1])[:28]:
             print(f"  {r[1] / 1e3:9.3f} ms  {100 * r[1] / tot:5.1f} %  x{r[0]:<3d} max {r[2] / 1e3:8.3f} ms  {name}")
+    if len(grads) < 2:
+        return
     rel = float((grads[0] - grads[1]).norm() / grads[1].norm())
     print(f"gradient rel-L2 difference tensor-core vs CUDA-core backward: {rel:.3e}")
     rows = sorted(((float((per[0][k] - per[1][k]).norm() / per[1][k].norm().clamp_min(1e-300)), k) for k in per[0]), reverse=True)
