@@ -149,6 +149,11 @@ class OptimizedUNet(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             if x.requires_grad:
                 raise NotImplementedError("gradient w.r.t. the input image is not implemented (the reference never needs it)")
+            if getattr(self, "_dg_direct_grads", False):
+                # train.GraphedTrainStep: inside a captured step the parameters are not autograd inputs (their AccumulateGrad nodes
+                # would join the stream they were created on into the capture); a fresh leaf anchors the node and the gradients go
+                # straight into the optimizer's flat bucket
+                return _OptimizedUNetFn.apply(self, x, torch.zeros((), device=x.device, requires_grad=True))
             return _OptimizedUNetFn.apply(self, x, *self.parameters())
         with _on_device_of(x):
             return self._run(x)
@@ -317,6 +322,7 @@ class _OptimizedUNetFn(torch.autograd.Function):
         with _on_device_of(x):
             y = module._run(x, keep)
         ctx.module, ctx.keep, ctx.n_inputs = module, keep, len(params)
+        ctx.direct = getattr(module, "_dg_direct_grads", False)
         return y
 
     @staticmethod
@@ -330,12 +336,15 @@ class _OptimizedUNetFn(torch.autograd.Function):
         grad_y = grad_y.detach().float().contiguous()
         with _on_device_of(grad_y):
             sink = _flat_grad_sink(params)
+            if ctx.direct and sink is None:
+                raise RuntimeError("GraphedTrainStep: the gradients must land in the optimizer's flat bucket (FusedAdamW.zero_grad "
+                                   "inside the step, no per-parameter hooks)")
             flat = sink if sink is not None else torch.zeros(total, dtype=torch.float32, device=grad_y.device)
             module._backward(keep, grad_y, flat)
         ctx.keep = None
         sync_gradients(flat, getattr(module, "ddp_sync", True))
         if sink is not None:
-            sink._dg_zero_version = None
+            sink._dg_zero_version = None      # the bucket now holds a gradient: a second backward accumulates the ordinary way
             return (None, None) + (None,) * ctx.n_inputs
         grads, off = [], 0
         for p in params:

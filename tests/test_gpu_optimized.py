@@ -276,3 +276,40 @@ def test_attention_backward_kernels_match_torch(dtype):
     # dL/dA = d * att (direct) + add (through the mean): autograd's A.grad holds both
     want_add = A.grad - d[..., C:] * att.detach()[:, None, None, :]
     assert float((add[:, None, None, :] - want_add).abs().max()) <= 3e-4 * float(want_add.abs().max()) + 1e-7
+
+
+def test_optimized_cuda_graph_training_step_equals_eager_loop(golden):
+    """train.GraphedTrainStep on OptimizedUNet: zero_grad, forward, L1, the per-op backward (~190 launches), clip, AdamW captured once
+    and replayed; same losses and parameters as the eager loop, and an eager forward after the replays sees the updated weights."""
+    from image_enhancement_deglaring_b200.train import FusedAdamW, GraphedTrainStep
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden import TRAIN_LR, TRAIN_WD
+    _, sd = _sd(golden)
+    xs = [_rand((2, 1, 32, 48), 30 + i).cuda() for i in range(3)]
+    ts = [_rand((2, 1, 32, 48), 40 + i).cuda() for i in range(3)]
+    crit = torch.nn.L1Loss()
+    # eager loop
+    a = _train_net(sd)
+    oa = FusedAdamW(a.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD, max_grad_norm=1.0)
+    la = []
+    for x, t in zip(xs, ts):
+        oa.zero_grad(set_to_none=True)
+        loss = crit(a(x), t)
+        loss.backward()
+        oa.step()
+        la.append(float(loss))
+    # captured step
+    b = _train_net(sd)
+    ob = FusedAdamW(b.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD, max_grad_norm=1.0, capturable=True)
+    step = GraphedTrainStep(b, ob, crit, xs[0].shape)
+    lb = [float(step(x, t)) for x, t in zip(xs, ts)]
+    for u, v in zip(la, lb):
+        assert abs(u - v) <= 2e-5 * max(1.0, abs(u)), (la, lb)
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        d = (pa.detach() - pb.detach()).abs()
+        assert float(d.max()) <= 2 * TRAIN_LR, k             # Adam turns atomics-order noise on a near-zero gradient into up to lr
+        moved = float((pa.detach().cpu() - sd[k]).norm())
+        assert float(d.norm()) <= 0.05 * moved + 1e-6, k
+    with torch.no_grad():
+        ya, yb = a.eval()(xs[0]).cpu(), b.eval()(xs[0]).cpu()
+    assert float((ya - yb).abs().max()) <= 5e-3 * max(1.0, float(ya.abs().max()))
