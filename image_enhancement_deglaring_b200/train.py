@@ -364,9 +364,13 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep needs FusedAdamW(..., capturable=True)")
         dev = next(module.parameters()).device
         self.module, self.optimizer, self.criterion, self.clip = module, optimizer, criterion, clip_grad_norm
-        self.x = torch.zeros(shape, dtype=torch.float32, device=dev)
-        self.t = torch.zeros((shape[0], module.out_channels) + tuple(shape[2:]), dtype=torch.float32, device=dev)
-        # the warm-up steps run on zeros with lr = 0 and weight decay 0 against saved moments: they must not train
+        # The warm-up steps run with lr = 0 and weight decay 0 against saved moments: they must not train.  Their input is uniform
+        # noise, NOT zeros: a bias-free freshly initialised network maps a constant image to constant activations, every GroupNorm
+        # then divides by sqrt(eps) (x 316 per layer in the backward), the gradient overflows, and 0 * inf in the AdamW update turns
+        # the parameters into NaN before the first real step (measured on a default-initialised OptimizedUNet at 256x256).
+        gen = torch.Generator().manual_seed(0)
+        self.x = torch.rand(tuple(shape), generator=gen).to(dev)
+        self.t = torch.rand((shape[0], module.out_channels) + tuple(shape[2:]), generator=gen).to(dev)
         g = optimizer.param_groups[0]
         saved = (g["lr"], g["weight_decay"], optimizer.exp_avg.clone(), optimizer.exp_avg_sq.clone(), optimizer._step_dev.clone())
         g["lr"], g["weight_decay"] = 0.0, 0.0
