@@ -107,6 +107,18 @@ class ClockSampler:
                 pass
             self._stop.wait(0.004)
 
+    def sample_now(self):
+        """One sample taken by the CALLER (the main thread, right after it has enqueued the timed steps: the GPU is still executing
+        them), so the timed region holds a reading under load even when it is shorter than the poll thread's NVML round trips."""
+        if self.nvml is None:
+            return
+        nv, h = self.nvml
+        try:
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+        except Exception:
+            pass
+
     def start(self):
         try:
             self.nvml = self._nvml_handle()
@@ -332,6 +344,8 @@ def main():
         for _ in range(args.steps):
             y = net(x)
         e1.record()
+        if rank == 0:
+            sampler.sample_now()
         barrier()
         t1 = time.perf_counter()
         launches = _lib.launch_count() - l0
@@ -614,7 +628,7 @@ def main():
             wtms = ev[0].elapsed_time(ev[1]) / 5
             wide["train_step"] = {"batch": wb, "ms_per_step": wtms, "value": wb / (wtms * 1e-3), "unit": UNIT,
                                   "tflops": 3 * flop * wb / (wtms * 1e-3) / 1e12, "frac": 3 * flop * wb / (wtms * 1e-3) / 1e12 / tpeak,
-                                  "loss": float(wl),
+                                  "loss": float(wl.detach()),
                                   "what": "forward + L1 + backward + clip 1.0 + AdamW (FusedAdamW), tensor-core backward; "
                                           "ConvTranspose data gradient, GroupNorm / activation backward above 128 channels on CUDA cores"}
             del wopt, wt
@@ -671,7 +685,7 @@ def main():
             ev[1].record()
             torch.cuda.synchronize()
             otms = ev[0].elapsed_time(ev[1]) / 5
-            optimized["train_step"] = {"batch": tb, "ms_per_step": otms, "value": tb / (otms * 1e-3), "unit": UNIT, "loss": float(ol),
+            optimized["train_step"] = {"batch": tb, "ms_per_step": otms, "value": tb / (otms * 1e-3), "unit": UNIT, "loss": float(ol.detach()),
                                        "what": "forward + L1 + backward (all 76 parameter tensors) + clip 1.0 + AdamW (FusedAdamW); "
                                                "tensor-core wgrad / dgrad where the channel pair is covered, CUDA-core kernels elsewhere"}
             del oopt, otx, ott

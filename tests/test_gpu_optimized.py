@@ -125,7 +125,7 @@ def test_optimized_reference_loop_step_fp32(golden):
     opt.zero_grad(set_to_none=True)
     loss = torch.nn.L1Loss()(net(x.cuda()), t.cuda())
     loss.backward()
-    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * max(1.0, float(g["loss"]))
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-5 * max(1.0, float(g["loss"]))
     grads = {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()}
     for k, gr in grads.items():
         ref = r["grads"][k].numpy()
@@ -167,7 +167,7 @@ def test_optimized_reference_amp_gradscaler_branch_verbatim(golden):
     total = torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)   # :215
     scaler.step(opt)                                      # :218
     scaler.update()                                       # :219
-    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * max(1.0, float(g["loss"]))
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-5 * max(1.0, float(g["loss"]))
     assert abs(float(total) - float(g["total_norm"])) <= 2e-3 * float(g["total_norm"])
     loose = n = 0
     for k, p in net.named_parameters():
@@ -297,7 +297,7 @@ def test_optimized_cuda_graph_training_step_equals_eager_loop(golden):
         loss = crit(a(x), t)
         loss.backward()
         oa.step()
-        la.append(float(loss))
+        la.append(float(loss.detach()))
     # captured step
     b = _train_net(sd)
     ob = FusedAdamW(b.parameters(), lr=TRAIN_LR, weight_decay=TRAIN_WD, max_grad_norm=1.0, capturable=True)
