@@ -94,9 +94,12 @@ class OptimizedUNet(nn.Module):
         dt = DTYPE_CODES[self.storage]
         pk = {}
 
+        pk["_convs"] = []
+
         def conv(name, m):
             w = ops.pack_conv3x3(m.weight)
             pk[name] = (w, ops.pack_conv3x3_tc(w, dt) if self.path != 1 else None)
+            pk["_convs"].append(name)
 
         def gn(name, m):
             pk[name] = (m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous(), m.num_groups)
@@ -121,9 +124,8 @@ class OptimizedUNet(nn.Module):
         pk = self._packs()
         if pk.get("_bwd") is None:
             bk = {}
-            for name, v in list(pk.items()):
-                if not (isinstance(v, tuple) and len(v) == 2 and name[-2:] in (".0", ".3", ".1") and "attention" not in name):
-                    continue
+            for name in pk["_convs"]:          # every 3x3 conv: "enc1.0" ... "dec1.3", "upconv4.1" ... "upconv1.1"
+                v = pk[name]
                 blk, idx = name.rsplit(".", 1)
                 w = getattr(self, blk)[int(idx)].weight
                 tc = tcf = None
