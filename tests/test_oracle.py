@@ -167,6 +167,48 @@ def test_optimized_train_step_oracle_matches_reference(golden):
         assert np.abs(got[:32] - g["gy_ghead/" + k]).max() <= 1e-9 + 1e-3 * np.abs(g["gy_ghead/" + k]).max(), k
 
 
+# ---- second oracle: the shipped ONNX artefact itself (what api/app.py:84,171 and evaluate.py:95,122 execute through onnxruntime) ------
+ONNX_PATH = "/root/reference/best_model.onnx"     # build container only; absent on the GPU box
+
+
+@pytest.mark.skipif(not os.path.exists(ONNX_PATH), reason="the reference mount (best_model.onnx) exists only in the build container")
+def test_onnx_artefact_interpreter_matches_reference_goldens(best_sd, golden):
+    """oracle/onnx_interp.py evaluates the exported graph (opset 11, 229 nodes, eleven operator types) with the ONNX operator
+    semantics: it must land on the outputs the reference MODULE produced (golden vectors), i.e. artefact == module == oracle."""
+    from oracle.onnx_interp import OnnxGraph
+    g = OnnxGraph(ONNX_PATH)
+    assert g.opset == 11 and g.inputs == ["input"] and g.outputs == ["output"]
+    assert g.op_types() == ["Add", "AveragePool", "Concat", "Constant", "Conv", "ConvTranspose", "InstanceNormalization", "Mul",
+                            "Reshape", "Shape", "Sigmoid"]
+    png = golden("lw_png.npz")
+    for i in (1, 2):   # the two sample images through the /infer preprocessing (api/app.py:136-157)
+        x = png[f"x{i}_u8"].astype(np.float32)[None, None] / 255.0
+        assert np.abs(g.run(x)[0, 0] - png[f"y{i}"]).max() <= 1e-5
+    rnd = golden("lw_rand.npz")
+    assert np.abs(g.run(_rand((2, 1, 64, 64), 0).numpy()) - rnd["y_2x64x64_seed0"]).max() <= 1e-5
+    assert np.abs(g.run(_rand((1, 1, 96, 80), 1).numpy()) - rnd["y_1x96x80_seed1"]).max() <= 1e-5      # dynamic axes
+    # every raw conv / ConvTranspose output of the graph against the reference module's forward hooks
+    taps = {}
+    g.run(_rand((2, 1, 64, 64), 0).numpy(), taps=taps)
+    assert len(taps) == 23
+    for name, v in taps.items():     # "/enc1/enc1.0/Conv_output_0" -> "enc1.0";  "/upconv4/ConvTranspose_output_0" -> "upconv4"
+        parts = name.strip("/").split("/")
+        key = parts[-2] if len(parts) >= 2 else parts[0]
+        key = "output_conv" if name == "output" else key
+        ref = rnd["tap/" + key]        # all 23: 18 conv3x3, 4 ConvTranspose, the head
+        assert np.abs(v.numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), key
+    # and against the restated oracle on an input neither golden file holds
+    x = _rand((3, 1, 48, 32), 77)
+    with torch.no_grad():
+        want = tpo.lightweight_forward(x, best_sd).numpy()
+    assert np.abs(g.run(x.numpy()) - want).max() <= 1e-5
+    # the artefact's initializers are the 486,409 weights of weights/best_model.pth
+    named = {k: v for k, v in g.inits.items() if not k.startswith("onnx::")}
+    assert sum(v.size for v in g.inits.values() if v.dtype == np.float32) == 486409
+    for k, v in named.items():
+        assert np.array_equal(v, best_sd[k].numpy()), k
+
+
 def test_l1_grad_restatement():
     o = np.array([[0.2, 0.5], [0.7, 0.1]])
     t = np.array([[0.5, 0.5], [0.1, 0.4]])
