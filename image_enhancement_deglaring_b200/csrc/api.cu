@@ -920,7 +920,7 @@ int dg_channel_attention(const double* act_sum, double plane, const float* w1, c
 static int check_gn(const char* who, const void* raw, const double* stats, const float* gamma, const float* beta, int N, int H, int W,
                     int C, int groups) {
     if (raw == nullptr || stats == nullptr || gamma == nullptr || beta == nullptr) { set_error("%s: null pointer", who); return 2; }
-    if (N < 1 || H < 1 || W < 1 || C < 1) { set_error("%s: bad shape", who); return 3; }
+    if (N < 1 || N > 65535 || H < 1 || W < 1 || C < 1) { set_error("%s: bad shape (N must be 1..65535: images are grid.y)", who); return 3; }
     if (groups < 1 || C % groups != 0) { set_error("%s: %d channels not divisible into %d groups", who, C, groups); return 2; }
     return 0;
 }
