@@ -113,3 +113,74 @@ def test_bridge_averages_gradients_over_two_ranks(golden, tmp_path):
     want = torch.cat([r["grads"][k].reshape(-1) for k in sd if k in dict(dg.OptimizedUNet().named_parameters())])
     assert got.shape == want.shape
     assert float((got - want).abs().max()) <= 2e-5 + 1e-3 * float(want.abs().max())
+
+
+def test_data_gradient_fallback_chain(golden, monkeypatch):
+    """16-bit tier dispatch of the conv data gradient: mma.sync kernel where it has the channel pair, else the tcgen05 kernel where it
+    has a plan, else the generic kernel -- a refusal (rc 3, raised before any launch) is remembered per pair / shape and must not
+    change the result.  Stand-ins refuse like the library does and count who served what."""
+    from image_enhancement_deglaring_b200 import ops
+    from image_enhancement_deglaring_b200.model_optimized import OptimizedUNet
+    net, sd = _net(golden, monkeypatch)
+    net.storage = "fp16"            # steers the dispatch; the stand-ins round the stored raws to fp16 like the kernels do
+    monkeypatch.setattr(ops, "pack_conv3x3_tc", lambda w, dtype, stream=None: w)      # "a packing exists": hand the fp32 taps through
+    monkeypatch.setattr(OptimizedUNet, "_tc_dgrad_ok", {})
+    monkeypatch.setattr(OptimizedUNet, "_t5_dgrad_ok", {})
+    served = {"tc": 0, "t5": 0, "generic": 0, "refused": 0}
+
+    def via_forward_weights(dR, w_packed, cin):     # w_packed [3,3,cin,cout] (forward layout): flip + swap = the dgrad conv
+        wflip = w_packed.flip(0, 1).permute(0, 1, 3, 2).contiguous()
+        N, H, W, _ = dR.shape
+        return opt_standins.conv3x3_dgrad_generic(dR, wflip, cin, N, H, W)
+
+    def tc(dR, w_packed, cin, cout, stream=None):
+        if max(cin, cout) > 128:
+            served["refused"] += 1
+            raise RuntimeError("libdeglare error 3: dgrad: no tensor-core kernel for %d -> %d channels" % (cin, cout))
+        served["tc"] += 1
+        return via_forward_weights(dR, w_packed, cin)
+
+    def t5(dR, wflip, cin, cout, stream=None):
+        if cin < 32:
+            served["refused"] += 1
+            raise RuntimeError("libdeglare error 3: wide dgrad: no tcgen05 plan for %d -> %d channels" % (cin, cout))
+        served["t5"] += 1
+        N, H, W, _ = dR.shape
+        return opt_standins.conv3x3_dgrad_generic(dR, wflip, cin, N, H, W)
+
+    def generic(dR, wflip, cin, N, H, W, out=None, stream=None):
+        served["generic"] += 1
+        return opt_standins.conv3x3_dgrad_generic(dR, wflip, cin, N, H, W)
+
+    monkeypatch.setattr(ops, "conv3x3_dgrad", tc)
+    monkeypatch.setattr(ops, "conv3x3_dgrad_wide", t5)
+    monkeypatch.setattr(ops, "conv3x3_dgrad_generic", generic)
+    x = _rand((1, 1, 32, 32), 5)
+    gy = torch.randn(1, 1, 32, 32, generator=torch.Generator().manual_seed(9)) / x.numel()
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    ref = dict(zip(params, torch.autograd.grad((tpo.optimized_forward(x, params) * gy).sum(), list(params.values()))))
+    # the same tier with every data gradient on the generic kernel (path = 1): the dispatch must not change the arithmetic
+    net.path = 1
+    keep = {}
+    net._run(x, keep)
+    base = torch.zeros(sum(p.numel() for p in net.parameters()))
+    net._backward(keep, gy, base)
+    assert served == {"tc": 0, "t5": 0, "generic": 21, "refused": 0}, served
+    served["generic"] = 0
+    net.path = 0
+    for rnd in range(2):            # the second pass runs from the remembered refusals: nobody is asked twice
+        keep = {}
+        net._run(x, keep)
+        flat = torch.zeros(sum(p.numel() for p in net.parameters()))
+        net._backward(keep, gy, flat)
+        assert float((flat - base).abs().max()) <= 1e-6 * float(base.abs().max()), rnd
+        off = 0
+        for k, p in net.named_parameters():
+            got = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            assert float((got - ref[k]).abs().max()) <= 1e-9 + 3e-2 * float(ref[k].abs().max()), (rnd, k)   # fp16 storage of the raws
+        if rnd == 0:
+            # 21 convs have a data gradient (all but enc1.0); the 256-channel pairs go to tcgen05, nothing needs the generic kernel
+            assert served["tc"] + served["t5"] + served["generic"] == 21 and served["t5"] == 4 and served["generic"] == 0, served
+            first = dict(served)
+    assert served["refused"] == first["refused"] and served["t5"] == 2 * first["t5"], (first, served)
