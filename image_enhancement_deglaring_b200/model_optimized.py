@@ -2,7 +2,9 @@
 
 Same constructor (`in_channels=1, out_channels=1`), the same 76 state_dict keys / shapes (parameter containers only), and
 `forward(x[N,in,H,W]) -> [N,out,H,W]`.  No checkpoint ships for this architecture; parity is taken on deterministic
-weights against the reference module (tests/golden/opt_rand.npz).  Inference only for now.
+weights against the reference module (tests/golden/opt_rand.npz forward, opt_train.npz one training step).  Training: under
+autograd the forward keeps the raw activations and `_backward` mirrors it op by op (per-op backward entry points of
+include/deglare.h).
 
 Mapping onto the fused 3x3 conv (include/deglare.h):
   _block conv .0 / .3          -> DG_X_SAME / DG_X_POOL2 sources (GroupNorm+SiLU[+AvgPool] on load)       :91-98, :33-42
