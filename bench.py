@@ -607,6 +607,7 @@ def main():
         try:
             from image_enhancement_deglaring_b200.train import FusedAdamW, L1Loss
             wnet.train()
+            wnet.ddp_sync = False   # a rank-0-only side measurement: no gradient all-reduce (the other ranks are not in this step)
             wopt = FusedAdamW(wnet.parameters(), lr=2.3e-3, weight_decay=6.75e-5, max_grad_norm=1.0)
             wcrit = L1Loss()
             wt = torch.rand(wb, 1, H, W, generator=torch.Generator().manual_seed(6)).to(dev)
@@ -666,6 +667,7 @@ def main():
             from image_enhancement_deglaring_b200.train import FusedAdamW
             tb = 8
             onet.train()
+            onet.ddp_sync = False   # rank-0-only side measurement: no gradient all-reduce
             oopt = FusedAdamW(onet.parameters(), lr=2.3e-3, weight_decay=6.75e-5, max_grad_norm=1.0)
             ocrit = torch.nn.L1Loss()
             otx, ott = ox[:tb].contiguous(), torch.rand(tb, 1, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
